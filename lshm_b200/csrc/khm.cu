@@ -1,0 +1,473 @@
+// K-harmonic means on latent vectors: loss, analytic gradient, assignment, centre sums.
+//
+// Reference semantics: Kmeans.forward  /root/reference/src/lofar_models.py:199-209,
+// offline_update :231-261 (intent), eval loop src/evaluate_clustering.py:110-119.
+//
+// Design (B200): the direct-difference form sum_l (x_l - m_kl)^2 is kept in fp32 (the GEMM
+// form cancels exactly where the harmonic mean is dominated).  A point is held in
+// registers by TPP adjacent lanes (<= 32 floats per lane, interleaved float4 chunks so the lanes
+// of one point read consecutive 16-byte words of the row), centres live in shared memory and are
+// read as broadcast float4; the per-point harmonic sum is reduced across the TPP lanes with
+// warp shuffles.  The centre-gradient / centre-update sums are a [K x pts] x [pts x L] product,
+// done per tile from shared memory with one owner thread per output (no atomics inside the tile
+// loop); blocks are persistent (grid = multiple of the SM count) and flush once.
+#include "common.cuh"
+
+namespace lshm {
+namespace {
+
+constexpr int KHM_THREADS = 128;
+constexpr int KHM_KC = 32;        // centres per staged chunk (streaming mode) / per w-tile
+constexpr int KHM_MAXCH = 8;      // float4 chunks per lane  (<= 32 floats of a point per lane)
+constexpr float KHM_EPS = 1e-9f;  // src/lofar_models.py:195
+
+struct KhmArgs {
+  const float* X; int64_t ldx; const float* M; int64_t N; int K; int L;
+  float p; int pmode;                       // pmode: 2, 4 or 0 (generic powf)
+  // pass 1 outputs
+  double* loss_sum; float* e_out; int32_t* ids; float* dist; int group;
+  // pass 2
+  float gscale; float* gX; int64_t ldg; int accumulate_x; float* gM;  // BWD
+  float* num; float* den;                                              // SUMS
+};
+
+__device__ __forceinline__ float pow_p(float d2, float p, int pmode) {    // d^p from d^2
+  if (pmode == 2) return d2;
+  if (pmode == 4) return d2 * d2;
+  return powf(d2, 0.5f * p);
+}
+__device__ __forceinline__ float pow_pm2(float d2, float p, int pmode) {  // d^(p-2)
+  if (pmode == 2) return 1.f;
+  if (pmode == 4) return d2;
+  return powf(d2, 0.5f * (p - 2.f));
+}
+
+template <int TPP>
+__device__ __forceinline__ float lanes_sum(float v) {
+#pragma unroll
+  for (int o = 1; o < TPP; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// squared distance between the lane's slice of x and the matching slice of centre row `mrow`
+template <int TPP>
+__device__ __forceinline__ float dist2(const float4 (&x4)[KHM_MAXCH], const float* mrow, int s, int nch) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int c = 0; c < KHM_MAXCH; ++c) {
+    if (c < nch) {
+      const float4 m = *reinterpret_cast<const float4*>(mrow + ((c * TPP + s) << 2));
+      const float dx = x4[c].x - m.x, dy = x4[c].y - m.y, dz = x4[c].z - m.z, dw = x4[c].w - m.w;
+      a0 = fmaf(dx, dx, a0); a1 = fmaf(dy, dy, a1); a2 = fmaf(dz, dz, a2); a3 = fmaf(dw, dw, a3);
+    }
+  }
+  return lanes_sum<TPP>((a0 + a1) + (a2 + a3));
+}
+
+template <int TPP>
+__device__ __forceinline__ void load_point(float4 (&x4)[KHM_MAXCH], const float* X, int64_t ldx,
+                                           int64_t i, bool valid, int s, int nch) {
+#pragma unroll
+  for (int c = 0; c < KHM_MAXCH; ++c) {
+    x4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < nch && valid) x4[c] = *reinterpret_cast<const float4*>(X + i * ldx + ((c * TPP + s) << 2));
+  }
+}
+
+__device__ __forceinline__ void stage_centres(float* ms, const float* M, int k0, int kc, int L) {
+  const int n4 = (kc * L) >> 2;
+  const float4* src = reinterpret_cast<const float4*>(M + (int64_t)k0 * L);
+  float4* dst = reinterpret_cast<float4*>(ms);
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// pass 1: e_i = sum_k 1/(d_ik^p + eps); loss, e_out, argmin ids, group distances
+// ------------------------------------------------------------------------------------------
+template <int TPP, bool RESIDENT>
+__global__ void __launch_bounds__(KHM_THREADS) khm_pass1_kernel(KhmArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* ms = smem;  // RESIDENT: K*L, else KC*L
+  __shared__ double red[32];
+  constexpr int PTS = KHM_THREADS / TPP;
+  const int L = a.L, K = a.K, nch = L / (4 * TPP);
+  const int pt = threadIdx.x / TPP, s = threadIdx.x % TPP;
+  const int64_t ntiles = (a.N + PTS - 1) / PTS;
+  const float Kf = (float)K;
+  double lsum = 0.0;
+  if (RESIDENT) { stage_centres(ms, a.M, 0, K, L); __syncthreads(); }
+  const float inv_group = a.group > 0 ? 1.f / (float)a.group : 0.f;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t i = t * PTS + pt;
+    const bool valid = i < a.N;
+    float4 x4[KHM_MAXCH];
+    load_point<TPP>(x4, a.X, a.ldx, i, valid, s, nch);
+    float e = 0.f, best = 3.4e38f;
+    int besti = 0;
+    for (int k0 = 0; k0 < K; k0 += (RESIDENT ? K : KHM_KC)) {
+      const int kc = RESIDENT ? K : min(KHM_KC, K - k0);
+      if (!RESIDENT) { __syncthreads(); stage_centres(ms, a.M, k0, kc, L); __syncthreads(); }
+      for (int kk = 0; kk < kc; ++kk) {
+        const float d2 = dist2<TPP>(x4, ms + kk * L, s, nch);
+        const float dp = pow_p(d2, a.p, a.pmode);
+        e += 1.0f / (dp + KHM_EPS);
+        if (d2 < best) { best = d2; besti = k0 + kk; }
+        if (a.dist != nullptr && valid && s == 0)
+          atomicAdd(a.dist + (i / a.group) * K + (k0 + kk), dp * inv_group);
+      }
+    }
+    if (valid && s == 0) {
+      lsum += (double)(Kf / (e + KHM_EPS));
+      if (a.e_out) a.e_out[i] = e;
+      if (a.ids) a.ids[i] = besti;
+    }
+  }
+  if (a.loss_sum != nullptr) {
+    const double tot = block_sum<double>(lsum, red);
+    if (threadIdx.x == 0) atomicAdd(a.loss_sum, tot);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pass 2: weights w_ik (gradient) or Q_ik (centre update); gX in registers; [K,L] sums via a
+// shared-memory tile product
+// ------------------------------------------------------------------------------------------
+template <int TPP, bool RESIDENT, bool SUMS>
+__global__ void __launch_bounds__(KHM_THREADS) khm_pass2_kernel(KhmArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int PTS = KHM_THREADS / TPP;
+  const int L = a.L, K = a.K, nch = L / (4 * TPP), L4 = L >> 2;
+  // smem carve-up
+  float* ms = smem;                                       // RESIDENT: K*L else KC*L
+  float* acc_s = ms + (RESIDENT ? K * L : KHM_KC * L);    // RESIDENT: K*L accumulators
+  float* wsum_s = acc_s + (RESIDENT ? K * L : 0);         // RESIDENT: K
+  float* xs = wsum_s + (RESIDENT ? ((K + 3) & ~3) : 0);   // PTS*L
+  float* ws = xs + PTS * L;                               // PTS*KC
+  __shared__ double red[32];
+  const int pt = threadIdx.x / TPP, s = threadIdx.x % TPP;
+  const int64_t ntiles = (a.N + PTS - 1) / PTS;
+  const float Kf = (float)K;
+  double lsum = 0.0;
+  if (RESIDENT) {
+    stage_centres(ms, a.M, 0, K, L);
+    for (int i = threadIdx.x; i < K * L; i += blockDim.x) acc_s[i] = 0.f;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) wsum_s[i] = 0.f;
+    __syncthreads();
+  }
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t i = t * PTS + pt;
+    const bool valid = i < a.N;
+    float4 x4[KHM_MAXCH];
+    load_point<TPP>(x4, a.X, a.ldx, i, valid, s, nch);
+    // ---- harmonic sum e_i
+    float e = 0.f;
+    for (int k0 = 0; k0 < K; k0 += (RESIDENT ? K : KHM_KC)) {
+      const int kc = RESIDENT ? K : min(KHM_KC, K - k0);
+      if (!RESIDENT) { __syncthreads(); stage_centres(ms, a.M, k0, kc, L); __syncthreads(); }
+      for (int kk = 0; kk < kc; ++kk) {
+        const float d2 = dist2<TPP>(x4, ms + kk * L, s, nch);
+        e += 1.0f / (pow_p(d2, a.p, a.pmode) + KHM_EPS);
+      }
+    }
+    if (valid && s == 0) lsum += (double)(Kf / (e + KHM_EPS));
+    // per-point coefficient: gradient K/(e+eps)^2 ; centre update alpha = 1/(e^2+eps)
+    const float coef = SUMS ? 1.0f / (e * e + KHM_EPS) : Kf / ((e + KHM_EPS) * (e + KHM_EPS));
+    // ---- x tile to shared memory for the [K x pts] x [pts x L] product
+#pragma unroll
+    for (int c = 0; c < KHM_MAXCH; ++c)
+      if (c < nch) *reinterpret_cast<float4*>(xs + pt * L + ((c * TPP + s) << 2)) = x4[c];
+    float4 g4[KHM_MAXCH];
+#pragma unroll
+    for (int c = 0; c < KHM_MAXCH; ++c) g4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k0 = 0; k0 < K; k0 += KHM_KC) {
+      const int kc = min(KHM_KC, K - k0);
+      if (!RESIDENT) { __syncthreads(); stage_centres(ms, a.M, k0, kc, L); __syncthreads(); }
+      const float* mbase = RESIDENT ? ms + k0 * L : ms;
+      for (int kk = 0; kk < kc; ++kk) {
+        const float* mrow = mbase + kk * L;
+        const float d2 = dist2<TPP>(x4, mrow, s, nch);
+        const float dp = pow_p(d2, a.p, a.pmode);
+        float w;
+        if (SUMS) {
+          w = coef / (dp * d2 + KHM_EPS);                 // alpha_i / (d^(p+2) + eps)
+        } else {
+          const float tt = dp + KHM_EPS;
+          w = d2 > 0.f ? coef * a.p * pow_pm2(d2, a.p, a.pmode) / (tt * tt) : 0.f;
+        }
+        if (!valid) w = 0.f;
+        if (!SUMS) {
+#pragma unroll
+          for (int c = 0; c < KHM_MAXCH; ++c) {
+            if (c < nch) {
+              const float4 m = *reinterpret_cast<const float4*>(mrow + ((c * TPP + s) << 2));
+              g4[c].x = fmaf(w, x4[c].x - m.x, g4[c].x);
+              g4[c].y = fmaf(w, x4[c].y - m.y, g4[c].y);
+              g4[c].z = fmaf(w, x4[c].z - m.z, g4[c].z);
+              g4[c].w = fmaf(w, x4[c].w - m.w, g4[c].w);
+            }
+          }
+        }
+        if (s == 0) ws[pt * KHM_KC + kk] = w;
+      }
+      __syncthreads();
+      // tile product: thread owns output (kk, l4)
+      for (int o = threadIdx.x; o < kc * L4; o += blockDim.x) {
+        const int kk = o / L4, l4 = o - kk * L4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float wsum = 0.f;
+#pragma unroll 4
+        for (int q = 0; q < PTS; ++q) {
+          const float wv = ws[q * KHM_KC + kk];
+          const float4 xv = *reinterpret_cast<const float4*>(xs + q * L + (l4 << 2));
+          acc.x = fmaf(wv, xv.x, acc.x); acc.y = fmaf(wv, xv.y, acc.y);
+          acc.z = fmaf(wv, xv.z, acc.z); acc.w = fmaf(wv, xv.w, acc.w);
+          wsum += wv;
+        }
+        const int k = k0 + kk;
+        if (RESIDENT) {
+          float4* dst = reinterpret_cast<float4*>(acc_s + k * L + (l4 << 2));
+          float4 cur = *dst;
+          cur.x += acc.x; cur.y += acc.y; cur.z += acc.z; cur.w += acc.w;
+          *dst = cur;
+          if (l4 == 0) wsum_s[k] += wsum;
+        } else if (SUMS) {
+          float* dst = a.num + (int64_t)k * L + (l4 << 2);
+          atomicAdd(dst + 0, acc.x); atomicAdd(dst + 1, acc.y);
+          atomicAdd(dst + 2, acc.z); atomicAdd(dst + 3, acc.w);
+          if (l4 == 0) atomicAdd(a.den + k, wsum);
+        } else {
+          const float4 m = *reinterpret_cast<const float4*>(mbase + kk * L + (l4 << 2));
+          float* dst = a.gM + (int64_t)k * L + (l4 << 2);
+          atomicAdd(dst + 0, -a.gscale * (acc.x - m.x * wsum));
+          atomicAdd(dst + 1, -a.gscale * (acc.y - m.y * wsum));
+          atomicAdd(dst + 2, -a.gscale * (acc.z - m.z * wsum));
+          atomicAdd(dst + 3, -a.gscale * (acc.w - m.w * wsum));
+        }
+      }
+      __syncthreads();
+    }
+    if (!SUMS && valid && a.gX != nullptr) {
+#pragma unroll
+      for (int c = 0; c < KHM_MAXCH; ++c) {
+        if (c < nch) {
+          float4* dst = reinterpret_cast<float4*>(a.gX + i * a.ldg + ((c * TPP + s) << 2));
+          float4 v = make_float4(a.gscale * g4[c].x, a.gscale * g4[c].y, a.gscale * g4[c].z, a.gscale * g4[c].w);
+          if (a.accumulate_x) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+          *dst = v;
+        }
+      }
+    }
+  }
+  if (RESIDENT) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < K * L; idx += blockDim.x) {
+      const int k = idx / L;
+      if (SUMS) atomicAdd(a.num + idx, acc_s[idx]);
+      else atomicAdd(a.gM + idx, -a.gscale * (acc_s[idx] - ms[idx] * wsum_s[k]));
+    }
+    if (SUMS) for (int k = threadIdx.x; k < K; k += blockDim.x) atomicAdd(a.den + k, wsum_s[k]);
+  }
+  if (a.loss_sum != nullptr) {
+    const double tot = block_sum<double>(lsum, red);
+    if (threadIdx.x == 0) atomicAdd(a.loss_sum, tot);
+  }
+}
+
+__global__ void group_argmin_kernel(const float* dist, int64_t G, int K, int32_t* gid) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  float best = dist[g * K];
+  int bi = 0;
+  for (int k = 1; k < K; ++k) {
+    const float v = dist[g * K + k];
+    if (v < best) { best = v; bi = k; }
+  }
+  gid[g] = bi;
+}
+
+__global__ void center_apply_kernel(const float* num, const float* den, float* M, int K, int L) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < K * L) M[idx] = num[idx] / den[idx / L];
+}
+
+constexpr int RESIDENT_SMEM_LIMIT = 96 * 1024;
+
+int pick_tpp(int L) {
+  if (L <= 0 || (L & 3)) return 0;
+  for (int tpp = 1; tpp <= 32; tpp <<= 1)
+    if (L % (4 * tpp) == 0 && L / (4 * tpp) <= KHM_MAXCH) return tpp;
+  return 0;
+}
+
+int check_common(const char* name, const float* X, int64_t ldx, const float* M, int64_t N, int K, int L) {
+  LSHM_REQUIRE(X && M, "%s: null pointer", name);
+  LSHM_REQUIRE(N >= 0 && K > 0 && L > 0, "%s: bad sizes N=%lld K=%d L=%d", name, (long long)N, K, L);
+  LSHM_REQUIRE(pick_tpp(L) != 0, "%s: latent dim L=%d unsupported (need L%%4==0 and L<=1024 with L/(4*2^j)<=8)", name, L);
+  LSHM_REQUIRE(ldx >= L && (ldx & 3) == 0, "%s: row stride %lld must be >=L and a multiple of 4", name, (long long)ldx);
+  LSHM_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(M) & 15) == 0,
+               "%s: X and M must be 16-byte aligned", name);
+  return LSHM_OK;
+}
+
+int pmode_of(float p) { return p == 2.f ? 2 : (p == 4.f ? 4 : 0); }
+
+template <int TPP, bool RES>
+int launch_pass1_t(const KhmArgs& a, size_t smem, int grid, cudaStream_t st) {
+  if (smem > 48 * 1024)
+    LSHM_CUDA(cudaFuncSetAttribute(khm_pass1_kernel<TPP, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "khm_pass1");
+  khm_pass1_kernel<TPP, RES><<<grid, KHM_THREADS, smem, st>>>(a);
+  LSHM_CHECK_LAUNCH("khm_pass1");
+  return LSHM_OK;
+}
+
+template <int TPP, bool RES, bool SUMS>
+int launch_pass2_t(const KhmArgs& a, size_t smem, int grid, cudaStream_t st) {
+  if (smem > 48 * 1024)
+    LSHM_CUDA(cudaFuncSetAttribute(khm_pass2_kernel<TPP, RES, SUMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "khm_pass2");
+  khm_pass2_kernel<TPP, RES, SUMS><<<grid, KHM_THREADS, smem, st>>>(a);
+  LSHM_CHECK_LAUNCH("khm_pass2");
+  return LSHM_OK;
+}
+
+int grid_for(int64_t N, int tpp, int blocks_per_sm) {
+  const int pts = KHM_THREADS / tpp;
+  const int64_t ntiles = ceil_div(N, pts);
+  const int64_t cap = (int64_t)sm_count() * blocks_per_sm;
+  return (int)(ntiles < cap ? (ntiles > 0 ? ntiles : 1) : cap);
+}
+
+int launch_pass1(const KhmArgs& a, cudaStream_t st) {
+  const int tpp = pick_tpp(a.L);
+  const size_t res_bytes = (size_t)a.K * a.L * sizeof(float);
+  const bool res = res_bytes <= RESIDENT_SMEM_LIMIT;
+  const size_t smem = res ? res_bytes : (size_t)KHM_KC * a.L * sizeof(float);
+  const int grid = grid_for(a.N, tpp, 8);
+#define P1(T) (res ? launch_pass1_t<T, true>(a, smem, grid, st) : launch_pass1_t<T, false>(a, smem, grid, st))
+  switch (tpp) {
+    case 1: return P1(1);
+    case 2: return P1(2);
+    case 4: return P1(4);
+    case 8: return P1(8);
+    case 16: return P1(16);
+    default: return P1(32);
+  }
+#undef P1
+}
+
+template <bool SUMS>
+int launch_pass2(const KhmArgs& a, cudaStream_t st) {
+  const int tpp = pick_tpp(a.L);
+  const int pts = KHM_THREADS / tpp;
+  const size_t tile = ((size_t)pts * a.L + (size_t)pts * KHM_KC) * sizeof(float);
+  const size_t res_bytes = ((size_t)2 * a.K * a.L + ((a.K + 3) & ~3)) * sizeof(float) + tile;
+  const bool res = res_bytes <= RESIDENT_SMEM_LIMIT;
+  const size_t smem = res ? res_bytes : (size_t)KHM_KC * a.L * sizeof(float) + tile;
+  const int grid = grid_for(a.N, tpp, 4);
+#define P2(T) (res ? launch_pass2_t<T, true, SUMS>(a, smem, grid, st) : launch_pass2_t<T, false, SUMS>(a, smem, grid, st))
+  switch (tpp) {
+    case 1: return P2(1);
+    case 2: return P2(2);
+    case 4: return P2(4);
+    case 8: return P2(8);
+    case 16: return P2(16);
+    default: return P2(32);
+  }
+#undef P2
+}
+
+}  // namespace
+}  // namespace lshm
+
+using namespace lshm;
+
+extern "C" {
+
+int lshm_khm_fwd(const float* X, int64_t ldx, const float* M, int64_t N, int K, int L, float p,
+                 double* loss_sum, float* e_out, lshm_stream_t stream) {
+  if (int rc = check_common("lshm_khm_fwd", X, ldx, M, N, K, L)) return rc;
+  LSHM_REQUIRE(loss_sum != nullptr, "lshm_khm_fwd: loss_sum is null");
+  if (N == 0) return LSHM_OK;
+  KhmArgs a{};
+  a.X = X; a.ldx = ldx; a.M = M; a.N = N; a.K = K; a.L = L; a.p = p; a.pmode = pmode_of(p);
+  a.loss_sum = loss_sum; a.e_out = e_out;
+  return launch_pass1(a, as_stream(stream));
+}
+
+int lshm_khm_assign(const float* X, int64_t ldx, const float* M, int64_t N, int K, int L,
+                    int32_t* ids, lshm_stream_t stream) {
+  if (int rc = check_common("lshm_khm_assign", X, ldx, M, N, K, L)) return rc;
+  LSHM_REQUIRE(ids != nullptr, "lshm_khm_assign: ids is null");
+  if (N == 0) return LSHM_OK;
+  KhmArgs a{};
+  a.X = X; a.ldx = ldx; a.M = M; a.N = N; a.K = K; a.L = L; a.p = 2.f; a.pmode = 2;
+  a.ids = ids;
+  return launch_pass1(a, as_stream(stream));
+}
+
+int lshm_khm_group_dist(const float* X, int64_t ldx, const float* M, int64_t N, int K, int L,
+                        float p, int group, float* dist, int32_t* gid, lshm_stream_t stream) {
+  if (int rc = check_common("lshm_khm_group_dist", X, ldx, M, N, K, L)) return rc;
+  LSHM_REQUIRE(dist && gid, "lshm_khm_group_dist: null output");
+  LSHM_REQUIRE(group > 0 && N % group == 0, "lshm_khm_group_dist: N=%lld not a multiple of group=%d", (long long)N, group);
+  if (N == 0) return LSHM_OK;
+  const int64_t G = N / group;
+  cudaStream_t st = as_stream(stream);
+  LSHM_CUDA(cudaMemsetAsync(dist, 0, sizeof(float) * G * K, st), "lshm_khm_group_dist");
+  KhmArgs a{};
+  a.X = X; a.ldx = ldx; a.M = M; a.N = N; a.K = K; a.L = L; a.p = p; a.pmode = pmode_of(p);
+  a.dist = dist; a.group = group;
+  if (int rc = launch_pass1(a, st)) return rc;
+  group_argmin_kernel<<<(unsigned)ceil_div(G, 128), 128, 0, st>>>(dist, G, K, gid);
+  LSHM_CHECK_LAUNCH("lshm_khm_group_dist");
+  return LSHM_OK;
+}
+
+static int khm_bwd_common(const char* name, const float* X, int64_t ldx, const float* M, int64_t N,
+                          int K, int L, float p, float gscale, double* loss_sum, float* gX,
+                          int64_t ldg, int accumulate_x, float* gM, lshm_stream_t stream) {
+  if (int rc = check_common(name, X, ldx, M, N, K, L)) return rc;
+  LSHM_REQUIRE(gM != nullptr, "%s: gM is null", name);
+  if (gX) {
+    LSHM_REQUIRE(ldg >= L && (ldg & 3) == 0 && (reinterpret_cast<uintptr_t>(gX) & 15) == 0,
+                 "%s: gX must be 16-byte aligned with row stride %%4==0", name);
+  }
+  if (N == 0) return LSHM_OK;
+  KhmArgs a{};
+  a.X = X; a.ldx = ldx; a.M = M; a.N = N; a.K = K; a.L = L; a.p = p; a.pmode = pmode_of(p);
+  a.loss_sum = loss_sum; a.gscale = gscale; a.gX = gX; a.ldg = ldg; a.accumulate_x = accumulate_x; a.gM = gM;
+  return launch_pass2<false>(a, as_stream(stream));
+}
+
+int lshm_khm_bwd(const float* X, int64_t ldx, const float* M, int64_t N, int K, int L, float p,
+                 float gscale, float* gX, int64_t ldg, int accumulate_x, float* gM,
+                 lshm_stream_t stream) {
+  return khm_bwd_common("lshm_khm_bwd", X, ldx, M, N, K, L, p, gscale, nullptr, gX, ldg, accumulate_x, gM, stream);
+}
+
+int lshm_khm_fwd_bwd(const float* X, int64_t ldx, const float* M, int64_t N, int K, int L,
+                     float p, float gscale, double* loss_sum, float* gX, int64_t ldg,
+                     int accumulate_x, float* gM, lshm_stream_t stream) {
+  LSHM_REQUIRE(loss_sum != nullptr, "lshm_khm_fwd_bwd: loss_sum is null");
+  return khm_bwd_common("lshm_khm_fwd_bwd", X, ldx, M, N, K, L, p, gscale, loss_sum, gX, ldg, accumulate_x, gM, stream);
+}
+
+int lshm_khm_center_sums(const float* X, int64_t ldx, const float* M, int64_t N, int K, int L,
+                         float p, float* num, float* den, lshm_stream_t stream) {
+  if (int rc = check_common("lshm_khm_center_sums", X, ldx, M, N, K, L)) return rc;
+  LSHM_REQUIRE(num && den, "lshm_khm_center_sums: null output");
+  if (N == 0) return LSHM_OK;
+  KhmArgs a{};
+  a.X = X; a.ldx = ldx; a.M = M; a.N = N; a.K = K; a.L = L; a.p = p; a.pmode = pmode_of(p);
+  a.num = num; a.den = den;
+  return launch_pass2<true>(a, as_stream(stream));
+}
+
+int lshm_khm_center_apply(const float* num, const float* den, float* M, int K, int L,
+                          lshm_stream_t stream) {
+  LSHM_REQUIRE(num && den && M && K > 0 && L > 0, "lshm_khm_center_apply: bad arguments");
+  center_apply_kernel<<<(unsigned)ceil_div((int64_t)K * L, 256), 256, 0, as_stream(stream)>>>(num, den, M, K, L);
+  LSHM_CHECK_LAUNCH("lshm_khm_center_apply");
+  return LSHM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,217 @@
+// Dense head of the autoencoders: F.linear forward / backward with fused ELU, the uv
+// harmonic features, and small elementwise helpers.
+//
+// Reference semantics: fcuv1, fc1, fc2in, fc2out, fcuv3, fc3 and torch.kron/sin/cos at
+// /root/reference/src/lofar_models.py:60-69,80-91 (and :145-154,:165-176 for the 1-D nets).
+//
+// One shared-memory tiled SGEMM with arbitrary element strides serves the three products
+// (y = x W^T, dx = dz W, dW = dz^T x); the weight-gradient product splits the long sample
+// dimension over blockIdx.z and combines with atomics.
+#include "common.cuh"
+
+namespace lshm {
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, GEMM_THREADS = 256;
+
+struct GemmArgs {
+  const float* A; int64_t sam, sak;    // A(m,k) = A[m*sam + k*sak]
+  const float* B; int64_t sbn, sbk;    // B(n,k) = B[n*sbn + k*sbk]
+  float* C; int64_t ldc;               // C(m,n) = C[m*ldc + n]
+  const float* bias;                   // [n] or null
+  const float* add; int64_t ldadd;     // added before the epilogue, or null
+  const float* aux; int64_t ldaux;     // DELU operand
+  int64_t M; int N; int64_t K;
+  int64_t kchunk;                      // K range per blockIdx.z
+  int epi; int atomic;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS) sgemm_strided_kernel(GemmArgs g) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int64_t kbeg = (int64_t)blockIdx.z * g.kchunk;
+  const int64_t kend = min(kbeg + g.kchunk, g.K);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const bool a_kfast = g.sak == 1, b_kfast = g.sbk == 1;
+  for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+    for (int it = 0; it < (BM * BK) / GEMM_THREADS; ++it) {
+      const int idx = threadIdx.x + it * GEMM_THREADS;
+      int mm, kk;
+      if (a_kfast) { kk = idx % BK; mm = idx / BK; } else { mm = idx % BM; kk = idx / BM; }
+      const int64_t m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < g.M && k < kend) ? __ldg(g.A + m * g.sam + k * g.sak) : 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < (BN * BK) / GEMM_THREADS; ++it) {
+      const int idx = threadIdx.x + it * GEMM_THREADS;
+      int nn, kk;
+      if (b_kfast) { kk = idx % BK; nn = idx / BK; } else { nn = idx % BN; kk = idx / BN; }
+      const int64_t n = n0 + nn, k = k0 + kk;
+      Bs[kk][nn] = (n < g.N && k < kend) ? __ldg(g.B + n * g.sbn + k * g.sbk) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.N) continue;
+      float v = acc[i][j];
+      if (g.atomic) { atomicAdd(g.C + m * g.ldc + n, v); continue; }
+      if (g.bias) v += g.bias[n];
+      if (g.add) v += g.add[m * g.ldadd + n];
+      if (g.epi == LSHM_EPI_ELU) v = elu_f(v);
+      else if (g.epi == LSHM_EPI_DELU) v *= delu_from_out(g.aux[m * g.ldaux + n]);
+      g.C[m * g.ldc + n] = v;
+    }
+  }
+}
+
+int launch_gemm(GemmArgs g, int ksplit, cudaStream_t st, const char* name) {
+  g.kchunk = ceil_div(ceil_div(g.K, ksplit), BK) * BK;
+  if (g.kchunk <= 0) g.kchunk = BK;
+  const int zs = (int)std::max<int64_t>(1, ceil_div(g.K, g.kchunk));
+  dim3 grid((unsigned)ceil_div(g.M, BM), (unsigned)ceil_div(g.N, BN), (unsigned)zs);
+  sgemm_strided_kernel<<<grid, GEMM_THREADS, 0, st>>>(g);
+  LSHM_CHECK_LAUNCH(name);
+  return LSHM_OK;
+}
+
+__global__ void colsum_kernel(const float* __restrict__ dz, int64_t ld, float* __restrict__ db,
+                              int64_t N, int J, int64_t chunk) {
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int64_t start = (int64_t)blockIdx.y * chunk, stop = min(start + chunk, N);
+  float s = 0.f;
+  if (j < J)
+    for (int64_t n = start + (threadIdx.x >> 5); n < stop; n += blockDim.x >> 5) s += __ldg(dz + n * ld + j);
+  __shared__ float red[8][33];
+  red[threadIdx.x >> 5][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (threadIdx.x < 32 && j < J) {
+    float t = 0.f;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) t += red[q][threadIdx.x];
+    atomicAdd(db + j, t);
+  }
+}
+
+__global__ void uv_harmonics_kernel(const float* __restrict__ uv, const float* __restrict__ scales,
+                                    int64_t N, int H, float* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * H) return;
+  const int64_t n = idx / H;
+  const int hh = (int)(idx - n * H);
+  const float s = scales[hh];
+  const float zu = s * uv[2 * n], zv = s * uv[2 * n + 1];
+  float* o = out + n * 4 * H;
+  o[2 * hh] = sinf(zu);
+  o[2 * hh + 1] = sinf(zv);
+  o[2 * H + 2 * hh] = cosf(zu);
+  o[2 * H + 2 * hh + 1] = cosf(zv);
+}
+
+__global__ void delu_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ aux,
+                            int64_t ldaux, float* __restrict__ dz, int64_t lddz, int64_t N, int J) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * J) return;
+  const int64_t n = idx / J;
+  const int j = (int)(idx - n * J);
+  dz[n * lddz + j] = g[n * ldg + j] * delu_from_out(aux[n * ldaux + j]);
+}
+
+}  // namespace
+}  // namespace lshm
+
+using namespace lshm;
+
+extern "C" {
+
+int lshm_uv_harmonics(const float* uv, const float* scales, int64_t N, int H, float* out,
+                      lshm_stream_t stream) {
+  LSHM_REQUIRE(uv && scales && out && N >= 0 && H > 0, "lshm_uv_harmonics: bad arguments");
+  if (N == 0) return LSHM_OK;
+  uv_harmonics_kernel<<<(unsigned)ceil_div(N * H, 256), 256, 0, as_stream(stream)>>>(uv, scales, N, H, out);
+  LSHM_CHECK_LAUNCH("lshm_uv_harmonics");
+  return LSHM_OK;
+}
+
+int lshm_linear_fwd(const float* x, int64_t ldx, const float* w, const float* b,
+                    float* y, int64_t ldy, int64_t N, int K, int J, int epilogue,
+                    lshm_stream_t stream) {
+  LSHM_REQUIRE(x && w && y && N >= 0 && K > 0 && J > 0, "lshm_linear_fwd: bad arguments");
+  LSHM_REQUIRE(epilogue == LSHM_EPI_NONE || epilogue == LSHM_EPI_ELU, "lshm_linear_fwd: bad epilogue");
+  if (N == 0) return LSHM_OK;
+  GemmArgs g{};
+  g.A = x; g.sam = ldx; g.sak = 1;
+  g.B = w; g.sbn = K; g.sbk = 1;
+  g.C = y; g.ldc = ldy; g.bias = b; g.M = N; g.N = J; g.K = K; g.epi = epilogue;
+  return launch_gemm(g, 1, as_stream(stream), "lshm_linear_fwd");
+}
+
+int lshm_linear_bwd_data(const float* dz, int64_t lddz, const float* w, const float* add,
+                         int64_t ldadd, const float* aux, int64_t ldaux, float* dx, int64_t lddx,
+                         int64_t N, int K, int J, lshm_stream_t stream) {
+  LSHM_REQUIRE(dz && w && dx && N >= 0 && K > 0 && J > 0, "lshm_linear_bwd_data: bad arguments");
+  if (N == 0) return LSHM_OK;
+  GemmArgs g{};
+  g.A = dz; g.sam = lddz; g.sak = 1;          // A(n, j)
+  g.B = w; g.sbn = 1; g.sbk = K;              // B(k, j) = w[j*K + k]
+  g.C = dx; g.ldc = lddx; g.add = add; g.ldadd = ldadd; g.aux = aux; g.ldaux = ldaux;
+  g.M = N; g.N = K; g.K = J; g.epi = aux ? LSHM_EPI_DELU : LSHM_EPI_NONE;
+  return launch_gemm(g, 1, as_stream(stream), "lshm_linear_bwd_data");
+}
+
+int lshm_linear_bwd_weight(const float* x, int64_t ldx, const float* dz, int64_t lddz,
+                           float* dw, float* db, int64_t N, int K, int J, lshm_stream_t stream) {
+  LSHM_REQUIRE(x && dz && dw && N >= 0 && K > 0 && J > 0, "lshm_linear_bwd_weight: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  LSHM_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)J * K, st), "lshm_linear_bwd_weight");
+  if (db) LSHM_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * J, st), "lshm_linear_bwd_weight");
+  if (N == 0) return LSHM_OK;
+  GemmArgs g{};
+  g.A = dz; g.sam = 1; g.sak = lddz;          // A(j, n) = dz[n*lddz + j]
+  g.B = x; g.sbn = 1; g.sbk = ldx;            // B(k, n) = x[n*ldx + k]
+  g.C = dw; g.ldc = K; g.M = J; g.N = K; g.K = N; g.atomic = 1;
+  const int64_t tiles = ceil_div(J, BM) * ceil_div(K, BN);
+  int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(N, 4 * BK), (int64_t)sm_count() * 4 / tiles));
+  if (int rc = launch_gemm(g, ksplit, st, "lshm_linear_bwd_weight")) return rc;
+  if (db) {
+    const int64_t chunk = std::max<int64_t>(64, ceil_div(N, (int64_t)sm_count()));
+    dim3 grid((unsigned)ceil_div(J, 32), (unsigned)ceil_div(N, chunk));
+    colsum_kernel<<<grid, 256, 0, st>>>(dz, lddz, db, N, J, chunk);
+    LSHM_CHECK_LAUNCH("lshm_linear_bwd_weight(colsum)");
+  }
+  return LSHM_OK;
+}
+
+int lshm_delu(const float* g, int64_t ldg, const float* aux, int64_t ldaux, float* dz,
+              int64_t lddz, int64_t N, int J, lshm_stream_t stream) {
+  LSHM_REQUIRE(g && aux && dz && N >= 0 && J > 0, "lshm_delu: bad arguments");
+  if (N == 0) return LSHM_OK;
+  delu_kernel<<<(unsigned)ceil_div(N * J, 256), 256, 0, as_stream(stream)>>>(g, ldg, aux, ldaux, dz, lddz, N, J);
+  LSHM_CHECK_LAUNCH("lshm_delu");
+  return LSHM_OK;
+}
+
+}  // extern "C"

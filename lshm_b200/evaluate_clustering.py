@@ -1,0 +1,74 @@
+"""Inference / assignment loop of /root/reference/src/evaluate_clustering.py:75-119.
+
+Per baseline: cascade forward -> Mu = cat(mu, muT, muF) -> kdist = mod(Mu) ->
+dist[k] = mean_n ||Mu_n - M_k||^p -> argmin_k.  The t-SNE / agglomerative / PNG part
+(:121-163) is CPU post-processing on the returned ``X [K,nbase]`` and is out of scope.
+
+`encode_assign` is the batched form used for many baselines at once (BASELINE config 3):
+the same arithmetic on all patches of a shard, then one grouped reduction.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ._lib import lib
+from .lofar_models import AutoEncoder1DCNN, AutoEncoderCNN2, Kmeans
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+@torch.no_grad()
+def cascade_latents(net: AutoEncoderCNN2, net1D1: AutoEncoder1DCNN, net1D2: AutoEncoder1DCNN,
+                    x: torch.Tensor, uv: torch.Tensor) -> torch.Tensor:
+    """src/evaluate_clustering.py:81-89,108: Mu [N, L+2Lt] for patches x [N,C,128,128]."""
+    N, C = x.shape[:2]
+    L, Lt = net.latent_dim, net1D1.latent_dim
+    st = _stream()
+    x = x.contiguous()
+    uv = uv.contiguous()
+    Mu = torch.empty(N, L + 2 * Lt, dtype=torch.float32, device=x.device)
+    scales = net.harmonic_scales.to(x.device).float().contiguous()
+    e0, e1, e2 = net.engine(), net1D1.engine(), net1D2.engine()
+    ws0 = e0.workspace(N, x.device, False)
+    x1, _ = e0.forward(x.view(N, -1), uv, scales, net.named_param_dict(), ws0, st, mu_out=Mu[:, :L])
+    iy1 = torch.empty(N, C * 16384, dtype=torch.float32, device=x.device)
+    iy2 = torch.empty_like(iy1)
+    lib().residual_split(x.data_ptr(), x1.data_ptr(), iy1.data_ptr(), iy2.data_ptr(), N, C, 128, st)
+    del ws0
+    ws1 = e1.workspace(N, x.device, False)
+    e1.forward(iy1, uv, scales, net1D1.named_param_dict(), ws1, st, mu_out=Mu[:, L:L + Lt])
+    e2.forward(iy2, uv, scales, net1D2.named_param_dict(), ws1, st, mu_out=Mu[:, L + Lt:])
+    return Mu
+
+
+@torch.no_grad()
+def encode_assign(net, net1D1, net1D2, mod: Kmeans, x, uv, batch_per_bline: int):
+    """Returns (dist [nbase,K] fp32, baseline cluster id [nbase] int32, per-patch id [N] int32,
+    Mu [N,Ltot])."""
+    Mu = cascade_latents(net, net1D1, net1D2, x, uv)
+    dist, gid = mod.group_distances(Mu, batch_per_bline)
+    return dist, gid, mod.assign(Mu), Mu
+
+
+@torch.no_grad()
+def evaluate(net, net1D1, net1D2, mod: Kmeans, baseline_loader, nbase: int, log=None):
+    """The per-baseline loop of src/evaluate_clustering.py:75-119.
+
+    baseline_loader(nb) -> (patchx, patchy, x, uv) (e.g. a partial of get_data_for_baseline with
+    uvdist=True).  Returns (X [K,nbase] float64, clusid [nbase] float64) like the reference.
+    """
+    X = np.zeros([mod.K, nbase], dtype=np.float64)
+    clusid = np.zeros(nbase, dtype=np.float64)
+    for nb in range(nbase):
+        patchx, patchy, x, uv = baseline_loader(nb)
+        Mu = cascade_latents(net, net1D1, net1D2, x, uv)
+        kdist = mod(Mu)
+        dist, gid = mod.group_distances(Mu, Mu.shape[0])
+        X[:, nb] = dist[0].double().cpu().numpy()
+        clusid[nb] = int(gid[0])
+        if log is not None:
+            log("%d %e %d" % (nb, float(kdist), int(gid[0])))
+    return X, clusid

@@ -1,0 +1,265 @@
+"""Deep K-harmonic training step: the closure of /root/reference/src/kharmonic_lofar.py:132-182,
+the multiplier update of :187-202 and the loop of :115-208, on liblshm_sm100 kernels.
+
+Two ways to use it:
+
+* the drop-in modules of :mod:`lshm_b200.lofar_models` work in the reference loop *unchanged*
+  (autograd sees one node per module);
+* :class:`DeepKHarmonicStep` is the fused path used by ``bench.py``: one flat parameter buffer
+  and one flat gradient buffer for ``net``/``netT``/``netF``/``mod``, the whole closure as a
+  fixed sequence of kernel launches with analytic gradients (no autograd graph, no host sync),
+  and - under data parallelism - ONE all-reduce per closure evaluation over
+  ``[all gradients | 16 loss scalars]``.
+
+The closure honours the ``lbfgsnew.LBFGSNew`` contract (src/lbfgsnew.py:498-759): with grad
+enabled it leaves ``.grad`` on every leaf Parameter; under ``torch.set_grad_enabled(False)``
+(:686-693) it is forward-only; it returns a 0-dim tensor whose ``float()`` is the loss and is
+identical on every rank.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from ._lib import lib
+from .lofar_models import AutoEncoder1DCNN, AutoEncoderCNN2, Kmeans
+
+LOSS_TAIL = 16  # floats appended to the flat gradient buffer: total + the 8 printed terms
+TERM_NAMES = ("loss0", "loss1", "loss2", "loss3", "kdist", "aug", "sim", "rica")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class FlatParams:
+    """Re-homes every Parameter of `modules` into one flat fp32 buffer (and `.grad` into a
+    second one).  Parameters stay ordinary dense leaf tensors (views), so ``torch.optim.Adam``,
+    ``LBFGSNew`` (``p.data.add_``, ``p.copy_``, ``p.grad.data`` - src/lbfgsnew.py:84-112) and
+    ``state_dict`` keep working; the flat layout makes the data-parallel exchange one call."""
+
+    ALIGN = 64  # floats: every tensor starts 256-byte aligned
+
+    def __init__(self, modules, device):
+        self.params: List[torch.nn.Parameter] = []
+        self.names: List[str] = []
+        for mi, m in enumerate(modules):
+            for nm, p in m.named_parameters():
+                self.params.append(p)
+                self.names.append(f"{mi}.{nm}")
+        offs, off = [], 0
+        for p in self.params:
+            offs.append(off)
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.offsets, self.numel = offs, off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(off + LOSS_TAIL, dtype=torch.float32, device=device)
+        self.grad_views = []
+        with torch.no_grad():
+            for p, o in zip(self.params, offs):
+                v = self.flat[o:o + p.numel()].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+                gv = self.grad[o:o + p.numel()].view(p.shape)
+                p.grad = gv
+                self.grad_views.append(gv)
+        self.loss_tail = self.grad[off:off + LOSS_TAIL]
+
+    def attach_grads(self):
+        for p, gv in zip(self.params, self.grad_views):
+            if p.grad is not gv:
+                p.grad = gv
+
+
+class FlatAdam:
+    """torch.optim.Adam semantics (src/kharmonic_lofar.py:92) as ONE kernel over the flat
+    buffer (lshm_adam_step)."""
+
+    def __init__(self, flat: FlatParams, lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
+        self.flat, self.lr, self.betas, self.eps = flat, lr, betas, eps
+        self.m = torch.zeros_like(flat.flat)
+        self.v = torch.zeros_like(flat.flat)
+        self.t = 0
+
+    def zero_grad(self):
+        pass  # the fused closure overwrites every gradient
+
+    def step(self, closure):
+        with torch.enable_grad():
+            loss = closure()
+        self.t += 1
+        lib().adam_step(self.flat.flat.data_ptr(), self.flat.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                        self.flat.numel, self.lr, self.betas[0], self.betas[1], self.eps, self.t, _stream())
+        return loss
+
+
+class DeepKHarmonicStep:
+    """Fused closure + multiplier update for one minibatch (see module docstring).
+
+    Hyper-parameter names and defaults follow src/kharmonic_lofar.py:37-48.
+    `group` is an optional torch.distributed process group: each rank then holds a shard of
+    whole baseline groups (rows [g*bpb,(g+1)*bpb)) and `global_patches` is the global N.
+    """
+
+    def __init__(self, net: AutoEncoderCNN2, netT: AutoEncoder1DCNN, netF: AutoEncoder1DCNN, mod: Kmeans, *,
+                 alpha=0.01, beta=0.01, gamma=0.01, rho=1.0, use_rica=True, rica_lambda=0.01,
+                 group: Optional[dist.ProcessGroup] = None, distributed: bool = False):
+        self.net, self.netT, self.netF, self.mod = net, netT, netF, mod
+        self.alpha, self.beta, self.gamma, self.rho = alpha, beta, gamma, rho
+        self.use_rica, self.rica_lambda = use_rica, rica_lambda
+        self.distributed, self.group = distributed, group
+        self.world = dist.get_world_size(group) if distributed else 1
+        dev = next(net.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("lshm_b200: DeepKHarmonicStep needs CUDA modules (no CPU path)")
+        self.device = dev
+        self.flat = FlatParams([net, netT, netF, mod], dev)
+        self.L, self.Lt = net.latent_dim, netT.latent_dim
+        self.Ltot = self.L + 2 * self.Lt
+        if mod.latent_dim != self.Ltot:
+            raise RuntimeError("lshm_b200: Kmeans.latent_dim must equal L + 2*Lt")
+        self._pd = [m.named_param_dict() for m in (net, netT, netF)]
+        self._gd = []
+        views = dict(zip(self.flat.names, self.flat.grad_views))
+        for mi, m in enumerate((net, netT, netF)):
+            self._gd.append({nm: views[f"{mi}.{nm}"] for nm in m._names})
+        self._gM = views["3.M"]
+        self.N = 0
+        self.launches = 0
+        if distributed:
+            self.broadcast_parameters()
+
+    # ------------------------------------------------------------------ data parallel
+    def broadcast_parameters(self, src: int = 0):
+        dist.broadcast(self.flat.flat, src=src, group=self.group)
+
+    # ------------------------------------------------------------------ batch
+    def set_batch(self, x: torch.Tensor, uv: torch.Tensor, batch_per_bline: int,
+                  global_patches: Optional[int] = None):
+        """x [N,C,128,128], uv [N,2] (this rank's shard); resets y1..y3 (src/kharmonic_lofar.py:128-130)."""
+        N, C = x.shape[0], x.shape[1]
+        if N % batch_per_bline:
+            raise RuntimeError("lshm_b200: shard must hold whole baseline groups")
+        self.x = x.contiguous()
+        self.uv = uv.contiguous()
+        self.bpb = batch_per_bline
+        self.Nglobal = int(global_patches) if global_patches is not None else N * self.world
+        if N != self.N or getattr(self, "C", None) != C:
+            dev, f = self.device, dict(device=self.device, dtype=torch.float32)
+            self.N, self.C = N, C
+            e = self.net.engine(), self.netT.engine(), self.netF.engine()
+            self.ws = [e[0].workspace(N, dev, True, False), e[1].workspace(N, dev, True, True),
+                       e[2].workspace(N, dev, True, True)]
+            n = N * C * 16384
+            self.iyT, self.iyF = torch.empty(n, **f), torch.empty(n, **f)
+            self.g1p, self.g2, self.g3f, self.gx1 = (torch.empty(n, **f) for _ in range(4))
+            self.y1, self.y2, self.y3 = (torch.empty(n, **f) for _ in range(3))
+            self.Mu = torch.empty(N, self.Ltot, **f)
+            self.gMu = torch.empty(N, self.Ltot, **f)
+            self.terms = torch.zeros(16, dtype=torch.float64, device=dev)
+            K = self.mod.K
+            self.simwork = torch.empty(2 * K * K, **f)
+            self.scales = self.net.harmonic_scales.to(dev).float().contiguous()
+        self.y1.zero_(); self.y2.zero_(); self.y3.zero_()
+
+    # ------------------------------------------------------------------ forward pieces
+    def _forward(self, st):
+        L, Lt, N, C = self.L, self.Lt, self.N, self.C
+        e = self.net.engine(), self.netT.engine(), self.netF.engine()
+        xf = self.x.view(N, -1)
+        x1, _ = e[0].forward(xf, self.uv, self.scales, self._pd[0], self.ws[0], st, mu_out=self.Mu[:, :L])
+        lib().residual_split(self.x.data_ptr(), x1.data_ptr(), self.iyT.data_ptr(), self.iyF.data_ptr(), N, C, 128, st)
+        x2, _ = e[1].forward(self.iyT.view(N, -1), self.uv, self.scales, self._pd[1], self.ws[1], st,
+                             mu_out=self.Mu[:, L:L + Lt])
+        x3f, _ = e[2].forward(self.iyF.view(N, -1), self.uv, self.scales, self._pd[2], self.ws[2], st,
+                              mu_out=self.Mu[:, L + Lt:])
+        return x1, x2, x3f
+
+    def closure(self) -> torch.Tensor:
+        """src/kharmonic_lofar.py:132-182.  Returns the total loss (0-dim device tensor)."""
+        lb, st = lib(), _stream()
+        grads = torch.is_grad_enabled()
+        start = lb.launches
+        N, C, L, Lt, Ltot, K = self.N, self.C, self.L, self.Lt, self.Ltot, self.mod.K
+        M = self.mod.M
+        numel_g = float(self.Nglobal) * C * 16384
+        self.terms.zero_()
+        tp = self.terms.data_ptr()
+        x1, x2, x3f = self._forward(st)
+        g1p, g2, g3f = (self.g1p.data_ptr(), self.g2.data_ptr(), self.g3f.data_ptr()) if grads else (None, None, None)
+        lb.cascade_losses(self.x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(),
+                          self.y1.data_ptr(), self.y2.data_ptr(), self.y3.data_ptr(), self.rho,
+                          N, C, 128, 1.0 / numel_g, tp, g1p, g2, g3f, st)
+        khm_scale = self.alpha / (float(self.Nglobal) * K * Ltot)
+        p = float(self.mod.p)
+        bs_global = self.Nglobal // self.bpb
+        aug_scale = self.gamma / (float(self.bpb) * bs_global * self.bpb)
+        sim_scale = self.beta / self.world      # M is replicated: count its penalty once
+        frac = float(N) / float(self.Nglobal)   # logcosh divides by the local numel
+        Mu, gMu = self.Mu, self.gMu
+        if grads:
+            self.flat.attach_grads()
+            self._gM.zero_()
+            lb.khm_fwd_bwd(Mu.data_ptr(), Ltot, M.data_ptr(), N, K, Ltot, p, khm_scale, tp + 8 * 8,
+                           gMu.data_ptr(), Ltot, 0, self._gM.data_ptr(), st)
+        else:
+            lb.khm_fwd(Mu.data_ptr(), Ltot, M.data_ptr(), N, K, Ltot, p, tp + 8 * 8, None, st)
+        lb.similarity(M.data_ptr(), K, Ltot, sim_scale, tp + 9 * 8, self._gM.data_ptr() if grads else None,
+                      self.simwork.data_ptr(), st)
+        lb.augment(Mu.data_ptr(), Ltot, N, Ltot, self.bpb, aug_scale, tp + 10 * 8,
+                   gMu.data_ptr() if grads else None, Ltot, st)
+        if self.use_rica:
+            for off, width in ((0, L), (L, Lt), (L + Lt, Lt)):
+                lb.logcosh(Mu.data_ptr() + 4 * off, Ltot, N, width, self.rica_lambda * frac, tp + 11 * 8,
+                           gMu.data_ptr() + 4 * off if grads else None, Ltot, st)
+        if grads:
+            e = self.net.engine(), self.netT.engine(), self.netF.engine()
+            dT = e[1].backward(self.iyT.view(N, -1), self._pd[1], self._gd[1], self.ws[1], st, self.g2.view(N, -1),
+                               gMu[:, L:L + Lt], Mu[:, L:L + Lt], True)
+            dF = e[2].backward(self.iyF.view(N, -1), self._pd[2], self._gd[2], self.ws[2], st, self.g3f.view(N, -1),
+                               gMu[:, L + Lt:], Mu[:, L + Lt:], True)
+            lb.cascade_combine(self.g1p.data_ptr(), dT.data_ptr(), dF.data_ptr(), self.gx1.data_ptr(), N, C, 128, st)
+            e[0].backward(self.x.view(N, -1), self._pd[0], self._gd[0], self.ws[0], st, self.gx1.view(N, -1),
+                          gMu[:, :L], Mu[:, :L], False)
+        tail = self.flat.loss_tail
+        lb.closure_total(tp, self.rho, numel_g, khm_scale, tail.data_ptr(), st)
+        if self.distributed:
+            # ONE exchange per closure evaluation: gradients + loss scalars (forward-only: scalars)
+            buf = self.flat.grad if grads else tail
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+        self.launches = lb.launches - start
+        return tail[0]
+
+    def loss_terms(self) -> dict:
+        """The columns printed at src/kharmonic_lofar.py:179 (one device->host copy)."""
+        v = self.flat.loss_tail[:9].tolist()
+        d = dict(total=v[0])
+        d.update(zip(TERM_NAMES, v[1:]))
+        return d
+
+    def update_multipliers(self):
+        """src/kharmonic_lofar.py:187-202: no-grad forward of the cascade, then y_i += rho*r_i."""
+        st = _stream()
+        with torch.no_grad():
+            x1, x2, x3f = self._forward(st)
+            lib().multiplier_update(self.x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(), self.rho,
+                                    self.y1.data_ptr(), self.y2.data_ptr(), self.y3.data_ptr(),
+                                    self.N, self.C, 128, st)
+
+    def latents(self) -> torch.Tensor:
+        return self.Mu
+
+
+def train(step: DeepKHarmonicStep, optimizer, batches, Nadmm=10, log=None):
+    """The loop of src/kharmonic_lofar.py:115-208 over an iterable of
+    (patchx, patchy, x, uv) minibatches (e.g. lofar_tools.get_data_minibatch(..., uvdist=True))."""
+    for i, (patchx, patchy, x, uv) in enumerate(batches):
+        step.set_batch(x, uv, patchx * patchy)
+        for admm in range(Nadmm):
+            optimizer.step(step.closure)
+            if log is not None:
+                t = step.loss_terms()
+                log("%d %d %f %f %f %f %f %f %f %f" % ((i, admm) + tuple(t[k] for k in TERM_NAMES)))
+            step.update_multipliers()

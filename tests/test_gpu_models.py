@@ -1,0 +1,265 @@
+"""Module-level and step-level parity: the drop-in modules under autograd, the fused closure,
+the multiplier update, the optimiser contracts, and the inference loop - against the CPU
+oracle (oracle/lofar_oracle.py) on identical seeded inputs.
+
+Tolerances: north_star asks loss and gradients within 1e-3 relative; the fp32 kernels are held
+to 2e-4 here (per-tensor L2-relative), losses to 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+from common import SCALES, closure_case, golden, max_abs, oracle_closure, rel_err
+from oracle import lofar_oracle as O
+
+pytestmark = pytest.mark.gpu
+GRAD_TOL = 2e-4
+
+
+def build_modules(case, cuda, rica=True):
+    from lshm_b200.lofar_models import AutoEncoder1DCNN, AutoEncoderCNN2, Kmeans
+    hs = torch.tensor(SCALES).to(cuda)
+    net = AutoEncoderCNN2(case["L"], case["C"], hs, rica)
+    netT = AutoEncoder1DCNN(case["Lt"], case["C"], hs, rica)
+    netF = AutoEncoder1DCNN(case["Lt"], case["C"], hs, rica)
+    mod = Kmeans(case["L"] + 2 * case["Lt"], case["K"], 4)
+    net.load_state_dict(case["pn"]); netT.load_state_dict(case["pT"]); netF.load_state_dict(case["pF"])
+    mod.load_state_dict({"M": case["M"]})
+    return [m.to(cuda) for m in (net, netT, netF, mod)]
+
+
+def check_grads(got, ref, tol=GRAD_TOL):
+    bad = []
+    for k, r in ref.items():
+        e = rel_err(got[k], r)
+        if not e < tol:
+            bad.append((k, e))
+    assert not bad, f"gradient mismatch (rel L2 > {tol}): {bad}"
+
+
+@pytest.mark.parametrize("ndim,C,L", [(2, 8, 32), (2, 4, 224), (1, 8, 16), (1, 4, 16)])
+def test_autoencoder_module_forward_backward(cuda, ndim, C, L):
+    from lshm_b200.lofar_models import AutoEncoder1DCNN, AutoEncoderCNN2
+    from lshm_b200 import synthetic as S
+    hs = torch.tensor(SCALES)
+    p = O.make_ae_params(L, C, ndim=ndim, seed=3)
+    N = 3
+    x = torch.from_numpy(S.make_patches(N, C, seed=4))
+    if ndim == 1:
+        x = x.flatten(2, 3)
+    uv = torch.from_numpy(S.make_uv(N, seed=4))
+    pr = {k: v.clone().requires_grad_() for k, v in p.items()}
+    xr = x.clone().requires_grad_()
+    xh_ref, mu_ref = O.ae_forward(pr, xr, uv, hs, ndim, True)
+    w1, w2 = torch.randn_like(xh_ref), torch.randn_like(mu_ref)
+    ((xh_ref * w1).sum() + (mu_ref * w2).sum()).backward()
+    cls = AutoEncoderCNN2 if ndim == 2 else AutoEncoder1DCNN
+    net = cls(L, C, hs.to(cuda), True)
+    net.load_state_dict(p)
+    net = net.to(cuda)
+    assert list(net.state_dict().keys()) == list(p.keys())
+    xg = x.to(cuda).requires_grad_()
+    xh, mu = net(xg, uv.to(cuda))
+    assert rel_err(xh, xh_ref) < 1e-5 and rel_err(mu, mu_ref) < 1e-5
+    ((xh * w1.to(cuda)).sum() + (mu * w2.to(cuda)).sum()).backward()
+    check_grads({k: v.grad for k, v in net.named_parameters()}, {k: v.grad for k, v in pr.items()})
+    assert rel_err(xg.grad, xr.grad) < GRAD_TOL
+    # no-grad forward gives the same numbers and keeps no graph
+    with torch.no_grad():
+        xh2, mu2 = net(xg, uv.to(cuda))
+    assert max_abs(xh2, xh) == 0 and not xh2.requires_grad
+    # encode/decode helpers (reference signatures take the harmonic vector)
+    uvh = O.uv_harmonics(uv, hs)
+    enc = net.encode(x.to(cuda), uvh.to(cuda))
+    assert rel_err(enc, O.ae_encode(p, x, uvh, ndim)) < 1e-5
+    z = torch.randn(N, L)
+    assert rel_err(net.decode(z.to(cuda), uvh.to(cuda)), O.ae_decode(p, z, uvh, ndim)) < 1e-5
+
+
+def test_kmeans_module(cuda):
+    from lshm_b200.lofar_models import Kmeans, augmented_loss
+    g = golden("kmeans.npz")
+    X, M = torch.from_numpy(g["X"]), torch.from_numpy(g["M"])
+    for p in (2, 4):
+        km = Kmeans(64, 10, p)
+        km.load_state_dict({"M": M})
+        km = km.to(cuda)
+        Xg = X.to(cuda).requires_grad_()
+        loss = 3.0 * km(Xg)
+        loss.backward()
+        assert abs(float(loss) / 3.0 - float(g[f"loss_p{p}"])) < 1e-5 * float(g[f"loss_p{p}"])
+        assert rel_err(Xg.grad / 3.0, g[f"gX_p{p}"]) < GRAD_TOL and rel_err(km.M.grad / 3.0, g[f"gM_p{p}"]) < GRAD_TOL
+        km.zero_grad()
+        sim = km.cluster_similarity()
+        sim.backward()
+        assert abs(float(sim) - float(g["sim"])) < 1e-5 * float(g["sim"]) and rel_err(km.M.grad, g["gsim"]) < GRAD_TOL
+    mu = torch.randn(12, 64)
+    mur = mu.clone().requires_grad_()
+    ref = O.augmented_loss(mur, 4, 3)
+    ref.sum().backward()
+    mg = mu.to(cuda).requires_grad_()
+    got = augmented_loss(mg, 4, 3)
+    got.sum().backward()
+    assert got.shape == (1,) and abs(float(got) - float(ref)) < 1e-5 * float(ref) and rel_err(mg.grad, mur.grad) < GRAD_TOL
+    # offline update == oracle restatement of Zhang 7.1-7.5
+    km = Kmeans(64, 10, 4)
+    km.load_state_dict({"M": M})
+    km = km.to(cuda)
+    km.offline_update(X.to(cuda))
+    assert rel_err(km.M, O.offline_update(X, M, 4)[0]) < 1e-3
+
+
+@pytest.mark.parametrize("C,L,Lt,N,bpb", [(8, 32, 16, 8, 4), (4, 48, 8, 6, 3)])
+def test_fused_closure_matches_oracle(cuda, C, L, Lt, N, bpb):
+    from lshm_b200.kharmonic_lofar import DeepKHarmonicStep
+    case = closure_case(C=C, L=L, Lt=Lt, N=N, bpb=bpb, seed=0 if C == 8 else 20)
+    ref = oracle_closure(case)
+    net, netT, netF, mod = build_modules(case, cuda)
+    step = DeepKHarmonicStep(net, netT, netF, mod)
+    step.set_batch(case["x"].to(cuda), case["uv"].to(cuda), bpb)
+    for dst, src in zip((step.y1, step.y2, step.y3), case["ys"]):
+        dst.copy_(src.to(cuda))
+    loss = step.closure()
+    terms = step.loss_terms()
+    for k in ("total", "loss0", "loss1", "loss2", "loss3", "kdist", "aug", "sim", "rica"):
+        assert abs(terms[k] - ref[k]) <= 1e-5 * abs(ref[k]) + 1e-9, (k, terms[k], ref[k])
+    assert abs(float(loss) - ref["total"]) <= 1e-5 * abs(ref["total"])
+    assert rel_err(step.latents(), ref["Mu"]) < 1e-5
+    got = {nm: p.grad for nm, p in zip(step.flat.names, step.flat.params)}
+    check_grads(got, ref["grads"])
+    # forward-only evaluation (LBFGSNew line search, src/lbfgsnew.py:686-693): same loss, grads untouched
+    before = step.flat.grad.clone()
+    with torch.no_grad():
+        l2 = step.closure()
+    assert abs(float(l2) - ref["total"]) <= 1e-5 * abs(ref["total"])
+    assert max_abs(step.flat.grad[:step.flat.numel], before[:step.flat.numel]) == 0
+    # multiplier update against the oracle
+    y_ref = O.multiplier_update(case["pn"], case["pT"], case["pF"], case["x"], case["uv"], torch.tensor(SCALES), *case["ys"])
+    step.update_multipliers()
+    for got_y, ref_y in zip((step.y1, step.y2, step.y3), y_ref):
+        assert rel_err(got_y, ref_y) < 1e-5
+
+
+def test_reference_loop_with_dropin_modules(cuda):
+    """The closure body of src/kharmonic_lofar.py:135-175 written exactly as in the reference, but
+    on the drop-in modules: autograd must deliver the oracle's gradients."""
+    from lshm_b200.lofar_models import augmented_loss
+    case = closure_case()
+    ref = oracle_closure(case)
+    net, netT, netF, mod = build_modules(case, cuda)
+    x, uv = case["x"].to(cuda), case["uv"].to(cuda)
+    y1, y2, y3 = (t.to(cuda) for t in case["ys"])
+    criterion = torch.nn.MSELoss(reduction="sum")
+    alpha = beta = gamma = 0.01; rho = 1; rica_lambda = 0.01
+    x1, mu = net(x, uv)
+    x11 = (x - x1) / 2
+    iy1 = torch.flatten(x11, start_dim=2, end_dim=3)
+    yyT, yyTmu = netT(iy1, uv)
+    x2 = yyT.view_as(x11)
+    iy2 = torch.flatten(torch.transpose(x11, 2, 3), start_dim=2, end_dim=3)
+    yyF, yyFmu = netF(iy2, uv)
+    x3 = torch.transpose(yyF.view_as(x11), 2, 3)
+    xrecon = x1 + x2 + x3
+    loss0 = (criterion(xrecon, x)) / (x.numel())
+    loss1 = (torch.dot(y1, (x - x1).view(-1)) + rho / 2 * criterion(x, x1)) / (x.numel())
+    loss2 = (torch.dot(y2, (x11 - x2).view(-1)) + rho / 2 * criterion(x11, x2)) / (x.numel())
+    loss3 = (torch.dot(y3, (x11 - x3).reshape(-1)) + rho / 2 * criterion(x11, x3)) / (x.numel())
+    Mu = torch.cat((mu, yyTmu, yyFmu), 1)
+    kdist = alpha * mod.clustering_error(Mu)
+    clus_sim = beta * mod.cluster_similarity()
+    augmentation_loss = gamma * augmented_loss(Mu, case["bpb"], case["N"] // case["bpb"])
+    loss = loss0 + loss1 + loss2 + loss3 + kdist + augmentation_loss + clus_sim
+    rica_loss = rica_lambda * (torch.sum(torch.log(torch.cosh(mu))) / mu.numel()
+                               + torch.sum(torch.log(torch.cosh(yyTmu))) / yyTmu.numel()
+                               + torch.sum(torch.log(torch.cosh(yyFmu))) / yyFmu.numel())
+    loss += rica_loss
+    loss.backward(retain_graph=True)
+    assert abs(float(loss) - ref["total"]) < 1e-5 * abs(ref["total"])
+    got = {}
+    for mi, m in enumerate((net, netT, netF, mod)):
+        for nm, p in m.named_parameters():
+            got[f"{mi}.{nm}"] = p.grad
+    check_grads(got, ref["grads"])
+
+
+def test_optimiser_contracts(cuda):
+    """Adam (flat kernel and torch.optim.Adam) and an LBFGSNew-style client: grad closures leave
+    .grad on leaf parameters, no-grad closures are forward-only, in-place p.data.add_ is seen."""
+    from lshm_b200.kharmonic_lofar import DeepKHarmonicStep, FlatAdam
+    case = closure_case(N=4, bpb=2)
+    mods = build_modules(case, cuda)
+    step = DeepKHarmonicStep(*mods)
+    step.set_batch(case["x"].to(cuda), case["uv"].to(cuda), 2)
+    opt = FlatAdam(step.flat, lr=1e-3)
+    l0 = float(opt.step(step.closure))
+    for _ in range(5):
+        opt.step(step.closure)
+    with torch.no_grad():
+        l1 = float(step.closure())
+    assert np.isfinite(l1) and l1 < l0
+    topt = torch.optim.Adam(step.flat.params, lr=1e-3)
+    for _ in range(3):
+        topt.zero_grad()
+        topt.step(step.closure)
+    with torch.no_grad():
+        l2 = float(step.closure())
+    assert l2 < l1
+    # LBFGS-style client: gather flat grad, step along -g with p.data.add_, evaluate without grad
+    loss = float(step.closure())
+    params = step.flat.params
+    assert all(p.is_leaf and p.grad is not None for p in params)
+    flat_g = torch.cat([p.grad.data.view(-1) for p in params])
+    off = 0
+    for p in params:
+        n = p.numel()
+        p.data.add_(flat_g[off:off + n].view_as(p.data), alpha=-1e-2)
+        off += n
+    torch.set_grad_enabled(False)
+    try:
+        f_new = float(step.closure())
+    finally:
+        torch.set_grad_enabled(True)
+    assert f_new < loss
+    # NaN data propagates to float(closure()) instead of raising (src/lbfgsnew.py:153)
+    step.x[0, 0, 0, 0] = float("nan")
+    with torch.no_grad():
+        assert np.isnan(float(step.closure()))
+
+
+def test_inference_loop(cuda):
+    from lshm_b200.evaluate_clustering import encode_assign, evaluate
+    case = closure_case(N=8, bpb=4)
+    net, netT, netF, mod = build_modules(case, cuda)
+    x, uv = case["x"].to(cuda), case["uv"].to(cuda)
+    dist, gid, ids, Mu = encode_assign(net, netT, netF, mod, x, uv, 4)
+    hs = torch.tensor(SCALES)
+    *_, mu, muT, muF = O.cascade_forward(case["pn"], case["pT"], case["pF"], case["x"], case["uv"], hs)
+    Mu_ref = torch.cat((mu, muT, muF), 1)
+    assert rel_err(Mu, Mu_ref) < 1e-5
+    for g in range(2):
+        d, idx, pp = O.eval_distances(Mu_ref[g * 4:(g + 1) * 4], case["M"], 4)
+        assert rel_err(dist[g], d) < 1e-4 and int(gid[g]) == idx
+        assert (ids[g * 4:(g + 1) * 4].cpu().long() == pp).all()
+    X, clusid = evaluate(net, netT, netF, mod, lambda nb: (2, 2, x[nb * 4:(nb + 1) * 4], uv[nb * 4:(nb + 1) * 4]), 2)
+    assert X.shape == (case["K"], 2) and X.dtype == np.float64
+    assert np.allclose(X[:, 0], dist[0].double().cpu().numpy(), rtol=1e-6) and clusid[0] == float(gid[0])
+
+
+def test_closure_matches_golden_from_live_reference(cuda):
+    """Same comparison as test_oracle_golden.test_closure_matches_golden, CUDA path vs the
+    fixtures generated from the LIVE reference modules."""
+    from lshm_b200.kharmonic_lofar import DeepKHarmonicStep
+    g = golden("closure_cfg1.npz")
+    case = closure_case()
+    step = DeepKHarmonicStep(*build_modules(case, cuda))
+    step.set_batch(case["x"].to(cuda), case["uv"].to(cuda), case["bpb"])
+    for dst, src in zip((step.y1, step.y2, step.y3), case["ys"]):
+        dst.copy_(src.to(cuda))
+    step.closure()
+    t = step.loss_terms()
+    for k in ("total", "loss0", "loss1", "loss2", "loss3", "kdist", "aug", "sim", "rica"):
+        assert abs(t[k] - float(g[k])) <= 1e-5 * abs(float(g[k])) + 1e-9, k
+    for nm, p in zip(step.flat.names, step.flat.params):
+        tag, name = nm.split(".", 1)
+        gk = {"0": "n", "1": "T", "2": "F", "3": "k"}[tag] + "." + name
+        ref_norm = float(g[gk + ":norm"])
+        assert abs(p.grad.double().norm().item() - ref_norm) <= 1e-3 * ref_norm, nm
