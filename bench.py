@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py - headline metric of BASELINE.json: deep-K-harmonic TRAINING patches/sec
+(fwd + bwd + K-harmonic + Adam + multiplier update) on N B200s, with roofline and CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W            # ours (torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path on host cores
+
+Workload (config.workload = "cfg2"): 256 baselines x 2x2 half-overlapping 128x128 patches =
+1024 patches per GPU per step, 8 channels, L=32, Lt=16 (Ltot=64), K=10, p=4, RICA on, Adam over
+all four modules, rho=1.  A "step" is one ADMM iteration of
+/root/reference/src/kharmonic_lofar.py:131-202: optimizer.step(closure) [cascade forward, losses,
+analytic backward, Adam] + the no-grad multiplier-update forward.  Weak scaling: every rank
+holds its own 1024 patches; one all-reduce of [gradients | loss scalars] per closure.
+
+`value` = patches/s with the batch resident in HBM.  `e2e` = the same step driven through the
+loader API from HOST memory: pinned int8 visibilities of the step's baselines -> H2D ->
+scale/patchify/z-score kernels -> step -> D2H of the loss columns, a fresh minibatch every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+CFG = dict(workload="cfg2", baselines_per_gpu=256, patches_per_baseline=4, patches_per_gpu=1024, channels=8,
+           patch=128, L=32, Lt=16, K=10, p=4, rica=True, optimizer="Adam(lr=1e-4) over net+netT+netF+mod",
+           admm_iterations_per_step=1, l2="inputs larger than L2 (x alone is 537 MB per GPU)")
+SCALES = [1e-4, 1e-3, 1e-2, 1e-1]
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (the sampler is
+    started early because nvidia-smi needs ~1 s to produce its first row; rows are time-stamped
+    on arrival and only those inside [mark_start, mark_stop] are summarised)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_stop(self):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t)]
+        window = "timed region"
+        if not inside:   # region shorter than the sampling period: fall back to the rows under load around it
+            inside = [r for t, r in self.rows if self.t0 is not None and t >= self.t0 - 1.0]
+            window = "timed region +-1s"
+        sm, mx, reasons = [], [], set()
+        for r in inside:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    samples=len(sm), window=window, reasons=sorted(reasons))
+
+
+# ------------------------------------------------------------------------------------------
+# algorithmic bytes / flops of one call (DESIGN.md "Kernels"); used for the per-kernel roofline
+# ------------------------------------------------------------------------------------------
+def call_cost(name, a):
+    """(key, algorithmic HBM bytes, flops) for one library call with ctypes args `a`."""
+    if name in ("down2d", "up2d", "wgrad2d", "down1d", "up1d", "wgrad1d"):
+        two_d = name.endswith("2d")
+        if name.startswith("wgrad"):
+            N, A, B = a[5], a[6], a[7]
+            small_px = a[8] * a[9] if two_d else a[8]
+        else:
+            N, A, B = a[8], a[9], a[10]
+            small_px = a[11] * a[12] if two_d else a[11]
+        taps = 16 if two_d else 4
+        small, big, w = N * A * small_px, N * B * small_px * 4, A * B * taps
+        flops = 2.0 * N * small_px * A * B * taps
+        epi = None if name.startswith("wgrad") else a[-2]
+        byts = 4.0 * (small + big + w) + (4.0 * (small if name.startswith("down") else big) if epi == 2 else 0.0)
+        return f"{name}[A={A},B={B},px={small_px}]", byts, flops
+    if name in ("cascade_losses",):
+        n = a[8] * a[9] * a[10] * a[10]
+        return name, 4.0 * n * (7 + (3 if a[13] else 0)), 30.0 * n
+    if name in ("residual_split", "cascade_combine"):
+        n = a[4] * a[5] * a[6] * a[6]
+        return name, 4.0 * n * 4, 3.0 * n
+    if name == "multiplier_update":
+        n = a[8] * a[9] * a[10] * a[10]
+        return name, 4.0 * n * 10, 8.0 * n
+    if name in ("khm_fwd", "khm_fwd_bwd", "khm_bwd"):
+        N, K, L = a[3], a[4], a[5]
+        bwd = name != "khm_fwd"
+        return f"{name}[K={K},L={L}]", 4.0 * N * L * (2 if bwd else 1), (3.0 * L + 6) * K * N * (3 if bwd else 1)
+    return name, 0.0, 0.0
+
+
+class KernelProfiler:
+    """CUDA-event timing of every library call (events on the launching stream)."""
+
+    def __init__(self, L):
+        self.L, self.records, self.saved = L, [], {}
+
+    def __enter__(self):
+        for name in self.L.protos:
+            short = name[len("lshm_"):]
+            fn = getattr(self.L, short, None)
+            if fn is None or short in ("version", "device_info"):
+                continue
+            self.saved[short] = fn
+            setattr(self.L, short, self._wrap(short, fn))
+        return self
+
+    def _wrap(self, short, fn):
+        def call(*args):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(*args)
+            e1.record()
+            self.records.append((short, args, e0, e1))
+        return call
+
+    def __exit__(self, *exc):
+        for short, fn in self.saved.items():
+            setattr(self.L, short, fn)
+
+    def summary(self, steps):
+        torch.cuda.synchronize()
+        agg = {}
+        for short, args, e0, e1 in self.records:
+            key, byts, flops = call_cost(short, args)
+            d = agg.setdefault(key, dict(ms=0.0, calls=0, bytes=0.0, flops=0.0))
+            d["ms"] += e0.elapsed_time(e1); d["calls"] += 1; d["bytes"] += byts; d["flops"] += flops
+        for d in agg.values():
+            d["ms_per_step"] = d["ms"] / steps
+        return agg
+
+
+def build_step(dev, rank, world, distributed):
+    from lshm_b200.kharmonic_lofar import DeepKHarmonicStep, FlatAdam
+    from lshm_b200.lofar_models import AutoEncoder1DCNN, AutoEncoderCNN2, Kmeans
+    torch.manual_seed(0)  # identical random init on every rank
+    hs = torch.tensor(SCALES).to(dev)
+    C, L, Lt, K = CFG["channels"], CFG["L"], CFG["Lt"], CFG["K"]
+    net = AutoEncoderCNN2(L, C, hs, True).to(dev)
+    netT = AutoEncoder1DCNN(Lt, C, hs, True).to(dev)
+    netF = AutoEncoder1DCNN(Lt, C, hs, True).to(dev)
+    mod = Kmeans(L + 2 * Lt, K, CFG["p"]).to(dev)
+    step = DeepKHarmonicStep(net, netT, netF, mod, distributed=distributed)
+    opt = FlatAdam(step.flat, lr=1e-4)
+    return step, opt
+
+
+def run_ours(args):
+    from lshm_b200 import lofar_tools as T
+    from lshm_b200 import synthetic as S
+    from lshm_b200._lib import lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    distributed = world > 1
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if distributed:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    sampler = ClockSampler(local)
+    sampler.start()
+    step, opt = build_step(dev, rank, world, distributed)
+    nb, bpb = CFG["baselines_per_gpu"], CFG["patches_per_baseline"]
+    Np = nb * bpb
+    # synthetic observation of this rank: 192x192 -> 2x2 patches per baseline
+    meas = S.make_measurement(nb, 192, 192, seed=100 + rank)
+    sap = meas["measurement"]["saps"]["0"]
+    vis_h = torch.from_numpy(sap["visibilities"]).pin_memory()
+    sc_h = torch.from_numpy(sap["visibility_scale_factors"]).pin_memory()
+    uv_h = torch.from_numpy(S.make_uv(Np, seed=rank, per_group=bpb)).pin_memory()
+    sel = torch.arange(nb, dtype=torch.int32, device=dev)
+
+    def load_from_host():
+        vis = vis_h.to(dev, non_blocking=True)
+        sc = sc_h.to(dev, non_blocking=True)
+        uv = uv_h.to(dev, non_blocking=True)
+        px, py, x = T.patchify_device(vis, sc, sel, 128, CFG["channels"], 1e3, True)
+        # the reference orders uv rows baseline-major while patches are patch-major (SURVEY.md bug 3);
+        # reproduced as is
+        return px * py, x, uv
+
+    bpb_, x, uv = load_from_host()
+    step.set_batch(x, uv, bpb_, global_patches=Np * world)
+
+    def one_step():
+        opt.step(step.closure)
+        step.update_multipliers()
+
+    def barrier():
+        if distributed:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    barrier()
+    L = lib()
+    sampler.mark_start()
+    l0 = L.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one_step()
+    e1.record()
+    barrier()
+    sampler.mark_stop()
+    ms = e0.elapsed_time(e1)
+    launches = L.launches - l0
+    clocks = sampler.stop()
+    if distributed:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t)
+    ms_per_step = ms / args.steps
+    value = Np * world / (ms_per_step * 1e-3)
+
+    # ---- end to end through the loader API from host memory
+    for _ in range(2):
+        b, x2, uv2 = load_from_host(); step.set_batch(x2, uv2, b, global_patches=Np * world); one_step(); step.loss_terms()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        b, x2, uv2 = load_from_host()
+        step.set_batch(x2, uv2, b, global_patches=Np * world)
+        one_step()
+        terms = step.loss_terms()   # D2H of the 9 loss columns (synchronises)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if distributed:
+        t = torch.tensor([e2e_s], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_s = float(t)
+    e2e = dict(value=Np * world / (e2e_s / e2e_steps), unit="patches/s",
+               h2d_bytes_per_step=int(vis_h.numel() + sc_h.numel() * 4 + uv_h.numel() * 4), d2h_bytes_per_step=9 * 4,
+               steps=e2e_steps, note="fresh minibatch from pinned host int8 every step + loss read-back")
+
+    out = None
+    if rank == 0:
+        pk = peaks()
+        # ---- per-kernel device times (CUDA events) over two extra steps -> dominant kernel roofline
+        prof_steps = 2
+        with KernelProfiler(L) as kp:
+            for _ in range(prof_steps):
+                one_step()
+            agg = kp.summary(prof_steps)
+        total_ms = sum(d["ms_per_step"] for d in agg.values())
+        top = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
+        name, d = top[0]
+        sec = d["ms"] * 1e-3
+        hbm_frac = (d["bytes"] / sec / 1e9) / pk["hbm_gbs"] if sec > 0 else 0.0
+        intensity = d["flops"] / d["bytes"] if d["bytes"] else 0.0
+        roof = dict(kernel=name, bound="hbm", achieved=d["bytes"] / sec / 1e9, peak=pk["hbm_gbs"], unit="GB/s",
+                    frac=hbm_frac, traffic=None, peak_source=pk["source"], ms_per_launch=d["ms"] / d["calls"],
+                    share_of_step=d["ms_per_step"] / total_ms if total_ms else None, flop_per_byte=intensity,
+                    achieved_tflops=d["flops"] / sec / 1e12,
+                    top5=[dict(kernel=k, ms_per_step=round(v["ms_per_step"], 4), calls_per_step=v["calls"] // prof_steps,
+                               gbs=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] else 0,
+                               tflops=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] else 0) for k, v in top[:5]])
+        if args.kernel_table:
+            with open(args.kernel_table, "w") as fh:
+                fh.write("kernel,calls_per_step,ms_per_step,share,GB/s(algorithmic),TFLOP/s\n")
+                for k, v in top:
+                    s_ = v["ms"] * 1e-3
+                    fh.write(f"{k},{v['calls'] // prof_steps},{v['ms_per_step']:.4f},{v['ms_per_step'] / total_ms:.4f},"
+                             f"{v['bytes'] / s_ / 1e9 if s_ else 0:.1f},{v['flops'] / s_ / 1e12 if s_ else 0:.2f}\n")
+                fh.write(f"TOTAL,,{total_ms:.4f},1.0,,\n")
+        cpu = cpu_baseline(sample_patches=args.cpu_patches, steps=1)
+        out = {
+            "metric": "train patches/sec (fwd+bwd+K-harmonic)", "value": value, "unit": "patches/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(CFG, global_patches=Np * world, parallelism=f"dp{world}"),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "loss_terms_last": terms,
+        }
+    if distributed:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_step_factory(n_patches):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from lshm_b200 import synthetic as S
+    from oracle import lofar_oracle as O
+    C, L, Lt, K, bpb = CFG["channels"], CFG["L"], CFG["Lt"], CFG["K"], CFG["patches_per_baseline"]
+    hs = torch.tensor(SCALES)
+    pn = O.make_ae_params(L, C, ndim=2, seed=1); pT = O.make_ae_params(Lt, C, ndim=1, seed=2)
+    pF = O.make_ae_params(Lt, C, ndim=1, seed=3); M = O.make_centres(K, L + 2 * Lt, seed=4).requires_grad_()
+    params = []
+    for p in (pn, pT, pF):
+        for v in p.values():
+            v.requires_grad_(); params.append(v)
+    params.append(M)
+    opt = torch.optim.Adam(params, lr=1e-4)
+    x = torch.from_numpy(S.make_patches(n_patches, C, seed=5))
+    uv = torch.from_numpy(S.make_uv(n_patches, seed=5, per_group=bpb))
+    ys = [torch.zeros(x.numel()) for _ in range(3)]
+
+    def closure():
+        opt.zero_grad()
+        total, _ = O.closure_losses(pn, pT, pF, M, x, uv, hs, *ys, batch_per_bline=bpb, batch_size=n_patches // bpb,
+                                    Khp=CFG["p"])
+        total.backward()
+        return total
+
+    def one_step():
+        opt.step(closure)
+        ys[:] = O.multiplier_update(pn, pT, pF, x, uv, hs, *ys)
+    return one_step
+
+
+def cpu_baseline(sample_patches=64, steps=1):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    one_step = cpu_step_factory(sample_patches)
+    one_step()  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = (time.perf_counter() - t0) / steps
+    return dict(value=sample_patches / dt, unit="patches/s", cores=cores, kind="port",
+                sample=f"{steps} step(s) of the same closure+Adam+multiplier update on {sample_patches} patches "
+                       f"({sample_patches // 4} baselines x 4), torch CPU fp32, vectorised K-harmonic "
+                       "(the reference's Python N x K loop would be slower)")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = args.cpu_patches
+    one_step = cpu_step_factory(n)
+    for _ in range(min(args.warmup, 1)):
+        one_step()
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = (time.perf_counter() - t0) / steps
+    value = n / dt
+    sample = (f"each step = closure+Adam+multiplier update on a {n}-patch sample of the cfg2 batch; oracle port of "
+              "/root/reference/src/kharmonic_lofar.py:131-202 (the Python reference cannot travel to the GPU box)")
+    print(json.dumps({
+        "impl": "reference", "metric": "train patches/sec (fwd+bwd+K-harmonic)", "value": value, "unit": "patches/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": dict(CFG, sample_patches=n),
+        "cpu_baseline": dict(value=value, unit="patches/s", cores=cores, kind="port", sample=sample),
+        "e2e": dict(value=value, unit="patches/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-patches", type=int, default=64)
+    ap.add_argument("--kernel-table", default=None, help="write the per-kernel CUDA-event table (CSV) here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -25,6 +25,7 @@ import torch.distributed as dist
 
 from ._lib import lib
 from .lofar_models import AutoEncoder1DCNN, AutoEncoderCNN2, Kmeans
+from .parallel import ShardPlan, exchange
 
 LOSS_TAIL = 16  # floats appended to the flat gradient buffer: total + the 8 printed terms
 TERM_NAMES = ("loss0", "loss1", "loss2", "loss3", "kdist", "aug", "sim", "rica")
@@ -184,7 +185,8 @@ class DeepKHarmonicStep:
         start = lb.launches
         N, C, L, Lt, Ltot, K = self.N, self.C, self.L, self.Lt, self.Ltot, self.mod.K
         M = self.mod.M
-        numel_g = float(self.Nglobal) * C * 16384
+        plan = ShardPlan(N, self.Nglobal, self.world, self.bpb, C, K, Ltot)
+        numel_g = plan.numel_global
         self.terms.zero_()
         tp = self.terms.data_ptr()
         x1, x2, x3f = self._forward(st)
@@ -192,12 +194,11 @@ class DeepKHarmonicStep:
         lb.cascade_losses(self.x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(),
                           self.y1.data_ptr(), self.y2.data_ptr(), self.y3.data_ptr(), self.rho,
                           N, C, 128, 1.0 / numel_g, tp, g1p, g2, g3f, st)
-        khm_scale = self.alpha / (float(self.Nglobal) * K * Ltot)
+        khm_scale = plan.khm_scale(self.alpha)
         p = float(self.mod.p)
-        bs_global = self.Nglobal // self.bpb
-        aug_scale = self.gamma / (float(self.bpb) * bs_global * self.bpb)
-        sim_scale = self.beta / self.world      # M is replicated: count its penalty once
-        frac = float(N) / float(self.Nglobal)   # logcosh divides by the local numel
+        aug_scale = plan.aug_scale(self.gamma)
+        sim_scale = plan.sim_scale(self.beta)        # M is replicated: count its penalty once
+        rica_scale = plan.rica_scale(self.rica_lambda)  # the kernel divides by the LOCAL numel
         Mu, gMu = self.Mu, self.gMu
         if grads:
             self.flat.attach_grads()
@@ -212,7 +213,7 @@ class DeepKHarmonicStep:
                    gMu.data_ptr() if grads else None, Ltot, st)
         if self.use_rica:
             for off, width in ((0, L), (L, Lt), (L + Lt, Lt)):
-                lb.logcosh(Mu.data_ptr() + 4 * off, Ltot, N, width, self.rica_lambda * frac, tp + 11 * 8,
+                lb.logcosh(Mu.data_ptr() + 4 * off, Ltot, N, width, rica_scale, tp + 11 * 8,
                            gMu.data_ptr() + 4 * off if grads else None, Ltot, st)
         if grads:
             e = self.net.engine(), self.netT.engine(), self.netF.engine()
@@ -228,7 +229,7 @@ class DeepKHarmonicStep:
         if self.distributed:
             # ONE exchange per closure evaluation: gradients + loss scalars (forward-only: scalars)
             buf = self.flat.grad if grads else tail
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+            exchange(buf, self.group)
         self.launches = lb.launches - start
         return tail[0]
 

@@ -266,28 +266,37 @@ def cascade_forward(pn, pT, pF, x, uv, scales, rica=True):
 
 
 def closure_losses(pn, pT, pF, M, x, uv, scales, y1, y2, y3, *, batch_per_bline, batch_size,
-                   Khp=4, alpha=0.01, beta=0.01, gamma=0.01, rho=1.0, rica=True, rica_lambda=0.01):
+                   Khp=4, alpha=0.01, beta=0.01, gamma=0.01, rho=1.0, rica=True, rica_lambda=0.01,
+                   shard=None):
     """Loss terms of src/kharmonic_lofar.py:132-172, in the order of its print at :179.
 
     Returns (total, dict of terms).  Differentiable w.r.t. every tensor in pn/pT/pF and M.
+
+    shard=(global_patches, world): the rows given are one data-parallel shard (whole baseline
+    groups) of a global batch; every per-patch sum is divided by the GLOBAL constant and the
+    replicated centre penalty is divided by `world`, so that the SUM over shards of the returned
+    totals (and of their gradients) equals the unsharded value.  shard=None is the reference.
     """
+    n_local = x.shape[0]
+    n_global, world = (n_local, 1) if shard is None else shard
     x1, x11, x2, x3, mu, muT, muF = cascade_forward(pn, pT, pF, x, uv, scales, rica)
     xrecon = x1 + x2 + x3
-    n = x.numel()
+    n = x.numel() // n_local * n_global
     sse = lambda a, b: ((a - b) ** 2).sum()
     loss0 = sse(xrecon, x) / n
     loss1 = (torch.dot(y1, (x - x1).reshape(-1)) + rho / 2 * sse(x, x1)) / n
     loss2 = (torch.dot(y2, (x11 - x2).reshape(-1)) + rho / 2 * sse(x11, x2)) / n
     loss3 = (torch.dot(y3, (x11 - x3).reshape(-1)) + rho / 2 * sse(x11, x3)) / n
     Mu = torch.cat((mu, muT, muF), 1)
-    kdist = alpha * khm_loss(Mu, M, Khp)
-    sim = beta * cluster_similarity(M)
-    aug = gamma * augmented_loss(Mu, batch_per_bline, batch_size).reshape(())
+    frac = n_local / n_global
+    kdist = alpha * khm_loss(Mu, M, Khp) * frac
+    sim = beta * cluster_similarity(M) / world
+    aug = gamma * augmented_loss(Mu, batch_per_bline, batch_size).reshape(()) * frac
     total = loss0 + loss1 + loss2 + loss3 + kdist + aug + sim
     terms = dict(loss0=loss0, loss1=loss1, loss2=loss2, loss3=loss3, kdist=kdist, aug=aug, sim=sim)
     if rica:
         logcosh = lambda z: torch.log(torch.cosh(z)).sum() / z.numel()
-        rl = rica_lambda * (logcosh(mu) + logcosh(muT) + logcosh(muF))
+        rl = rica_lambda * (logcosh(mu) + logcosh(muT) + logcosh(muF)) * frac
         total = total + rl
         terms["rica"] = rl
     terms["Mu"] = Mu

@@ -53,7 +53,8 @@ def test_conv2d_family(cuda, lvl, C):
     ref_up = F.elu(F.conv_transpose2d(small, w, bias_b, stride=2, padding=1))
     sg = small.to(cuda)
     out_up = torch.empty(N, Bc, 2 * s, 2 * s, device=cuda)
-    lib().up2d(dp(sg), A * s * s, dp(wg), dp(bias_b.to(cuda)), None, 0, dp(out_up), Bc * 4 * s * s, N, A, Bc, s, s, 1, st())
+    bbg = bias_b.to(cuda)
+    lib().up2d(dp(sg), A * s * s, dp(wg), dp(bbg), None, 0, dp(out_up), Bc * 4 * s * s, N, A, Bc, s, s, 1, st())
     assert rel_err(out_up, ref_up) < 2e-6
     # up with DELU epilogue = dgrad through the ELU of the layer below
     act = F.elu(torch.randn(N, Bc, 2 * s, 2 * s))
@@ -64,7 +65,8 @@ def test_conv2d_family(cuda, lvl, C):
     # down with DELU and no bias = ConvTranspose2d dgrad
     act_s = F.elu(torch.randn(N, A, s, s))
     ref_dd = F.conv2d(big, w, None, stride=2, padding=1) * elu_grad_from_out(act_s)
-    lib().down2d(dp(bg), Bc * 4 * s * s, dp(wg), None, dp(act_s.to(cuda)), A * s * s, dp(out), A * s * s, N, A, Bc, s, s, 2, st())
+    asg = act_s.to(cuda)
+    lib().down2d(dp(bg), Bc * 4 * s * s, dp(wg), None, dp(asg), A * s * s, dp(out), A * s * s, N, A, Bc, s, s, 2, st())
     assert rel_err(out, ref_dd) < 2e-6
     # wgrad
     bigr = big.clone().requires_grad_()
@@ -93,17 +95,19 @@ def test_conv1d_family(cuda, lvl):
     out_s = torch.empty(N, A, l, device=cuda)
     out_b = torch.empty(N, Bc, 4 * l, device=cuda)
     # Conv1d(k4,s4,p1) forward
-    lib().down1d(dp(bg), Bc * 4 * l, dp(wg), dp(bias_a.to(cuda)), None, 0, dp(out_s), A * l, N, A, Bc, l, 1, 1, st())
+    bag, bbg = bias_a.to(cuda), bias_b.to(cuda)
+    lib().down1d(dp(bg), Bc * 4 * l, dp(wg), dp(bag), None, 0, dp(out_s), A * l, N, A, Bc, l, 1, 1, st())
     assert rel_err(out_s, F.elu(F.conv1d(big, wg_, bias_a, stride=4, padding=1))) < 2e-6
     # ConvTranspose1d(k4,s4,p0) forward
-    lib().up1d(dp(sg), A * l, dp(wg), dp(bias_b.to(cuda)), None, 0, dp(out_b), Bc * 4 * l, N, A, Bc, l, 0, 1, st())
+    lib().up1d(dp(sg), A * l, dp(wg), dp(bbg), None, 0, dp(out_b), Bc * 4 * l, N, A, Bc, l, 0, 1, st())
     assert rel_err(out_b, F.elu(F.conv_transpose1d(small, wg_, bias_b, stride=4, padding=0))) < 2e-6
     # Conv1d dgrad (pad 1) with DELU
     act = F.elu(torch.randn(N, Bc, 4 * l))
     bigr = big.clone().requires_grad_()
     wr = wg_.clone().requires_grad_()
     F.conv1d(bigr, wr, None, stride=4, padding=1).backward(small)
-    lib().up1d(dp(sg), A * l, dp(wg), None, dp(act.to(cuda)), Bc * 4 * l, dp(out_b), Bc * 4 * l, N, A, Bc, l, 1, 2, st())
+    actg = act.to(cuda)
+    lib().up1d(dp(sg), A * l, dp(wg), None, dp(actg), Bc * 4 * l, dp(out_b), Bc * 4 * l, N, A, Bc, l, 1, 2, st())
     assert rel_err(out_b, bigr.grad * elu_grad_from_out(act)) < 2e-6
     dw = torch.empty(A, Bc, 4, device=cuda)
     lib().wgrad1d(dp(sg), A * l, dp(bg), Bc * 4 * l, dp(dw), N, A, Bc, l, 1, st())
@@ -135,7 +139,8 @@ def test_linear(cuda, N, K, J):
     dzg = dz.to(cuda)
     dx = torch.empty(N, K, device=cuda)
     aux = F.elu(torch.randn(N, K))
-    lib().linear_bwd_data(dp(dzg), J, dp(wg), dp(add.to(cuda)), K, dp(aux.to(cuda)), K, dp(dx), K, N, K, J, st())
+    addg, auxg = add.to(cuda), aux.to(cuda)
+    lib().linear_bwd_data(dp(dzg), J, dp(wg), dp(addg), K, dp(auxg), K, dp(dx), K, N, K, J, st())
     assert rel_err(dx, (dz @ w + add) * elu_grad_from_out(aux)) < 2e-6
     dw, db = torch.empty(J, K, device=cuda), torch.empty(J, device=cuda)
     lib().linear_bwd_weight(dp(xg), K + 3, dp(dzg), J, dp(dw), dp(db), N, K, J, st())
@@ -146,7 +151,8 @@ def test_uv_harmonics(cuda):
     uv = torch.randn(9, 2) * 300
     sc = torch.tensor([1e-4, 1e-3, 1e-2, 1e-1])
     out = torch.empty(9, 16, device=cuda)
-    lib().uv_harmonics(dp(uv.to(cuda)), dp(sc.to(cuda)), 9, 4, dp(out), st())
+    uvg, scg = uv.to(cuda), sc.to(cuda)
+    lib().uv_harmonics(dp(uvg), dp(scg), 9, 4, dp(out), st())
     assert max_abs(out, O.uv_harmonics(uv, sc)) < 5e-6
 
 
@@ -207,7 +213,8 @@ def test_khm_group_dist_and_strides(cuda):
     bg = buf.to(cuda)
     dist = torch.empty(N // grp, K, device=cuda)
     gid = torch.empty(N // grp, dtype=torch.int32, device=cuda)
-    lib().khm_group_dist(bg.data_ptr() + 16, L + 8, dp(M.to(cuda)), N, K, L, p, grp, dp(dist), dp(gid), st())
+    Mg = M.to(cuda)
+    lib().khm_group_dist(bg.data_ptr() + 16, L + 8, dp(Mg), N, K, L, p, grp, dp(dist), dp(gid), st())
     for g in range(N // grp):
         d, idx, _ = O.eval_distances(X[g * grp:(g + 1) * grp], M, p)
         assert rel_err(dist[g], d) < 1e-5 and int(gid[g]) == idx
@@ -235,7 +242,8 @@ def test_similarity(cuda, K, L):
     acc = torch.zeros(1, dtype=torch.float64, device=cuda)
     gM = torch.zeros(K, L, device=cuda)
     work = torch.empty(2 * K * K, device=cuda)
-    lib().similarity(dp(M.to(cuda)), K, L, 0.5, dp(acc), dp(gM), dp(work), st())
+    Mg = M.to(cuda)
+    lib().similarity(dp(Mg), K, L, 0.5, dp(acc), dp(gM), dp(work), st())
     assert abs(float(acc) - 0.5 * float(ref)) < 1e-5 * abs(float(ref))
     assert rel_err(gM, 0.5 * Mr.grad) < 1e-4
 
@@ -249,7 +257,8 @@ def test_augment(cuda, bpb, groups, L):
     acc = torch.zeros(1, dtype=torch.float64, device=cuda)
     g = torch.zeros(bpb * groups, L, device=cuda)
     scale = 1.0 / (bpb * groups * bpb)
-    lib().augment(dp(mu.to(cuda)), L, bpb * groups, L, bpb, scale, dp(acc), dp(g), L, st())
+    mug = mu.to(cuda)
+    lib().augment(dp(mug), L, bpb * groups, L, bpb, scale, dp(acc), dp(g), L, st())
     assert abs(float(acc) - float(ref)) <= 1e-5 * max(abs(float(ref)), 1e-12)
     if bpb > 1:
         ref.backward()
@@ -264,7 +273,8 @@ def test_logcosh_and_adam(cuda):
     ref.backward()
     acc = torch.zeros(1, dtype=torch.float64, device=cuda)
     g = torch.zeros(33, 48, device=cuda)
-    lib().logcosh(dp(mu.to(cuda)), 48, 33, 48, 0.01, dp(acc), dp(g), 48, st())
+    mug = mu.to(cuda)
+    lib().logcosh(dp(mug), 48, 33, 48, 0.01, dp(acc), dp(g), 48, st())
     assert abs(float(acc) - float(ref)) < 1e-5 * abs(float(ref)) and rel_err(g, mur.grad) < 1e-5
     # Adam: three steps against torch.optim.Adam
     p = torch.randn(1000)
@@ -275,7 +285,8 @@ def test_logcosh_and_adam(cuda):
         gr = torch.randn(1000)
         pr.grad = gr.clone()
         opt.step()
-        lib().adam_step(dp(pg), dp(gr.to(cuda)), dp(m), dp(v), 1000, 1e-3, 0.9, 0.999, 1e-8, t, st())
+        grg = gr.to(cuda)
+        lib().adam_step(dp(pg), dp(grg), dp(m), dp(v), 1000, 1e-3, 0.9, 0.999, 1e-8, t, st())
     assert max_abs(pg, pr.detach()) < 1e-6
 
 
@@ -316,7 +327,8 @@ def test_cascade_kernels(cuda):
     assert torch.allclose(sums2, sums, rtol=1e-12)
     gT, gF = torch.randn(N, C, P, P), torch.randn(N, C, P, P)
     gx1 = torch.empty_like(g[0])
-    lib().cascade_combine(dp(g1p), dp(gT.to(cuda)), dp(gF.to(cuda)), dp(gx1), N, C, P, st())
+    gTg, gFg = gT.to(cuda), gF.to(cuda)
+    lib().cascade_combine(dp(g1p), dp(gTg), dp(gFg), dp(gx1), N, C, P, st())
     assert rel_err(gx1, g1p.cpu() - 0.5 * (gT + gF.transpose(2, 3))) < 1e-6
     lib().multiplier_update(dp(g[0]), dp(g[1]), dp(g[2]), dp(g[3]), rho, dp(g[4]), dp(g[5]), dp(g[6]), N, C, P, st())
     assert rel_err(g[4], y1 + rho * (x - x1).reshape(-1)) < 1e-6

@@ -1,0 +1,72 @@
+"""Host-side logic that needs no GPU: drop-in module surface (names, state_dict keys and shapes,
+loud failure without CUDA), flat parameter re-homing, synthetic generator."""
+import numpy as np
+import pytest
+import torch
+
+from common import SCALES
+from lshm_b200 import synthetic as S
+from oracle import lofar_oracle as O
+
+
+@pytest.mark.parametrize("ndim", [2, 1])
+def test_module_surface_matches_reference_layout(ndim):
+    from lshm_b200.lofar_models import AutoEncoder1DCNN, AutoEncoderCNN2, Kmeans
+    hs = torch.tensor(SCALES)
+    cls = AutoEncoderCNN2 if ndim == 2 else AutoEncoder1DCNN
+    for C, L, rica in ((8, 32, True), (4, 224, True), (4, 16, False)):
+        net = cls(latent_dim=L, channels=C, harmonic_scales=hs, rica=rica)
+        shapes = O.ae_param_shapes(L, C, 16, rica, ndim)   # = reference state_dict (see test_oracle_golden)
+        sd = net.state_dict()
+        assert list(sd.keys()) == list(shapes.keys())
+        assert all(tuple(sd[k].shape) == tuple(v) for k, v in shapes.items())
+        assert net.rica == rica and net.latent_dim == L and net.harmonic_dim == 16
+        assert net.harmonic_scales is hs
+    km = Kmeans(latent_dim=64, K=10, p=4)
+    assert list(km.state_dict().keys()) == ["M"] and km.M.shape == (10, 64)
+    assert (km.K, km.p, km.EPS, km.latent_dim) == (10, 4, 1e-9, 64)
+    assert float(km.M.min()) >= 0 and float(km.M.max()) <= 1
+
+
+def test_cpu_tensors_fail_loudly():
+    from lshm_b200.lofar_models import AutoEncoderCNN2, Kmeans
+    net = AutoEncoderCNN2(32, 8, torch.tensor(SCALES), True)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(1, 8, 128, 128), torch.zeros(1, 2))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Kmeans(64, 10, 4)(torch.zeros(3, 64))
+
+
+def test_flat_params_keep_parameters_ordinary_leaves():
+    from lshm_b200.kharmonic_lofar import FlatParams
+    from lshm_b200.lofar_models import AutoEncoder1DCNN, Kmeans
+    net = AutoEncoder1DCNN(16, 8, torch.tensor(SCALES), True)
+    km = Kmeans(48, 5, 4)
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    flat = FlatParams([net, km], torch.device("cpu"))
+    assert all(p.is_leaf and p.requires_grad for p in flat.params)
+    assert all(torch.equal(before[k], v) for k, v in net.state_dict().items())
+    assert all(o % FlatParams.ALIGN == 0 for o in flat.offsets)
+    # in-place updates through the views reach the flat buffer (LBFGSNew: p.data.add_, src/lbfgsnew.py:101)
+    flat.params[0].data.add_(1.0)
+    o = flat.offsets[0]
+    assert torch.equal(flat.flat[o:o + flat.params[0].numel()].view_as(flat.params[0]), flat.params[0].data)
+    # optimizer.zero_grad(set_to_none=True) detaches .grad; attach_grads restores the views
+    for p in flat.params:
+        p.grad = None
+    flat.attach_grads()
+    assert all(p.grad is gv for p, gv in zip(flat.params, flat.grad_views))
+    flat.grad.fill_(2.0)
+    assert float(flat.params[-1].grad.sum()) == 2.0 * flat.params[-1].numel()
+    assert flat.loss_tail.numel() == 16
+
+
+def test_synthetic_measurement_layout():
+    m = S.make_measurement(5, 140, 130, seed=1)
+    sap = m["measurement"]["saps"]["0"]
+    assert sap["visibilities"].shape == (5, 140, 130, 4, 2) and sap["visibilities"].dtype == np.int8
+    assert sap["visibility_scale_factors"].shape == (5, 130, 4) and sap["visibility_scale_factors"].min() > 0
+    assert sap["baselines"].shape == (5, 2)
+    assert all(nm in sap["antenna_locations"]["XYZ"] for nm in sap["baselines"].reshape(-1))
+    assert np.array_equal(S.make_measurement(5, 140, 130, seed=1)["measurement"]["saps"]["0"]["visibilities"],
+                          sap["visibilities"])
