@@ -89,8 +89,17 @@ LSHM_API int lshm_fft2_reim_shift_clamp(const float* x, const float* xhat, float
 LSHM_API int lshm_uv_harmonics(const float* uv, const float* scales, int64_t N, int H, float* out,
                       lshm_stream_t stream);
 
-/* Conv2d(k4,s2,p1) forward (src/lofar_models.py:73-78) and ConvTranspose2d dgrad. */
-LSHM_API int lshm_down2d(const float* big, int64_t big_ns, const float* w, const float* bias,
+/* Weight "images" for the tensor-core conv kernels: the fp32 weight W[A,Bc,4(,4)] split into
+ * bf16 hi/lo halves and permuted into the shared-memory operand layout of each kernel, so a CTA
+ * fetches its weight tile with one bulk copy.  Must be re-made whenever W changes (once per
+ * closure evaluation).  which: 0 = image for lshm_down*, 1 = image for lshm_up*. */
+LSHM_API int lshm_conv_image_bytes(int dim, int A, int Bc, int which, int64_t* bytes);
+LSHM_API int lshm_conv_prep(const float* w, int dim, int A, int Bc, void* down_img, void* up_img,
+                   lshm_stream_t stream);
+
+/* Conv2d(k4,s2,p1) forward (src/lofar_models.py:73-78) and ConvTranspose2d dgrad.
+ * wimg = "down" image of W (lshm_conv_prep). */
+LSHM_API int lshm_down2d(const float* big, int64_t big_ns, const void* wimg, const float* bias,
                 const float* aux, int64_t aux_ns, float* small_, int64_t small_ns,
                 int64_t N, int A, int Bc, int h, int w_, int epilogue, lshm_stream_t stream);
 /* ConvTranspose2d(k4,s2,p1) forward (src/lofar_models.py:93-98) and Conv2d dgrad. */
@@ -102,7 +111,7 @@ LSHM_API int lshm_wgrad2d(const float* small_, int64_t small_ns, const float* bi
                  float* dw, int64_t N, int A, int Bc, int h, int w_, lshm_stream_t stream);
 
 /* Conv1d(k4,s4,p1) forward (src/lofar_models.py:158-163), ConvTranspose1d dgrad (pad=0). */
-LSHM_API int lshm_down1d(const float* big, int64_t big_ns, const float* w, const float* bias,
+LSHM_API int lshm_down1d(const float* big, int64_t big_ns, const void* wimg, const float* bias,
                 const float* aux, int64_t aux_ns, float* small_, int64_t small_ns,
                 int64_t N, int A, int Bc, int l, int pad, int epilogue, lshm_stream_t stream);
 /* ConvTranspose1d(k4,s4,p0) forward (src/lofar_models.py:178-183), Conv1d dgrad (pad=1). */

@@ -67,7 +67,7 @@ class _Library:
             fn = getattr(self.cdll, name)
             fn.argtypes = [_to_ctype(t) for t, _ in args]
             fn.restype = ctypes.c_char_p if "char" in ret else ctypes.c_int
-            if name in ("lshm_last_error", "lshm_version", "lshm_device_info"):
+            if name in ("lshm_last_error", "lshm_version", "lshm_device_info", "lshm_conv_image_bytes"):
                 continue
             setattr(self, name[len("lshm_"):], self._wrap(name, fn))
 
@@ -79,6 +79,13 @@ class _Library:
                 raise LshmError(f"{name} failed ({rc}): {self.cdll.lshm_last_error().decode()}")
         call.__name__ = name
         return call
+
+    def conv_image_bytes(self, dim: int, A: int, Bc: int, which: int) -> int:
+        n = ctypes.c_int64()
+        rc = self.cdll.lshm_conv_image_bytes(dim, A, Bc, which, ctypes.byref(n))
+        if rc != 0:
+            raise LshmError(f"lshm_conv_image_bytes failed: {self.cdll.lshm_last_error().decode()}")
+        return int(n.value)
 
     def version(self) -> int:
         return int(self.cdll.lshm_version())

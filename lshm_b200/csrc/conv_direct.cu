@@ -406,23 +406,6 @@ using namespace lshm;
 
 extern "C" {
 
-int lshm_down2d(const float* big, int64_t big_ns, const float* w, const float* bias,
-                const float* aux, int64_t aux_ns, float* small_, int64_t small_ns,
-                int64_t N, int A, int Bc, int h, int w_, int epilogue, lshm_stream_t stream) {
-  CHECK_CONV_ARGS("lshm_down2d");
-  LSHM_REQUIRE(h > 0 && w_ > 0, "lshm_down2d: bad map size");
-  if (N == 0) return LSHM_OK;
-  if (aux == nullptr) { aux = small_; aux_ns = small_ns; }
-  const int64_t px = N * h * w_;
-  constexpr int AT = 8;
-  const size_t smem = (size_t)AT * Bc * 16 * sizeof(float);
-  if (smem > 48 * 1024)
-    LSHM_CUDA(cudaFuncSetAttribute(down2d_kernel<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "lshm_down2d");
-  dim3 grid((unsigned)ceil_div(px, CONV_THREADS), (unsigned)ceil_div(A, AT));
-  down2d_kernel<AT><<<grid, CONV_THREADS, smem, as_stream(stream)>>>(big, big_ns, w, bias, aux, aux_ns, small_, small_ns, N, A, Bc, h, w_, epilogue);
-  LSHM_CHECK_LAUNCH("lshm_down2d");
-  return LSHM_OK;
-}
 
 int lshm_up2d(const float* small_, int64_t small_ns, const float* w, const float* bias,
               const float* aux, int64_t aux_ns, float* big, int64_t big_ns,
@@ -465,21 +448,6 @@ int lshm_wgrad2d(const float* small_, int64_t small_ns, const float* big, int64_
   return LSHM_OK;
 }
 
-int lshm_down1d(const float* big, int64_t big_ns, const float* w, const float* bias,
-                const float* aux, int64_t aux_ns, float* small_, int64_t small_ns,
-                int64_t N, int A, int Bc, int l, int pad, int epilogue, lshm_stream_t stream) {
-  CHECK_CONV_ARGS("lshm_down1d");
-  LSHM_REQUIRE(l > 0 && (pad == 0 || pad == 1), "lshm_down1d: bad l/pad");
-  if (N == 0) return LSHM_OK;
-  if (aux == nullptr) { aux = small_; aux_ns = small_ns; }
-  constexpr int AT = 8;
-  const size_t smem = (size_t)AT * Bc * 4 * sizeof(float);
-  const int vec_ok = aligned16(big) && (big_ns & 3) == 0;
-  dim3 grid((unsigned)ceil_div(N * l, CONV_THREADS), (unsigned)ceil_div(A, AT));
-  down1d_kernel<AT><<<grid, CONV_THREADS, smem, as_stream(stream)>>>(big, big_ns, w, bias, aux, aux_ns, small_, small_ns, N, A, Bc, l, pad, epilogue, vec_ok);
-  LSHM_CHECK_LAUNCH("lshm_down1d");
-  return LSHM_OK;
-}
 
 int lshm_up1d(const float* small_, int64_t small_ns, const float* w, const float* bias,
               const float* aux, int64_t aux_ns, float* big, int64_t big_ns,

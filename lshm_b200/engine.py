@@ -68,6 +68,17 @@ class Workspace:
             self.dx = torch.empty(N, sz[0], **f) if need_dx else None
 
 
+def conv_image(w: torch.Tensor, dim: int, which: int, st: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bf16 hi/lo operand image of a conv / transposed-conv weight W[A,Bc,4(,4)] for the tensor-core
+    kernels (which: 0 = lshm_down*, 1 = lshm_up*); lshm_conv_prep."""
+    A, Bc = w.shape[0], w.shape[1]
+    if out is None:
+        out = torch.empty(max(16, lib().conv_image_bytes(dim, A, Bc, which)), dtype=torch.uint8, device=w.device)
+    lib().conv_prep(w.data_ptr(), dim, A, Bc, out.data_ptr() if which == 0 else None,
+                    out.data_ptr() if which == 1 else None, st)
+    return out
+
+
 class AEEngine:
     """Forward / backward of one autoencoder (ndim=2: AutoEncoderCNN2, ndim=1: AutoEncoder1DCNN)."""
 
@@ -76,6 +87,17 @@ class AEEngine:
         self.ndim, self.C, self.L, self.H4, self.rica = ndim, channels, latent_dim, harmonic_dim, rica
         self.ch = (channels,) + CONV_CHANNELS
         self.lib = lib()
+        self.img = {}   # (layer name, which) -> weight image buffer (re-filled every closure)
+
+    def prepare_images(self, p: Dict[str, torch.Tensor], st: int, grads: bool):
+        """Re-make the weight images the coming forward (and backward) will read.  Conv layers use
+        their 'down' image forward; transposed-conv layers use theirs in the backward (dgrad)."""
+        for i in range(6):
+            nm = f"conv{i}.weight"
+            self.img[(nm, 0)] = conv_image(p[nm], self.ndim, 0, st, self.img.get((nm, 0)))
+            if grads:
+                nm = f"tconv{i}.weight"
+                self.img[(nm, 0)] = conv_image(p[nm], self.ndim, 0, st, self.img.get((nm, 0)))
 
     def workspace(self, N, device, with_grad, need_dx=False) -> Workspace:
         return Workspace(N, self.C, self.L, self.H4, device, with_grad, need_dx)
@@ -119,7 +141,7 @@ class AEEngine:
                 dst, dst_ns = ws.enc[i + 1], sz[i + 1]
             else:
                 dst, dst_ns = ws.cat1, ld1
-            self._down(_p(src), src_ns, _p(p[f"conv{i}.weight"]), _p(p[f"conv{i}.bias"]), None, 0,
+            self._down(_p(src), src_ns, _p(self.img[(f"conv{i}.weight", 0)]), _p(p[f"conv{i}.bias"]), None, 0,
                        _p(dst), dst_ns, N, ch[i + 1], ch[i], i + 1, 1, EPI_ELU, st)
             src, src_ns = dst, dst_ns
         lb.linear_fwd(_p(uvh), uvh.stride(0), _p(p["fcuv1.weight"]), _p(p["fcuv1.bias"]),
@@ -154,6 +176,7 @@ class AEEngine:
         (lets the three nets write straight into the concatenated Mu buffer).
         """
         lb, N, L, H4 = self.lib, ws.N, self.L, self.H4
+        self.prepare_images(p, st, hasattr(ws, "g_enc"))
         lb.uv_harmonics(_p(uv), _p(scales), N, scales.numel(), _p(ws.uvh), st)
         mu_final = mu_out if mu_out is not None else ws.mu
         mu_ld, zc_ld = mu_final.stride(0), L + H4
@@ -198,7 +221,7 @@ class AEEngine:
                 lb.channel_sum(_p(dz), sz[lvl - 1], _p(g[f"tconv{i}.bias"]), N, Bc, sz[lvl - 1] // Bc, st)
                 nxt = ws.g_dec[i]
                 # dgrad of the transposed conv = "down"; ELU' of the producing layer unless it is fc3
-                self._down(_p(dz), sz[lvl - 1], _p(p[f"tconv{i}.weight"]), None,
+                self._down(_p(dz), sz[lvl - 1], _p(self.img[(f"tconv{i}.weight", 0)]), None,
                            _p(inp) if i > 0 else None, sz[lvl], _p(nxt), sz[lvl], N, A, Bc, lvl, 0,
                            EPI_DELU if i > 0 else EPI_NONE, st)
                 dz = nxt

@@ -129,6 +129,7 @@ class _AutoEncoderBase(nn.Module):
         N = x.shape[0]
         eng = self.engine()
         ws = eng.workspace(N, x.device, with_grad=False)
+        eng.prepare_images(self.named_param_dict(), _stream(), False)
         return eng.encode(x.contiguous().view(N, -1), uv.contiguous(), self.named_param_dict(), ws, _stream())
 
     @torch.no_grad()

@@ -12,6 +12,9 @@ from oracle import lofar_oracle as O
 
 pytestmark = pytest.mark.gpu
 CH = (8, 12, 24, 48, 96, 192)
+# tensor-core convs: fp32 operands split into bf16 hi+lo, 3 MMAs, fp32 accumulate:
+# ~3e-6 relative per output; the parity contract (north_star) is 1e-3 on losses / gradients
+TC_TOL = 2e-5
 
 
 def st():
@@ -20,6 +23,11 @@ def st():
 
 def dp(t):
     return None if t is None else t.data_ptr()
+
+
+def image(w, dim, which=0):
+    from lshm_b200.engine import conv_image
+    return conv_image(w, dim, which, st())
 
 
 def elu_grad_from_out(a):
@@ -41,12 +49,13 @@ def test_conv2d_family(cuda, lvl, C):
     ref = F.elu(F.conv2d(big, w, bias, stride=2, padding=1))
     out = torch.empty(N, A, s, s, device=cuda)
     bg, wg, bsg = big.to(cuda), w.to(cuda), bias.to(cuda)
-    lib().down2d(dp(bg), Bc * 4 * s * s, dp(wg), dp(bsg), None, 0, dp(out), A * s * s, N, A, Bc, s, s, 1, st())
-    assert rel_err(out, ref) < 2e-6
+    wdn = image(wg, 2)
+    lib().down2d(dp(bg), Bc * 4 * s * s, dp(wdn), dp(bsg), None, 0, dp(out), A * s * s, N, A, Bc, s, s, 1, st())
+    assert rel_err(out, ref) < TC_TOL
     # strided destination (conv5 writes into the concat buffer)
     pad = torch.zeros(N, A * s * s + 16, device=cuda)
-    lib().down2d(dp(bg), Bc * 4 * s * s, dp(wg), dp(bsg), None, 0, dp(pad), A * s * s + 16, N, A, Bc, s, s, 1, st())
-    assert rel_err(pad[:, :A * s * s].reshape(N, A, s, s), ref) < 2e-6 and float(pad[:, A * s * s:].abs().max()) == 0
+    lib().down2d(dp(bg), Bc * 4 * s * s, dp(wdn), dp(bsg), None, 0, dp(pad), A * s * s + 16, N, A, Bc, s, s, 1, st())
+    assert rel_err(pad[:, :A * s * s].reshape(N, A, s, s), ref) < TC_TOL and float(pad[:, A * s * s:].abs().max()) == 0
     # up = ConvTranspose2d forward with weight [A,Bc,4,4] (+ELU) and = Conv2d dgrad
     small = torch.randn(N, A, s, s)
     bias_b = torch.randn(Bc)
@@ -66,8 +75,8 @@ def test_conv2d_family(cuda, lvl, C):
     act_s = F.elu(torch.randn(N, A, s, s))
     ref_dd = F.conv2d(big, w, None, stride=2, padding=1) * elu_grad_from_out(act_s)
     asg = act_s.to(cuda)
-    lib().down2d(dp(bg), Bc * 4 * s * s, dp(wg), None, dp(asg), A * s * s, dp(out), A * s * s, N, A, Bc, s, s, 2, st())
-    assert rel_err(out, ref_dd) < 2e-6
+    lib().down2d(dp(bg), Bc * 4 * s * s, dp(wdn), None, dp(asg), A * s * s, dp(out), A * s * s, N, A, Bc, s, s, 2, st())
+    assert rel_err(out, ref_dd) < TC_TOL
     # wgrad
     bigr = big.clone().requires_grad_()
     wr = w.clone().requires_grad_()
@@ -96,8 +105,9 @@ def test_conv1d_family(cuda, lvl):
     out_b = torch.empty(N, Bc, 4 * l, device=cuda)
     # Conv1d(k4,s4,p1) forward
     bag, bbg = bias_a.to(cuda), bias_b.to(cuda)
-    lib().down1d(dp(bg), Bc * 4 * l, dp(wg), dp(bag), None, 0, dp(out_s), A * l, N, A, Bc, l, 1, 1, st())
-    assert rel_err(out_s, F.elu(F.conv1d(big, wg_, bias_a, stride=4, padding=1))) < 2e-6
+    wdn = image(wg, 1)
+    lib().down1d(dp(bg), Bc * 4 * l, dp(wdn), dp(bag), None, 0, dp(out_s), A * l, N, A, Bc, l, 1, 1, st())
+    assert rel_err(out_s, F.elu(F.conv1d(big, wg_, bias_a, stride=4, padding=1))) < TC_TOL
     # ConvTranspose1d(k4,s4,p0) forward
     lib().up1d(dp(sg), A * l, dp(wg), dp(bbg), None, 0, dp(out_b), Bc * 4 * l, N, A, Bc, l, 0, 1, st())
     assert rel_err(out_b, F.elu(F.conv_transpose1d(small, wg_, bias_b, stride=4, padding=0))) < 2e-6
@@ -116,8 +126,8 @@ def test_conv1d_family(cuda, lvl):
     smr = small.clone().requires_grad_()
     wr2 = wg_.clone().requires_grad_()
     F.conv_transpose1d(smr, wr2, None, stride=4, padding=0).backward(big)
-    lib().down1d(dp(bg), Bc * 4 * l, dp(wg), None, None, 0, dp(out_s), A * l, N, A, Bc, l, 0, 0, st())
-    assert rel_err(out_s, smr.grad) < 2e-6
+    lib().down1d(dp(bg), Bc * 4 * l, dp(wdn), None, None, 0, dp(out_s), A * l, N, A, Bc, l, 0, 0, st())
+    assert rel_err(out_s, smr.grad) < TC_TOL
     lib().wgrad1d(dp(sg), A * l, dp(bg), Bc * 4 * l, dp(dw), N, A, Bc, l, 0, st())
     assert rel_err(dw, wr2.grad) < 1e-5
 

@@ -2,8 +2,9 @@
 the multiplier update, the optimiser contracts, and the inference loop - against the CPU
 oracle (oracle/lofar_oracle.py) on identical seeded inputs.
 
-Tolerances: north_star asks loss and gradients within 1e-3 relative; the fp32 kernels are held
-to 2e-4 here (per-tensor L2-relative), losses to 1e-5."""
+Tolerances: north_star asks loss and gradients within 1e-3 relative; here every gradient tensor is
+held to 2e-4 (L2-relative), activations / latents to 5e-5 and loss terms to 5e-5 (the convs run on
+tensor cores with a bf16 hi/lo split, ~3e-6 per layer, everything else is fp32)."""
 import numpy as np
 import pytest
 import torch
@@ -13,6 +14,8 @@ from oracle import lofar_oracle as O
 
 pytestmark = pytest.mark.gpu
 GRAD_TOL = 2e-4
+ACT_TOL = 5e-5
+LOSS_TOL = 5e-5
 
 
 def build_modules(case, cuda, rica=True):
@@ -59,7 +62,7 @@ def test_autoencoder_module_forward_backward(cuda, ndim, C, L):
     assert list(net.state_dict().keys()) == list(p.keys())
     xg = x.to(cuda).requires_grad_()
     xh, mu = net(xg, uv.to(cuda))
-    assert rel_err(xh, xh_ref) < 1e-5 and rel_err(mu, mu_ref) < 1e-5
+    assert rel_err(xh, xh_ref) < ACT_TOL and rel_err(mu, mu_ref) < ACT_TOL
     ((xh * w1.to(cuda)).sum() + (mu * w2.to(cuda)).sum()).backward()
     check_grads({k: v.grad for k, v in net.named_parameters()}, {k: v.grad for k, v in pr.items()})
     assert rel_err(xg.grad, xr.grad) < GRAD_TOL
@@ -70,9 +73,9 @@ def test_autoencoder_module_forward_backward(cuda, ndim, C, L):
     # encode/decode helpers (reference signatures take the harmonic vector)
     uvh = O.uv_harmonics(uv, hs)
     enc = net.encode(x.to(cuda), uvh.to(cuda))
-    assert rel_err(enc, O.ae_encode(p, x, uvh, ndim)) < 1e-5
+    assert rel_err(enc, O.ae_encode(p, x, uvh, ndim)) < ACT_TOL
     z = torch.randn(N, L)
-    assert rel_err(net.decode(z.to(cuda), uvh.to(cuda)), O.ae_decode(p, z, uvh, ndim)) < 1e-5
+    assert rel_err(net.decode(z.to(cuda), uvh.to(cuda)), O.ae_decode(p, z, uvh, ndim)) < ACT_TOL
 
 
 def test_kmeans_module(cuda):
@@ -121,22 +124,22 @@ def test_fused_closure_matches_oracle(cuda, C, L, Lt, N, bpb):
     loss = step.closure()
     terms = step.loss_terms()
     for k in ("total", "loss0", "loss1", "loss2", "loss3", "kdist", "aug", "sim", "rica"):
-        assert abs(terms[k] - ref[k]) <= 1e-5 * abs(ref[k]) + 1e-9, (k, terms[k], ref[k])
-    assert abs(float(loss) - ref["total"]) <= 1e-5 * abs(ref["total"])
-    assert rel_err(step.latents(), ref["Mu"]) < 1e-5
+        assert abs(terms[k] - ref[k]) <= LOSS_TOL * abs(ref[k]) + 1e-9, (k, terms[k], ref[k])
+    assert abs(float(loss) - ref["total"]) <= LOSS_TOL * abs(ref["total"])
+    assert rel_err(step.latents(), ref["Mu"]) < ACT_TOL
     got = {nm: p.grad for nm, p in zip(step.flat.names, step.flat.params)}
     check_grads(got, ref["grads"])
     # forward-only evaluation (LBFGSNew line search, src/lbfgsnew.py:686-693): same loss, grads untouched
     before = step.flat.grad.clone()
     with torch.no_grad():
         l2 = step.closure()
-    assert abs(float(l2) - ref["total"]) <= 1e-5 * abs(ref["total"])
+    assert abs(float(l2) - ref["total"]) <= LOSS_TOL * abs(ref["total"])
     assert max_abs(step.flat.grad[:step.flat.numel], before[:step.flat.numel]) == 0
     # multiplier update against the oracle
     y_ref = O.multiplier_update(case["pn"], case["pT"], case["pF"], case["x"], case["uv"], torch.tensor(SCALES), *case["ys"])
     step.update_multipliers()
     for got_y, ref_y in zip((step.y1, step.y2, step.y3), y_ref):
-        assert rel_err(got_y, ref_y) < 1e-5
+        assert rel_err(got_y, ref_y) < ACT_TOL
 
 
 def test_reference_loop_with_dropin_modules(cuda):
@@ -173,7 +176,7 @@ def test_reference_loop_with_dropin_modules(cuda):
                                + torch.sum(torch.log(torch.cosh(yyFmu))) / yyFmu.numel())
     loss += rica_loss
     loss.backward(retain_graph=True)
-    assert abs(float(loss) - ref["total"]) < 1e-5 * abs(ref["total"])
+    assert abs(float(loss) - ref["total"]) < LOSS_TOL * abs(ref["total"])
     got = {}
     for mi, m in enumerate((net, netT, netF, mod)):
         for nm, p in m.named_parameters():
@@ -234,7 +237,7 @@ def test_inference_loop(cuda):
     hs = torch.tensor(SCALES)
     *_, mu, muT, muF = O.cascade_forward(case["pn"], case["pT"], case["pF"], case["x"], case["uv"], hs)
     Mu_ref = torch.cat((mu, muT, muF), 1)
-    assert rel_err(Mu, Mu_ref) < 1e-5
+    assert rel_err(Mu, Mu_ref) < ACT_TOL
     for g in range(2):
         d, idx, pp = O.eval_distances(Mu_ref[g * 4:(g + 1) * 4], case["M"], 4)
         assert rel_err(dist[g], d) < 1e-4 and int(gid[g]) == idx
@@ -257,7 +260,7 @@ def test_closure_matches_golden_from_live_reference(cuda):
     step.closure()
     t = step.loss_terms()
     for k in ("total", "loss0", "loss1", "loss2", "loss3", "kdist", "aug", "sim", "rica"):
-        assert abs(t[k] - float(g[k])) <= 1e-5 * abs(float(g[k])) + 1e-9, k
+        assert abs(t[k] - float(g[k])) <= LOSS_TOL * abs(float(g[k])) + 1e-9, k
     for nm, p in zip(step.flat.names, step.flat.params):
         tag, name = nm.split(".", 1)
         gk = {"0": "n", "1": "T", "2": "F", "3": "k"}[tag] + "." + name
