@@ -102,8 +102,9 @@ LSHM_API int lshm_conv_prep(const float* w, int dim, int A, int Bc, void* down_i
 LSHM_API int lshm_down2d(const float* big, int64_t big_ns, const void* wimg, const float* bias,
                 const float* aux, int64_t aux_ns, float* small_, int64_t small_ns,
                 int64_t N, int A, int Bc, int h, int w_, int epilogue, lshm_stream_t stream);
-/* ConvTranspose2d(k4,s2,p1) forward (src/lofar_models.py:93-98) and Conv2d dgrad. */
-LSHM_API int lshm_up2d(const float* small_, int64_t small_ns, const float* w, const float* bias,
+/* ConvTranspose2d(k4,s2,p1) forward (src/lofar_models.py:93-98) and Conv2d dgrad.
+ * wimg = "up" image of W (lshm_conv_prep). */
+LSHM_API int lshm_up2d(const float* small_, int64_t small_ns, const void* wimg, const float* bias,
               const float* aux, int64_t aux_ns, float* big, int64_t big_ns,
               int64_t N, int A, int Bc, int h, int w_, int epilogue, lshm_stream_t stream);
 /* dW[A,Bc,4,4] = sum_n small (x) big ; written, not accumulated. */
@@ -115,7 +116,7 @@ LSHM_API int lshm_down1d(const float* big, int64_t big_ns, const void* wimg, con
                 const float* aux, int64_t aux_ns, float* small_, int64_t small_ns,
                 int64_t N, int A, int Bc, int l, int pad, int epilogue, lshm_stream_t stream);
 /* ConvTranspose1d(k4,s4,p0) forward (src/lofar_models.py:178-183), Conv1d dgrad (pad=1). */
-LSHM_API int lshm_up1d(const float* small_, int64_t small_ns, const float* w, const float* bias,
+LSHM_API int lshm_up1d(const float* small_, int64_t small_ns, const void* wimg, const float* bias,
               const float* aux, int64_t aux_ns, float* big, int64_t big_ns,
               int64_t N, int A, int Bc, int l, int pad, int epilogue, lshm_stream_t stream);
 LSHM_API int lshm_wgrad1d(const float* small_, int64_t small_ns, const float* big, int64_t big_ns,

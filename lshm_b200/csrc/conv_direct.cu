@@ -407,30 +407,6 @@ using namespace lshm;
 extern "C" {
 
 
-int lshm_up2d(const float* small_, int64_t small_ns, const float* w, const float* bias,
-              const float* aux, int64_t aux_ns, float* big, int64_t big_ns,
-              int64_t N, int A, int Bc, int h, int w_, int epilogue, lshm_stream_t stream) {
-  CHECK_CONV_ARGS("lshm_up2d");
-  LSHM_REQUIRE(h > 0 && w_ > 0, "lshm_up2d: bad map size");
-  if (N == 0) return LSHM_OK;
-  if (aux == nullptr) { aux = big; aux_ns = big_ns; }
-  const int64_t px = N * 4 * (int64_t)h * w_;
-  cudaStream_t st = as_stream(stream);
-  if ((size_t)A * 16 * 8 * sizeof(float) <= 48 * 1024 && Bc > 4) {
-    constexpr int BT = 8;
-    dim3 grid((unsigned)ceil_div(px, CONV_THREADS), (unsigned)ceil_div(Bc, BT));
-    up2d_kernel<BT><<<grid, CONV_THREADS, (size_t)A * 16 * BT * sizeof(float), st>>>(small_, small_ns, w, bias, aux, aux_ns, big, big_ns, N, A, Bc, h, w_, epilogue);
-  } else {
-    constexpr int BT = 4;
-    const size_t smem = (size_t)A * 16 * BT * sizeof(float);
-    if (smem > 48 * 1024)
-      LSHM_CUDA(cudaFuncSetAttribute(up2d_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "lshm_up2d");
-    dim3 grid((unsigned)ceil_div(px, CONV_THREADS), (unsigned)ceil_div(Bc, BT));
-    up2d_kernel<BT><<<grid, CONV_THREADS, smem, st>>>(small_, small_ns, w, bias, aux, aux_ns, big, big_ns, N, A, Bc, h, w_, epilogue);
-  }
-  LSHM_CHECK_LAUNCH("lshm_up2d");
-  return LSHM_OK;
-}
 
 int lshm_wgrad2d(const float* small_, int64_t small_ns, const float* big, int64_t big_ns,
                  float* dw, int64_t N, int A, int Bc, int h, int w_, lshm_stream_t stream) {
@@ -449,21 +425,6 @@ int lshm_wgrad2d(const float* small_, int64_t small_ns, const float* big, int64_
 }
 
 
-int lshm_up1d(const float* small_, int64_t small_ns, const float* w, const float* bias,
-              const float* aux, int64_t aux_ns, float* big, int64_t big_ns,
-              int64_t N, int A, int Bc, int l, int pad, int epilogue, lshm_stream_t stream) {
-  CHECK_CONV_ARGS("lshm_up1d");
-  LSHM_REQUIRE(l > 0 && (pad == 0 || pad == 1), "lshm_up1d: bad l/pad");
-  if (N == 0) return LSHM_OK;
-  if (aux == nullptr) { aux = big; aux_ns = big_ns; }
-  constexpr int BT = 4;
-  const size_t smem = (size_t)A * BT * 4 * sizeof(float);
-  const int vec_ok = aligned16(big) && (big_ns & 3) == 0;
-  dim3 grid((unsigned)ceil_div(N * l, CONV_THREADS), (unsigned)ceil_div(Bc, BT));
-  up1d_kernel<BT><<<grid, CONV_THREADS, smem, as_stream(stream)>>>(small_, small_ns, w, bias, aux, aux_ns, big, big_ns, N, A, Bc, l, pad, epilogue, vec_ok);
-  LSHM_CHECK_LAUNCH("lshm_up1d");
-  return LSHM_OK;
-}
 
 int lshm_wgrad1d(const float* small_, int64_t small_ns, const float* big, int64_t big_ns,
                  float* dw, int64_t N, int A, int Bc, int l, int pad, lshm_stream_t stream) {

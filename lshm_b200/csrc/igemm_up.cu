@@ -1,0 +1,409 @@
+// "up" implicit GEMM on tcgen05: ConvTranspose2d(k4,s2,p1) / ConvTranspose1d(k4,s4,p0) forward and the
+// dgrad of Conv2d(k4,s2,p1) / Conv1d(k4,s4,p1).  Reference semantics: F.conv_transpose2d /
+// F.conv_transpose1d at /root/reference/src/lofar_models.py:93-98,:178-183 (and the autograd of
+// :73-78,:158-163).
+//
+// 2-D: an output pixel (2m+ry, 2n+rx) receives exactly 2x2 taps, so the four parity classes are
+// four GEMMs over the SAME staged tile of the small map S (positions of the zero-padded
+// (h+1)x(w+1) grid, rows at a 16-byte pitch, channels = K):
+//     out[(2m+ry,2n+rx), b] = sum_{d,e} sum_a S[q + dy(ry,d)*(w+1) + dx(rx,e), a] * W[a,b,ky(ry,d),kx(rx,e)]
+// with (ry=0: ky=1,dy=0 | ky=3,dy=-1) (ry=1: ky=0,dy=+1 | ky=2,dy=0).  The nine shifted views of S
+// are nine descriptor start addresses into one shared-memory copy; the four classes accumulate in
+// four TMEM column ranges and the epilogue writes complete 2x2 output blocks (float2 stores).
+// 1-D (k=s=4): out[b, 4i+t-pad] = sum_a S[i,a] W[a,b,t], a plain GEMM with N = (b,t).
+#include "tc_common.cuh"
+
+namespace lshm {
+namespace {
+
+using namespace tc;
+
+struct UpArgs {
+  const float* small_; int64_t small_ns;
+  const uint8_t* wimg;
+  const float* bias;
+  const float* aux; int64_t aux_ns;
+  float* big; int64_t big_ns;
+  int64_t N; int A; int Bc; int h; int w; int pad; int epi;
+  int slots; int nstage; int64_t Q;
+};
+
+__device__ __forceinline__ float epi_apply(float acc, float bias, int epi, float aux) {
+  float r = acc + bias;
+  if (epi == LSHM_EPI_ELU) r = elu_f(r);
+  else if (epi == LSHM_EPI_DELU) r *= delu_from_out(aux);
+  return r;
+}
+
+template <int DIM, int NT, int KC>
+__global__ void __launch_bounds__(192) igemm_up_kernel(UpArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], acc_bar;
+  __shared__ uint32_t tmem_base;
+  constexpr int NCLS = DIM == 2 ? 4 : 1;
+  constexpr int COMBOS = DIM == 2 ? 16 : 1;       // class x tap weight tiles per K block
+  constexpr int CC = KC / 8;
+  constexpr uint32_t IMG = 2u * COMBOS * CC * NT * 16;
+  constexpr uint32_t TCOLS = NCLS * NT;
+  constexpr uint32_t TMEM_COLS = TCOLS <= 32 ? 32 : (TCOLS <= 64 ? 64 : (TCOLS <= 128 ? 128 : (TCOLS <= 256 ? 256 : 512)));
+  const int SLOTS = a.slots, NS = a.nstage;
+  const uint32_t zbytes = (uint32_t)CC * SLOTS * 16;
+  const uint32_t stage_bytes = 2 * zbytes + IMG;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t q0 = (int64_t)blockIdx.x * 128;
+  const int nt = blockIdx.y;
+  const int Apad = (a.A + 15) / 16 * 16;
+  const int KB = (Apad + KC - 1) / KC;
+  const int PW = a.w + 1, PH = a.h + 1;
+  const int halo = DIM == 2 ? PW + 1 : 0;           // slots in front of the tile
+
+  if (warp == 4) tmem_alloc(&tmem_base, TMEM_COLS);
+  if (tid == 0) {
+    for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], 5); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&acc_bar, 1);
+    mbar_init_fence();
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = tmem_base;
+
+  if (warp < 4) {
+    // ------------------------------------------------ producers: stage S (hi/lo bf16), K = channels
+    const int64_t hw = DIM == 2 ? (int64_t)a.h * a.w : (int64_t)a.w;
+    const float* sp[3]; bool sv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int s = tid + i * 128;
+      const int64_t q = q0 - halo + s;
+      sv[i] = s < SLOTS && q >= 0 && q < a.Q;
+      sp[i] = a.small_;
+      if (sv[i]) {
+        if (DIM == 2) {
+          const int64_t pp = (int64_t)PH * PW;
+          const int64_t n = q / pp;
+          const int r = (int)(q - n * pp);
+          const int m = r / PW, x = r - m * PW;
+          sv[i] = m < a.h && x < a.w;
+          sp[i] = a.small_ + n * a.small_ns + (int64_t)m * a.w + x;
+        } else {
+          const int64_t n = q / a.w;
+          sp[i] = a.small_ + n * a.small_ns + (q - n * a.w);
+        }
+      }
+    }
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % NS, ph = (kb / NS) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* zhi = smem + (size_t)s * stage_bytes;
+      uint8_t* zlo = zhi + zbytes;
+      const int ccb = (min(KC, Apad - kb * KC)) >> 3;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int slot = tid + i * 128;
+        if (slot >= SLOTS) continue;
+        for (int cc = 0; cc < ccb; ++cc) {
+          const int a0 = kb * KC + cc * 8;
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = (sv[i] && a0 + e < a.A) ? __ldg(sp[i] + (int64_t)(a0 + e) * hw) : 0.f;
+          uint4 hi, lo;
+          split8(v, hi, lo);
+          *reinterpret_cast<uint4*>(zhi + ((size_t)cc * SLOTS + slot) * 16) = hi;
+          *reinterpret_cast<uint4*>(zlo + ((size_t)cc * SLOTS + slot) * 16) = lo;
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+    }
+    // ------------------------------------------------ epilogue
+    mbar_wait(&acc_bar, 0);
+    fence_after();
+    const int64_t q = q0 + tid;
+    bool ok = q < a.Q;
+    int64_t n = 0; int m = 0, x = 0;
+    if (ok) {
+      if (DIM == 2) {
+        const int64_t pp = (int64_t)PH * PW;
+        n = q / pp;
+        const int r = (int)(q - n * pp);
+        m = r / PW; x = r - m * PW;
+        ok = m < a.h && x < a.w;
+      } else {
+        n = q / a.w; x = (int)(q - n * a.w);
+      }
+    }
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    if (DIM == 2) {
+      const int W = 2 * a.w;
+      const int64_t HW = 4 * (int64_t)a.h * a.w;
+      float* outp = a.big + n * a.big_ns + (int64_t)(2 * m) * W + 2 * x;
+      const float* auxp = a.aux != nullptr ? a.aux + n * a.aux_ns + (int64_t)(2 * m) * W + 2 * x : nullptr;
+#pragma unroll 1
+      for (int g = 0; g < NT / 16; ++g) {
+        float v[4][16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld16(trow + c * NT + g * 16, v[c]);
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int b = nt * NT + g * 16 + j;
+            if (b < a.Bc) {
+              const float bs = a.bias != nullptr ? __ldg(a.bias + b) : 0.f;
+              float2 ax0 = make_float2(0.f, 0.f), ax1 = make_float2(0.f, 0.f);
+              if (a.epi == LSHM_EPI_DELU) {
+                ax0 = *reinterpret_cast<const float2*>(auxp + b * HW);
+                ax1 = *reinterpret_cast<const float2*>(auxp + b * HW + W);
+              }
+              // class index = ry*2 + rx
+              const float2 o0 = make_float2(epi_apply(v[0][j], bs, a.epi, ax0.x), epi_apply(v[1][j], bs, a.epi, ax0.y));
+              const float2 o1 = make_float2(epi_apply(v[2][j], bs, a.epi, ax1.x), epi_apply(v[3][j], bs, a.epi, ax1.y));
+              *reinterpret_cast<float2*>(outp + b * HW) = o0;
+              *reinterpret_cast<float2*>(outp + b * HW + W) = o1;
+            }
+          }
+        }
+      }
+    } else {
+      const int64_t Lb = 4 * (int64_t)a.w;
+      float* outp = a.big + n * a.big_ns + 4 * (int64_t)x - a.pad;
+      const float* auxp = a.aux != nullptr ? a.aux + n * a.aux_ns + 4 * (int64_t)x - a.pad : nullptr;
+#pragma unroll 1
+      for (int g = 0; g < NT / 16; ++g) {
+        float v[16];
+        tmem_ld16(trow + g * 16, v);
+        if (ok) {
+#pragma unroll
+          for (int jb = 0; jb < 4; ++jb) {
+            const int b = (nt * NT + g * 16) / 4 + jb;
+            if (b < a.Bc) {
+              const float bs = a.bias != nullptr ? __ldg(a.bias + b) : 0.f;
+              float* o = outp + b * Lb;
+              if (a.pad == 0 && a.epi != LSHM_EPI_DELU) {
+                float4 r;
+                r.x = epi_apply(v[jb * 4 + 0], bs, a.epi, 0.f); r.y = epi_apply(v[jb * 4 + 1], bs, a.epi, 0.f);
+                r.z = epi_apply(v[jb * 4 + 2], bs, a.epi, 0.f); r.w = epi_apply(v[jb * 4 + 3], bs, a.epi, 0.f);
+                *reinterpret_cast<float4*>(o) = r;
+              } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  if (a.pad == 1 && x == 0 && t == 0) continue;        // position -1 does not exist
+                  const float ax = a.epi == LSHM_EPI_DELU ? auxp[b * Lb + t] : 0.f;
+                  o[t] = epi_apply(v[jb * 4 + t], bs, a.epi, ax);
+                }
+                if (a.pad == 1 && x == a.w - 1) {                       // last position: no tap reaches it
+                  const float ax = a.epi == LSHM_EPI_DELU ? auxp[b * Lb + 4] : 0.f;
+                  o[4] = epi_apply(0.f, bs, a.epi, ax);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(NT, 0, 0);
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % NS, ph = (kb / NS) & 1;
+        mbar_wait(&full_bar[s], ph);
+        fence_after();
+        const uint32_t zhi = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t zlo = zhi + zbytes;
+        const uint32_t bhi = zlo + zbytes;
+        const uint32_t blo = bhi + IMG / 2;
+        const int ksteps = (min(KC, Apad - kb * KC)) >> 4;
+        if (DIM == 2) {
+#pragma unroll
+          for (int cls = 0; cls < 4; ++cls) {
+            const int ry = cls >> 1, rx = cls & 1;
+#pragma unroll
+            for (int tap = 0; tap < 4; ++tap) {
+              const int d = tap >> 1, e = tap & 1;
+              const int dy = ry == 0 ? (d == 0 ? 0 : -1) : (d == 0 ? 1 : 0);
+              const int dx = rx == 0 ? (e == 0 ? 0 : -1) : (e == 0 ? 1 : 0);
+              const uint32_t row0 = (uint32_t)(halo + dy * PW + dx);
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint32_t aoff = ((uint32_t)(2 * ks) * SLOTS + row0) * 16;
+                const uint32_t boff = ((uint32_t)((cls * 4 + tap) * CC + 2 * ks) * NT) * 16;
+                mma_split3(tmem + cls * NT, make_desc(zhi + aoff, SLOTS * 16, 128), make_desc(zlo + aoff, SLOTS * 16, 128),
+                           make_desc(bhi + boff, NT * 16, 128), make_desc(blo + boff, NT * 16, 128), idesc,
+                           (kb > 0 || tap > 0 || ks > 0) ? 1u : 0u);
+              }
+            }
+          }
+        } else {
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t aoff = ((uint32_t)(2 * ks) * SLOTS) * 16;
+            const uint32_t boff = ((uint32_t)(2 * ks) * NT) * 16;
+            mma_split3(tmem, make_desc(zhi + aoff, SLOTS * 16, 128), make_desc(zlo + aoff, SLOTS * 16, 128),
+                       make_desc(bhi + boff, NT * 16, 128), make_desc(blo + boff, NT * 16, 128), idesc,
+                       (kb > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        commit(&empty_bar[s]);
+      }
+      commit(&acc_bar);
+    }
+  } else {
+    if (lane == 0) {
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % NS, ph = (kb / NS) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], IMG);
+        bulk_g2s(smem + (size_t)s * stage_bytes + 2 * zbytes, a.wimg + ((size_t)nt * KB + kb) * IMG, IMG, &full_bar[s]);
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight image: [ntile][kblock][half][class*4+tap][chunk][n_local][8 x bf16 over a]
+// ---------------------------------------------------------------------------------------------
+struct UpGeom { int NT, KC, ntiles, KB, combos, ncols; size_t img; };
+
+UpGeom up_geom(int dim, int A, int Bc) {
+  UpGeom g;
+  g.ncols = dim == 2 ? Bc : 4 * Bc;                 // GEMM N extent
+  const int n16 = (g.ncols + 15) / 16 * 16;
+  if (dim == 2) g.NT = n16 <= 16 ? 16 : (n16 <= 32 ? 32 : 48);
+  else g.NT = n16 <= 16 ? 16 : (n16 <= 32 ? 32 : (n16 <= 48 ? 48 : 96));
+  g.KC = dim == 2 ? 16 : 32;
+  g.ntiles = (g.ncols + g.NT - 1) / g.NT;
+  g.KB = ((A + 15) / 16 * 16 + g.KC - 1) / g.KC;
+  g.combos = dim == 2 ? 16 : 1;
+  g.img = (size_t)2 * g.combos * (g.KC / 8) * g.NT * 16;
+  return g;
+}
+
+__global__ void prep_up_kernel(const float* __restrict__ w, int dim, int A, int Bc, int NT, int KC, int KB, int combos,
+                               int64_t total, uint8_t* __restrict__ img) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int CC = KC / 8;
+  int64_t r = idx;
+  const int nl = (int)(r % NT); r /= NT;
+  const int cc = (int)(r % CC); r /= CC;
+  const int combo = (int)(r % combos); r /= combos;
+  const int kb = (int)(r % KB); r /= KB;
+  const int nt = (int)r;
+  const int col = nt * NT + nl;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int ch = kb * KC + cc * 8 + e;
+    float x = 0.f;
+    if (ch < A) {
+      if (dim == 2) {
+        if (col < Bc) {
+          const int cls = combo >> 2, tap = combo & 3;
+          const int ry = cls >> 1, rx = cls & 1, d = tap >> 1, ee = tap & 1;
+          const int ky = ry == 0 ? (d == 0 ? 1 : 3) : (d == 0 ? 0 : 2);
+          const int kx = rx == 0 ? (ee == 0 ? 1 : 3) : (ee == 0 ? 0 : 2);
+          x = w[(((int64_t)ch * Bc + col) * 4 + ky) * 4 + kx];
+        }
+      } else if (col < 4 * Bc) {
+        x = w[(int64_t)ch * Bc * 4 + col];          // col = b*4 + t
+      }
+    }
+    v[e] = x;
+  }
+  uint4 hi, lo;
+  tc::split8(v, hi, lo);
+  const size_t blk = (size_t)2 * combos * CC * NT * 16;
+  uint8_t* base = img + ((size_t)nt * KB + kb) * blk + (((size_t)combo * CC + cc) * NT + nl) * 16;
+  *reinterpret_cast<uint4*>(base) = hi;
+  *reinterpret_cast<uint4*>(base + blk / 2) = lo;
+}
+
+template <int DIM, int NT, int KC>
+int launch_up_t(const UpArgs& a, const UpGeom& g, cudaStream_t st) {
+  const size_t stage = (size_t)2 * (KC / 8) * a.slots * 16 + g.img;
+  const size_t smem = stage * a.nstage;
+  LSHM_CUDA(cudaFuncSetAttribute(igemm_up_kernel<DIM, NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_up");
+  dim3 grid((unsigned)ceil_div(a.Q, 128), (unsigned)g.ntiles);
+  igemm_up_kernel<DIM, NT, KC><<<grid, 192, smem, st>>>(a);
+  LSHM_CHECK_LAUNCH("igemm_up");
+  return LSHM_OK;
+}
+
+int launch_up(int dim, UpArgs a, cudaStream_t st) {
+  const UpGeom g = up_geom(dim, a.A, a.Bc);
+  a.slots = dim == 2 ? (128 + 2 * (a.w + 2) + 7) / 8 * 8 : 128;
+  a.Q = dim == 2 ? a.N * (int64_t)(a.h + 1) * (a.w + 1) : a.N * (int64_t)a.w;
+  const size_t stage = (size_t)2 * (g.KC / 8) * a.slots * 16 + g.img;
+  int ns = (int)std::min<size_t>(4, std::max<size_t>(1, (96 * 1024) / stage));
+  if (ns < 2 && 2 * stage <= 200 * 1024) ns = 2;
+  a.nstage = std::min(ns, g.KB);
+#define LU(D, NTV, KCV) return launch_up_t<D, NTV, KCV>(a, g, st)
+  if (dim == 2) {
+    switch (g.NT) { case 16: LU(2, 16, 16); case 32: LU(2, 32, 16); default: LU(2, 48, 16); }
+  } else {
+    switch (g.NT) { case 16: LU(1, 16, 32); case 32: LU(1, 32, 32); case 48: LU(1, 48, 32); default: LU(1, 96, 32); }
+  }
+#undef LU
+}
+
+}  // namespace
+
+size_t up_image_bytes(int dim, int A, int Bc) {
+  const UpGeom g = up_geom(dim, A, Bc);
+  return g.img * g.ntiles * g.KB;
+}
+
+int prep_up_image(const float* w, int dim, int A, int Bc, void* img, cudaStream_t st) {
+  const UpGeom g = up_geom(dim, A, Bc);
+  const int64_t total = (int64_t)g.ntiles * g.KB * g.combos * (g.KC / 8) * g.NT;
+  prep_up_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(w, dim, A, Bc, g.NT, g.KC, g.KB, g.combos, total,
+                                                                  reinterpret_cast<uint8_t*>(img));
+  LSHM_CHECK_LAUNCH("lshm_conv_prep(up)");
+  return LSHM_OK;
+}
+
+}  // namespace lshm
+
+using namespace lshm;
+
+extern "C" {
+
+int lshm_up2d(const float* small_, int64_t small_ns, const void* wimg, const float* bias,
+              const float* aux, int64_t aux_ns, float* big, int64_t big_ns,
+              int64_t N, int A, int Bc, int h, int w_, int epilogue, lshm_stream_t stream) {
+  LSHM_REQUIRE(small_ && wimg && big, "lshm_up2d: null pointer");
+  LSHM_REQUIRE(N >= 0 && A > 0 && Bc > 0 && h > 0 && w_ > 0 && w_ <= 512, "lshm_up2d: bad sizes");
+  LSHM_REQUIRE(epilogue >= 0 && epilogue <= 2, "lshm_up2d: bad epilogue %d", epilogue);
+  LSHM_REQUIRE(epilogue != LSHM_EPI_DELU || aux != nullptr, "lshm_up2d: DELU epilogue needs aux");
+  LSHM_REQUIRE((reinterpret_cast<uintptr_t>(wimg) & 15) == 0 && (reinterpret_cast<uintptr_t>(big) & 7) == 0 &&
+               (big_ns & 1) == 0 && (reinterpret_cast<uintptr_t>(aux) & 7) == 0 && (aux_ns & 1) == 0,
+               "lshm_up2d: misaligned buffer");
+  if (N == 0) return LSHM_OK;
+  UpArgs a{};
+  a.small_ = small_; a.small_ns = small_ns; a.wimg = reinterpret_cast<const uint8_t*>(wimg); a.bias = bias;
+  a.aux = epilogue == LSHM_EPI_DELU ? aux : nullptr; a.aux_ns = aux_ns; a.big = big; a.big_ns = big_ns;
+  a.N = N; a.A = A; a.Bc = Bc; a.h = h; a.w = w_; a.pad = 0; a.epi = epilogue;
+  return launch_up(2, a, as_stream(stream));
+}
+
+int lshm_up1d(const float* small_, int64_t small_ns, const void* wimg, const float* bias,
+              const float* aux, int64_t aux_ns, float* big, int64_t big_ns,
+              int64_t N, int A, int Bc, int l, int pad, int epilogue, lshm_stream_t stream) {
+  LSHM_REQUIRE(small_ && wimg && big, "lshm_up1d: null pointer");
+  LSHM_REQUIRE(N >= 0 && A > 0 && Bc > 0 && l > 0 && (pad == 0 || pad == 1), "lshm_up1d: bad sizes");
+  LSHM_REQUIRE(epilogue >= 0 && epilogue <= 2, "lshm_up1d: bad epilogue %d", epilogue);
+  LSHM_REQUIRE(epilogue != LSHM_EPI_DELU || aux != nullptr, "lshm_up1d: DELU epilogue needs aux");
+  LSHM_REQUIRE((reinterpret_cast<uintptr_t>(wimg) & 15) == 0, "lshm_up1d: weight image must be 16-byte aligned");
+  LSHM_REQUIRE(pad == 1 || ((reinterpret_cast<uintptr_t>(big) & 15) == 0 && (big_ns & 3) == 0),
+               "lshm_up1d: output must be 16-byte aligned for pad=0");
+  if (N == 0) return LSHM_OK;
+  UpArgs a{};
+  a.small_ = small_; a.small_ns = small_ns; a.wimg = reinterpret_cast<const uint8_t*>(wimg); a.bias = bias;
+  a.aux = epilogue == LSHM_EPI_DELU ? aux : nullptr; a.aux_ns = aux_ns; a.big = big; a.big_ns = big_ns;
+  a.N = N; a.A = A; a.Bc = Bc; a.h = 1; a.w = l; a.pad = pad; a.epi = epilogue;
+  return launch_up(1, a, as_stream(stream));
+}
+
+}  // extern "C"

@@ -88,16 +88,19 @@ class AEEngine:
         self.ch = (channels,) + CONV_CHANNELS
         self.lib = lib()
         self.img = {}   # (layer name, which) -> weight image buffer (re-filled every closure)
+        self.need_input_grad = ndim == 1   # the 1-D nets sit behind the 2-D net: dx is always wanted
 
     def prepare_images(self, p: Dict[str, torch.Tensor], st: int, grads: bool):
         """Re-make the weight images the coming forward (and backward) will read.  Conv layers use
         their 'down' image forward; transposed-conv layers use theirs in the backward (dgrad)."""
         for i in range(6):
-            nm = f"conv{i}.weight"
-            self.img[(nm, 0)] = conv_image(p[nm], self.ndim, 0, st, self.img.get((nm, 0)))
+            cn, tn = f"conv{i}.weight", f"tconv{i}.weight"
+            self.img[(cn, 0)] = conv_image(p[cn], self.ndim, 0, st, self.img.get((cn, 0)))
+            self.img[(tn, 1)] = conv_image(p[tn], self.ndim, 1, st, self.img.get((tn, 1)))
             if grads:
-                nm = f"tconv{i}.weight"
-                self.img[(nm, 0)] = conv_image(p[nm], self.ndim, 0, st, self.img.get((nm, 0)))
+                self.img[(tn, 0)] = conv_image(p[tn], self.ndim, 0, st, self.img.get((tn, 0)))
+                if i > 0 or self.need_input_grad:
+                    self.img[(cn, 1)] = conv_image(p[cn], self.ndim, 1, st, self.img.get((cn, 1)))
 
     def workspace(self, N, device, with_grad, need_dx=False) -> Workspace:
         return Workspace(N, self.C, self.L, self.H4, device, with_grad, need_dx)
@@ -162,7 +165,7 @@ class AEEngine:
         src = ws.dec[0]
         for i in range(6):
             dst = ws.dec[i + 1] if i < 5 else ws.xhat
-            self._up(_p(src), sz[6 - i], _p(p[f"tconv{i}.weight"]), _p(p[f"tconv{i}.bias"]), None, 0,
+            self._up(_p(src), sz[6 - i], _p(self.img[(f"tconv{i}.weight", 1)]), _p(p[f"tconv{i}.bias"]), None, 0,
                      _p(dst), sz[5 - i], N, rch[i], rch[i + 1], 6 - i, 0, EPI_ELU if i < 5 else EPI_NONE, st)
             src = dst
         return ws.xhat
@@ -256,8 +259,10 @@ class AEEngine:
             lb.channel_sum(_p(dz), dz_ns, _p(g[f"conv{i}.bias"]), N, A, sz[lvl] // A, st)
             if i > 0:
                 nxt = ws.g_enc[i]
-                self._up(_p(dz), dz_ns, _p(p[f"conv{i}.weight"]), None, _p(inp), inp_ns, _p(nxt), sz[i], N, A, Bc, lvl, 1, EPI_DELU, st)
+                self._up(_p(dz), dz_ns, _p(self.img[(f"conv{i}.weight", 1)]), None, _p(inp), inp_ns, _p(nxt), sz[i], N, A, Bc, lvl, 1, EPI_DELU, st)
                 dz, dz_ns = nxt, sz[i]
             elif need_dx:
-                self._up(_p(dz), dz_ns, _p(p["conv0.weight"]), None, None, 0, _p(ws.dx), sz[0], N, A, Bc, lvl, 1, EPI_NONE, st)
+                if ("conv0.weight", 1) not in self.img:
+                    self.img[("conv0.weight", 1)] = conv_image(p["conv0.weight"], self.ndim, 1, st)
+                self._up(_p(dz), dz_ns, _p(self.img[("conv0.weight", 1)]), None, None, 0, _p(ws.dx), sz[0], N, A, Bc, lvl, 1, EPI_NONE, st)
         return ws.dx if need_dx else None

@@ -140,6 +140,7 @@ class _AutoEncoderBase(nn.Module):
         eng = self.engine()
         ws = eng.workspace(N, z.device, with_grad=False)
         ws.zcat[:, :self.latent_dim].copy_(z)
+        eng.prepare_images(self.named_param_dict(), _stream(), False)
         xhat = eng.decode(uv.contiguous(), self.named_param_dict(), ws, _stream())
         shape = (N, self._channels, 128, 128) if self._ndim == 2 else (N, self._channels, 16384)
         return xhat.view(shape)

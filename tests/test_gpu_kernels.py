@@ -63,14 +63,15 @@ def test_conv2d_family(cuda, lvl, C):
     sg = small.to(cuda)
     out_up = torch.empty(N, Bc, 2 * s, 2 * s, device=cuda)
     bbg = bias_b.to(cuda)
-    lib().up2d(dp(sg), A * s * s, dp(wg), dp(bbg), None, 0, dp(out_up), Bc * 4 * s * s, N, A, Bc, s, s, 1, st())
-    assert rel_err(out_up, ref_up) < 2e-6
+    wup = image(wg, 2, 1)
+    lib().up2d(dp(sg), A * s * s, dp(wup), dp(bbg), None, 0, dp(out_up), Bc * 4 * s * s, N, A, Bc, s, s, 1, st())
+    assert rel_err(out_up, ref_up) < TC_TOL
     # up with DELU epilogue = dgrad through the ELU of the layer below
     act = F.elu(torch.randn(N, Bc, 2 * s, 2 * s))
     ref_d = F.conv_transpose2d(small, w, None, stride=2, padding=1) * elu_grad_from_out(act)
     ag = act.to(cuda)
-    lib().up2d(dp(sg), A * s * s, dp(wg), None, dp(ag), Bc * 4 * s * s, dp(out_up), Bc * 4 * s * s, N, A, Bc, s, s, 2, st())
-    assert rel_err(out_up, ref_d) < 2e-6
+    lib().up2d(dp(sg), A * s * s, dp(wup), None, dp(ag), Bc * 4 * s * s, dp(out_up), Bc * 4 * s * s, N, A, Bc, s, s, 2, st())
+    assert rel_err(out_up, ref_d) < TC_TOL
     # down with DELU and no bias = ConvTranspose2d dgrad
     act_s = F.elu(torch.randn(N, A, s, s))
     ref_dd = F.conv2d(big, w, None, stride=2, padding=1) * elu_grad_from_out(act_s)
@@ -109,16 +110,17 @@ def test_conv1d_family(cuda, lvl):
     lib().down1d(dp(bg), Bc * 4 * l, dp(wdn), dp(bag), None, 0, dp(out_s), A * l, N, A, Bc, l, 1, 1, st())
     assert rel_err(out_s, F.elu(F.conv1d(big, wg_, bias_a, stride=4, padding=1))) < TC_TOL
     # ConvTranspose1d(k4,s4,p0) forward
-    lib().up1d(dp(sg), A * l, dp(wg), dp(bbg), None, 0, dp(out_b), Bc * 4 * l, N, A, Bc, l, 0, 1, st())
-    assert rel_err(out_b, F.elu(F.conv_transpose1d(small, wg_, bias_b, stride=4, padding=0))) < 2e-6
+    wup = image(wg, 1, 1)
+    lib().up1d(dp(sg), A * l, dp(wup), dp(bbg), None, 0, dp(out_b), Bc * 4 * l, N, A, Bc, l, 0, 1, st())
+    assert rel_err(out_b, F.elu(F.conv_transpose1d(small, wg_, bias_b, stride=4, padding=0))) < TC_TOL
     # Conv1d dgrad (pad 1) with DELU
     act = F.elu(torch.randn(N, Bc, 4 * l))
     bigr = big.clone().requires_grad_()
     wr = wg_.clone().requires_grad_()
     F.conv1d(bigr, wr, None, stride=4, padding=1).backward(small)
     actg = act.to(cuda)
-    lib().up1d(dp(sg), A * l, dp(wg), None, dp(actg), Bc * 4 * l, dp(out_b), Bc * 4 * l, N, A, Bc, l, 1, 2, st())
-    assert rel_err(out_b, bigr.grad * elu_grad_from_out(act)) < 2e-6
+    lib().up1d(dp(sg), A * l, dp(wup), None, dp(actg), Bc * 4 * l, dp(out_b), Bc * 4 * l, N, A, Bc, l, 1, 2, st())
+    assert rel_err(out_b, bigr.grad * elu_grad_from_out(act)) < TC_TOL
     dw = torch.empty(A, Bc, 4, device=cuda)
     lib().wgrad1d(dp(sg), A * l, dp(bg), Bc * 4 * l, dp(dw), N, A, Bc, l, 1, st())
     assert rel_err(dw, wr.grad) < 1e-5
