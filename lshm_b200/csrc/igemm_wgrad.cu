@@ -1,0 +1,301 @@
+// Weight-gradient implicit GEMM on tcgen05 for the k4/s2 2-D and k4/s4 1-D (transposed) convolutions:
+//     dW[a, b, ky, kx] = sum_{n,oy,ox} S[n,a,oy,ox] * B[n,b,2oy-1+ky,2ox-1+kx]
+// (autograd of F.conv2d/conv_transpose2d/conv1d/conv_transpose1d,
+//  /root/reference/src/lofar_models.py:73-78,:93-98,:158-163,:178-183).
+//
+// With the space-to-depth view Z[q, c=4b+sub] of the big map (see igemm_down.cu) this is, per tap,
+//     D_tap[a, c] = sum_q S[q, a] * Z[q + shift(tap), c]          (contraction over POSITIONS q)
+// so both operands are "MN-major": the staged tiles hold positions as rows at a 16-byte pitch with
+// 8 channels per 16 bytes, exactly what the producers of the down/up kernels write; the four taps
+// are again four descriptor start addresses into one Z tile and accumulate in four TMEM column
+// ranges.  The position range is split over CTAs (split-K); partial results are combined with
+// fp32 atomics into dW (zeroed first), already in the reference weight layout.
+#include "tc_common.cuh"
+
+namespace lshm {
+namespace {
+
+using namespace tc;
+
+constexpr int KP = 64;   // positions per K block
+
+struct WgArgs {
+  const float* small_; int64_t small_ns;
+  const float* big; int64_t big_ns;
+  float* dw;
+  int64_t N; int A; int Bc; int h; int w; int pad;
+  int zslots; int nstage; int64_t Q; int64_t kblocks; int64_t kb_per_cta; int ntiles;
+};
+
+template <int DIM, int NT>
+__global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], acc_bar;
+  __shared__ uint32_t tmem_base;
+  constexpr int T = DIM == 2 ? 4 : 1;
+  constexpr int CZ = NT / 8;
+  constexpr uint32_t TCOLS = T * NT;
+  constexpr uint32_t TMEM_COLS = TCOLS <= 32 ? 32 : (TCOLS <= 64 ? 64 : (TCOLS <= 128 ? 128 : (TCOLS <= 256 ? 256 : 512)));
+  constexpr uint32_t SBYTES = 16u * KP * 16;            // S tile: 16 chunk columns x KP positions
+  const int ZS = a.zslots, NS = a.nstage;
+  const uint32_t zbytes = (uint32_t)CZ * ZS * 16;
+  const uint32_t stage_bytes = 2 * SBYTES + 2 * zbytes;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mt = blockIdx.y / a.ntiles, nt = blockIdx.y % a.ntiles;
+  const int64_t kb0 = (int64_t)blockIdx.x * a.kb_per_cta;
+  const int64_t kb1 = min(kb0 + a.kb_per_cta, a.kblocks);
+  const int nkb = (int)(kb1 - kb0);
+  const int PW = a.w + 1, PH = a.h + 1;
+  const int a0 = mt * 128, c0 = nt * NT;
+  const int sch = min(16, (a.A - a0 + 7) / 8);          // S chunk columns that hold data
+
+  // zero the S tiles once: chunk columns beyond `sch` (padding rows of the M=128 MMA) stay zero
+  for (uint32_t i = tid; i < (uint32_t)NS * 2 * SBYTES / 16; i += blockDim.x) {
+    const uint32_t st = i / (2 * SBYTES / 16), r = i % (2 * SBYTES / 16);
+    *reinterpret_cast<uint4*>(smem + (size_t)st * stage_bytes + (size_t)r * 16) = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == 4) tmem_alloc(&tmem_base, TMEM_COLS);
+  if (tid == 0) {
+    for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], 4); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&acc_bar, 1);
+    mbar_init_fence();
+  }
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = tmem_base;
+
+  if (warp < 4) {
+    const int H = 2 * a.h, W = 2 * a.w;
+    const int64_t hw = DIM == 2 ? (int64_t)a.h * a.w : (int64_t)a.w;
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % NS, ph = (it / NS) & 1;
+      const int64_t p0 = (kb0 + it) * KP;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* shi = smem + (size_t)s * stage_bytes;
+      uint8_t* slo = shi + SBYTES;
+      uint8_t* zhi = slo + SBYTES;
+      uint8_t* zlo = zhi + zbytes;
+      // ---- S tile: item = (position, chunk of 8 channels)
+      for (int item = tid; item < KP * sch; item += 128) {
+        const int p = item % KP, ca = item / KP;
+        const int64_t q = p0 + p;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (q < a.Q) {
+          const float* sp = nullptr;
+          if (DIM == 2) {
+            const int64_t pp = (int64_t)PH * PW;
+            const int64_t n = q / pp;
+            const int r = (int)(q - n * pp);
+            const int m = r / PW, x = r - m * PW;
+            if (m < a.h && x < a.w) sp = a.small_ + n * a.small_ns + (int64_t)m * a.w + x;
+          } else {
+            const int64_t n = q / a.w;
+            sp = a.small_ + n * a.small_ns + (q - n * a.w);
+          }
+          if (sp != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int ch = a0 + ca * 8 + e;
+              if (ch < a.A) v[e] = __ldg(sp + (int64_t)ch * hw);
+            }
+          }
+        }
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4*>(shi + ((size_t)ca * KP + p) * 16) = hi;
+        *reinterpret_cast<uint4*>(slo + ((size_t)ca * KP + p) * 16) = lo;
+      }
+      // ---- Z tile: item = (slot, chunk of 8 s2d channels)
+      for (int item = tid; item < ZS * CZ; item += 128) {
+        const int slot = item % ZS, cz = item / ZS;
+        const int64_t q = p0 + slot;
+        const int b0 = (c0 + cz * 8) >> 2;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (q < a.Q) {
+          if (DIM == 2) {
+            const int64_t pp = (int64_t)PH * PW;
+            const int64_t n = q / pp;
+            const int r = (int)(q - n * pp);
+            const int by = r / PW, bx = r - by * PW;
+            const int r0 = 2 * by - 1, cc0 = 2 * bx - 1;
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb) {
+              const int b = b0 + bb;
+              if (b < a.Bc) {
+                const float* base = a.big + n * a.big_ns + (int64_t)b * H * W;
+#pragma unroll
+                for (int yy = 0; yy < 2; ++yy) {
+                  const int rr = r0 + yy;
+                  const bool rin = rr >= 0 && rr < H;
+#pragma unroll
+                  for (int xx = 0; xx < 2; ++xx) {
+                    const int cx = cc0 + xx;
+                    if (rin && cx >= 0 && cx < W) v[bb * 4 + yy * 2 + xx] = __ldg(base + (int64_t)rr * W + cx);
+                  }
+                }
+              }
+            }
+          } else {
+            const int64_t n = q / a.w;
+            const int j = (int)(q - n * a.w);
+            const int64_t Lb = 4 * (int64_t)a.w;
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb) {
+              const int b = b0 + bb;
+              if (b < a.Bc) {
+                const float* base = a.big + n * a.big_ns + (int64_t)b * Lb + 4 * (int64_t)j - a.pad;
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                  if (a.pad == 0 || t > 0 || j > 0) v[bb * 4 + t] = __ldg(base + t);
+              }
+            }
+          }
+        }
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4*>(zhi + ((size_t)cz * ZS + slot) * 16) = hi;
+        *reinterpret_cast<uint4*>(zlo + ((size_t)cz * ZS + slot) * 16) = lo;
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+    }
+    // ------------------------------------------------ epilogue: scatter-add into dW
+    mbar_wait(&acc_bar, 0);
+    fence_after();
+    const int ch = a0 + tid;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int tap = 0; tap < T; ++tap) {
+#pragma unroll 1
+      for (int g = 0; g < NT / 16; ++g) {
+        float v[16];
+        tmem_ld16(trow + tap * NT + g * 16, v);
+        if (ch < a.A && nkb > 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c = c0 + g * 16 + j;
+            const int b = c >> 2, sub = c & 3;
+            if (b < a.Bc) {
+              if (DIM == 2) {
+                const int ky = 2 * (tap >> 1) + (sub >> 1), kx = 2 * (tap & 1) + (sub & 1);
+                atomicAdd(a.dw + (((int64_t)ch * a.Bc + b) * 4 + ky) * 4 + kx, v[j]);
+              } else {
+                atomicAdd(a.dw + ((int64_t)ch * a.Bc + b) * 4 + sub, v[j]);
+              }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(NT, 1, 1);
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % NS, ph = (it / NS) & 1;
+        mbar_wait(&full_bar[s], ph);
+        fence_after();
+        const uint32_t shi = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t slo = shi + SBYTES;
+        const uint32_t zhi = slo + SBYTES;
+        const uint32_t zlo = zhi + zbytes;
+#pragma unroll
+        for (int tap = 0; tap < T; ++tap) {
+          const uint32_t shift = DIM == 2 ? (uint32_t)((tap >> 1) * PW + (tap & 1)) : 0u;
+#pragma unroll
+          for (int ks = 0; ks < KP / 16; ++ks) {
+            const uint32_t aoff = (uint32_t)ks * 256;
+            const uint32_t boff = ((uint32_t)ks * 16 + shift) * 16;
+            mma_split3(tmem + tap * NT, make_desc(shi + aoff, 128, KP * 16), make_desc(slo + aoff, 128, KP * 16),
+                       make_desc(zhi + boff, 128, ZS * 16), make_desc(zlo + boff, 128, ZS * 16), idesc,
+                       (it > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        commit(&empty_bar[s]);
+      }
+      commit(&acc_bar);
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+template <int DIM, int NT>
+int launch_wgrad_t(const WgArgs& a, int64_t splits, int mtiles, cudaStream_t st) {
+  const size_t stage = (size_t)2 * 16 * KP * 16 + (size_t)2 * (NT / 8) * a.zslots * 16;
+  const size_t smem = stage * a.nstage;
+  LSHM_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<DIM, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_wgrad");
+  dim3 grid((unsigned)splits, (unsigned)(mtiles * a.ntiles));
+  igemm_wgrad_kernel<DIM, NT><<<grid, 160, smem, st>>>(a);
+  LSHM_CHECK_LAUNCH("igemm_wgrad");
+  return LSHM_OK;
+}
+
+int launch_wgrad(int dim, WgArgs a, cudaStream_t st) {
+  const int Kc = 4 * a.Bc;
+  const int k16 = (Kc + 15) / 16 * 16;
+  const int NT = k16 <= 16 ? 16 : (k16 <= 32 ? 32 : (k16 <= 48 ? 48 : 96));
+  a.ntiles = (Kc + NT - 1) / NT;
+  const int mtiles = (a.A + 127) / 128;
+  a.Q = dim == 2 ? a.N * (int64_t)(a.h + 1) * (a.w + 1) : a.N * (int64_t)a.w;
+  a.kblocks = ceil_div(a.Q, KP);
+  a.zslots = dim == 2 ? (KP + a.w + 2 + 7) / 8 * 8 : KP;
+  const size_t stage = (size_t)2 * 16 * KP * 16 + (size_t)2 * (NT / 8) * a.zslots * 16;
+  a.nstage = (int)std::min<size_t>(3, std::max<size_t>(2, (160 * 1024) / stage));
+  const int64_t tiles = (int64_t)mtiles * a.ntiles;
+  int64_t splits = std::max<int64_t>(1, ceil_div((int64_t)sm_count() * 3, tiles));
+  splits = std::min(splits, std::max<int64_t>(1, a.kblocks / 4));   // at least 4 K blocks per CTA
+  a.kb_per_cta = ceil_div(a.kblocks, splits);
+  splits = ceil_div(a.kblocks, a.kb_per_cta);
+  a.nstage = (int)std::min<int64_t>(a.nstage, std::max<int64_t>(1, a.kb_per_cta));
+#define LW(D, NTV) return launch_wgrad_t<D, NTV>(a, splits, mtiles, st)
+  if (dim == 2) {
+    switch (NT) { case 16: LW(2, 16); case 32: LW(2, 32); case 48: LW(2, 48); default: LW(2, 96); }
+  } else {
+    switch (NT) { case 16: LW(1, 16); case 32: LW(1, 32); case 48: LW(1, 48); default: LW(1, 96); }
+  }
+#undef LW
+}
+
+}  // namespace
+}  // namespace lshm
+
+using namespace lshm;
+
+extern "C" {
+
+int lshm_wgrad2d(const float* small_, int64_t small_ns, const float* big, int64_t big_ns,
+                 float* dw, int64_t N, int A, int Bc, int h, int w_, lshm_stream_t stream) {
+  LSHM_REQUIRE(small_ && big && dw, "lshm_wgrad2d: null pointer");
+  LSHM_REQUIRE(N >= 0 && A > 0 && Bc > 0 && (Bc & 3) == 0 && h > 0 && w_ > 0 && w_ <= 512, "lshm_wgrad2d: bad sizes");
+  cudaStream_t st = as_stream(stream);
+  LSHM_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)A * Bc * 16, st), "lshm_wgrad2d");
+  if (N == 0) return LSHM_OK;
+  WgArgs a{};
+  a.small_ = small_; a.small_ns = small_ns; a.big = big; a.big_ns = big_ns; a.dw = dw;
+  a.N = N; a.A = A; a.Bc = Bc; a.h = h; a.w = w_; a.pad = 0;
+  return launch_wgrad(2, a, st);
+}
+
+int lshm_wgrad1d(const float* small_, int64_t small_ns, const float* big, int64_t big_ns,
+                 float* dw, int64_t N, int A, int Bc, int l, int pad, lshm_stream_t stream) {
+  LSHM_REQUIRE(small_ && big && dw, "lshm_wgrad1d: null pointer");
+  LSHM_REQUIRE(N >= 0 && A > 0 && Bc > 0 && (Bc & 3) == 0 && l > 0 && (pad == 0 || pad == 1), "lshm_wgrad1d: bad sizes");
+  cudaStream_t st = as_stream(stream);
+  LSHM_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)A * Bc * 4, st), "lshm_wgrad1d");
+  if (N == 0) return LSHM_OK;
+  WgArgs a{};
+  a.small_ = small_; a.small_ns = small_ns; a.big = big; a.big_ns = big_ns; a.dw = dw;
+  a.N = N; a.A = A; a.Bc = Bc; a.h = 1; a.w = l; a.pad = pad;
+  return launch_wgrad(1, a, st);
+}
+
+}  // extern "C"
