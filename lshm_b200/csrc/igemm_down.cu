@@ -92,12 +92,14 @@ __global__ void __launch_bounds__(192) igemm_down_kernel(DownArgs a) {
       for (int i = 0; i < 2; ++i) {
         const int slot = tid + i * 128;
         if (slot >= SLOTS) continue;
-        for (int cc = 0; cc < ccb; ++cc) {
-          const int b0 = 2 * (kb * CC + cc);
-          float v[8];
+        // all chunk columns of this slot are fetched before any is converted (loads in flight)
+        float v[CC][8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = 0.f;
-          if (sv[i]) {
+        for (int cc = 0; cc < CC; ++cc) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[cc][e] = 0.f;
+          if (cc < ccb && sv[i]) {
+            const int b0 = 2 * (kb * CC + cc);
 #pragma unroll
             for (int bb = 0; bb < 2; ++bb) {
               const int b = b0 + bb;
@@ -112,23 +114,33 @@ __global__ void __launch_bounds__(192) igemm_down_kernel(DownArgs a) {
 #pragma unroll
                     for (int xx = 0; xx < 2; ++xx) {
                       const int c = c0 + xx;
-                      if (rin && c >= 0 && c < W) v[bb * 4 + yy * 2 + xx] = __ldg(base + (int64_t)r * W + c);
+                      if (rin && c >= 0 && c < W) v[cc][bb * 4 + yy * 2 + xx] = __ldg(base + (int64_t)r * W + c);
                     }
                   }
                 } else {
                   const int64_t Lb = 4 * (int64_t)a.w;
                   const float* base = a.big + sn[i] * a.big_ns + (int64_t)b * Lb + 4 * (int64_t)sx_[i] - a.pad;
+                  if (a.pad == 0) {
+                    const float4 q4 = __ldg(reinterpret_cast<const float4*>(base));
+                    v[cc][bb * 4 + 0] = q4.x; v[cc][bb * 4 + 1] = q4.y; v[cc][bb * 4 + 2] = q4.z; v[cc][bb * 4 + 3] = q4.w;
+                  } else {
 #pragma unroll
-                  for (int t = 0; t < 4; ++t)
-                    if (a.pad == 0 || t > 0 || sx_[i] > 0) v[bb * 4 + t] = __ldg(base + t);
+                    for (int t = 0; t < 4; ++t)
+                      if (t > 0 || sx_[i] > 0) v[cc][bb * 4 + t] = __ldg(base + t);
+                  }
                 }
               }
             }
           }
-          uint4 hi, lo;
-          split8(v, hi, lo);
-          *reinterpret_cast<uint4*>(zhi + ((size_t)cc * SLOTS + slot) * 16) = hi;
-          *reinterpret_cast<uint4*>(zlo + ((size_t)cc * SLOTS + slot) * 16) = lo;
+        }
+#pragma unroll
+        for (int cc = 0; cc < CC; ++cc) {
+          if (cc < ccb) {
+            uint4 hi, lo;
+            split8(v[cc], hi, lo);
+            *reinterpret_cast<uint4*>(zhi + ((size_t)cc * SLOTS + slot) * 16) = hi;
+            *reinterpret_cast<uint4*>(zlo + ((size_t)cc * SLOTS + slot) * 16) = lo;
+          }
         }
       }
       fence_async_smem();
@@ -336,6 +348,8 @@ int lshm_down1d(const float* big, int64_t big_ns, const void* wimg, const float*
   LSHM_REQUIRE(epilogue >= 0 && epilogue <= 2, "lshm_down1d: bad epilogue %d", epilogue);
   LSHM_REQUIRE(epilogue != LSHM_EPI_DELU || aux != nullptr, "lshm_down1d: DELU epilogue needs aux");
   LSHM_REQUIRE((reinterpret_cast<uintptr_t>(wimg) & 15) == 0, "lshm_down1d: weight image must be 16-byte aligned");
+  LSHM_REQUIRE(pad == 1 || ((reinterpret_cast<uintptr_t>(big) & 15) == 0 && (big_ns & 3) == 0),
+               "lshm_down1d: input must be 16-byte aligned for pad=0");
   if (N == 0) return LSHM_OK;
   DownArgs a{};
   a.big = big; a.big_ns = big_ns; a.wimg = reinterpret_cast<const uint8_t*>(wimg); a.bias = bias;

@@ -102,15 +102,22 @@ __global__ void __launch_bounds__(192) igemm_up_kernel(UpArgs a) {
       for (int i = 0; i < 3; ++i) {
         const int slot = tid + i * 128;
         if (slot >= SLOTS) continue;
-        for (int cc = 0; cc < ccb; ++cc) {
-          const int a0 = kb * KC + cc * 8;
-          float v[8];
+        float v[CC][8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = (sv[i] && a0 + e < a.A) ? __ldg(sp[i] + (int64_t)(a0 + e) * hw) : 0.f;
-          uint4 hi, lo;
-          split8(v, hi, lo);
-          *reinterpret_cast<uint4*>(zhi + ((size_t)cc * SLOTS + slot) * 16) = hi;
-          *reinterpret_cast<uint4*>(zlo + ((size_t)cc * SLOTS + slot) * 16) = lo;
+        for (int cc = 0; cc < CC; ++cc) {
+          const int a0 = kb * KC + cc * 8;
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            v[cc][e] = (cc < ccb && sv[i] && a0 + e < a.A) ? __ldg(sp[i] + (int64_t)(a0 + e) * hw) : 0.f;
+        }
+#pragma unroll
+        for (int cc = 0; cc < CC; ++cc) {
+          if (cc < ccb) {
+            uint4 hi, lo;
+            split8(v[cc], hi, lo);
+            *reinterpret_cast<uint4*>(zhi + ((size_t)cc * SLOTS + slot) * 16) = hi;
+            *reinterpret_cast<uint4*>(zlo + ((size_t)cc * SLOTS + slot) * 16) = lo;
+          }
         }
       }
       fence_async_smem();

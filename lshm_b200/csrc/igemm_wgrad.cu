@@ -24,7 +24,7 @@ struct WgArgs {
   const float* big; int64_t big_ns;
   float* dw;
   int64_t N; int A; int Bc; int h; int w; int pad;
-  int zslots; int nstage; int64_t Q; int64_t kblocks; int64_t kb_per_cta; int ntiles;
+  int zslots; int nstage; int64_t Q; int64_t kblocks; int64_t kb_per_cta; int ntiles; int scols; int vec_ok;
 };
 
 template <int DIM, int NT>
@@ -36,8 +36,11 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
   constexpr int CZ = NT / 8;
   constexpr uint32_t TCOLS = T * NT;
   constexpr uint32_t TMEM_COLS = TCOLS <= 32 ? 32 : (TCOLS <= 64 ? 64 : (TCOLS <= 128 ? 128 : (TCOLS <= 256 ? 256 : 512)));
-  constexpr uint32_t SBYTES = 16u * KP * 16;            // S tile: 16 chunk columns x KP positions
   const int ZS = a.zslots, NS = a.nstage;
+  // S tile: only the chunk columns that hold data are staged.  The M=128 MMA still walks 16 column
+  // groups; the extra groups read bytes that follow the tile (inside this CTA's allocation, see the
+  // slack added by the launcher) and produce rows >= A of the accumulator, which nobody reads.
+  const uint32_t SBYTES = (uint32_t)a.scols * KP * 16;
   const uint32_t zbytes = (uint32_t)CZ * ZS * 16;
   const uint32_t stage_bytes = 2 * SBYTES + 2 * zbytes;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -47,13 +50,8 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
   const int nkb = (int)(kb1 - kb0);
   const int PW = a.w + 1, PH = a.h + 1;
   const int a0 = mt * 128, c0 = nt * NT;
-  const int sch = min(16, (a.A - a0 + 7) / 8);          // S chunk columns that hold data
+  const int sch = min(a.scols, (a.A - a0 + 7) / 8);     // S chunk columns that hold data in this M tile
 
-  // zero the S tiles once: chunk columns beyond `sch` (padding rows of the M=128 MMA) stay zero
-  for (uint32_t i = tid; i < (uint32_t)NS * 2 * SBYTES / 16; i += blockDim.x) {
-    const uint32_t st = i / (2 * SBYTES / 16), r = i % (2 * SBYTES / 16);
-    *reinterpret_cast<uint4*>(smem + (size_t)st * stage_bytes + (size_t)r * 16) = make_uint4(0, 0, 0, 0);
-  }
   if (warp == 4) tmem_alloc(&tmem_base, TMEM_COLS);
   if (tid == 0) {
     for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], 4); mbar_init(&empty_bar[s], 1); }
@@ -77,90 +75,117 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
       uint8_t* slo = shi + SBYTES;
       uint8_t* zhi = slo + SBYTES;
       uint8_t* zlo = zhi + zbytes;
-      // ---- S tile: item = (position, chunk of 8 channels)
-      for (int item = tid; item < KP * sch; item += 128) {
-        const int p = item % KP, ca = item / KP;
-        const int64_t q = p0 + p;
-        float v[8];
+      const uint32_t up0 = (uint32_t)p0;              // Q < 2^31 (checked by the launcher): 32-bit index math
+      const uint32_t uQ = (uint32_t)a.Q, uPW = (uint32_t)PW, upp = (uint32_t)(PH * PW), uw = (uint32_t)a.w;
+      // ---- S tile: item = (position, chunk of 8 channels); U items are fetched before any is converted
+      constexpr int U = 2;
+      for (int item0 = tid; item0 < KP * a.scols; item0 += 128 * U) {
+        float v[U][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-        if (q < a.Q) {
-          const float* sp = nullptr;
-          if (DIM == 2) {
-            const int64_t pp = (int64_t)PH * PW;
-            const int64_t n = q / pp;
-            const int r = (int)(q - n * pp);
-            const int m = r / PW, x = r - m * PW;
-            if (m < a.h && x < a.w) sp = a.small_ + n * a.small_ns + (int64_t)m * a.w + x;
-          } else {
-            const int64_t n = q / a.w;
-            sp = a.small_ + n * a.small_ns + (q - n * a.w);
-          }
-          if (sp != nullptr) {
+        for (int u = 0; u < U; ++u) {
+          const int item = item0 + u * 128;
+          const int p = item % KP, ca = item / KP;
+          const uint32_t q = up0 + p;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int ch = a0 + ca * 8 + e;
-              if (ch < a.A) v[e] = __ldg(sp + (int64_t)ch * hw);
+          for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
+          if (item < KP * a.scols && ca < sch && q < uQ) {
+            const float* sp = nullptr;
+            if (DIM == 2) {
+              const uint32_t n = q / upp, r = q - n * upp;
+              const uint32_t m = r / uPW, x = r - m * uPW;
+              if (m < (uint32_t)a.h && x < uw) sp = a.small_ + (int64_t)n * a.small_ns + (int64_t)m * a.w + x;
+            } else {
+              const uint32_t n = q / uw;
+              sp = a.small_ + (int64_t)n * a.small_ns + (q - n * uw);
+            }
+            if (sp != nullptr) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int ch = a0 + ca * 8 + e;
+                if (ch < a.A) v[u][e] = __ldg(sp + (int64_t)ch * hw);
+              }
             }
           }
         }
-        uint4 hi, lo;
-        split8(v, hi, lo);
-        *reinterpret_cast<uint4*>(shi + ((size_t)ca * KP + p) * 16) = hi;
-        *reinterpret_cast<uint4*>(slo + ((size_t)ca * KP + p) * 16) = lo;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int item = item0 + u * 128;
+          if (item < KP * a.scols) {
+            const int p = item % KP, ca = item / KP;
+            uint4 hi, lo;
+            split8(v[u], hi, lo);
+            *reinterpret_cast<uint4*>(shi + ((size_t)ca * KP + p) * 16) = hi;
+            *reinterpret_cast<uint4*>(slo + ((size_t)ca * KP + p) * 16) = lo;
+          }
+        }
       }
       // ---- Z tile: item = (slot, chunk of 8 s2d channels)
-      for (int item = tid; item < ZS * CZ; item += 128) {
-        const int slot = item % ZS, cz = item / ZS;
-        const int64_t q = p0 + slot;
-        const int b0 = (c0 + cz * 8) >> 2;
-        float v[8];
+      constexpr int UZ = 4;
+      for (int item0 = tid; item0 < ZS * CZ; item0 += 128 * UZ) {
+        float v[UZ][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-        if (q < a.Q) {
-          if (DIM == 2) {
-            const int64_t pp = (int64_t)PH * PW;
-            const int64_t n = q / pp;
-            const int r = (int)(q - n * pp);
-            const int by = r / PW, bx = r - by * PW;
-            const int r0 = 2 * by - 1, cc0 = 2 * bx - 1;
+        for (int u = 0; u < UZ; ++u) {
+          const int item = item0 + u * 128;
+          const int slot = item % ZS, cz = item / ZS;
+          const uint32_t q = up0 + slot;
+          const int b0 = (c0 + cz * 8) >> 2;
 #pragma unroll
-            for (int bb = 0; bb < 2; ++bb) {
-              const int b = b0 + bb;
-              if (b < a.Bc) {
-                const float* base = a.big + n * a.big_ns + (int64_t)b * H * W;
+          for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
+          if (item < ZS * CZ && q < uQ) {
+            if (DIM == 2) {
+              const uint32_t n = q / upp, r = q - n * upp;
+              const int by = (int)(r / uPW), bx = (int)(r - (r / uPW) * uPW);
+              const int r0 = 2 * by - 1, cc0 = 2 * bx - 1;
 #pragma unroll
-                for (int yy = 0; yy < 2; ++yy) {
-                  const int rr = r0 + yy;
-                  const bool rin = rr >= 0 && rr < H;
+              for (int bb = 0; bb < 2; ++bb) {
+                const int b = b0 + bb;
+                if (b < a.Bc) {
+                  const float* base = a.big + (int64_t)n * a.big_ns + (int64_t)b * H * W;
 #pragma unroll
-                  for (int xx = 0; xx < 2; ++xx) {
-                    const int cx = cc0 + xx;
-                    if (rin && cx >= 0 && cx < W) v[bb * 4 + yy * 2 + xx] = __ldg(base + (int64_t)rr * W + cx);
+                  for (int yy = 0; yy < 2; ++yy) {
+                    const int rr = r0 + yy;
+                    const bool rin = rr >= 0 && rr < H;
+#pragma unroll
+                    for (int xx = 0; xx < 2; ++xx) {
+                      const int cx = cc0 + xx;
+                      if (rin && cx >= 0 && cx < W) v[u][bb * 4 + yy * 2 + xx] = __ldg(base + (int64_t)rr * W + cx);
+                    }
+                  }
+                }
+              }
+            } else {
+              const uint32_t n = q / uw;
+              const int j = (int)(q - n * uw);
+              const int64_t Lb = 4 * (int64_t)a.w;
+#pragma unroll
+              for (int bb = 0; bb < 2; ++bb) {
+                const int b = b0 + bb;
+                if (b < a.Bc) {
+                  const float* base = a.big + (int64_t)n * a.big_ns + (int64_t)b * Lb + 4 * (int64_t)j - a.pad;
+                  if (a.pad == 0 && a.vec_ok) {
+                    const float4 q4 = __ldg(reinterpret_cast<const float4*>(base));
+                    v[u][bb * 4 + 0] = q4.x; v[u][bb * 4 + 1] = q4.y; v[u][bb * 4 + 2] = q4.z; v[u][bb * 4 + 3] = q4.w;
+                  } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                      if (a.pad == 0 || t > 0 || j > 0) v[u][bb * 4 + t] = __ldg(base + t);
                   }
                 }
               }
             }
-          } else {
-            const int64_t n = q / a.w;
-            const int j = (int)(q - n * a.w);
-            const int64_t Lb = 4 * (int64_t)a.w;
-#pragma unroll
-            for (int bb = 0; bb < 2; ++bb) {
-              const int b = b0 + bb;
-              if (b < a.Bc) {
-                const float* base = a.big + n * a.big_ns + (int64_t)b * Lb + 4 * (int64_t)j - a.pad;
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                  if (a.pad == 0 || t > 0 || j > 0) v[bb * 4 + t] = __ldg(base + t);
-              }
-            }
           }
         }
-        uint4 hi, lo;
-        split8(v, hi, lo);
-        *reinterpret_cast<uint4*>(zhi + ((size_t)cz * ZS + slot) * 16) = hi;
-        *reinterpret_cast<uint4*>(zlo + ((size_t)cz * ZS + slot) * 16) = lo;
+#pragma unroll
+        for (int u = 0; u < UZ; ++u) {
+          const int item = item0 + u * 128;
+          if (item < ZS * CZ) {
+            const int slot = item % ZS, cz = item / ZS;
+            uint4 hi, lo;
+            split8(v[u], hi, lo);
+            *reinterpret_cast<uint4*>(zhi + ((size_t)cz * ZS + slot) * 16) = hi;
+            *reinterpret_cast<uint4*>(zlo + ((size_t)cz * ZS + slot) * 16) = lo;
+          }
+        }
       }
       fence_async_smem();
       __syncwarp();
@@ -230,8 +255,9 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
 
 template <int DIM, int NT>
 int launch_wgrad_t(const WgArgs& a, int64_t splits, int mtiles, cudaStream_t st) {
-  const size_t stage = (size_t)2 * 16 * KP * 16 + (size_t)2 * (NT / 8) * a.zslots * 16;
-  const size_t smem = stage * a.nstage;
+  const size_t stage = (size_t)2 * a.scols * KP * 16 + (size_t)2 * (NT / 8) * a.zslots * 16;
+  // slack: the padding row groups of the last stage's S tile are read (and ignored) up to 16 groups
+  const size_t smem = stage * a.nstage + (size_t)16 * KP * 16;
   LSHM_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<DIM, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_wgrad");
   dim3 grid((unsigned)splits, (unsigned)(mtiles * a.ntiles));
   igemm_wgrad_kernel<DIM, NT><<<grid, 160, smem, st>>>(a);
@@ -246,10 +272,13 @@ int launch_wgrad(int dim, WgArgs a, cudaStream_t st) {
   a.ntiles = (Kc + NT - 1) / NT;
   const int mtiles = (a.A + 127) / 128;
   a.Q = dim == 2 ? a.N * (int64_t)(a.h + 1) * (a.w + 1) : a.N * (int64_t)a.w;
+  LSHM_REQUIRE(a.Q < (1LL << 31) - 4096, "lshm_wgrad: too many positions (%lld) for one call; split the batch", (long long)a.Q);
   a.kblocks = ceil_div(a.Q, KP);
   a.zslots = dim == 2 ? (KP + a.w + 2 + 7) / 8 * 8 : KP;
-  const size_t stage = (size_t)2 * 16 * KP * 16 + (size_t)2 * (NT / 8) * a.zslots * 16;
-  a.nstage = (int)std::min<size_t>(3, std::max<size_t>(2, (160 * 1024) / stage));
+  a.scols = std::min(16, (std::min(a.A, 128) + 7) / 8);
+  a.vec_ok = ((reinterpret_cast<uintptr_t>(a.big) & 15) == 0 && (a.big_ns & 3) == 0) ? 1 : 0;
+  const size_t stage = (size_t)2 * a.scols * KP * 16 + (size_t)2 * (NT / 8) * a.zslots * 16;
+  a.nstage = (int)std::min<size_t>(3, std::max<size_t>(2, (64 * 1024) / stage));
   const int64_t tiles = (int64_t)mtiles * a.ntiles;
   int64_t splits = std::max<int64_t>(1, ceil_div((int64_t)sm_count() * 3, tiles));
   splits = std::min(splits, std::max<int64_t>(1, a.kblocks / 4));   // at least 4 K blocks per CTA
