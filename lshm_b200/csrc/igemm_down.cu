@@ -26,32 +26,37 @@ struct DownArgs {
   const float* aux; int64_t aux_ns;
   float* small_; int64_t small_ns;
   int64_t N; int A; int Bc; int h; int w; int pad; int epi;
-  int slots; int nstage; int64_t Q;
+  int slots; int nstage; int64_t Q; int64_t mtiles; int ntn;
 };
 
+constexpr int DOWN_THREADS = 320;   // warps 0-3 epilogue, 4-7 producers, 8 MMA issuer, 9 weight loader
+constexpr int MAXST = 6;
+
+// Persistent, warp-specialised: every CTA walks work items (position tile x channel tile); the
+// producers run ahead through a ring of shared-memory stages, the MMA warp alternates between two
+// TMEM accumulators, the epilogue warps drain one while the next is being computed.
 template <int DIM, int NT, int KC>
-__global__ void __launch_bounds__(192) igemm_down_kernel(DownArgs a) {
+__global__ void __launch_bounds__(DOWN_THREADS) igemm_down_kernel(DownArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], acc_bar;
+  __shared__ __align__(8) uint64_t full_bar[MAXST], empty_bar[MAXST], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base;
   constexpr int T = DIM == 2 ? 4 : 1;
   constexpr int CC = KC / 8;
   constexpr uint32_t IMG = 2u * T * CC * NT * 16;
-  constexpr uint32_t TMEM_COLS = NT <= 32 ? 32 : (NT <= 64 ? 64 : 128);
+  constexpr uint32_t TMEM_COLS = 2 * NT <= 32 ? 32 : (2 * NT <= 64 ? 64 : (2 * NT <= 128 ? 128 : 256));
   const int SLOTS = a.slots, NS = a.nstage;
   const uint32_t zbytes = (uint32_t)CC * SLOTS * 16;
   const uint32_t stage_bytes = 2 * zbytes + IMG;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t q0 = (int64_t)blockIdx.x * 128;
-  const int nt = blockIdx.y;
   const int Kc = 4 * a.Bc;
   const int KB = (Kc + KC - 1) / KC;
   const int PW = a.w + 1, PH = a.h + 1;
+  const int64_t total = a.mtiles * a.ntn;
 
-  if (warp == 4) tmem_alloc(&tmem_base, TMEM_COLS);
+  if (warp == 8) tmem_alloc(&tmem_base, TMEM_COLS);
   if (tid == 0) {
-    for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], 5); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&acc_bar, 1);
+    for (int s = 0; s < MAXST; ++s) { mbar_init(&full_bar[s], 5); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
     mbar_init_fence();
   }
   fence_before();
@@ -59,162 +64,206 @@ __global__ void __launch_bounds__(192) igemm_down_kernel(DownArgs a) {
   fence_after();
   const uint32_t tmem = tmem_base;
 
-  if (warp < 4) {
+  if (warp >= 4 && warp < 8) {
     // ------------------------------------------------ producers: stage the Z tile (hi/lo bf16)
-    // decode this thread's slots once
-    int64_t sn[2]; int sy_[2], sx_[2]; bool sv[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int s = tid + i * 128;
-      const int64_t q = q0 + s;
-      sv[i] = s < SLOTS && q < a.Q;
-      sn[i] = 0; sy_[i] = 0; sx_[i] = 0;
-      if (sv[i]) {
-        if (DIM == 2) {
-          const int64_t pp = (int64_t)PH * PW;
-          sn[i] = q / pp;
-          const int r = (int)(q - sn[i] * pp);
-          sy_[i] = r / PW; sx_[i] = r - sy_[i] * PW;
-        } else {
-          sn[i] = q / a.w;                      // 1-D: a.w holds the small length l
-          sx_[i] = (int)(q - sn[i] * a.w);
-        }
-      }
-    }
+    // Per slot the source window is described once (base pointer of the first channel, validity
+    // of the two rows / two columns); a chunk column is then 8 loads at fixed offsets from it.
+    const int ptid = tid - 128;
     const int H = 2 * a.h, W = 2 * a.w;
-    for (int kb = 0; kb < KB; ++kb) {
-      const int s = kb % NS, ph = (kb / NS) & 1;
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      uint8_t* zhi = smem + (size_t)s * stage_bytes;
-      uint8_t* zlo = zhi + zbytes;
-      const int ccb = (min(KC, Kc - kb * KC)) >> 3;
+    const int64_t HW = (int64_t)H * W;
+    uint32_t it = 0;
+    for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+      const int64_t q0 = (item / a.ntn) * 128;
+      const float* sp[2]; bool sv[2], full[2], r0ok[2], r1ok[2], c0ok[2], c1ok[2]; int sj[2];
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const int slot = tid + i * 128;
-        if (slot >= SLOTS) continue;
-        // all chunk columns of this slot are fetched before any is converted (loads in flight)
-        float v[CC][8];
+        const int s = ptid + i * 128;
+        const int64_t q = q0 + s;
+        sv[i] = s < SLOTS && q < a.Q;
+        sp[i] = a.big; full[i] = false; r0ok[i] = r1ok[i] = c0ok[i] = c1ok[i] = false; sj[i] = 0;
+        if (sv[i]) {
+          if (DIM == 2) {
+            const int64_t pp = (int64_t)PH * PW;
+            const int64_t n = q / pp;
+            const int r = (int)(q - n * pp);
+            const int by = r / PW, bx = r - by * PW;
+            r0ok[i] = by > 0; r1ok[i] = by < a.h; c0ok[i] = bx > 0; c1ok[i] = bx < a.w;
+            full[i] = r0ok[i] && r1ok[i] && c0ok[i] && c1ok[i];
+            sp[i] = a.big + n * a.big_ns + (int64_t)(2 * by - 1) * W + (2 * bx - 1);
+          } else {
+            const int64_t n = q / a.w;                // 1-D: a.w holds the small length l
+            sj[i] = (int)(q - n * a.w);
+            sp[i] = a.big + n * a.big_ns + 4 * (int64_t)sj[i] - a.pad;
+          }
+        }
+      }
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int s = it % NS, ph = (it / NS) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* zhi = smem + (size_t)s * stage_bytes;
+        uint8_t* zlo = zhi + zbytes;
+        const int ccb = (min(KC, Kc - kb * KC)) >> 3;
+        // fetch every chunk column of both slots before converting any (loads in flight)
+        float v[2][CC][8];
 #pragma unroll
-        for (int cc = 0; cc < CC; ++cc) {
+        for (int i = 0; i < 2; ++i) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[cc][e] = 0.f;
-          if (cc < ccb && sv[i]) {
-            const int b0 = 2 * (kb * CC + cc);
+          for (int cc = 0; cc < CC; ++cc) {
 #pragma unroll
-            for (int bb = 0; bb < 2; ++bb) {
-              const int b = b0 + bb;
-              if (b < a.Bc) {
-                if (DIM == 2) {
-                  const float* base = a.big + sn[i] * a.big_ns + (int64_t)b * H * W;
-                  const int r0 = 2 * sy_[i] - 1, c0 = 2 * sx_[i] - 1;
-#pragma unroll
-                  for (int yy = 0; yy < 2; ++yy) {
-                    const int r = r0 + yy;
-                    const bool rin = r >= 0 && r < H;
-#pragma unroll
-                    for (int xx = 0; xx < 2; ++xx) {
-                      const int c = c0 + xx;
-                      if (rin && c >= 0 && c < W) v[cc][bb * 4 + yy * 2 + xx] = __ldg(base + (int64_t)r * W + c);
-                    }
-                  }
+            for (int e = 0; e < 8; ++e) v[i][cc][e] = 0.f;
+            const int b0 = 2 * (kb * CC + cc);          // Bc % 4 == 0: a chunk column is all-valid or all-padding
+            if (cc < ccb && sv[i] && b0 < a.Bc) {
+              if (DIM == 2) {
+                const float* p0 = sp[i] + (int64_t)b0 * HW;
+                const float* p1 = p0 + HW;
+                if (full[i]) {
+                  v[i][cc][0] = __ldg(p0); v[i][cc][1] = __ldg(p0 + 1); v[i][cc][2] = __ldg(p0 + W); v[i][cc][3] = __ldg(p0 + W + 1);
+                  v[i][cc][4] = __ldg(p1); v[i][cc][5] = __ldg(p1 + 1); v[i][cc][6] = __ldg(p1 + W); v[i][cc][7] = __ldg(p1 + W + 1);
                 } else {
-                  const int64_t Lb = 4 * (int64_t)a.w;
-                  const float* base = a.big + sn[i] * a.big_ns + (int64_t)b * Lb + 4 * (int64_t)sx_[i] - a.pad;
-                  if (a.pad == 0) {
-                    const float4 q4 = __ldg(reinterpret_cast<const float4*>(base));
-                    v[cc][bb * 4 + 0] = q4.x; v[cc][bb * 4 + 1] = q4.y; v[cc][bb * 4 + 2] = q4.z; v[cc][bb * 4 + 3] = q4.w;
-                  } else {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t)
-                      if (t > 0 || sx_[i] > 0) v[cc][bb * 4 + t] = __ldg(base + t);
-                  }
+                  if (r0ok[i] && c0ok[i]) { v[i][cc][0] = __ldg(p0); v[i][cc][4] = __ldg(p1); }
+                  if (r0ok[i] && c1ok[i]) { v[i][cc][1] = __ldg(p0 + 1); v[i][cc][5] = __ldg(p1 + 1); }
+                  if (r1ok[i] && c0ok[i]) { v[i][cc][2] = __ldg(p0 + W); v[i][cc][6] = __ldg(p1 + W); }
+                  if (r1ok[i] && c1ok[i]) { v[i][cc][3] = __ldg(p0 + W + 1); v[i][cc][7] = __ldg(p1 + W + 1); }
+                }
+              } else {
+                const int64_t Lb = 4 * (int64_t)a.w;
+                const float* p0 = sp[i] + (int64_t)b0 * Lb;
+                const float* p1 = p0 + Lb;
+                if (a.pad == 0) {
+                  const float4 x0 = __ldg(reinterpret_cast<const float4*>(p0));
+                  const float4 x1 = __ldg(reinterpret_cast<const float4*>(p1));
+                  v[i][cc][0] = x0.x; v[i][cc][1] = x0.y; v[i][cc][2] = x0.z; v[i][cc][3] = x0.w;
+                  v[i][cc][4] = x1.x; v[i][cc][5] = x1.y; v[i][cc][6] = x1.z; v[i][cc][7] = x1.w;
+                } else {
+                  if (sj[i] > 0) { v[i][cc][0] = __ldg(p0); v[i][cc][4] = __ldg(p1); }
+                  v[i][cc][1] = __ldg(p0 + 1); v[i][cc][2] = __ldg(p0 + 2); v[i][cc][3] = __ldg(p0 + 3);
+                  v[i][cc][5] = __ldg(p1 + 1); v[i][cc][6] = __ldg(p1 + 2); v[i][cc][7] = __ldg(p1 + 3);
                 }
               }
             }
           }
         }
 #pragma unroll
-        for (int cc = 0; cc < CC; ++cc) {
-          if (cc < ccb) {
-            uint4 hi, lo;
-            split8(v[cc], hi, lo);
-            *reinterpret_cast<uint4*>(zhi + ((size_t)cc * SLOTS + slot) * 16) = hi;
-            *reinterpret_cast<uint4*>(zlo + ((size_t)cc * SLOTS + slot) * 16) = lo;
-          }
-        }
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[s]);
-    }
-    // ------------------------------------------------ epilogue: TMEM -> bias/act -> global
-    mbar_wait(&acc_bar, 0);
-    fence_after();
-    const bool ok = sv[0] && (DIM == 1 || (sy_[0] < a.h && sx_[0] < a.w));
-    const int64_t hw = DIM == 2 ? (int64_t)a.h * a.w : (int64_t)a.w;
-    const int64_t pos = DIM == 2 ? (int64_t)sy_[0] * a.w + sx_[0] : (int64_t)sx_[0];
-    float* outp = a.small_ + sn[0] * a.small_ns + pos;
-    const float* auxp = a.aux != nullptr ? a.aux + sn[0] * a.aux_ns + pos : nullptr;
-#pragma unroll 1
-    for (int g = 0; g < NT / 16; ++g) {
-      float v[16];
-      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + g * 16, v);
-      if (ok) {
+        for (int i = 0; i < 2; ++i) {
+          const int slot = ptid + i * 128;
+          if (slot < SLOTS) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int ch = nt * NT + g * 16 + j;
-          if (ch < a.A) {
-            float r = v[j] + (a.bias != nullptr ? __ldg(a.bias + ch) : 0.f);
-            if (a.epi == LSHM_EPI_ELU) r = elu_f(r);
-            else if (a.epi == LSHM_EPI_DELU) r *= delu_from_out(__ldg(auxp + ch * hw));
-            outp[ch * hw] = r;
+            for (int cc = 0; cc < CC; ++cc) {
+              if (cc < ccb) {
+                uint4 hi, lo;
+                split8(v[i][cc], hi, lo);
+                *reinterpret_cast<uint4*>(zhi + ((size_t)cc * SLOTS + slot) * 16) = hi;
+                *reinterpret_cast<uint4*>(zlo + ((size_t)cc * SLOTS + slot) * 16) = lo;
+              }
+            }
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+      }
+    }
+  } else if (warp < 4) {
+    // ------------------------------------------------ epilogue: TMEM -> bias/act -> global
+    const int64_t hw = DIM == 2 ? (int64_t)a.h * a.w : (int64_t)a.w;
+    uint32_t tc_ = 0;
+    for (int64_t item = blockIdx.x; item < total; item += gridDim.x, ++tc_) {
+      const int nt = (int)(item % a.ntn);
+      const int64_t q = (item / a.ntn) * 128 + tid;
+      bool ok = q < a.Q;
+      int64_t n = 0, pos = 0;
+      if (ok) {
+        if (DIM == 2) {
+          const int64_t pp = (int64_t)PH * PW;
+          n = q / pp;
+          const int r = (int)(q - n * pp);
+          const int by = r / PW, bx = r - by * PW;
+          ok = by < a.h && bx < a.w;
+          pos = (int64_t)by * a.w + bx;
+        } else {
+          n = q / a.w;
+          pos = q - n * a.w;
+        }
+      }
+      float* outp = a.small_ + n * a.small_ns + pos;
+      const float* auxp = a.aux != nullptr ? a.aux + n * a.aux_ns + pos : nullptr;
+      const uint32_t buf = tc_ & 1;
+      mbar_wait(&acc_full[buf], (tc_ >> 1) & 1);
+      fence_after();
+#pragma unroll 1
+      for (int g = 0; g < NT / 16; ++g) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + buf * NT + g * 16, v);
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int ch = nt * NT + g * 16 + j;
+            if (ch < a.A) {
+              float r = v[j] + (a.bias != nullptr ? __ldg(a.bias + ch) : 0.f);
+              if (a.epi == LSHM_EPI_ELU) r = elu_f(r);
+              else if (a.epi == LSHM_EPI_DELU) r *= delu_from_out(__ldg(auxp + ch * hw));
+              outp[ch * hw] = r;
+            }
           }
         }
       }
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ------------------------------------------------ MMA issuer (one elected lane)
     if (lane == 0) {
       const uint32_t idesc = make_idesc(NT, 0, 0);
-      uint32_t acc = 0;
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % NS, ph = (kb / NS) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, tc_ = 0;
+      for (int64_t item = blockIdx.x; item < total; item += gridDim.x, ++tc_) {
+        const uint32_t buf = tc_ & 1;
+        mbar_wait(&acc_empty[buf], ((tc_ >> 1) & 1) ^ 1);
         fence_after();
-        const uint32_t zhi = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t zlo = zhi + zbytes;
-        const uint32_t bhi = zlo + zbytes;
-        const uint32_t blo = bhi + IMG / 2;
-        const int ksteps = (min(KC, Kc - kb * KC)) >> 4;
+        uint32_t acc = 0;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % NS, ph = (it / NS) & 1;
+          mbar_wait(&full_bar[s], ph);
+          fence_after();
+          const uint32_t zhi = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t zlo = zhi + zbytes;
+          const uint32_t bhi = zlo + zbytes;
+          const uint32_t blo = bhi + IMG / 2;
+          const int ksteps = (min(KC, Kc - kb * KC)) >> 4;
 #pragma unroll
-        for (int tap = 0; tap < T; ++tap) {
-          const uint32_t shift = DIM == 2 ? (uint32_t)((tap >> 1) * PW + (tap & 1)) : 0u;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t aoff = ((uint32_t)(2 * ks) * SLOTS + shift) * 16;
-            const uint32_t boff = ((uint32_t)(tap * CC + 2 * ks) * NT) * 16;
-            mma_split3(tmem, make_desc(zhi + aoff, SLOTS * 16, 128), make_desc(zlo + aoff, SLOTS * 16, 128),
-                       make_desc(bhi + boff, NT * 16, 128), make_desc(blo + boff, NT * 16, 128), idesc, acc);
-            acc = 1;
+          for (int tap = 0; tap < T; ++tap) {
+            const uint32_t shift = DIM == 2 ? (uint32_t)((tap >> 1) * PW + (tap & 1)) : 0u;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint32_t aoff = ((uint32_t)(2 * ks) * SLOTS + shift) * 16;
+              const uint32_t boff = ((uint32_t)(tap * CC + 2 * ks) * NT) * 16;
+              mma_split3(tmem + buf * NT, make_desc(zhi + aoff, SLOTS * 16, 128), make_desc(zlo + aoff, SLOTS * 16, 128),
+                         make_desc(bhi + boff, NT * 16, 128), make_desc(blo + boff, NT * 16, 128), idesc, acc);
+              acc = 1;
+            }
           }
+          commit(&empty_bar[s]);
         }
-        commit(&empty_bar[s]);
+        commit(&acc_full[buf]);
       }
-      commit(&acc_bar);
     }
   } else {
     // ------------------------------------------------ weight image loader
     if (lane == 0) {
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % NS, ph = (kb / NS) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], IMG);
-        bulk_g2s(smem + (size_t)s * stage_bytes + 2 * zbytes, a.wimg + ((size_t)nt * KB + kb) * IMG, IMG, &full_bar[s]);
+      uint32_t it = 0;
+      for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+        const int nt = (int)(item % a.ntn);
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % NS, ph = (it / NS) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], IMG);
+          bulk_g2s(smem + (size_t)s * stage_bytes + 2 * zbytes, a.wimg + ((size_t)nt * KB + kb) * IMG, IMG, &full_bar[s]);
+        }
       }
     }
   }
   fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == 8) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -271,14 +320,18 @@ __global__ void prep_down_kernel(const float* __restrict__ w, int dim, int A, in
 }
 
 template <int DIM, int NT, int KC>
-int launch_down_t(const DownArgs& a, int ntiles, cudaStream_t st) {
-  constexpr int T = DIM == 2 ? 4 : 1;
-  const uint32_t zbytes = (uint32_t)(KC / 8) * a.slots * 16;
-  const size_t stage = 2 * (size_t)zbytes + (size_t)2 * T * (KC / 8) * NT * 16;
+int launch_down_t(DownArgs a, const DownGeom& g, cudaStream_t st) {
+  const size_t stage = (size_t)2 * (KC / 8) * a.slots * 16 + g.img;
+  const int64_t units = a.mtiles * g.ntiles * g.KB;
+  int ns = (int)std::min<size_t>(MAXST, std::max<size_t>(2, (100 * 1024) / stage));
+  if ((size_t)ns * stage > 200 * 1024) ns = (int)((200 * 1024) / stage);
+  LSHM_REQUIRE(ns >= 1, "igemm_down: tile does not fit in shared memory");
+  a.nstage = (int)std::min<int64_t>(ns, std::max<int64_t>(1, units));
   const size_t smem = stage * a.nstage;
   LSHM_CUDA(cudaFuncSetAttribute(igemm_down_kernel<DIM, NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_down");
-  dim3 grid((unsigned)ceil_div(a.Q, 128), (unsigned)ntiles);
-  igemm_down_kernel<DIM, NT, KC><<<grid, 192, smem, st>>>(a);
+  const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+  const int64_t grid = std::min<int64_t>(a.mtiles * g.ntiles, (int64_t)sm_count() * per_sm);
+  igemm_down_kernel<DIM, NT, KC><<<(unsigned)grid, DOWN_THREADS, smem, st>>>(a);
   LSHM_CHECK_LAUNCH("igemm_down");
   return LSHM_OK;
 }
@@ -287,11 +340,9 @@ int launch_down(int dim, DownArgs a, cudaStream_t st) {
   const DownGeom g = down_geom(dim, a.A, a.Bc);
   a.slots = dim == 2 ? (128 + a.w + 2 + 7) / 8 * 8 : 128;
   a.Q = dim == 2 ? a.N * (int64_t)(a.h + 1) * (a.w + 1) : a.N * (int64_t)a.w;
-  const size_t stage = (size_t)2 * (g.KC / 8) * a.slots * 16 + g.img;
-  int ns = (int)std::min<size_t>(4, std::max<size_t>(1, (96 * 1024) / stage));
-  if (ns < 2 && 2 * stage <= 200 * 1024) ns = 2;
-  a.nstage = std::min(ns, g.KB);
-#define LD(D, NTV, KCV) return launch_down_t<D, NTV, KCV>(a, g.ntiles, st)
+  a.mtiles = ceil_div(a.Q, 128);
+  a.ntn = g.ntiles;
+#define LD(D, NTV, KCV) return launch_down_t<D, NTV, KCV>(a, g, st)
   if (dim == 2) {
     switch (g.NT) { case 16: LD(2, 16, 32); case 32: LD(2, 32, 32); case 48: LD(2, 48, 32); default: LD(2, 96, 16); }
   } else {

@@ -77,12 +77,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Waiting warps must not steal issue slots from the producer warps (an ncu capture of the first
+// version showed 55% of all executed instructions were try_wait/branch spins): the try_wait carries
+// a suspend-time hint and the retry path backs off with nanosleep.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t backoff_ns = 64) {
   uint32_t done = 0;
   const uint32_t addr = smem_u32(bar);
-  while (!done) {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  while (true) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(addr), "r"(parity), "r"(100000u) : "memory");
+    if (done) break;
+    __nanosleep(backoff_ns);
   }
 }
 // 1-D bulk copy global -> shared, completion counted on `bar` (bytes multiple of 16, 16 B aligned)
@@ -96,11 +101,13 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    // packed converts: 2 cvt + 2 unpack + 2 sub per pair of values
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const uint32_t hp = *reinterpret_cast<const uint32_t*>(&h2);
+    const float h0 = __uint_as_float(hp << 16), h1 = __uint_as_float(hp & 0xffff0000u);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * i] - h0, v[2 * i + 1] - h1);
+    h[i] = hp;
+    l[i] = *reinterpret_cast<const uint32_t*>(&l2);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
