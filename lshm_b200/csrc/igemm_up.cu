@@ -30,7 +30,7 @@ struct UpArgs {
 
 __device__ __forceinline__ float epi_apply(float acc, float bias, int epi, float aux) {
   float r = acc + bias;
-  if (epi == LSHM_EPI_ELU) r = elu_f(r);
+  if (epi == LSHM_EPI_ELU) r = elu_fast(r);
   else if (epi == LSHM_EPI_DELU) r *= delu_from_out(aux);
   return r;
 }
@@ -149,25 +149,32 @@ __global__ void __launch_bounds__(192) igemm_up_kernel(UpArgs a) {
       const float* auxp = a.aux != nullptr ? a.aux + n * a.aux_ns + (int64_t)(2 * m) * W + 2 * x : nullptr;
 #pragma unroll 1
       for (int g = 0; g < NT / 16; ++g) {
+        const int b0 = nt * NT + g * 16;
+        const int nch = min(16, a.Bc - b0);
+        if (nch <= 0) break;                       // warp-uniform
         float v[4][16];
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld16(trow + c * NT + g * 16, v[c]);
         if (ok) {
+          float* op = outp + (int64_t)b0 * HW;
+          const float* xp = a.epi == LSHM_EPI_DELU ? auxp + (int64_t)b0 * HW : nullptr;
+          const float* bp = a.bias != nullptr ? a.bias + b0 : nullptr;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int b = nt * NT + g * 16 + j;
-            if (b < a.Bc) {
-              const float bs = a.bias != nullptr ? __ldg(a.bias + b) : 0.f;
+            if (j < nch) {
+              const float bs = bp != nullptr ? __ldg(bp + j) : 0.f;
               float2 ax0 = make_float2(0.f, 0.f), ax1 = make_float2(0.f, 0.f);
               if (a.epi == LSHM_EPI_DELU) {
-                ax0 = *reinterpret_cast<const float2*>(auxp + b * HW);
-                ax1 = *reinterpret_cast<const float2*>(auxp + b * HW + W);
+                ax0 = *reinterpret_cast<const float2*>(xp);
+                ax1 = *reinterpret_cast<const float2*>(xp + W);
+                xp += HW;
               }
               // class index = ry*2 + rx
               const float2 o0 = make_float2(epi_apply(v[0][j], bs, a.epi, ax0.x), epi_apply(v[1][j], bs, a.epi, ax0.y));
               const float2 o1 = make_float2(epi_apply(v[2][j], bs, a.epi, ax1.x), epi_apply(v[3][j], bs, a.epi, ax1.y));
-              *reinterpret_cast<float2*>(outp + b * HW) = o0;
-              *reinterpret_cast<float2*>(outp + b * HW + W) = o1;
+              *reinterpret_cast<float2*>(op) = o0;
+              *reinterpret_cast<float2*>(op + W) = o1;
+              op += HW;
             }
           }
         }

@@ -78,14 +78,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // Waiting warps must not steal issue slots from the producer warps (an ncu capture of the first
-// version showed 55% of all executed instructions were try_wait/branch spins): the try_wait carries
-// a suspend-time hint and the retry path backs off with nanosleep.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t backoff_ns = 64) {
+// version showed 55% of all executed instructions were try_wait/branch spins): the retry path backs
+// off with a short nanosleep.  (A suspend-time hint on try_wait made every hand-off slower.)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t backoff_ns = 20) {
   uint32_t done = 0;
   const uint32_t addr = smem_u32(bar);
   while (true) {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(done) : "r"(addr), "r"(parity), "r"(100000u) : "memory");
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     if (done) break;
     __nanosleep(backoff_ns);
   }
@@ -94,6 +94,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// 16-byte asynchronous copy global -> shared (LDGSTS, L1 bypass); src_bytes = 0 zero-fills
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have landed (count pre-set at init)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
 // ---- fp32 -> (hi, lo) bf16 split, 8 values -> two 16-byte chunks
