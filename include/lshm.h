@@ -96,6 +96,11 @@ LSHM_API int lshm_uv_harmonics(const float* uv, const float* scales, int64_t N, 
 LSHM_API int lshm_conv_image_bytes(int dim, int A, int Bc, int which, int64_t* bytes);
 LSHM_API int lshm_conv_prep(const float* w, int dim, int A, int Bc, void* down_img, void* up_img,
                    lshm_stream_t stream);
+/* Batched form: the caller fills one 8 x int64 record per image on the HOST with
+ * lshm_conv_prep_record, uploads the table once (weight and image addresses are stable), and
+ * lshm_conv_prep_batch re-makes all n images with a single launch. */
+LSHM_API int lshm_conv_prep_record(const float* w, int dim, int A, int Bc, int which, void* img, int64_t* record);
+LSHM_API int lshm_conv_prep_batch(const int64_t* table, int n, lshm_stream_t stream);
 
 /* Conv2d(k4,s2,p1) forward (src/lofar_models.py:73-78) and ConvTranspose2d dgrad.
  * wimg = "down" image of W (lshm_conv_prep). */

@@ -72,9 +72,12 @@ class _Library:
             setattr(self, name[len("lshm_"):], self._wrap(name, fn))
 
     def _wrap(self, name, fn):
+        host_only = name in ("lshm_conv_prep_record",)
+
         def call(*args):
             rc = fn(*args)
-            self.launches += 1
+            if not host_only:
+                self.launches += 1
             if rc != 0:
                 raise LshmError(f"{name} failed ({rc}): {self.cdll.lshm_last_error().decode()}")
         call.__name__ = name

@@ -1,11 +1,36 @@
 // Weight-image management for the tensor-core conv kernels (see include/lshm.h).
-#include "common.cuh"
+#include "conv_geom.cuh"
 
 namespace lshm {
-size_t down_image_bytes(int dim, int A, int Bc);
-int prep_down_image(const float* w, int dim, int A, int Bc, void* img, cudaStream_t st);
-size_t up_image_bytes(int dim, int A, int Bc);
-int prep_up_image(const float* w, int dim, int A, int Bc, void* img, cudaStream_t st);
+namespace {
+
+__global__ void prep_single_kernel(const float* __restrict__ w, int dim, int A, int Bc, int which, int64_t total,
+                                   uint8_t* __restrict__ img) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  if (which == 0) prep_down_chunk(w, dim, A, Bc, down_geom(dim, A, Bc), idx, img);
+  else prep_up_chunk(w, dim, A, Bc, up_geom(dim, A, Bc), idx, img);
+}
+
+// table record (8 x int64): w pointer, image pointer, dim, A, Bc, which, chunk count, unused
+__global__ void prep_batch_kernel(const int64_t* __restrict__ table) {
+  const int64_t* rec = table + 8 * (int64_t)blockIdx.y;
+  const float* w = reinterpret_cast<const float*>(rec[0]);
+  uint8_t* img = reinterpret_cast<uint8_t*>(rec[1]);
+  const int dim = (int)rec[2], A = (int)rec[3], Bc = (int)rec[4], which = (int)rec[5];
+  const int64_t total = rec[6];
+  if (which == 0) {
+    const DownGeom g = down_geom(dim, A, Bc);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x)
+      prep_down_chunk(w, dim, A, Bc, g, idx, img);
+  } else {
+    const UpGeom g = up_geom(dim, A, Bc);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x)
+      prep_up_chunk(w, dim, A, Bc, g, idx, img);
+  }
+}
+
+}  // namespace
 }  // namespace lshm
 
 using namespace lshm;
@@ -15,16 +40,43 @@ extern "C" {
 int lshm_conv_image_bytes(int dim, int A, int Bc, int which, int64_t* bytes) {
   LSHM_REQUIRE(bytes && (dim == 1 || dim == 2) && A > 0 && Bc > 0 && (which == 0 || which == 1),
                "lshm_conv_image_bytes: bad arguments");
-  *bytes = which == 0 ? (int64_t)down_image_bytes(dim, A, Bc) : (int64_t)up_image_bytes(dim, A, Bc);
+  if (which == 0) { const DownGeom g = down_geom(dim, A, Bc); *bytes = (int64_t)(g.img * g.ntiles * g.KB); }
+  else { const UpGeom g = up_geom(dim, A, Bc); *bytes = (int64_t)(g.img * g.ntiles * g.KB); }
   return LSHM_OK;
 }
 
 int lshm_conv_prep(const float* w, int dim, int A, int Bc, void* down_img, void* up_img, lshm_stream_t stream) {
   LSHM_REQUIRE(w && (dim == 1 || dim == 2) && A > 0 && Bc > 0, "lshm_conv_prep: bad arguments");
-  if (down_img)
-    if (int rc = prep_down_image(w, dim, A, Bc, down_img, as_stream(stream))) return rc;
-  if (up_img)
-    if (int rc = prep_up_image(w, dim, A, Bc, up_img, as_stream(stream))) return rc;
+  cudaStream_t st = as_stream(stream);
+  if (down_img) {
+    const int64_t total = down_chunks(down_geom(dim, A, Bc));
+    prep_single_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(w, dim, A, Bc, 0, total, reinterpret_cast<uint8_t*>(down_img));
+  }
+  if (up_img) {
+    const int64_t total = up_chunks(up_geom(dim, A, Bc));
+    prep_single_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(w, dim, A, Bc, 1, total, reinterpret_cast<uint8_t*>(up_img));
+  }
+  LSHM_CHECK_LAUNCH("lshm_conv_prep");
+  return LSHM_OK;
+}
+
+int lshm_conv_prep_record(const float* w, int dim, int A, int Bc, int which, void* img, int64_t* record) {
+  LSHM_REQUIRE(w && img && record && (dim == 1 || dim == 2) && A > 0 && Bc > 0 && (which == 0 || which == 1),
+               "lshm_conv_prep_record: bad arguments");
+  record[0] = (int64_t)reinterpret_cast<uintptr_t>(w);
+  record[1] = (int64_t)reinterpret_cast<uintptr_t>(img);
+  record[2] = dim; record[3] = A; record[4] = Bc; record[5] = which;
+  record[6] = which == 0 ? down_chunks(down_geom(dim, A, Bc)) : up_chunks(up_geom(dim, A, Bc));
+  record[7] = 0;
+  return LSHM_OK;
+}
+
+int lshm_conv_prep_batch(const int64_t* table, int n, lshm_stream_t stream) {
+  LSHM_REQUIRE(table && n >= 0, "lshm_conv_prep_batch: bad arguments");
+  if (n == 0) return LSHM_OK;
+  dim3 grid(48, (unsigned)n);
+  prep_batch_kernel<<<grid, 256, 0, as_stream(stream)>>>(table);
+  LSHM_CHECK_LAUNCH("lshm_conv_prep_batch");
   return LSHM_OK;
 }
 

@@ -13,7 +13,7 @@
 // shared-memory stages (mbarrier full/empty), fp32 accumulators in TMEM, bias/ELU/ELU' fused in
 // the epilogue which writes NCHW / NCL directly.
 #include <stdlib.h>
-#include "tc_common.cuh"
+#include "conv_geom.cuh"
 
 namespace lshm {
 namespace {
@@ -215,18 +215,18 @@ __global__ void __launch_bounds__(DOWN_THREADS) igemm_down_kernel(DownArgs a) {
         sv[i] = s < SLOTS && q < a.Q;
         sp[i] = a.big; full[i] = false; r0ok[i] = r1ok[i] = c0ok[i] = c1ok[i] = false; sj[i] = 0;
         if (sv[i]) {
+          const uint32_t uq = (uint32_t)q;            // Q < 2^31 (launcher): 32-bit divisions only
           if (DIM == 2) {
-            const int64_t pp = (int64_t)PH * PW;
-            const int64_t n = q / pp;
-            const int r = (int)(q - n * pp);
-            const int by = r / PW, bx = r - by * PW;
+            const uint32_t n = uq / (uint32_t)(PH * PW);
+            const uint32_t r = uq - n * (uint32_t)(PH * PW);
+            const int by = (int)(r / (uint32_t)PW), bx = (int)(r - (r / (uint32_t)PW) * PW);
             r0ok[i] = by > 0; r1ok[i] = by < a.h; c0ok[i] = bx > 0; c1ok[i] = bx < a.w;
             full[i] = r0ok[i] && r1ok[i] && c0ok[i] && c1ok[i];
-            sp[i] = a.big + n * a.big_ns + (int64_t)(2 * by - 1) * W + (2 * bx - 1);
+            sp[i] = a.big + (int64_t)n * a.big_ns + (int64_t)(2 * by - 1) * W + (2 * bx - 1);
           } else {
-            const int64_t n = q / a.w;                // 1-D: a.w holds the small length l
-            sj[i] = (int)(q - n * a.w);
-            sp[i] = a.big + n * a.big_ns + 4 * (int64_t)sj[i] - a.pad;
+            const uint32_t n = uq / (uint32_t)a.w;    // 1-D: a.w holds the small length l
+            sj[i] = (int)(uq - n * (uint32_t)a.w);
+            sp[i] = a.big + (int64_t)n * a.big_ns + 4 * (int64_t)sj[i] - a.pad;
           }
         }
       }
@@ -307,16 +307,16 @@ __global__ void __launch_bounds__(DOWN_THREADS) igemm_down_kernel(DownArgs a) {
       bool ok = q < a.Q;
       int64_t n = 0, pos = 0;
       if (ok) {
+        const uint32_t uq = (uint32_t)q;
         if (DIM == 2) {
-          const int64_t pp = (int64_t)PH * PW;
-          n = q / pp;
-          const int r = (int)(q - n * pp);
-          const int by = r / PW, bx = r - by * PW;
+          const uint32_t un = uq / (uint32_t)(PH * PW);
+          const uint32_t r = uq - un * (uint32_t)(PH * PW);
+          const int by = (int)(r / (uint32_t)PW), bx = (int)(r - (r / (uint32_t)PW) * PW);
           ok = by < a.h && bx < a.w;
-          pos = (int64_t)by * a.w + bx;
+          n = un; pos = (int64_t)by * a.w + bx;
         } else {
-          n = q / a.w;
-          pos = q - n * a.w;
+          const uint32_t un = uq / (uint32_t)a.w;
+          n = un; pos = uq - un * (uint32_t)a.w;
         }
       }
       float* outp = a.small_ + n * a.small_ns + pos;
@@ -428,59 +428,6 @@ __global__ void __launch_bounds__(DOWN_THREADS) igemm_down_kernel(DownArgs a) {
   if (warp == 8) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-// ---------------------------------------------------------------------------------------------
-// weight image:  [ntile][kblock][half hi/lo][tap][chunk][a_local][8 x bf16]
-// ---------------------------------------------------------------------------------------------
-struct DownGeom { int NT, KC, ntiles, KB, T; size_t img; };
-
-DownGeom down_geom(int dim, int A, int Bc) {
-  DownGeom g;
-  const int a16 = (A + 15) / 16 * 16;
-  g.NT = a16 <= 16 ? 16 : (a16 <= 32 ? 32 : (a16 <= 48 ? 48 : 96));
-  g.KC = (dim == 2 && g.NT == 96) ? 16 : 32;
-  g.ntiles = (A + g.NT - 1) / g.NT;
-  g.KB = (4 * Bc + g.KC - 1) / g.KC;
-  g.T = dim == 2 ? 4 : 1;
-  g.img = (size_t)2 * g.T * (g.KC / 8) * g.NT * 16;
-  return g;
-}
-
-__global__ void prep_down_kernel(const float* __restrict__ w, int dim, int A, int Bc, int NT, int KC, int KB, int T,
-                                 int64_t total, uint8_t* __restrict__ img) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one 8-element chunk
-  if (idx >= total) return;
-  const int CC = KC / 8;
-  int64_t r = idx;
-  const int al = (int)(r % NT); r /= NT;
-  const int cc = (int)(r % CC); r /= CC;
-  const int tap = (int)(r % T); r /= T;
-  const int kb = (int)(r % KB); r /= KB;
-  const int nt = (int)r;
-  const int a = nt * NT + al;
-  float v[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int c = kb * KC + cc * 8 + e;
-    const int b = c >> 2, sub = c & 3;
-    float x = 0.f;
-    if (a < A && b < Bc) {
-      if (dim == 2) {
-        const int ky = 2 * (tap >> 1) + (sub >> 1), kx = 2 * (tap & 1) + (sub & 1);
-        x = w[(((int64_t)a * Bc + b) * 4 + ky) * 4 + kx];
-      } else {
-        x = w[((int64_t)a * Bc + b) * 4 + sub];
-      }
-    }
-    v[e] = x;
-  }
-  uint4 hi, lo;
-  tc::split8(v, hi, lo);
-  const size_t blk = (size_t)2 * T * CC * NT * 16;
-  uint8_t* base = img + ((size_t)nt * KB + kb) * blk + (((size_t)tap * CC + cc) * NT + al) * 16;
-  *reinterpret_cast<uint4*>(base) = hi;
-  *reinterpret_cast<uint4*>(base + blk / 2) = lo;
-}
-
 template <int DIM, int NT, int KC, bool RAW>
 int launch_down_t(DownArgs a, const DownGeom& g, cudaStream_t st) {
   const size_t stage = (size_t)(RAW ? a.rawbytes : 0) + (size_t)2 * (KC / 8) * a.slots * 16 + g.img;
@@ -503,6 +450,7 @@ int launch_down(int dim, DownArgs a, cudaStream_t st) {
   const DownGeom g = down_geom(dim, a.A, a.Bc);
   a.slots = dim == 2 ? (128 + a.w + 2 + 7) / 8 * 8 : 128;
   a.Q = dim == 2 ? a.N * (int64_t)(a.h + 1) * (a.w + 1) : a.N * (int64_t)a.w;
+  LSHM_REQUIRE(a.Q < (1LL << 31) - 4096, "lshm_down: too many positions (%lld) for one call; split the batch", (long long)a.Q);
   a.mtiles = ceil_div(a.Q, 128);
   a.ntn = g.ntiles;
   const bool aligned = (reinterpret_cast<uintptr_t>(a.big) & 15) == 0 && (a.big_ns & 3) == 0;
@@ -539,21 +487,6 @@ int launch_down(int dim, DownArgs a, cudaStream_t st) {
 }
 
 }  // namespace
-
-// shared with igemm_up.cu / igemm_wgrad.cu through conv_tc.h-style forward declarations
-size_t down_image_bytes(int dim, int A, int Bc) {
-  const DownGeom g = down_geom(dim, A, Bc);
-  return g.img * g.ntiles * g.KB;
-}
-
-int prep_down_image(const float* w, int dim, int A, int Bc, void* img, cudaStream_t st) {
-  const DownGeom g = down_geom(dim, A, Bc);
-  const int64_t total = (int64_t)g.ntiles * g.KB * g.T * (g.KC / 8) * g.NT;
-  prep_down_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(w, dim, A, Bc, g.NT, g.KC, g.KB, g.T, total,
-                                                                    reinterpret_cast<uint8_t*>(img));
-  LSHM_CHECK_LAUNCH("lshm_conv_prep(down)");
-  return LSHM_OK;
-}
 
 }  // namespace lshm
 

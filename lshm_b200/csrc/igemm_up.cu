@@ -11,7 +11,7 @@
 // are nine descriptor start addresses into one shared-memory copy; the four classes accumulate in
 // four TMEM column ranges and the epilogue writes complete 2x2 output blocks (float2 stores).
 // 1-D (k=s=4): out[b, 4i+t-pad] = sum_a S[i,a] W[a,b,t], a plain GEMM with N = (b,t).
-#include "tc_common.cuh"
+#include "conv_geom.cuh"
 
 namespace lshm {
 namespace {
@@ -79,16 +79,16 @@ __global__ void __launch_bounds__(192) igemm_up_kernel(UpArgs a) {
       sv[i] = s < SLOTS && q >= 0 && q < a.Q;
       sp[i] = a.small_;
       if (sv[i]) {
+        const uint32_t uq = (uint32_t)q;              // Q < 2^31 (launcher): 32-bit divisions only
         if (DIM == 2) {
-          const int64_t pp = (int64_t)PH * PW;
-          const int64_t n = q / pp;
-          const int r = (int)(q - n * pp);
-          const int m = r / PW, x = r - m * PW;
+          const uint32_t n = uq / (uint32_t)(PH * PW);
+          const uint32_t r = uq - n * (uint32_t)(PH * PW);
+          const int m = (int)(r / (uint32_t)PW), x = (int)(r - (r / (uint32_t)PW) * PW);
           sv[i] = m < a.h && x < a.w;
-          sp[i] = a.small_ + n * a.small_ns + (int64_t)m * a.w + x;
+          sp[i] = a.small_ + (int64_t)n * a.small_ns + (int64_t)m * a.w + x;
         } else {
-          const int64_t n = q / a.w;
-          sp[i] = a.small_ + n * a.small_ns + (q - n * a.w);
+          const uint32_t n = uq / (uint32_t)a.w;
+          sp[i] = a.small_ + (int64_t)n * a.small_ns + (uq - n * (uint32_t)a.w);
         }
       }
     }
@@ -131,14 +131,16 @@ __global__ void __launch_bounds__(192) igemm_up_kernel(UpArgs a) {
     bool ok = q < a.Q;
     int64_t n = 0; int m = 0, x = 0;
     if (ok) {
+      const uint32_t uq = (uint32_t)q;
       if (DIM == 2) {
-        const int64_t pp = (int64_t)PH * PW;
-        n = q / pp;
-        const int r = (int)(q - n * pp);
-        m = r / PW; x = r - m * PW;
+        const uint32_t un = uq / (uint32_t)(PH * PW);
+        const uint32_t r = uq - un * (uint32_t)(PH * PW);
+        m = (int)(r / (uint32_t)PW); x = (int)(r - (r / (uint32_t)PW) * PW);
         ok = m < a.h && x < a.w;
+        n = un;
       } else {
-        n = q / a.w; x = (int)(q - n * a.w);
+        const uint32_t un = uq / (uint32_t)a.w;
+        n = un; x = (int)(uq - un * (uint32_t)a.w);
       }
     }
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
@@ -275,65 +277,6 @@ __global__ void __launch_bounds__(192) igemm_up_kernel(UpArgs a) {
   if (warp == 4) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-// ---------------------------------------------------------------------------------------------
-// weight image: [ntile][kblock][half][class*4+tap][chunk][n_local][8 x bf16 over a]
-// ---------------------------------------------------------------------------------------------
-struct UpGeom { int NT, KC, ntiles, KB, combos, ncols; size_t img; };
-
-UpGeom up_geom(int dim, int A, int Bc) {
-  UpGeom g;
-  g.ncols = dim == 2 ? Bc : 4 * Bc;                 // GEMM N extent
-  const int n16 = (g.ncols + 15) / 16 * 16;
-  if (dim == 2) g.NT = n16 <= 16 ? 16 : (n16 <= 32 ? 32 : 48);
-  else g.NT = n16 <= 16 ? 16 : (n16 <= 32 ? 32 : (n16 <= 48 ? 48 : 96));
-  g.KC = dim == 2 ? 16 : 32;
-  g.ntiles = (g.ncols + g.NT - 1) / g.NT;
-  g.KB = ((A + 15) / 16 * 16 + g.KC - 1) / g.KC;
-  g.combos = dim == 2 ? 16 : 1;
-  g.img = (size_t)2 * g.combos * (g.KC / 8) * g.NT * 16;
-  return g;
-}
-
-__global__ void prep_up_kernel(const float* __restrict__ w, int dim, int A, int Bc, int NT, int KC, int KB, int combos,
-                               int64_t total, uint8_t* __restrict__ img) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int CC = KC / 8;
-  int64_t r = idx;
-  const int nl = (int)(r % NT); r /= NT;
-  const int cc = (int)(r % CC); r /= CC;
-  const int combo = (int)(r % combos); r /= combos;
-  const int kb = (int)(r % KB); r /= KB;
-  const int nt = (int)r;
-  const int col = nt * NT + nl;
-  float v[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int ch = kb * KC + cc * 8 + e;
-    float x = 0.f;
-    if (ch < A) {
-      if (dim == 2) {
-        if (col < Bc) {
-          const int cls = combo >> 2, tap = combo & 3;
-          const int ry = cls >> 1, rx = cls & 1, d = tap >> 1, ee = tap & 1;
-          const int ky = ry == 0 ? (d == 0 ? 1 : 3) : (d == 0 ? 0 : 2);
-          const int kx = rx == 0 ? (ee == 0 ? 1 : 3) : (ee == 0 ? 0 : 2);
-          x = w[(((int64_t)ch * Bc + col) * 4 + ky) * 4 + kx];
-        }
-      } else if (col < 4 * Bc) {
-        x = w[(int64_t)ch * Bc * 4 + col];          // col = b*4 + t
-      }
-    }
-    v[e] = x;
-  }
-  uint4 hi, lo;
-  tc::split8(v, hi, lo);
-  const size_t blk = (size_t)2 * combos * CC * NT * 16;
-  uint8_t* base = img + ((size_t)nt * KB + kb) * blk + (((size_t)combo * CC + cc) * NT + nl) * 16;
-  *reinterpret_cast<uint4*>(base) = hi;
-  *reinterpret_cast<uint4*>(base + blk / 2) = lo;
-}
-
 template <int DIM, int NT, int KC>
 int launch_up_t(const UpArgs& a, const UpGeom& g, cudaStream_t st) {
   const size_t stage = (size_t)2 * (KC / 8) * a.slots * 16 + g.img;
@@ -349,6 +292,7 @@ int launch_up(int dim, UpArgs a, cudaStream_t st) {
   const UpGeom g = up_geom(dim, a.A, a.Bc);
   a.slots = dim == 2 ? (128 + 2 * (a.w + 2) + 7) / 8 * 8 : 128;
   a.Q = dim == 2 ? a.N * (int64_t)(a.h + 1) * (a.w + 1) : a.N * (int64_t)a.w;
+  LSHM_REQUIRE(a.Q < (1LL << 31) - 4096, "lshm_up: too many positions (%lld) for one call; split the batch", (long long)a.Q);
   const size_t stage = (size_t)2 * (g.KC / 8) * a.slots * 16 + g.img;
   int ns = (int)std::min<size_t>(4, std::max<size_t>(1, (96 * 1024) / stage));
   if (ns < 2 && 2 * stage <= 200 * 1024) ns = 2;
@@ -363,20 +307,6 @@ int launch_up(int dim, UpArgs a, cudaStream_t st) {
 }
 
 }  // namespace
-
-size_t up_image_bytes(int dim, int A, int Bc) {
-  const UpGeom g = up_geom(dim, A, Bc);
-  return g.img * g.ntiles * g.KB;
-}
-
-int prep_up_image(const float* w, int dim, int A, int Bc, void* img, cudaStream_t st) {
-  const UpGeom g = up_geom(dim, A, Bc);
-  const int64_t total = (int64_t)g.ntiles * g.KB * g.combos * (g.KC / 8) * g.NT;
-  prep_up_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(w, dim, A, Bc, g.NT, g.KC, g.KB, g.combos, total,
-                                                                  reinterpret_cast<uint8_t*>(img));
-  LSHM_CHECK_LAUNCH("lshm_conv_prep(up)");
-  return LSHM_OK;
-}
 
 }  // namespace lshm
 

@@ -42,45 +42,51 @@ __global__ void __launch_bounds__(TILE * TROWS)
 cascade_losses_kernel(const float* __restrict__ x, const float* __restrict__ x1,
                       const float* __restrict__ x2, const float* __restrict__ x3f,
                       const float* __restrict__ y1, const float* __restrict__ y2,
-                      const float* __restrict__ y3, float rho, float inv_n, int P,
+                      const float* __restrict__ y3, float rho, float inv_n, int P, int64_t ntiles,
                       double* __restrict__ sums, float* __restrict__ g1p, float* __restrict__ g2,
                       float* __restrict__ g3f) {
   __shared__ float tile[TILE][TILE + 1];
   __shared__ float gt[TILE][TILE + 1];
   __shared__ double red[32];
-  const int64_t plane = (int64_t)blockIdx.z * P * P;
-  const int t0 = blockIdx.y * TILE, f0 = blockIdx.x * TILE;
   const int tx = threadIdx.x, ty = threadIdx.y;
-#pragma unroll
-  for (int i = 0; i < TILE; i += TROWS)
-    tile[ty + i][tx] = x3f[plane + (int64_t)(f0 + ty + i) * P + t0 + tx];
-  __syncthreads();
+  const int tpr = P / TILE, tpp = tpr * tpr;     // tiles per row / per plane
   float s[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int i = 0; i < TILE; i += TROWS) {
-    const int64_t off = plane + (int64_t)(t0 + ty + i) * P + f0 + tx;
-    const float xv = x[off], a1 = x1[off], a2 = x2[off], a3 = tile[tx][ty + i];
-    const float m1 = y1[off], m2 = y2[off], m3 = y3[off];
-    const float r0 = a1 + a2 + a3 - xv;
-    const float r1 = xv - a1;
-    const float x11 = 0.5f * r1;
-    const float r2 = x11 - a2, r3 = x11 - a3;
-    s[0] = fmaf(r0, r0, s[0]);
-    s[1] = fmaf(m1, r1, s[1]); s[2] = fmaf(r1, r1, s[2]);
-    s[3] = fmaf(m2, r2, s[3]); s[4] = fmaf(r2, r2, s[4]);
-    s[5] = fmaf(m3, r3, s[5]); s[6] = fmaf(r3, r3, s[6]);
-    if (GRADS) {
-      const float e2 = m2 + rho * r2, e3 = m3 + rho * r3;
-      g2[off] = (2.f * r0 - e2) * inv_n;
-      gt[ty + i][tx] = (2.f * r0 - e3) * inv_n;
-      g1p[off] = (2.f * r0 - m1 - rho * r1 - 0.5f * (e2 + e3)) * inv_n;
-    }
-  }
-  if (GRADS) {
+  // a block walks a strided list of 32x32 tiles and reduces once at the end
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t plane = (t / tpp) * (int64_t)P * P;
+    const int tin = (int)(t % tpp);
+    const int t0 = (tin / tpr) * TILE, f0 = (tin % tpr) * TILE;
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < TILE; i += TROWS)
-      g3f[plane + (int64_t)(f0 + ty + i) * P + t0 + tx] = gt[tx][ty + i];
+      tile[ty + i][tx] = x3f[plane + (int64_t)(f0 + ty + i) * P + t0 + tx];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < TILE; i += TROWS) {
+      const int64_t off = plane + (int64_t)(t0 + ty + i) * P + f0 + tx;
+      const float xv = x[off], a1 = x1[off], a2 = x2[off], a3 = tile[tx][ty + i];
+      const float m1 = y1[off], m2 = y2[off], m3 = y3[off];
+      const float r0 = a1 + a2 + a3 - xv;
+      const float r1 = xv - a1;
+      const float x11 = 0.5f * r1;
+      const float r2 = x11 - a2, r3 = x11 - a3;
+      s[0] = fmaf(r0, r0, s[0]);
+      s[1] = fmaf(m1, r1, s[1]); s[2] = fmaf(r1, r1, s[2]);
+      s[3] = fmaf(m2, r2, s[3]); s[4] = fmaf(r2, r2, s[4]);
+      s[5] = fmaf(m3, r3, s[5]); s[6] = fmaf(r3, r3, s[6]);
+      if (GRADS) {
+        const float e2 = m2 + rho * r2, e3 = m3 + rho * r3;
+        g2[off] = (2.f * r0 - e2) * inv_n;
+        gt[ty + i][tx] = (2.f * r0 - e3) * inv_n;
+        g1p[off] = (2.f * r0 - m1 - rho * r1 - 0.5f * (e2 + e3)) * inv_n;
+      }
+    }
+    if (GRADS) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < TILE; i += TROWS)
+        g3f[plane + (int64_t)(f0 + ty + i) * P + t0 + tx] = gt[tx][ty + i];
+    }
   }
   const int tid = ty * TILE + tx;
 #pragma unroll
@@ -341,16 +347,13 @@ int lshm_cascade_losses(const float* x, const float* x1, const float* x2, const 
   if (int rc = check_cascade("lshm_cascade_losses", N, C, P)) return rc;
   if (N == 0) return LSHM_OK;
   const float inv_n = grad_scale;
-  const int64_t planes = N * C;
-  for (int64_t z0 = 0; z0 < planes; z0 += 65535) {
-    const int64_t nz = planes - z0 < 65535 ? planes - z0 : 65535;
-    const int64_t o = z0 * P * P;
-    dim3 grid(P / TILE, P / TILE, (unsigned)nz), block(TILE, TROWS);
-    if (g1p)
-      cascade_losses_kernel<true><<<grid, block, 0, as_stream(stream)>>>(x + o, x1 + o, x2 + o, x3f + o, y1 + o, y2 + o, y3 + o, rho, inv_n, P, sums, g1p + o, g2 + o, g3f + o);
-    else
-      cascade_losses_kernel<false><<<grid, block, 0, as_stream(stream)>>>(x + o, x1 + o, x2 + o, x3f + o, y1 + o, y2 + o, y3 + o, rho, inv_n, P, sums, nullptr, nullptr, nullptr);
-  }
+  const int64_t ntiles = N * C * (int64_t)(P / TILE) * (P / TILE);
+  const int64_t blocks = std::min<int64_t>(ntiles, (int64_t)sm_count() * 16);
+  dim3 block(TILE, TROWS);
+  if (g1p)
+    cascade_losses_kernel<true><<<(unsigned)blocks, block, 0, as_stream(stream)>>>(x, x1, x2, x3f, y1, y2, y3, rho, inv_n, P, ntiles, sums, g1p, g2, g3f);
+  else
+    cascade_losses_kernel<false><<<(unsigned)blocks, block, 0, as_stream(stream)>>>(x, x1, x2, x3f, y1, y2, y3, rho, inv_n, P, ntiles, sums, nullptr, nullptr, nullptr);
   LSHM_CHECK_LAUNCH("lshm_cascade_losses");
   return LSHM_OK;
 }

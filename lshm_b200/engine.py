@@ -90,17 +90,39 @@ class AEEngine:
         self.img = {}   # (layer name, which) -> weight image buffer (re-filled every closure)
         self.need_input_grad = ndim == 1   # the 1-D nets sit behind the 2-D net: dx is always wanted
 
-    def prepare_images(self, p: Dict[str, torch.Tensor], st: int, grads: bool):
-        """Re-make the weight images the coming forward (and backward) will read.  Conv layers use
-        their 'down' image forward; transposed-conv layers use theirs in the backward (dgrad)."""
+    def _build_tables(self, p: Dict[str, torch.Tensor]):
+        """Allocate the weight images and the two device tables of preparation records
+        (forward-only, forward+backward).  Addresses are stable (parameters live in the flat
+        buffer), so this runs once; it re-runs if a parameter is re-homed."""
+        import numpy as np
+        dev = p["conv0.weight"].device
+        fwd, bwd = [], []
         for i in range(6):
             cn, tn = f"conv{i}.weight", f"tconv{i}.weight"
-            self.img[(cn, 0)] = conv_image(p[cn], self.ndim, 0, st, self.img.get((cn, 0)))
-            self.img[(tn, 1)] = conv_image(p[tn], self.ndim, 1, st, self.img.get((tn, 1)))
-            if grads:
-                self.img[(tn, 0)] = conv_image(p[tn], self.ndim, 0, st, self.img.get((tn, 0)))
-                if i > 0 or self.need_input_grad:
-                    self.img[(cn, 1)] = conv_image(p[cn], self.ndim, 1, st, self.img.get((cn, 1)))
+            fwd += [(cn, 0), (tn, 1)]
+            bwd += [(tn, 0)]
+            if i > 0 or self.need_input_grad:
+                bwd += [(cn, 1)]
+        self.img = {}
+        recs = np.zeros((len(fwd) + len(bwd), 8), dtype=np.int64)
+        for r, (nm, which) in enumerate(fwd + bwd):
+            w = p[nm]
+            A, Bc = w.shape[0], w.shape[1]
+            img = torch.empty(max(16, self.lib.conv_image_bytes(self.ndim, A, Bc, which)), dtype=torch.uint8, device=dev)
+            self.img[(nm, which)] = img
+            self.lib.conv_prep_record(w.data_ptr(), self.ndim, A, Bc, which, img.data_ptr(), recs[r].ctypes.data)
+        self._table = torch.from_numpy(recs).to(dev)
+        self._n_fwd, self._n_all = len(fwd), len(fwd) + len(bwd)
+        self._table_key = tuple(p[f"{k}{i}.weight"].data_ptr() for k in ("conv", "tconv") for i in range(6))
+
+    def prepare_images(self, p: Dict[str, torch.Tensor], st: int, grads: bool):
+        """Re-make (ONE launch) the weight images the coming forward (and backward) will read: conv
+        layers use their 'down' image forward and their 'up' image in dgrad, transposed convs the
+        other way round."""
+        key = tuple(p[f"{k}{i}.weight"].data_ptr() for k in ("conv", "tconv") for i in range(6))
+        if getattr(self, "_table_key", None) != key:
+            self._build_tables(p)
+        self.lib.conv_prep_batch(self._table.data_ptr(), self._n_all if grads else self._n_fwd, st)
 
     def workspace(self, N, device, with_grad, need_dx=False) -> Workspace:
         return Workspace(N, self.C, self.L, self.H4, device, with_grad, need_dx)
@@ -262,7 +284,9 @@ class AEEngine:
                 self._up(_p(dz), dz_ns, _p(self.img[(f"conv{i}.weight", 1)]), None, _p(inp), inp_ns, _p(nxt), sz[i], N, A, Bc, lvl, 1, EPI_DELU, st)
                 dz, dz_ns = nxt, sz[i]
             elif need_dx:
-                if ("conv0.weight", 1) not in self.img:
+                if ("conv0.weight", 1) not in self.img:   # 2-D net asked for dx (not on the training path)
                     self.img[("conv0.weight", 1)] = conv_image(p["conv0.weight"], self.ndim, 1, st)
+                elif not self.need_input_grad:
+                    conv_image(p["conv0.weight"], self.ndim, 1, st, self.img[("conv0.weight", 1)])
                 self._up(_p(dz), dz_ns, _p(self.img[("conv0.weight", 1)]), None, None, 0, _p(ws.dx), sz[0], N, A, Bc, lvl, 1, EPI_NONE, st)
         return ws.dx if need_dx else None
