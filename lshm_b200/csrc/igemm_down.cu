@@ -432,14 +432,16 @@ template <int DIM, int NT, int KC, bool RAW>
 int launch_down_t(DownArgs a, const DownGeom& g, cudaStream_t st) {
   const size_t stage = (size_t)(RAW ? a.rawbytes : 0) + (size_t)2 * (KC / 8) * a.slots * 16 + g.img;
   const int64_t units = a.mtiles * g.ntiles * g.KB;
-  const size_t budget = RAW ? 190 * 1024 : 100 * 1024;   // RAW: one CTA per SM with a deep ring
-  int ns = (int)std::min<size_t>(MAXST, std::max<size_t>(2, budget / stage));
-  if ((size_t)ns * stage > 200 * 1024) ns = (int)((200 * 1024) / stage);
+  // two CTAs per SM when the ring fits in ~110 KB each (227 KB per SM), else one CTA with a deep ring
+  const size_t half_sm = 110 * 1024, full_sm = 200 * 1024;
+  int ns = (int)((half_sm - g.img) / stage);
+  if (RAW || ns < 2) ns = (int)((full_sm - g.img) / stage);
+  ns = std::min(ns, MAXST);
   LSHM_REQUIRE(ns >= 1, "igemm_down: tile does not fit in shared memory");
   a.nstage = (int)std::min<int64_t>(ns, std::max<int64_t>(1, units));
   const size_t smem = stage * a.nstage + g.img;   // + resident weight image (used when KB == ntiles == 1)
   LSHM_CUDA(cudaFuncSetAttribute(igemm_down_kernel<DIM, NT, KC, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_down");
-  const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+  const int per_sm = smem <= 112 * 1024 ? 2 : 1;
   const int64_t grid = std::min<int64_t>(a.mtiles * g.ntiles, (int64_t)sm_count() * per_sm);
   igemm_down_kernel<DIM, NT, KC, RAW><<<(unsigned)grid, DOWN_THREADS, smem, st>>>(a);
   LSHM_CHECK_LAUNCH("igemm_down");

@@ -25,8 +25,11 @@ struct UpArgs {
   const float* aux; int64_t aux_ns;
   float* big; int64_t big_ns;
   int64_t N; int A; int Bc; int h; int w; int pad; int epi;
-  int slots; int nstage; int64_t Q;
+  int slots; int nstage; int64_t Q; int64_t mtiles; int ntn;
 };
+
+constexpr int UP_THREADS = 320;   // warps 0-3 epilogue, 4-7 producers, 8 MMA issuer, 9 weight loader
+constexpr int UP_MAXST = 6;
 
 __device__ __forceinline__ float epi_apply(float acc, float bias, int epi, float aux) {
   float r = acc + bias;
@@ -35,32 +38,35 @@ __device__ __forceinline__ float epi_apply(float acc, float bias, int epi, float
   return r;
 }
 
+// Persistent, warp-specialised (same skeleton as igemm_down.cu): producers run ahead through the
+// stage ring, the MMA warp alternates between two TMEM accumulator sets (each = 4 parity classes in
+// 2-D), the epilogue warps drain one set while the next is being computed.
 template <int DIM, int NT, int KC>
-__global__ void __launch_bounds__(192) igemm_up_kernel(UpArgs a) {
+__global__ void __launch_bounds__(UP_THREADS) igemm_up_kernel(UpArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], acc_bar;
+  __shared__ __align__(8) uint64_t full_bar[UP_MAXST], empty_bar[UP_MAXST], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base;
   constexpr int NCLS = DIM == 2 ? 4 : 1;
   constexpr int COMBOS = DIM == 2 ? 16 : 1;       // class x tap weight tiles per K block
   constexpr int CC = KC / 8;
   constexpr uint32_t IMG = 2u * COMBOS * CC * NT * 16;
-  constexpr uint32_t TCOLS = NCLS * NT;
+  constexpr uint32_t TSET = NCLS * NT;            // TMEM columns of one accumulator set
+  constexpr uint32_t TCOLS = 2 * TSET;
   constexpr uint32_t TMEM_COLS = TCOLS <= 32 ? 32 : (TCOLS <= 64 ? 64 : (TCOLS <= 128 ? 128 : (TCOLS <= 256 ? 256 : 512)));
   const int SLOTS = a.slots, NS = a.nstage;
   const uint32_t zbytes = (uint32_t)CC * SLOTS * 16;
   const uint32_t stage_bytes = 2 * zbytes + IMG;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t q0 = (int64_t)blockIdx.x * 128;
-  const int nt = blockIdx.y;
   const int Apad = (a.A + 15) / 16 * 16;
   const int KB = (Apad + KC - 1) / KC;
   const int PW = a.w + 1, PH = a.h + 1;
   const int halo = DIM == 2 ? PW + 1 : 0;           // slots in front of the tile
+  const int64_t total = a.mtiles * a.ntn;
 
-  if (warp == 4) tmem_alloc(&tmem_base, TMEM_COLS);
+  if (warp == 8) tmem_alloc(&tmem_base, TMEM_COLS);
   if (tid == 0) {
-    for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], 5); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&acc_bar, 1);
+    for (int s = 0; s < UP_MAXST; ++s) { mbar_init(&full_bar[s], 5); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
     mbar_init_fence();
   }
   fence_before();
@@ -68,222 +74,264 @@ __global__ void __launch_bounds__(192) igemm_up_kernel(UpArgs a) {
   fence_after();
   const uint32_t tmem = tmem_base;
 
-  if (warp < 4) {
+  if (warp >= 4 && warp < 8) {
     // ------------------------------------------------ producers: stage S (hi/lo bf16), K = channels
+    const int ptid = tid - 128;
     const int64_t hw = DIM == 2 ? (int64_t)a.h * a.w : (int64_t)a.w;
-    const float* sp[3]; bool sv[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int s = tid + i * 128;
-      const int64_t q = q0 - halo + s;
-      sv[i] = s < SLOTS && q >= 0 && q < a.Q;
-      sp[i] = a.small_;
-      if (sv[i]) {
-        const uint32_t uq = (uint32_t)q;              // Q < 2^31 (launcher): 32-bit divisions only
-        if (DIM == 2) {
-          const uint32_t n = uq / (uint32_t)(PH * PW);
-          const uint32_t r = uq - n * (uint32_t)(PH * PW);
-          const int m = (int)(r / (uint32_t)PW), x = (int)(r - (r / (uint32_t)PW) * PW);
-          sv[i] = m < a.h && x < a.w;
-          sp[i] = a.small_ + (int64_t)n * a.small_ns + (int64_t)m * a.w + x;
-        } else {
-          const uint32_t n = uq / (uint32_t)a.w;
-          sp[i] = a.small_ + (int64_t)n * a.small_ns + (uq - n * (uint32_t)a.w);
-        }
-      }
-    }
-    for (int kb = 0; kb < KB; ++kb) {
-      const int s = kb % NS, ph = (kb / NS) & 1;
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      uint8_t* zhi = smem + (size_t)s * stage_bytes;
-      uint8_t* zlo = zhi + zbytes;
-      const int ccb = (min(KC, Apad - kb * KC)) >> 3;
+    uint32_t it = 0;
+    for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+      const int64_t q0 = (item / a.ntn) * 128;
+      const float* sp[3]; bool sv[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        const int slot = tid + i * 128;
-        if (slot >= SLOTS) continue;
-        float v[CC][8];
-#pragma unroll
-        for (int cc = 0; cc < CC; ++cc) {
-          const int a0 = kb * KC + cc * 8;
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            v[cc][e] = (cc < ccb && sv[i] && a0 + e < a.A) ? __ldg(sp[i] + (int64_t)(a0 + e) * hw) : 0.f;
-        }
-#pragma unroll
-        for (int cc = 0; cc < CC; ++cc) {
-          if (cc < ccb) {
-            uint4 hi, lo;
-            split8(v[cc], hi, lo);
-            *reinterpret_cast<uint4*>(zhi + ((size_t)cc * SLOTS + slot) * 16) = hi;
-            *reinterpret_cast<uint4*>(zlo + ((size_t)cc * SLOTS + slot) * 16) = lo;
+        const int s = ptid + i * 128;
+        const int64_t q = q0 - halo + s;
+        sv[i] = s < SLOTS && q >= 0 && q < a.Q;
+        sp[i] = a.small_;
+        if (sv[i]) {
+          const uint32_t uq = (uint32_t)q;              // Q < 2^31 (launcher): 32-bit divisions only
+          if (DIM == 2) {
+            const uint32_t n = uq / (uint32_t)(PH * PW);
+            const uint32_t r = uq - n * (uint32_t)(PH * PW);
+            const int m = (int)(r / (uint32_t)PW), x = (int)(r - (r / (uint32_t)PW) * PW);
+            sv[i] = m < a.h && x < a.w;
+            sp[i] = a.small_ + (int64_t)n * a.small_ns + (int64_t)m * a.w + x;
+          } else {
+            const uint32_t n = uq / (uint32_t)a.w;
+            sp[i] = a.small_ + (int64_t)n * a.small_ns + (uq - n * (uint32_t)a.w);
           }
         }
       }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[s]);
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int s = it % NS, ph = (it / NS) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* zhi = smem + (size_t)s * stage_bytes;
+        uint8_t* zlo = zhi + zbytes;
+        const int ccb = (min(KC, Apad - kb * KC)) >> 3;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int slot = ptid + i * 128;
+          if (slot >= SLOTS) continue;
+          float v[CC][8];
+#pragma unroll
+          for (int cc = 0; cc < CC; ++cc) {
+            const int a0 = kb * KC + cc * 8;
+            const float* p = sp[i] + (int64_t)a0 * hw;
+            const bool on = cc < ccb && sv[i];
+            if (on && a0 + 8 <= a.A) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { v[cc][e] = __ldg(p); p += hw; }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { v[cc][e] = (on && a0 + e < a.A) ? __ldg(p) : 0.f; p += hw; }
+            }
+          }
+#pragma unroll
+          for (int cc = 0; cc < CC; ++cc) {
+            if (cc < ccb) {
+              uint4 hi, lo;
+              split8(v[cc], hi, lo);
+              *reinterpret_cast<uint4*>(zhi + ((size_t)cc * SLOTS + slot) * 16) = hi;
+              *reinterpret_cast<uint4*>(zlo + ((size_t)cc * SLOTS + slot) * 16) = lo;
+            }
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+      }
     }
+  } else if (warp < 4) {
     // ------------------------------------------------ epilogue
-    mbar_wait(&acc_bar, 0);
-    fence_after();
-    const int64_t q = q0 + tid;
-    bool ok = q < a.Q;
-    int64_t n = 0; int m = 0, x = 0;
-    if (ok) {
-      const uint32_t uq = (uint32_t)q;
+    uint32_t tc_ = 0;
+    for (int64_t item = blockIdx.x; item < total; item += gridDim.x, ++tc_) {
+      const int nt = (int)(item % a.ntn);
+      const int64_t q = (item / a.ntn) * 128 + tid;
+      bool ok = q < a.Q;
+      int64_t n = 0; int m = 0, x = 0;
+      if (ok) {
+        const uint32_t uq = (uint32_t)q;
+        if (DIM == 2) {
+          const uint32_t un = uq / (uint32_t)(PH * PW);
+          const uint32_t r = uq - un * (uint32_t)(PH * PW);
+          m = (int)(r / (uint32_t)PW); x = (int)(r - (r / (uint32_t)PW) * PW);
+          ok = m < a.h && x < a.w;
+          n = un;
+        } else {
+          const uint32_t un = uq / (uint32_t)a.w;
+          n = un; x = (int)(uq - un * (uint32_t)a.w);
+        }
+      }
+      const uint32_t buf = tc_ & 1;
+      mbar_wait(&acc_full[buf], (tc_ >> 1) & 1);
+      fence_after();
+      const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16) + buf * TSET;
       if (DIM == 2) {
-        const uint32_t un = uq / (uint32_t)(PH * PW);
-        const uint32_t r = uq - un * (uint32_t)(PH * PW);
-        m = (int)(r / (uint32_t)PW); x = (int)(r - (r / (uint32_t)PW) * PW);
-        ok = m < a.h && x < a.w;
-        n = un;
+        const int W = 2 * a.w;
+        const int64_t HW = 4 * (int64_t)a.h * a.w;
+        float* outp = a.big + n * a.big_ns + (int64_t)(2 * m) * W + 2 * x;
+        const float* auxp = a.aux != nullptr ? a.aux + n * a.aux_ns + (int64_t)(2 * m) * W + 2 * x : nullptr;
+#pragma unroll 1
+        for (int g = 0; g < NT / 16; ++g) {
+          const int b0 = nt * NT + g * 16;
+          const int nch = min(16, a.Bc - b0);
+          if (nch <= 0) break;                       // warp-uniform
+          float v[4][16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tmem_ld16(trow + c * NT + g * 16, v[c]);
+          if (ok) {
+            float* op = outp + (int64_t)b0 * HW;
+            const float* xp = a.epi == LSHM_EPI_DELU ? auxp + (int64_t)b0 * HW : nullptr;
+            const float* bp = a.bias != nullptr ? a.bias + b0 : nullptr;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (j < nch) {
+                const float bs = bp != nullptr ? __ldg(bp + j) : 0.f;
+                float2 ax0 = make_float2(0.f, 0.f), ax1 = make_float2(0.f, 0.f);
+                if (a.epi == LSHM_EPI_DELU) {
+                  ax0 = *reinterpret_cast<const float2*>(xp);
+                  ax1 = *reinterpret_cast<const float2*>(xp + W);
+                  xp += HW;
+                }
+                // class index = ry*2 + rx
+                const float2 o0 = make_float2(epi_apply(v[0][j], bs, a.epi, ax0.x), epi_apply(v[1][j], bs, a.epi, ax0.y));
+                const float2 o1 = make_float2(epi_apply(v[2][j], bs, a.epi, ax1.x), epi_apply(v[3][j], bs, a.epi, ax1.y));
+                *reinterpret_cast<float2*>(op) = o0;
+                *reinterpret_cast<float2*>(op + W) = o1;
+                op += HW;
+              }
+            }
+          }
+        }
       } else {
-        const uint32_t un = uq / (uint32_t)a.w;
-        n = un; x = (int)(uq - un * (uint32_t)a.w);
-      }
-    }
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    if (DIM == 2) {
-      const int W = 2 * a.w;
-      const int64_t HW = 4 * (int64_t)a.h * a.w;
-      float* outp = a.big + n * a.big_ns + (int64_t)(2 * m) * W + 2 * x;
-      const float* auxp = a.aux != nullptr ? a.aux + n * a.aux_ns + (int64_t)(2 * m) * W + 2 * x : nullptr;
+        const int64_t Lb = 4 * (int64_t)a.w;
+        float* outp = a.big + n * a.big_ns + 4 * (int64_t)x - a.pad;
+        const float* auxp = a.aux != nullptr ? a.aux + n * a.aux_ns + 4 * (int64_t)x - a.pad : nullptr;
 #pragma unroll 1
-      for (int g = 0; g < NT / 16; ++g) {
-        const int b0 = nt * NT + g * 16;
-        const int nch = min(16, a.Bc - b0);
-        if (nch <= 0) break;                       // warp-uniform
-        float v[4][16];
+        for (int g = 0; g < NT / 16; ++g) {
+          const int bb0 = (nt * NT + g * 16) / 4;
+          if (bb0 >= a.Bc) break;                    // warp-uniform
+          float v[16];
+          tmem_ld16(trow + g * 16, v);
+          if (ok) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld16(trow + c * NT + g * 16, v[c]);
-        if (ok) {
-          float* op = outp + (int64_t)b0 * HW;
-          const float* xp = a.epi == LSHM_EPI_DELU ? auxp + (int64_t)b0 * HW : nullptr;
-          const float* bp = a.bias != nullptr ? a.bias + b0 : nullptr;
+            for (int jb = 0; jb < 4; ++jb) {
+              const int b = bb0 + jb;
+              if (b < a.Bc) {
+                const float bs = a.bias != nullptr ? __ldg(a.bias + b) : 0.f;
+                float* o = outp + b * Lb;
+                if (a.pad == 0 && a.epi != LSHM_EPI_DELU) {
+                  float4 r;
+                  r.x = epi_apply(v[jb * 4 + 0], bs, a.epi, 0.f); r.y = epi_apply(v[jb * 4 + 1], bs, a.epi, 0.f);
+                  r.z = epi_apply(v[jb * 4 + 2], bs, a.epi, 0.f); r.w = epi_apply(v[jb * 4 + 3], bs, a.epi, 0.f);
+                  *reinterpret_cast<float4*>(o) = r;
+                } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (j < nch) {
-              const float bs = bp != nullptr ? __ldg(bp + j) : 0.f;
-              float2 ax0 = make_float2(0.f, 0.f), ax1 = make_float2(0.f, 0.f);
-              if (a.epi == LSHM_EPI_DELU) {
-                ax0 = *reinterpret_cast<const float2*>(xp);
-                ax1 = *reinterpret_cast<const float2*>(xp + W);
-                xp += HW;
-              }
-              // class index = ry*2 + rx
-              const float2 o0 = make_float2(epi_apply(v[0][j], bs, a.epi, ax0.x), epi_apply(v[1][j], bs, a.epi, ax0.y));
-              const float2 o1 = make_float2(epi_apply(v[2][j], bs, a.epi, ax1.x), epi_apply(v[3][j], bs, a.epi, ax1.y));
-              *reinterpret_cast<float2*>(op) = o0;
-              *reinterpret_cast<float2*>(op + W) = o1;
-              op += HW;
-            }
-          }
-        }
-      }
-    } else {
-      const int64_t Lb = 4 * (int64_t)a.w;
-      float* outp = a.big + n * a.big_ns + 4 * (int64_t)x - a.pad;
-      const float* auxp = a.aux != nullptr ? a.aux + n * a.aux_ns + 4 * (int64_t)x - a.pad : nullptr;
-#pragma unroll 1
-      for (int g = 0; g < NT / 16; ++g) {
-        float v[16];
-        tmem_ld16(trow + g * 16, v);
-        if (ok) {
-#pragma unroll
-          for (int jb = 0; jb < 4; ++jb) {
-            const int b = (nt * NT + g * 16) / 4 + jb;
-            if (b < a.Bc) {
-              const float bs = a.bias != nullptr ? __ldg(a.bias + b) : 0.f;
-              float* o = outp + b * Lb;
-              if (a.pad == 0 && a.epi != LSHM_EPI_DELU) {
-                float4 r;
-                r.x = epi_apply(v[jb * 4 + 0], bs, a.epi, 0.f); r.y = epi_apply(v[jb * 4 + 1], bs, a.epi, 0.f);
-                r.z = epi_apply(v[jb * 4 + 2], bs, a.epi, 0.f); r.w = epi_apply(v[jb * 4 + 3], bs, a.epi, 0.f);
-                *reinterpret_cast<float4*>(o) = r;
-              } else {
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  if (a.pad == 1 && x == 0 && t == 0) continue;        // position -1 does not exist
-                  const float ax = a.epi == LSHM_EPI_DELU ? auxp[b * Lb + t] : 0.f;
-                  o[t] = epi_apply(v[jb * 4 + t], bs, a.epi, ax);
-                }
-                if (a.pad == 1 && x == a.w - 1) {                       // last position: no tap reaches it
-                  const float ax = a.epi == LSHM_EPI_DELU ? auxp[b * Lb + 4] : 0.f;
-                  o[4] = epi_apply(0.f, bs, a.epi, ax);
+                  for (int t = 0; t < 4; ++t) {
+                    if (a.pad == 1 && x == 0 && t == 0) continue;        // position -1 does not exist
+                    const float ax = a.epi == LSHM_EPI_DELU ? auxp[b * Lb + t] : 0.f;
+                    o[t] = epi_apply(v[jb * 4 + t], bs, a.epi, ax);
+                  }
+                  if (a.pad == 1 && x == a.w - 1) {                       // last position: no tap reaches it
+                    const float ax = a.epi == LSHM_EPI_DELU ? auxp[b * Lb + 4] : 0.f;
+                    o[4] = epi_apply(0.f, bs, a.epi, ax);
+                  }
                 }
               }
             }
           }
         }
       }
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(NT, 0, 0);
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % NS, ph = (kb / NS) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, tc_ = 0;
+      for (int64_t item = blockIdx.x; item < total; item += gridDim.x, ++tc_) {
+        const uint32_t buf = tc_ & 1;
+        mbar_wait(&acc_empty[buf], ((tc_ >> 1) & 1) ^ 1);
         fence_after();
-        const uint32_t zhi = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t zlo = zhi + zbytes;
-        const uint32_t bhi = zlo + zbytes;
-        const uint32_t blo = bhi + IMG / 2;
-        const int ksteps = (min(KC, Apad - kb * KC)) >> 4;
-        if (DIM == 2) {
+        const uint32_t tset = tmem + buf * TSET;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % NS, ph = (it / NS) & 1;
+          mbar_wait(&full_bar[s], ph);
+          fence_after();
+          const uint32_t zhi = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t zlo = zhi + zbytes;
+          const uint32_t bhi = zlo + zbytes;
+          const uint32_t blo = bhi + IMG / 2;
+          const int ksteps = (min(KC, Apad - kb * KC)) >> 4;
+          if (DIM == 2) {
 #pragma unroll
-          for (int cls = 0; cls < 4; ++cls) {
-            const int ry = cls >> 1, rx = cls & 1;
+            for (int cls = 0; cls < 4; ++cls) {
+              const int ry = cls >> 1, rx = cls & 1;
 #pragma unroll
-            for (int tap = 0; tap < 4; ++tap) {
-              const int d = tap >> 1, e = tap & 1;
-              const int dy = ry == 0 ? (d == 0 ? 0 : -1) : (d == 0 ? 1 : 0);
-              const int dx = rx == 0 ? (e == 0 ? 0 : -1) : (e == 0 ? 1 : 0);
-              const uint32_t row0 = (uint32_t)(halo + dy * PW + dx);
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint32_t aoff = ((uint32_t)(2 * ks) * SLOTS + row0) * 16;
-                const uint32_t boff = ((uint32_t)((cls * 4 + tap) * CC + 2 * ks) * NT) * 16;
-                mma_split3(tmem + cls * NT, make_desc(zhi + aoff, SLOTS * 16, 128), make_desc(zlo + aoff, SLOTS * 16, 128),
-                           make_desc(bhi + boff, NT * 16, 128), make_desc(blo + boff, NT * 16, 128), idesc,
-                           (kb > 0 || tap > 0 || ks > 0) ? 1u : 0u);
+              for (int tap = 0; tap < 4; ++tap) {
+                const int d = tap >> 1, e = tap & 1;
+                const int dy = ry == 0 ? (d == 0 ? 0 : -1) : (d == 0 ? 1 : 0);
+                const int dx = rx == 0 ? (e == 0 ? 0 : -1) : (e == 0 ? 1 : 0);
+                const uint32_t row0 = (uint32_t)(halo + dy * PW + dx);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  const uint32_t aoff = ((uint32_t)(2 * ks) * SLOTS + row0) * 16;
+                  const uint32_t boff = ((uint32_t)((cls * 4 + tap) * CC + 2 * ks) * NT) * 16;
+                  mma_split3(tset + cls * NT, make_desc(zhi + aoff, SLOTS * 16, 128), make_desc(zlo + aoff, SLOTS * 16, 128),
+                             make_desc(bhi + boff, NT * 16, 128), make_desc(blo + boff, NT * 16, 128), idesc,
+                             (kb > 0 || tap > 0 || ks > 0) ? 1u : 0u);
+                }
               }
             }
+          } else {
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint32_t aoff = ((uint32_t)(2 * ks) * SLOTS) * 16;
+              const uint32_t boff = ((uint32_t)(2 * ks) * NT) * 16;
+              mma_split3(tset, make_desc(zhi + aoff, SLOTS * 16, 128), make_desc(zlo + aoff, SLOTS * 16, 128),
+                         make_desc(bhi + boff, NT * 16, 128), make_desc(blo + boff, NT * 16, 128), idesc,
+                         (kb > 0 || ks > 0) ? 1u : 0u);
+            }
           }
-        } else {
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t aoff = ((uint32_t)(2 * ks) * SLOTS) * 16;
-            const uint32_t boff = ((uint32_t)(2 * ks) * NT) * 16;
-            mma_split3(tmem, make_desc(zhi + aoff, SLOTS * 16, 128), make_desc(zlo + aoff, SLOTS * 16, 128),
-                       make_desc(bhi + boff, NT * 16, 128), make_desc(blo + boff, NT * 16, 128), idesc,
-                       (kb > 0 || ks > 0) ? 1u : 0u);
-          }
+          commit(&empty_bar[s]);
         }
-        commit(&empty_bar[s]);
+        commit(&acc_full[buf]);
       }
-      commit(&acc_bar);
     }
   } else {
     if (lane == 0) {
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % NS, ph = (kb / NS) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], IMG);
-        bulk_g2s(smem + (size_t)s * stage_bytes + 2 * zbytes, a.wimg + ((size_t)nt * KB + kb) * IMG, IMG, &full_bar[s]);
+      uint32_t it = 0;
+      for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+        const int nt = (int)(item % a.ntn);
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % NS, ph = (it / NS) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], IMG);
+          bulk_g2s(smem + (size_t)s * stage_bytes + 2 * zbytes, a.wimg + ((size_t)nt * KB + kb) * IMG, IMG, &full_bar[s]);
+        }
       }
     }
   }
   fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == 8) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 template <int DIM, int NT, int KC>
-int launch_up_t(const UpArgs& a, const UpGeom& g, cudaStream_t st) {
+int launch_up_t(UpArgs a, const UpGeom& g, cudaStream_t st) {
   const size_t stage = (size_t)2 * (KC / 8) * a.slots * 16 + g.img;
+  const int64_t units = a.mtiles * g.ntiles * g.KB;
+  constexpr int tcols = 2 * (DIM == 2 ? 4 : 1) * NT;
+  const bool two = tcols <= 256;                       // TMEM allows two CTAs per SM
+  int ns = two ? (int)((110 * 1024) / stage) : 0;
+  bool pair = ns >= 2;
+  if (!pair) ns = (int)((200 * 1024) / stage);
+  ns = std::min(ns, UP_MAXST);
+  LSHM_REQUIRE(ns >= 1, "igemm_up: tile does not fit in shared memory");
+  a.nstage = (int)std::min<int64_t>(ns, std::max<int64_t>(1, units));
   const size_t smem = stage * a.nstage;
   LSHM_CUDA(cudaFuncSetAttribute(igemm_up_kernel<DIM, NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_up");
-  dim3 grid((unsigned)ceil_div(a.Q, 128), (unsigned)g.ntiles);
-  igemm_up_kernel<DIM, NT, KC><<<grid, 192, smem, st>>>(a);
+  const int64_t grid = std::min<int64_t>(a.mtiles * g.ntiles, (int64_t)sm_count() * (pair ? 2 : 1));
+  igemm_up_kernel<DIM, NT, KC><<<(unsigned)grid, UP_THREADS, smem, st>>>(a);
   LSHM_CHECK_LAUNCH("igemm_up");
   return LSHM_OK;
 }
@@ -293,10 +341,8 @@ int launch_up(int dim, UpArgs a, cudaStream_t st) {
   a.slots = dim == 2 ? (128 + 2 * (a.w + 2) + 7) / 8 * 8 : 128;
   a.Q = dim == 2 ? a.N * (int64_t)(a.h + 1) * (a.w + 1) : a.N * (int64_t)a.w;
   LSHM_REQUIRE(a.Q < (1LL << 31) - 4096, "lshm_up: too many positions (%lld) for one call; split the batch", (long long)a.Q);
-  const size_t stage = (size_t)2 * (g.KC / 8) * a.slots * 16 + g.img;
-  int ns = (int)std::min<size_t>(4, std::max<size_t>(1, (96 * 1024) / stage));
-  if (ns < 2 && 2 * stage <= 200 * 1024) ns = 2;
-  a.nstage = std::min(ns, g.KB);
+  a.mtiles = ceil_div(a.Q, 128);
+  a.ntn = g.ntiles;
 #define LU(D, NTV, KCV) return launch_up_t<D, NTV, KCV>(a, g, st)
   if (dim == 2) {
     switch (g.NT) { case 16: LU(2, 16, 16); case 32: LU(2, 32, 16); default: LU(2, 48, 16); }
