@@ -1,0 +1,63 @@
+"""Multi-GPU parity check (run under torchrun on >= 2 GPUs; not collected by pytest):
+each rank takes its shard of whole baseline groups, runs the fused closure with the NCCL exchange,
+and rank 0 compares the all-reduced loss and gradients with the unsharded CPU oracle.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29533 tests/dp_check.py
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from common import SCALES, closure_case, oracle_closure, rel_err  # noqa: E402
+from lshm_b200 import parallel  # noqa: E402
+from lshm_b200.kharmonic_lofar import DeepKHarmonicStep  # noqa: E402
+from lshm_b200.lofar_models import AutoEncoder1DCNN, AutoEncoderCNN2, Kmeans  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    case = closure_case(N=8, bpb=2)
+    hs = torch.tensor(SCALES).to(dev)
+    net = AutoEncoderCNN2(case["L"], case["C"], hs, True)
+    netT = AutoEncoder1DCNN(case["Lt"], case["C"], hs, True)
+    netF = AutoEncoder1DCNN(case["Lt"], case["C"], hs, True)
+    mod = Kmeans(case["L"] + 2 * case["Lt"], case["K"], 4)
+    if rank == 0:   # only rank 0 gets the real parameters: the constructor must broadcast them
+        net.load_state_dict(case["pn"]); netT.load_state_dict(case["pT"]); netF.load_state_dict(case["pF"])
+        mod.load_state_dict({"M": case["M"]})
+    step = DeepKHarmonicStep(net.to(dev), netT.to(dev), netF.to(dev), mod.to(dev), distributed=True)
+    r0, r1 = parallel.shard_rows(case["N"], case["bpb"], rank, world)
+    npix = case["C"] * 16384
+    step.set_batch(case["x"][r0:r1].to(dev), case["uv"][r0:r1].to(dev), case["bpb"], global_patches=case["N"])
+    for dst, src in zip((step.y1, step.y2, step.y3), case["ys"]):
+        dst.copy_(src[r0 * npix:r1 * npix].to(dev))
+    loss = float(step.closure())
+    with torch.no_grad():
+        loss_fwd = float(step.closure())
+    losses = [None] * world
+    dist.all_gather_object(losses, loss)
+    if rank == 0:
+        ref = oracle_closure(case)
+        worst = max(rel_err(p.grad, ref["grads"][nm]) for nm, p in zip(step.flat.names, step.flat.params))
+        ok = (abs(loss - ref["total"]) < 5e-5 * abs(ref["total"]) and abs(loss_fwd - loss) < 1e-6 * abs(loss)
+              and worst < 2e-4 and len(set(losses)) == 1)
+        print(f"dp_check world={world}: loss {loss:.7f} oracle {ref['total']:.7f} worst grad rel err {worst:.2e} "
+              f"identical loss on all ranks: {len(set(losses)) == 1} -> {'PASS' if ok else 'FAIL'}")
+        if not ok:
+            sys.exit(1)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
