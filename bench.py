@@ -203,7 +203,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if distributed:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     sampler = ClockSampler(local)
     sampler.start()
     step, opt = build_step(dev, rank, world, distributed)
@@ -282,15 +283,22 @@ def run_ours(args):
                h2d_bytes_per_step=int(vis_h.numel() + sc_h.numel() * 4 + uv_h.numel() * 4), d2h_bytes_per_step=9 * 4,
                steps=e2e_steps, note="fresh minibatch from pinned host int8 every step + loss read-back")
 
-    out = None
+    # ---- per-kernel device times (CUDA events) over two extra steps -> dominant kernel roofline.
+    #      Every rank runs the steps (the closure contains the all-reduce); rank 0 records.
+    prof_steps = 2
+    agg = None
     if rank == 0:
-        pk = peaks()
-        # ---- per-kernel device times (CUDA events) over two extra steps -> dominant kernel roofline
-        prof_steps = 2
         with KernelProfiler(L) as kp:
             for _ in range(prof_steps):
                 one_step()
             agg = kp.summary(prof_steps)
+    else:
+        for _ in range(prof_steps):
+            one_step()
+    barrier()
+    out = None
+    if rank == 0:
+        pk = peaks()
         total_ms = sum(d["ms_per_step"] for d in agg.values())
         top = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
         name, d = top[0]
@@ -312,7 +320,8 @@ def run_ours(args):
                     fh.write(f"{k},{v['calls'] // prof_steps},{v['ms_per_step']:.4f},{v['ms_per_step'] / total_ms:.4f},"
                              f"{v['bytes'] / s_ / 1e9 if s_ else 0:.1f},{v['flops'] / s_ / 1e12 if s_ else 0:.2f}\n")
                 fh.write(f"TOTAL,,{total_ms:.4f},1.0,,\n")
-        cpu = cpu_baseline(sample_patches=args.cpu_patches, steps=1)
+        # the CPU arm is timed on rank 0 at N=1 only (contract); other world sizes report null
+        cpu = cpu_baseline(sample_patches=args.cpu_patches, steps=1) if world == 1 else None
         out = {
             "metric": "train patches/sec (fwd+bwd+K-harmonic)", "value": value, "unit": "patches/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
