@@ -42,6 +42,14 @@ __device__ __forceinline__ float pow_pm2(float d2, float p, int pmode) {  // d^(
   return powf(d2, 0.5f * (p - 2.f));
 }
 
+// ---- packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2): halves the issue slots of the distance loop,
+//      which is what bounds the K <= 16 (HBM-side) cases
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 template <int TPP>
 __device__ __forceinline__ float lanes_sum(float v) {
 #pragma unroll
@@ -52,16 +60,45 @@ __device__ __forceinline__ float lanes_sum(float v) {
 // squared distance between the lane's slice of x and the matching slice of centre row `mrow`
 template <int TPP>
 __device__ __forceinline__ float dist2(const float4 (&x4)[KHM_MAXCH], const float* mrow, int s, int nch) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  f32x2 a0 = 0ull, a1 = 0ull;   // two packed accumulators = four independent chains
 #pragma unroll
   for (int c = 0; c < KHM_MAXCH; ++c) {
     if (c < nch) {
       const float4 m = *reinterpret_cast<const float4*>(mrow + ((c * TPP + s) << 2));
-      const float dx = x4[c].x - m.x, dy = x4[c].y - m.y, dz = x4[c].z - m.z, dw = x4[c].w - m.w;
-      a0 = fmaf(dx, dx, a0); a1 = fmaf(dy, dy, a1); a2 = fmaf(dz, dz, a2); a3 = fmaf(dw, dw, a3);
+      const f32x2 d0 = sub2(pk2(x4[c].x, x4[c].y), pk2(m.x, m.y));
+      const f32x2 d1 = sub2(pk2(x4[c].z, x4[c].w), pk2(m.z, m.w));
+      a0 = fma2(d0, d0, a0);
+      a1 = fma2(d1, d1, a1);
     }
   }
-  return lanes_sum<TPP>((a0 + a1) + (a2 + a3));
+  float p, q, r, t;
+  upk2(a0, p, q); upk2(a1, r, t);
+  return lanes_sum<TPP>((p + q) + (r + t));
+}
+
+// two points against one centre row: every broadcast LDS.128 of the centre feeds both points.  A warp-wide
+// 16-byte shared load costs 4 crossbar cycles even when it is a broadcast, so with one point per thread
+// the distance loop is shared-memory-bound at ~32 (point,k,l) elements per clock per SM (measured: 25).
+template <int TPP>
+__device__ __forceinline__ void dist2x2(const float4 (&xa)[KHM_MAXCH], const float4 (&xb)[KHM_MAXCH], const float* mrow,
+                                        int s, int nch, float& da, float& db) {
+  f32x2 a0 = 0ull, a1 = 0ull, b0 = 0ull, b1 = 0ull;
+#pragma unroll
+  for (int c = 0; c < KHM_MAXCH; ++c) {
+    if (c < nch) {
+      const float4 m = *reinterpret_cast<const float4*>(mrow + ((c * TPP + s) << 2));
+      const f32x2 m0 = pk2(m.x, m.y), m1 = pk2(m.z, m.w);
+      const f32x2 p0 = sub2(pk2(xa[c].x, xa[c].y), m0), p1 = sub2(pk2(xa[c].z, xa[c].w), m1);
+      const f32x2 q0 = sub2(pk2(xb[c].x, xb[c].y), m0), q1 = sub2(pk2(xb[c].z, xb[c].w), m1);
+      a0 = fma2(p0, p0, a0); a1 = fma2(p1, p1, a1);
+      b0 = fma2(q0, q0, b0); b1 = fma2(q1, q1, b1);
+    }
+  }
+  float p, q, r, t;
+  upk2(a0, p, q); upk2(a1, r, t);
+  da = lanes_sum<TPP>((p + q) + (r + t));
+  upk2(b0, p, q); upk2(b1, r, t);
+  db = lanes_sum<TPP>((p + q) + (r + t));
 }
 
 template <int TPP>
@@ -89,37 +126,43 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass1_kernel(KhmArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* ms = smem;  // RESIDENT: K*L, else KC*L
   __shared__ double red[32];
-  constexpr int PTS = KHM_THREADS / TPP;
+  constexpr int PTS = KHM_THREADS / TPP;        // a tile is 2*PTS points: two per thread group
   const int L = a.L, K = a.K, nch = L / (4 * TPP);
   const int pt = threadIdx.x / TPP, s = threadIdx.x % TPP;
-  const int64_t ntiles = (a.N + PTS - 1) / PTS;
+  const int64_t ntiles = (a.N + 2 * PTS - 1) / (2 * PTS);
   const float Kf = (float)K;
   double lsum = 0.0;
   if (RESIDENT) { stage_centres(ms, a.M, 0, K, L); __syncthreads(); }
   const float inv_group = a.group > 0 ? 1.f / (float)a.group : 0.f;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int64_t i = t * PTS + pt;
-    const bool valid = i < a.N;
-    float4 x4[KHM_MAXCH];
-    load_point<TPP>(x4, a.X, a.ldx, i, valid, s, nch);
-    float e = 0.f, best = 3.4e38f;
-    int besti = 0;
+    const int64_t ia = t * 2 * PTS + pt, ib = ia + PTS;
+    const bool va = ia < a.N, vb = ib < a.N;
+    float4 xa[KHM_MAXCH], xb[KHM_MAXCH];
+    load_point<TPP>(xa, a.X, a.ldx, ia, va, s, nch);
+    load_point<TPP>(xb, a.X, a.ldx, ib, vb, s, nch);
+    float ea = 0.f, eb = 0.f, besta = 3.4e38f, bestb = 3.4e38f;
+    int bia = 0, bib = 0;
     for (int k0 = 0; k0 < K; k0 += (RESIDENT ? K : KHM_KC)) {
       const int kc = RESIDENT ? K : min(KHM_KC, K - k0);
       if (!RESIDENT) { __syncthreads(); stage_centres(ms, a.M, k0, kc, L); __syncthreads(); }
+#pragma unroll 2
       for (int kk = 0; kk < kc; ++kk) {
-        const float d2 = dist2<TPP>(x4, ms + kk * L, s, nch);
-        const float dp = pow_p(d2, a.p, a.pmode);
-        e += 1.0f / (dp + KHM_EPS);
-        if (d2 < best) { best = d2; besti = k0 + kk; }
-        if (a.dist != nullptr && valid && s == 0)
-          atomicAdd(a.dist + (i / a.group) * K + (k0 + kk), dp * inv_group);
+        float da, db;
+        dist2x2<TPP>(xa, xb, ms + kk * L, s, nch, da, db);
+        const float pa = pow_p(da, a.p, a.pmode), pb = pow_p(db, a.p, a.pmode);
+        ea += __frcp_rn(pa + KHM_EPS);
+        eb += __frcp_rn(pb + KHM_EPS);
+        if (da < besta) { besta = da; bia = k0 + kk; }
+        if (db < bestb) { bestb = db; bib = k0 + kk; }
+        if (a.dist != nullptr && s == 0) {
+          if (va) atomicAdd(a.dist + (ia / a.group) * K + (k0 + kk), pa * inv_group);
+          if (vb) atomicAdd(a.dist + (ib / a.group) * K + (k0 + kk), pb * inv_group);
+        }
       }
     }
-    if (valid && s == 0) {
-      lsum += (double)(Kf / (e + KHM_EPS));
-      if (a.e_out) a.e_out[i] = e;
-      if (a.ids) a.ids[i] = besti;
+    if (s == 0) {
+      if (va) { lsum += (double)(Kf / (ea + KHM_EPS)); if (a.e_out) a.e_out[ia] = ea; if (a.ids) a.ids[ia] = bia; }
+      if (vb) { lsum += (double)(Kf / (eb + KHM_EPS)); if (a.e_out) a.e_out[ib] = eb; if (a.ids) a.ids[ib] = bib; }
     }
   }
   if (a.loss_sum != nullptr) {
@@ -200,10 +243,11 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass2_kernel(KhmArgs a) {
           for (int c = 0; c < KHM_MAXCH; ++c) {
             if (c < nch) {
               const float4 m = *reinterpret_cast<const float4*>(mrow + ((c * TPP + s) << 2));
-              g4[c].x = fmaf(w, x4[c].x - m.x, g4[c].x);
-              g4[c].y = fmaf(w, x4[c].y - m.y, g4[c].y);
-              g4[c].z = fmaf(w, x4[c].z - m.z, g4[c].z);
-              g4[c].w = fmaf(w, x4[c].w - m.w, g4[c].w);
+              const f32x2 w2 = pk2(w, w);
+              const f32x2 r0 = fma2(w2, sub2(pk2(x4[c].x, x4[c].y), pk2(m.x, m.y)), pk2(g4[c].x, g4[c].y));
+              const f32x2 r1 = fma2(w2, sub2(pk2(x4[c].z, x4[c].w), pk2(m.z, m.w)), pk2(g4[c].z, g4[c].w));
+              upk2(r0, g4[c].x, g4[c].y);
+              upk2(r1, g4[c].z, g4[c].w);
             }
           }
         }
@@ -329,8 +373,8 @@ int launch_pass2_t(const KhmArgs& a, size_t smem, int grid, cudaStream_t st) {
   return LSHM_OK;
 }
 
-int grid_for(int64_t N, int tpp, int blocks_per_sm) {
-  const int pts = KHM_THREADS / tpp;
+int grid_for(int64_t N, int tpp, int blocks_per_sm, int ppt = 1) {
+  const int pts = ppt * KHM_THREADS / tpp;
   const int64_t ntiles = ceil_div(N, pts);
   const int64_t cap = (int64_t)sm_count() * blocks_per_sm;
   return (int)(ntiles < cap ? (ntiles > 0 ? ntiles : 1) : cap);
@@ -341,7 +385,7 @@ int launch_pass1(const KhmArgs& a, cudaStream_t st) {
   const size_t res_bytes = (size_t)a.K * a.L * sizeof(float);
   const bool res = res_bytes <= RESIDENT_SMEM_LIMIT;
   const size_t smem = res ? res_bytes : (size_t)KHM_KC * a.L * sizeof(float);
-  const int grid = grid_for(a.N, tpp, 8);
+  const int grid = grid_for(a.N, tpp, 8, 2);
 #define P1(T) (res ? launch_pass1_t<T, true>(a, smem, grid, st) : launch_pass1_t<T, false>(a, smem, grid, st))
   switch (tpp) {
     case 1: return P1(1);
