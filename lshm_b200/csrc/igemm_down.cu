@@ -43,7 +43,7 @@ constexpr int MAXST = 6;
 // so the bytes in flight per SM are set by the stage ring (tens of KB), not by the register file -
 // the register-staged path topped out near 25% of HBM bandwidth on the 16384-sample maps.
 template <int DIM, int NT, int KC, bool RAW>
-__global__ void __launch_bounds__(DOWN_THREADS) igemm_down_kernel(DownArgs a) {
+__global__ void __launch_bounds__(DOWN_THREADS, 3) igemm_down_kernel(DownArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[MAXST], empty_bar[MAXST], raw_bar[MAXST], acc_full[2], acc_empty[2], w_bar;
   __shared__ uint32_t tmem_base;
@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(DOWN_THREADS) igemm_down_kernel(DownArgs a) {
   constexpr uint32_t TMEM_COLS = 2 * NT <= 32 ? 32 : (2 * NT <= 64 ? 64 : (2 * NT <= 128 ? 128 : 256));
   const int SLOTS = a.slots, NS = a.nstage;
   constexpr int BPB = KC / 4;                      // big-map channels per K block
+  constexpr int NSLOT = DIM == 2 ? 2 : 1;          // staged slots per producer thread (1-D tiles: 128 slots)
   const uint32_t zbytes = (uint32_t)CC * SLOTS * 16;
   const uint32_t rawb = RAW ? (uint32_t)a.rawbytes : 0u;
   const uint32_t stage_bytes = rawb + 2 * zbytes + IMG;
@@ -207,9 +208,9 @@ __global__ void __launch_bounds__(DOWN_THREADS) igemm_down_kernel(DownArgs a) {
     uint32_t it = 0;
     for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
       const int64_t q0 = (item / a.ntn) * 128;
-      const float* sp[2]; bool sv[2], full[2], r0ok[2], r1ok[2], c0ok[2], c1ok[2]; int sj[2];
+      const float* sp[NSLOT]; bool sv[NSLOT], full[NSLOT], r0ok[NSLOT], r1ok[NSLOT], c0ok[NSLOT], c1ok[NSLOT]; int sj[NSLOT];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < NSLOT; ++i) {
         const int s = ptid + i * 128;
         const int64_t q = q0 + s;
         sv[i] = s < SLOTS && q < a.Q;
@@ -236,27 +237,29 @@ __global__ void __launch_bounds__(DOWN_THREADS) igemm_down_kernel(DownArgs a) {
         uint8_t* zlo = zhi + zbytes;
         const int ccb = (min(KC, Kc - kb * KC)) >> 3;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        // fetch every chunk column of both slots before converting any (loads in flight)
-        float v[2][CC][8];
+        // per slot: fetch every chunk column, then convert (32 data registers -> 3 CTAs per SM)
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NSLOT; ++i) {
+          const int slot = ptid + i * 128;
+          if (slot >= SLOTS) continue;
+          float v[CC][8];
 #pragma unroll
           for (int cc = 0; cc < CC; ++cc) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[i][cc][e] = 0.f;
+            for (int e = 0; e < 8; ++e) v[cc][e] = 0.f;
             const int b0 = 2 * (kb * CC + cc);          // Bc % 4 == 0: a chunk column is all-valid or all-padding
             if (cc < ccb && sv[i] && b0 < a.Bc) {
               if (DIM == 2) {
                 const float* p0 = sp[i] + (int64_t)b0 * HW;
                 const float* p1 = p0 + HW;
                 if (full[i]) {
-                  v[i][cc][0] = __ldg(p0); v[i][cc][1] = __ldg(p0 + 1); v[i][cc][2] = __ldg(p0 + W); v[i][cc][3] = __ldg(p0 + W + 1);
-                  v[i][cc][4] = __ldg(p1); v[i][cc][5] = __ldg(p1 + 1); v[i][cc][6] = __ldg(p1 + W); v[i][cc][7] = __ldg(p1 + W + 1);
+                  v[cc][0] = __ldg(p0); v[cc][1] = __ldg(p0 + 1); v[cc][2] = __ldg(p0 + W); v[cc][3] = __ldg(p0 + W + 1);
+                  v[cc][4] = __ldg(p1); v[cc][5] = __ldg(p1 + 1); v[cc][6] = __ldg(p1 + W); v[cc][7] = __ldg(p1 + W + 1);
                 } else {
-                  if (r0ok[i] && c0ok[i]) { v[i][cc][0] = __ldg(p0); v[i][cc][4] = __ldg(p1); }
-                  if (r0ok[i] && c1ok[i]) { v[i][cc][1] = __ldg(p0 + 1); v[i][cc][5] = __ldg(p1 + 1); }
-                  if (r1ok[i] && c0ok[i]) { v[i][cc][2] = __ldg(p0 + W); v[i][cc][6] = __ldg(p1 + W); }
-                  if (r1ok[i] && c1ok[i]) { v[i][cc][3] = __ldg(p0 + W + 1); v[i][cc][7] = __ldg(p1 + W + 1); }
+                  if (r0ok[i] && c0ok[i]) { v[cc][0] = __ldg(p0); v[cc][4] = __ldg(p1); }
+                  if (r0ok[i] && c1ok[i]) { v[cc][1] = __ldg(p0 + 1); v[cc][5] = __ldg(p1 + 1); }
+                  if (r1ok[i] && c0ok[i]) { v[cc][2] = __ldg(p0 + W); v[cc][6] = __ldg(p1 + W); }
+                  if (r1ok[i] && c1ok[i]) { v[cc][3] = __ldg(p0 + W + 1); v[cc][7] = __ldg(p1 + W + 1); }
                 }
               } else {
                 const int64_t Lb = 4 * (int64_t)a.w;
@@ -265,29 +268,23 @@ __global__ void __launch_bounds__(DOWN_THREADS) igemm_down_kernel(DownArgs a) {
                 if (a.pad == 0) {
                   const float4 x0 = __ldg(reinterpret_cast<const float4*>(p0));
                   const float4 x1 = __ldg(reinterpret_cast<const float4*>(p1));
-                  v[i][cc][0] = x0.x; v[i][cc][1] = x0.y; v[i][cc][2] = x0.z; v[i][cc][3] = x0.w;
-                  v[i][cc][4] = x1.x; v[i][cc][5] = x1.y; v[i][cc][6] = x1.z; v[i][cc][7] = x1.w;
+                  v[cc][0] = x0.x; v[cc][1] = x0.y; v[cc][2] = x0.z; v[cc][3] = x0.w;
+                  v[cc][4] = x1.x; v[cc][5] = x1.y; v[cc][6] = x1.z; v[cc][7] = x1.w;
                 } else {
-                  if (sj[i] > 0) { v[i][cc][0] = __ldg(p0); v[i][cc][4] = __ldg(p1); }
-                  v[i][cc][1] = __ldg(p0 + 1); v[i][cc][2] = __ldg(p0 + 2); v[i][cc][3] = __ldg(p0 + 3);
-                  v[i][cc][5] = __ldg(p1 + 1); v[i][cc][6] = __ldg(p1 + 2); v[i][cc][7] = __ldg(p1 + 3);
+                  if (sj[i] > 0) { v[cc][0] = __ldg(p0); v[cc][4] = __ldg(p1); }
+                  v[cc][1] = __ldg(p0 + 1); v[cc][2] = __ldg(p0 + 2); v[cc][3] = __ldg(p0 + 3);
+                  v[cc][5] = __ldg(p1 + 1); v[cc][6] = __ldg(p1 + 2); v[cc][7] = __ldg(p1 + 3);
                 }
               }
             }
           }
-        }
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int slot = ptid + i * 128;
-          if (slot < SLOTS) {
-#pragma unroll
-            for (int cc = 0; cc < CC; ++cc) {
-              if (cc < ccb) {
-                uint4 hi, lo;
-                split8(v[i][cc], hi, lo);
-                *reinterpret_cast<uint4*>(zhi + ((size_t)cc * SLOTS + slot) * 16) = hi;
-                *reinterpret_cast<uint4*>(zlo + ((size_t)cc * SLOTS + slot) * 16) = lo;
-              }
+          for (int cc = 0; cc < CC; ++cc) {
+            if (cc < ccb) {
+              uint4 hi, lo;
+              split8(v[cc], hi, lo);
+              *reinterpret_cast<uint4*>(zhi + ((size_t)cc * SLOTS + slot) * 16) = hi;
+              *reinterpret_cast<uint4*>(zlo + ((size_t)cc * SLOTS + slot) * 16) = lo;
             }
           }
         }
@@ -379,18 +376,17 @@ __global__ void __launch_bounds__(DOWN_THREADS) igemm_down_kernel(DownArgs a) {
           mbar_wait(&full_bar[s], ph);
           fence_after();
           const uint32_t zhi = smem_u32(smem + (size_t)s * stage_bytes) + rawb;
-          const uint32_t zlo = zhi + zbytes;
-          const uint32_t bhi = wres ? smem_u32(wres_ptr) : zlo + zbytes;
-          const uint32_t blo = bhi + IMG / 2;
+          const uint32_t bhi = wres ? smem_u32(wres_ptr) : zhi + 2 * zbytes;
+          const uint64_t dah = make_desc(zhi, SLOTS * 16, 128), dal = make_desc(zhi + zbytes, SLOTS * 16, 128);
+          const uint64_t dbh = make_desc(bhi, NT * 16, 128), dbl = make_desc(bhi + IMG / 2, NT * 16, 128);
           const int ksteps = (min(KC, Kc - kb * KC)) >> 4;
 #pragma unroll
           for (int tap = 0; tap < T; ++tap) {
             const uint32_t shift = DIM == 2 ? (uint32_t)((tap >> 1) * PW + (tap & 1)) : 0u;
             for (int ks = 0; ks < ksteps; ++ks) {
-              const uint32_t aoff = ((uint32_t)(2 * ks) * SLOTS + shift) * 16;
-              const uint32_t boff = ((uint32_t)(tap * CC + 2 * ks) * NT) * 16;
-              mma_split3(tmem + buf * NT, make_desc(zhi + aoff, SLOTS * 16, 128), make_desc(zlo + aoff, SLOTS * 16, 128),
-                         make_desc(bhi + boff, NT * 16, 128), make_desc(blo + boff, NT * 16, 128), idesc, acc);
+              const uint32_t ao = (uint32_t)(2 * ks) * SLOTS + shift;            // 16-byte units
+              const uint32_t bo = (uint32_t)(tap * CC + 2 * ks) * NT;
+              mma_split3(tmem + buf * NT, desc_off(dah, ao), desc_off(dal, ao), desc_off(dbh, bo), desc_off(dbl, bo), idesc, acc);
               acc = 1;
             }
           }
@@ -433,15 +429,17 @@ int launch_down_t(DownArgs a, const DownGeom& g, cudaStream_t st) {
   const size_t stage = (size_t)(RAW ? a.rawbytes : 0) + (size_t)2 * (KC / 8) * a.slots * 16 + g.img;
   const int64_t units = a.mtiles * g.ntiles * g.KB;
   // two CTAs per SM when the ring fits in ~110 KB each (227 KB per SM), else one CTA with a deep ring
-  const size_t half_sm = 110 * 1024, full_sm = 200 * 1024;
-  int ns = (int)((half_sm - g.img) / stage);
+  // three CTAs per SM when two stages fit in ~74 KB, else two, else one with a deep ring
+  const size_t third_sm = 74 * 1024, half_sm = 110 * 1024, full_sm = 200 * 1024;
+  int ns = (int)((third_sm - g.img) / stage);
+  if (ns < 2) ns = (int)((half_sm - g.img) / stage);
   if (RAW || ns < 2) ns = (int)((full_sm - g.img) / stage);
   ns = std::min(ns, MAXST);
   LSHM_REQUIRE(ns >= 1, "igemm_down: tile does not fit in shared memory");
   a.nstage = (int)std::min<int64_t>(ns, std::max<int64_t>(1, units));
   const size_t smem = stage * a.nstage + g.img;   // + resident weight image (used when KB == ntiles == 1)
   LSHM_CUDA(cudaFuncSetAttribute(igemm_down_kernel<DIM, NT, KC, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_down");
-  const int per_sm = smem <= 112 * 1024 ? 2 : 1;
+  const int per_sm = smem <= 74 * 1024 ? 3 : (smem <= 112 * 1024 ? 2 : 1);
   const int64_t grid = std::min<int64_t>(a.mtiles * g.ntiles, (int64_t)sm_count() * per_sm);
   igemm_down_kernel<DIM, NT, KC, RAW><<<(unsigned)grid, DOWN_THREADS, smem, st>>>(a);
   LSHM_CHECK_LAUNCH("igemm_down");

@@ -42,13 +42,14 @@ __device__ __forceinline__ float epi_apply(float acc, float bias, int epi, float
 // stage ring, the MMA warp alternates between two TMEM accumulator sets (each = 4 parity classes in
 // 2-D), the epilogue warps drain one set while the next is being computed.
 template <int DIM, int NT, int KC>
-__global__ void __launch_bounds__(UP_THREADS) igemm_up_kernel(UpArgs a) {
+__global__ void __launch_bounds__(UP_THREADS, (DIM == 1 ? 3 : 2)) igemm_up_kernel(UpArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[UP_MAXST], empty_bar[UP_MAXST], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base;
   constexpr int NCLS = DIM == 2 ? 4 : 1;
   constexpr int COMBOS = DIM == 2 ? 16 : 1;       // class x tap weight tiles per K block
   constexpr int CC = KC / 8;
+  constexpr int NSLOT = DIM == 2 ? 3 : 1;         // staged slots per producer thread (1-D tiles: 128 slots)
   constexpr uint32_t IMG = 2u * COMBOS * CC * NT * 16;
   constexpr uint32_t TSET = NCLS * NT;            // TMEM columns of one accumulator set
   constexpr uint32_t TCOLS = 2 * TSET;
@@ -81,9 +82,9 @@ __global__ void __launch_bounds__(UP_THREADS) igemm_up_kernel(UpArgs a) {
     uint32_t it = 0;
     for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
       const int64_t q0 = (item / a.ntn) * 128;
-      const float* sp[3]; bool sv[3];
+      const float* sp[NSLOT]; bool sv[NSLOT];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
+      for (int i = 0; i < NSLOT; ++i) {
         const int s = ptid + i * 128;
         const int64_t q = q0 - halo + s;
         sv[i] = s < SLOTS && q >= 0 && q < a.Q;
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(UP_THREADS) igemm_up_kernel(UpArgs a) {
         uint8_t* zlo = zhi + zbytes;
         const int ccb = (min(KC, Apad - kb * KC)) >> 3;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < NSLOT; ++i) {
           const int slot = ptid + i * 128;
           if (slot >= SLOTS) continue;
           float v[CC][8];
@@ -250,6 +251,22 @@ __global__ void __launch_bounds__(UP_THREADS) igemm_up_kernel(UpArgs a) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(NT, 0, 0);
       uint32_t it = 0, tc_ = 0;
+      // The issuing thread is a serial chain: descriptor offsets of the 16 (class, tap) pairs are
+      // computed once (16-byte units), per MMA only one 32-bit add per descriptor remains.
+      uint32_t aoff[COMBOS], boff[COMBOS];
+#pragma unroll
+      for (int cb = 0; cb < COMBOS; ++cb) {
+        if (DIM == 2) {
+          const int cls = cb >> 2, tap = cb & 3;
+          const int ry = cls >> 1, rx = cls & 1, d = tap >> 1, e = tap & 1;
+          const int dy = ry == 0 ? (d == 0 ? 0 : -1) : (d == 0 ? 1 : 0);
+          const int dx = rx == 0 ? (e == 0 ? 0 : -1) : (e == 0 ? 1 : 0);
+          aoff[cb] = (uint32_t)(halo + dy * PW + dx);
+          boff[cb] = (uint32_t)(cb * CC * NT);
+        } else {
+          aoff[cb] = 0; boff[cb] = 0;
+        }
+      }
       for (int64_t item = blockIdx.x; item < total; item += gridDim.x, ++tc_) {
         const uint32_t buf = tc_ & 1;
         mbar_wait(&acc_empty[buf], ((tc_ >> 1) & 1) ^ 1);
@@ -260,36 +277,17 @@ __global__ void __launch_bounds__(UP_THREADS) igemm_up_kernel(UpArgs a) {
           mbar_wait(&full_bar[s], ph);
           fence_after();
           const uint32_t zhi = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t zlo = zhi + zbytes;
-          const uint32_t bhi = zlo + zbytes;
-          const uint32_t blo = bhi + IMG / 2;
+          const uint64_t dah = make_desc(zhi, SLOTS * 16, 128), dal = make_desc(zhi + zbytes, SLOTS * 16, 128);
+          const uint64_t dbh = make_desc(zhi + 2 * zbytes, NT * 16, 128), dbl = make_desc(zhi + 2 * zbytes + IMG / 2, NT * 16, 128);
           const int ksteps = (min(KC, Apad - kb * KC)) >> 4;
-          if (DIM == 2) {
 #pragma unroll
-            for (int cls = 0; cls < 4; ++cls) {
-              const int ry = cls >> 1, rx = cls & 1;
-#pragma unroll
-              for (int tap = 0; tap < 4; ++tap) {
-                const int d = tap >> 1, e = tap & 1;
-                const int dy = ry == 0 ? (d == 0 ? 0 : -1) : (d == 0 ? 1 : 0);
-                const int dx = rx == 0 ? (e == 0 ? 0 : -1) : (e == 0 ? 1 : 0);
-                const uint32_t row0 = (uint32_t)(halo + dy * PW + dx);
-                for (int ks = 0; ks < ksteps; ++ks) {
-                  const uint32_t aoff = ((uint32_t)(2 * ks) * SLOTS + row0) * 16;
-                  const uint32_t boff = ((uint32_t)((cls * 4 + tap) * CC + 2 * ks) * NT) * 16;
-                  mma_split3(tset + cls * NT, make_desc(zhi + aoff, SLOTS * 16, 128), make_desc(zlo + aoff, SLOTS * 16, 128),
-                             make_desc(bhi + boff, NT * 16, 128), make_desc(blo + boff, NT * 16, 128), idesc,
-                             (kb > 0 || tap > 0 || ks > 0) ? 1u : 0u);
-                }
-              }
-            }
-          } else {
+          for (int cb = 0; cb < COMBOS; ++cb) {
+            const uint32_t td = DIM == 2 ? tset + (cb >> 2) * NT : tset;
+            const uint32_t first = DIM == 2 ? ((cb & 3) == 0 ? 1u : 0u) : 1u;   // first tap of a class
             for (int ks = 0; ks < ksteps; ++ks) {
-              const uint32_t aoff = ((uint32_t)(2 * ks) * SLOTS) * 16;
-              const uint32_t boff = ((uint32_t)(2 * ks) * NT) * 16;
-              mma_split3(tset, make_desc(zhi + aoff, SLOTS * 16, 128), make_desc(zlo + aoff, SLOTS * 16, 128),
-                         make_desc(bhi + boff, NT * 16, 128), make_desc(blo + boff, NT * 16, 128), idesc,
-                         (kb > 0 || ks > 0) ? 1u : 0u);
+              const uint32_t ao = aoff[cb] + (uint32_t)(2 * ks) * SLOTS, bo = boff[cb] + (uint32_t)(2 * ks) * NT;
+              mma_split3(td, desc_off(dah, ao), desc_off(dal, ao), desc_off(dbh, bo), desc_off(dbl, bo), idesc,
+                         (kb > 0 || !first || ks > 0) ? 1u : 0u);
             }
           }
           commit(&empty_bar[s]);
@@ -322,15 +320,18 @@ int launch_up_t(UpArgs a, const UpGeom& g, cudaStream_t st) {
   const int64_t units = a.mtiles * g.ntiles * g.KB;
   constexpr int tcols = 2 * (DIM == 2 ? 4 : 1) * NT;
   const bool two = tcols <= 256;                       // TMEM allows two CTAs per SM
-  int ns = two ? (int)((110 * 1024) / stage) : 0;
-  bool pair = ns >= 2;
+  int per_sm = 1;
+  int ns = 0;
+  if (DIM == 1 && tcols <= 128) { ns = (int)((74 * 1024) / stage); if (ns >= 2) per_sm = 3; }
+  if (per_sm == 1 && two) { ns = (int)((110 * 1024) / stage); if (ns >= 2) per_sm = 2; }
+  bool pair = per_sm > 1;
   if (!pair) ns = (int)((200 * 1024) / stage);
   ns = std::min(ns, UP_MAXST);
   LSHM_REQUIRE(ns >= 1, "igemm_up: tile does not fit in shared memory");
   a.nstage = (int)std::min<int64_t>(ns, std::max<int64_t>(1, units));
   const size_t smem = stage * a.nstage;
   LSHM_CUDA(cudaFuncSetAttribute(igemm_up_kernel<DIM, NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_up");
-  const int64_t grid = std::min<int64_t>(a.mtiles * g.ntiles, (int64_t)sm_count() * (pair ? 2 : 1));
+  const int64_t grid = std::min<int64_t>(a.mtiles * g.ntiles, (int64_t)sm_count() * per_sm);
   igemm_up_kernel<DIM, NT, KC><<<(unsigned)grid, UP_THREADS, smem, st>>>(a);
   LSHM_CHECK_LAUNCH("igemm_up");
   return LSHM_OK;

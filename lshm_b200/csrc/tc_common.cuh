@@ -20,6 +20,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
 
+// descriptor = {lo: start address (>>4) + LBO, hi: SBO + version}; moving the start address by `off16`
+// 16-byte units is one 32-bit add on the low word (shared-memory addresses stay below the 14-bit field)
+__device__ __forceinline__ uint64_t desc_off(uint64_t d, uint32_t off16) {
+  uint32_t lo, hi;
+  asm("mov.b64 {%0,%1}, %2;" : "=r"(lo), "=r"(hi) : "l"(d));
+  lo += off16;
+  uint64_t r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+
 // instruction descriptor: bf16 x bf16 -> fp32, M = 128
 __host__ __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
