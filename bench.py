@@ -333,8 +333,7 @@ def run_ours(args):
     if distributed:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
-    if out is not None:
-        print(json.dumps(out))
+    return json.dumps(out) if out is not None else None
 
 
 # ------------------------------------------------------------------------------------------
@@ -389,7 +388,7 @@ def cpu_baseline(sample_patches=64, steps=1):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     n = args.cpu_patches
@@ -404,13 +403,29 @@ def run_reference(args):
     value = n / dt
     sample = (f"each step = closure+Adam+multiplier update on a {n}-patch sample of the cfg2 batch; oracle port of "
               "/root/reference/src/kharmonic_lofar.py:131-202 (the Python reference cannot travel to the GPU box)")
-    print(json.dumps({
+    return json.dumps({
         "impl": "reference", "metric": "train patches/sec (fwd+bwd+K-harmonic)", "value": value, "unit": "patches/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": min(args.warmup, 1),
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": dict(CFG, sample_patches=n),
         "cpu_baseline": dict(value=value, unit="patches/s", cores=cores, kind="port", sample=sample),
-        "e2e": dict(value=value, unit="patches/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)}))
+        "e2e": dict(value=value, unit="patches/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)})
+
+
+class StdoutToStderr:
+    """Everything written to fd 1 while active goes to stderr (NCCL prints its version banner on
+    stdout); the contract is ONE JSON line on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 def main():
@@ -422,10 +437,10 @@ def main():
     ap.add_argument("--cpu-patches", type=int, default=64)
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel CUDA-event table (CSV) here")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    with StdoutToStderr():
+        line = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if line is not None:
+        print(line, flush=True)
 
 
 if __name__ == "__main__":

@@ -228,6 +228,29 @@ def test_optimiser_contracts(cuda):
         assert np.isnan(float(step.closure()))
 
 
+def test_lbfgs_optimiser_drives_the_closure(cuda):
+    """A real quasi-Newton client (torch.optim.LBFGS with strong-Wolfe line search: many closure
+    re-evaluations per step, in-place parameter updates between them) on the fused closure."""
+    from lshm_b200.kharmonic_lofar import DeepKHarmonicStep
+    case = closure_case(N=4, bpb=2)
+    step = DeepKHarmonicStep(*build_modules(case, cuda))
+    step.set_batch(case["x"].to(cuda), case["uv"].to(cuda), 2)
+    opt = torch.optim.LBFGS(step.flat.params, lr=1.0, max_iter=4, history_size=7, line_search_fn="strong_wolfe")
+    calls = [0]
+
+    def closure():
+        calls[0] += 1
+        return step.closure()
+
+    with torch.no_grad():
+        l0 = float(step.closure())
+    for _ in range(2):
+        opt.step(closure)
+    with torch.no_grad():
+        l1 = float(step.closure())
+    assert calls[0] >= 4 and np.isfinite(l1) and l1 < l0
+
+
 def test_inference_loop(cuda):
     from lshm_b200.evaluate_clustering import encode_assign, evaluate
     case = closure_case(N=8, bpb=4)
