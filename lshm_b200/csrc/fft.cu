@@ -7,9 +7,10 @@
 // 128 KB with xhat) and the two output planes are written once (128 KB) - the algorithmic
 // minimum.  Each 128-point transform is 16 x 8 (Cooley-Tukey): a 16-point FFT in registers over
 // the stride-8 samples, the inter-stage twiddle, an exchange through shared memory, an 8-point
-// FFT in registers.  A warp owns 16 rows for the whole row pass and 16 columns for the whole
+// FFT in registers.  A warp owns 16 rows for the whole row pass and 8 columns for the whole
 // column pass, so the two register stages of a pass are separated by __syncwarp only; the block
-// synchronises once between the passes.  The first stage reads its samples straight from global
+// synchronises once between the passes.  The input is real: rows go through the complex FFT in
+// pairs and only the half spectrum (columns 0..64) is computed, the rest is its conjugate mirror.  The first stage reads its samples straight from global
 // memory (8 lanes = one 32-byte sector), the last stage applies the ortho scale, the fftshift and
 // the clamp and stores rows coalesced (lanes = consecutive columns).
 #include "common.cuh"
@@ -17,7 +18,7 @@
 namespace lshm {
 namespace {
 
-constexpr int FN = 128, FFT_THREADS = 256, FS = 144;   // FS: padded row stride (floats): +16 banks per row
+constexpr int FN = 128, FFT_THREADS = 256;
 
 struct cpx { float r, i; };
 __device__ __forceinline__ cpx cmul(cpx a, cpx b) { return {a.r * b.r - a.i * b.i, a.r * b.i + a.i * b.r}; }
@@ -63,17 +64,27 @@ __device__ __forceinline__ constexpr int brev4(int v) { return ((v & 1) << 3) | 
 
 __device__ __forceinline__ float clampn(float a, float c) { return a != a ? a : fminf(fmaxf(a, -c), c); }
 
-__global__ void __launch_bounds__(FFT_THREADS)
+constexpr int YS = 136;   // row stride (floats) of the per-warp stage-1 -> stage-2 exchange buffer
+constexpr int XS = 72;    // row stride (floats) of the half-spectrum X[128 rows][65 columns]
+
+// Real input: rows are transformed in PAIRS (z = a + i*b, one complex 128-point FFT, then
+// A[k] = (Z[k] + conj Z[-k])/2, B[k] = (Z[k] - conj Z[-k])/(2i)), and only columns k = 0..64 are kept:
+// the other half of the 2-D spectrum is the conjugate mirror F[-u,-v] = conj F[u,v], written from
+// the same registers.  Half the butterflies, half the shared memory (two CTAs per SM).
+__global__ void __launch_bounds__(FFT_THREADS, 2)
 fft2_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* __restrict__ out,
             int C, float clamp) {
   extern __shared__ __align__(16) float sm[];
-  float* re = sm;                 // [128][FS]
-  float* im = sm + FN * FS;       // [128][FS]
+  float* xre = sm;                          // [128][XS]
+  float* xim = xre + FN * XS;               // [128][XS]
+  float* ybase = xim + FN * XS;             // per warp: re[4][YS], im[4][YS]
   __shared__ float twr[FN], twi[FN];
-  const int64_t plane = blockIdx.x;           // n*C + c
+  const int64_t plane = blockIdx.x;         // n*C + c
   const int64_t n = plane / C;
   const int c = (int)(plane - n * C);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* yre = ybase + warp * (8 * YS);
+  float* yim = yre + 4 * YS;
   if (tid < FN) {
     float sn, cs;
     sincospif(-(float)tid / 64.f, &sn, &cs);  // exp(-2*pi*i*tid/128)
@@ -83,87 +94,127 @@ fft2_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* 
   const float* src = x + plane * FN * FN;
   const float* src2 = xhat ? xhat + plane * FN * FN : nullptr;
 
-  // ------------------------------------------------------------------ rows: warp w owns rows 16w..16w+15
-  for (int it = 0; it < 4; ++it) {
-    // stage 1: lane -> (row = 16w + 4it + lane/8, n2 = lane%8): 16-point FFT over n = 8*n1 + n2
-    const int r = warp * 16 + it * 4 + (lane >> 3), n2 = lane & 7;
-    cpx v[16];
-#pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-      float a = __ldg(src + r * FN + n1 * 8 + n2);
-      if (src2) a -= __ldg(src2 + r * FN + n1 * 8 + n2);
-      v[n1] = {a, 0.f};
-    }
-    fft_dif<16>(v);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {                 // register j holds k1 = brev4(j)
-      const int k1 = brev4(j);
-      const int t = k1 * n2;                       // twiddle exp(-2*pi*i*k1*n2/128)
-      const cpx y = cmul(v[j], cpx{twr[t], twi[t]});
-      re[r * FS + k1 * 8 + n2] = y.r;
-      im[r * FS + k1 * 8 + n2] = y.i;
-    }
-  }
-  __syncwarp();
-  for (int it = 0; it < 8; ++it) {
-    // stage 2: lane -> (row = 16w + 2it + lane/16, k1 = lane%16): 8-point FFT over n2
-    const int r = warp * 16 + it * 2 + (lane >> 4), k1 = lane & 15;
-    cpx v[8];
+  // ------------------------------------------------------------------ rows: warp w owns row pairs 8w..8w+7
+  for (int half = 0; half < 2; ++half) {
     {
-      const float4 a0 = *reinterpret_cast<const float4*>(re + r * FS + k1 * 8);
-      const float4 a1 = *reinterpret_cast<const float4*>(re + r * FS + k1 * 8 + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(im + r * FS + k1 * 8);
-      const float4 b1 = *reinterpret_cast<const float4*>(im + r * FS + k1 * 8 + 4);
-      v[0] = {a0.x, b0.x}; v[1] = {a0.y, b0.y}; v[2] = {a0.z, b0.z}; v[3] = {a0.w, b0.w};
-      v[4] = {a1.x, b1.x}; v[5] = {a1.y, b1.y}; v[6] = {a1.z, b1.z}; v[7] = {a1.w, b1.w};
-    }
-    fft_dif<8>(v);
-    __syncwarp();                                  // every lane has read its inputs of these two rows
+      // stage 1: lane -> (pair = 8w + 4*half + lane/8, n2 = lane%8): 16-point FFT over n = 8*n1 + n2
+      const int pl = lane >> 3, n2 = lane & 7;
+      const int ra = 2 * (warp * 8 + half * 4 + pl);
+      cpx v[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {                  // register j holds k2 = brev3(j); k = k1 + 16*k2
-      const int k = k1 + 16 * brev3(j);
-      re[r * FS + k] = v[j].r;
-      im[r * FS + k] = v[j].i;
+      for (int n1 = 0; n1 < 16; ++n1) {
+        float a = __ldg(src + ra * FN + n1 * 8 + n2), b = __ldg(src + (ra + 1) * FN + n1 * 8 + n2);
+        if (src2) { a -= __ldg(src2 + ra * FN + n1 * 8 + n2); b -= __ldg(src2 + (ra + 1) * FN + n1 * 8 + n2); }
+        v[n1] = {a, b};
+      }
+      fft_dif<16>(v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {               // register j holds k1 = brev4(j)
+        const int k1 = brev4(j);
+        const int t = k1 * n2;                     // twiddle exp(-2*pi*i*k1*n2/128)
+        const cpx y = cmul(v[j], cpx{twr[t], twi[t]});
+        yre[pl * YS + k1 * 8 + n2] = y.r;
+        yim[pl * YS + k1 * 8 + n2] = y.i;
+      }
     }
+    __syncwarp();
+    for (int sub = 0; sub < 2; ++sub) {
+      // stage 2: lane -> (pair-in-half = 2*sub + lane/16, k1 = lane%16): 8-point FFT over n2, then unpack
+      const int pl = 2 * sub + (lane >> 4), k1 = lane & 15;
+      const int ra = 2 * (warp * 8 + half * 4 + pl);
+      cpx v[8];
+      {
+        const float4 a0 = *reinterpret_cast<const float4*>(yre + pl * YS + k1 * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(yre + pl * YS + k1 * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(yim + pl * YS + k1 * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(yim + pl * YS + k1 * 8 + 4);
+        v[0] = {a0.x, b0.x}; v[1] = {a0.y, b0.y}; v[2] = {a0.z, b0.z}; v[3] = {a0.w, b0.w};
+        v[4] = {a1.x, b1.x}; v[5] = {a1.y, b1.y}; v[6] = {a1.z, b1.z}; v[7] = {a1.w, b1.w};
+      }
+      fft_dif<8>(v);                               // register j holds Z[k1 + 16*brev3(j)]
+      const int srcl = (lane & 16) | ((16 - k1) & 15);   // lane holding k1' = 16 - k1 of the same pair
+#pragma unroll
+      for (int k2 = 0; k2 < 5; ++k2) {
+        // partner Z[128-k]: (k1' = 16-k1, k2' = 7-k2) for k1 != 0, (0, (8-k2)%8) for k1 == 0
+        const int jo = brev3(k2), ja = brev3((7 - k2) & 7), jb = brev3((8 - k2) & 7);
+        float pr = 0.f, pi = 0.f;
+        if (k2 < 4) {
+          pr = __shfl_sync(0xffffffffu, v[ja].r, srcl);
+          pi = __shfl_sync(0xffffffffu, v[ja].i, srcl);
+        }
+        if (k1 == 0) { pr = v[jb].r; pi = v[jb].i; }
+        if (k2 < 4 || k1 == 0) {
+          const int k = k1 + 16 * k2;
+          const float zr = v[jo].r, zi = v[jo].i;
+          xre[ra * XS + k] = 0.5f * (zr + pr);        // A[k] = (Z[k] + conj Zp)/2
+          xim[ra * XS + k] = 0.5f * (zi - pi);
+          xre[(ra + 1) * XS + k] = 0.5f * (zi + pi);  // B[k] = -i/2 (Z[k] - conj Zp)
+          xim[(ra + 1) * XS + k] = -0.5f * (zr - pr);
+        }
+      }
+    }
+    __syncwarp();
   }
   __syncthreads();
 
-  // ------------------------------------------------------------------ columns: warp w owns columns 16w..16w+15
-  for (int it = 0; it < 4; ++it) {
-    // stage 1: lane -> (col = 16w + lane%16, n2 = 2it + lane/16): 16-point FFT over rows 8*n1 + n2, in place
-    const int col = warp * 16 + (lane & 15), n2 = it * 2 + (lane >> 4);
-    cpx v[16];
-#pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) v[n1] = {re[(n1 * 8 + n2) * FS + col], im[(n1 * 8 + n2) * FS + col]};
-    fft_dif<16>(v);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int k1 = brev4(j);
-      const int t = k1 * n2;
-      const cpx y = cmul(v[j], cpx{twr[t], twi[t]});
-      re[(k1 * 8 + n2) * FS + col] = y.r;
-      im[(k1 * 8 + n2) * FS + col] = y.i;
-    }
-  }
-  __syncwarp();
+  // ------------------------------------------------------------------ columns 0..64: warp w owns 8w..8w+7, warp 0 also column 64
   float* ore = out + ((n * 2 * C + c) * (int64_t)FN) * FN;
   float* oim = out + ((n * 2 * C + C + c) * (int64_t)FN) * FN;
   const float sc = 1.f / 128.f;
-  for (int it = 0; it < 8; ++it) {
-    // stage 2: lane -> (col = 16w + lane%16, k1 = 2it + lane/16): 8-point FFT over n2, then store
-    const int col = warp * 16 + (lane & 15), k1 = it * 2 + (lane >> 4);
-    cpx v[8];
+  for (int grp = 0; grp < 2; ++grp) {
+    if (grp == 1 && warp != 0) break;              // the Nyquist column
+    const int ncol = grp == 0 ? 8 : 1;
+    const int cl = grp == 0 ? (lane & 7) : 0;
+    const int sub = grp == 0 ? (lane >> 3) : lane; // row-offset index within an iteration
+    const int per_it = grp == 0 ? 4 : 32;
+    const int col = grp == 0 ? warp * 8 + cl : 64;
+    (void)ncol;
+    // stage 1: (col, n2): 16-point FFT over rows 8*n1 + n2, in place
+    for (int it = 0; it * per_it < 8; ++it) {
+      const int n2 = it * per_it + sub;
+      if (n2 < 8) {
+        cpx v[16];
 #pragma unroll
-    for (int n2 = 0; n2 < 8; ++n2) v[n2] = {re[(k1 * 8 + n2) * FS + col], im[(k1 * 8 + n2) * FS + col]};
-    fft_dif<8>(v);
-    const int vcol = (col + 64) & 127;             // fftshift
+        for (int n1 = 0; n1 < 16; ++n1) v[n1] = {xre[(n1 * 8 + n2) * XS + col], xim[(n1 * 8 + n2) * XS + col]};
+        fft_dif<16>(v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int u = k1 + 16 * brev3(j);            // row frequency index
-      const int urow = (u + 64) & 127;
-      ore[urow * FN + vcol] = clampn(v[j].r * sc, clamp);
-      oim[urow * FN + vcol] = clampn(v[j].i * sc, clamp);
+        for (int j = 0; j < 16; ++j) {
+          const int k1 = brev4(j);
+          const int t = k1 * n2;
+          const cpx y = cmul(v[j], cpx{twr[t], twi[t]});
+          xre[(k1 * 8 + n2) * XS + col] = y.r;
+          xim[(k1 * 8 + n2) * XS + col] = y.i;
+        }
+      }
     }
+    __syncwarp();
+    // stage 2: (col, k1): 8-point FFT over n2, then the two mirrored stores
+    for (int it = 0; it * per_it < 16; ++it) {
+      const int k1 = it * per_it + sub;
+      if (k1 < 16) {
+        cpx v[8];
+#pragma unroll
+        for (int n2 = 0; n2 < 8; ++n2) v[n2] = {xre[(k1 * 8 + n2) * XS + col], xim[(k1 * 8 + n2) * XS + col]};
+        fft_dif<8>(v);
+        const int vc = (col + 64) & 127;             // fftshift of column v = col
+        const int vm = (128 - col + 64) & 127;       // ... and of the mirrored column -v
+        const bool mirror = col >= 1 && col <= 63;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int u = k1 + 16 * brev3(j);          // row frequency index
+          const float fr = clampn(v[j].r * sc, clamp), fi = clampn(v[j].i * sc, clamp);
+          const int ur = (u + 64) & 127;
+          ore[ur * FN + vc] = fr;
+          oim[ur * FN + vc] = fi;
+          if (mirror) {
+            const int um = ((128 - u) + 64) & 127;   // row of -u after the shift
+            ore[um * FN + vm] = fr;
+            oim[um * FN + vm] = clampn(-v[j].i * sc, clamp);
+          }
+        }
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -179,7 +230,7 @@ int lshm_fft2_reim_shift_clamp(const float* x, const float* xhat, float* out,
   LSHM_REQUIRE(x && out && N >= 0 && C > 0, "lshm_fft2_reim_shift_clamp: bad arguments");
   LSHM_REQUIRE(N * C < (1LL << 31), "lshm_fft2_reim_shift_clamp: too many planes for one launch");
   if (N == 0) return LSHM_OK;
-  const size_t smem = 2 * FN * FS * sizeof(float);
+  const size_t smem = (2 * FN * XS + 8 * 8 * YS) * sizeof(float);
   LSHM_CUDA(cudaFuncSetAttribute(fft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
             "lshm_fft2_reim_shift_clamp");
   fft2_kernel<<<(unsigned)(N * C), FFT_THREADS, smem, as_stream(stream)>>>(x, xhat, out, C, clamp);
