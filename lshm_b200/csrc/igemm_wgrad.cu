@@ -17,7 +17,6 @@ namespace {
 
 using namespace tc;
 
-constexpr int KP = 64;   // positions per K block
 
 struct WgArgs {
   const float* small_; int64_t small_ns;
@@ -27,7 +26,9 @@ struct WgArgs {
   int zslots; int nstage; int64_t Q; int64_t kblocks; int64_t kb_per_cta; int ntiles; int scols; int vec_ok;
 };
 
-template <int DIM, int NT>
+// KP = positions per K block: 128 for the shallow layers (fewer pipeline hand-offs per byte), 64 for the
+// deep ones (their two tiles are wide and would not fit twice in shared memory).
+template <int DIM, int NT, int KP>
 __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], acc_bar;
@@ -253,14 +254,15 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
   if (warp == 4) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-template <int DIM, int NT>
+template <int DIM, int NT, int KP>
 int launch_wgrad_t(const WgArgs& a, int64_t splits, int mtiles, cudaStream_t st) {
   const size_t stage = (size_t)2 * a.scols * KP * 16 + (size_t)2 * (NT / 8) * a.zslots * 16;
-  // slack: the padding row groups of the last stage's S tile are read (and ignored) up to 16 groups
-  const size_t smem = stage * a.nstage + (size_t)16 * KP * 16;
-  LSHM_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<DIM, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_wgrad");
+  // slack: the padding row groups of the last stage's S tiles are read (and ignored) up to 16 groups
+  const size_t reach = (size_t)a.scols * KP * 16 + (size_t)16 * KP * 16;     // from the stage start
+  const size_t smem = stage * a.nstage + (reach > stage ? reach - stage : 0) + 256;
+  LSHM_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<DIM, NT, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_wgrad");
   dim3 grid((unsigned)splits, (unsigned)(mtiles * a.ntiles));
-  igemm_wgrad_kernel<DIM, NT><<<grid, 160, smem, st>>>(a);
+  igemm_wgrad_kernel<DIM, NT, KP><<<grid, 160, smem, st>>>(a);
   LSHM_CHECK_LAUNCH("igemm_wgrad");
   return LSHM_OK;
 }
@@ -273,23 +275,34 @@ int launch_wgrad(int dim, WgArgs a, cudaStream_t st) {
   const int mtiles = (a.A + 127) / 128;
   a.Q = dim == 2 ? a.N * (int64_t)(a.h + 1) * (a.w + 1) : a.N * (int64_t)a.w;
   LSHM_REQUIRE(a.Q < (1LL << 31) - 4096, "lshm_wgrad: too many positions (%lld) for one call; split the batch", (long long)a.Q);
-  a.kblocks = ceil_div(a.Q, KP);
-  a.zslots = dim == 2 ? (KP + a.w + 2 + 7) / 8 * 8 : KP;
   a.scols = std::min(16, (std::min(a.A, 128) + 7) / 8);
   a.vec_ok = ((reinterpret_cast<uintptr_t>(a.big) & 15) == 0 && (a.big_ns & 3) == 0) ? 1 : 0;
+  const int KP = (a.scols <= 2 && NT <= 32) ? 128 : 64;
+  a.kblocks = ceil_div(a.Q, KP);
+  a.zslots = dim == 2 ? (KP + a.w + 2 + 7) / 8 * 8 : KP;
   const size_t stage = (size_t)2 * a.scols * KP * 16 + (size_t)2 * (NT / 8) * a.zslots * 16;
-  a.nstage = (int)std::min<size_t>(3, std::max<size_t>(2, (64 * 1024) / stage));
+  a.nstage = (int)std::min<size_t>(3, std::max<size_t>(2, (72 * 1024) / stage));
   const int64_t tiles = (int64_t)mtiles * a.ntiles;
   int64_t splits = std::max<int64_t>(1, ceil_div((int64_t)sm_count() * 3, tiles));
   splits = std::min(splits, std::max<int64_t>(1, a.kblocks / 4));   // at least 4 K blocks per CTA
   a.kb_per_cta = ceil_div(a.kblocks, splits);
   splits = ceil_div(a.kblocks, a.kb_per_cta);
   a.nstage = (int)std::min<int64_t>(a.nstage, std::max<int64_t>(1, a.kb_per_cta));
-#define LW(D, NTV) return launch_wgrad_t<D, NTV>(a, splits, mtiles, st)
+#define LW(D, NTV, KPV) return launch_wgrad_t<D, NTV, KPV>(a, splits, mtiles, st)
   if (dim == 2) {
-    switch (NT) { case 16: LW(2, 16); case 32: LW(2, 32); case 48: LW(2, 48); default: LW(2, 96); }
+    switch (NT) {
+      case 16: if (KP == 128) LW(2, 16, 128); else LW(2, 16, 64);
+      case 32: if (KP == 128) LW(2, 32, 128); else LW(2, 32, 64);
+      case 48: LW(2, 48, 64);
+      default: LW(2, 96, 64);
+    }
   } else {
-    switch (NT) { case 16: LW(1, 16); case 32: LW(1, 32); case 48: LW(1, 48); default: LW(1, 96); }
+    switch (NT) {
+      case 16: if (KP == 128) LW(1, 16, 128); else LW(1, 16, 64);
+      case 32: if (KP == 128) LW(1, 32, 128); else LW(1, 32, 64);
+      case 48: LW(1, 48, 64);
+      default: LW(1, 96, 64);
+    }
   }
 #undef LW
 }
