@@ -380,9 +380,11 @@ __global__ void __launch_bounds__(DOWN_THREADS, 3) igemm_down_kernel(DownArgs a)
           const uint64_t dah = make_desc(zhi, SLOTS * 16, 128), dal = make_desc(zhi + zbytes, SLOTS * 16, 128);
           const uint64_t dbh = make_desc(bhi, NT * 16, 128), dbl = make_desc(bhi + IMG / 2, NT * 16, 128);
           const int ksteps = (min(KC, Kc - kb * KC)) >> 4;
-#pragma unroll
+          // rolled on purpose: the issuing lane's code must stay small (instruction-cache footprint)
+#pragma unroll 1
           for (int tap = 0; tap < T; ++tap) {
             const uint32_t shift = DIM == 2 ? (uint32_t)((tap >> 1) * PW + (tap & 1)) : 0u;
+#pragma unroll 1
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint32_t ao = (uint32_t)(2 * ks) * SLOTS + shift;            // 16-byte units
               const uint32_t bo = (uint32_t)(tap * CC + 2 * ks) * NT;

@@ -28,7 +28,8 @@ struct UpArgs {
   int slots; int nstage; int64_t Q; int64_t mtiles; int ntn;
 };
 
-constexpr int UP_THREADS = 320;   // warps 0-3 epilogue, 4-7 producers, 8 MMA issuer, 9 weight loader
+// warps 0-3 epilogue, 4-7 producers, 8 MMA issuer, 9 weight loader, (2-D only) 10 second MMA issuer
+constexpr int up_threads(int dim) { return dim == 2 ? 352 : 320; }
 constexpr int UP_MAXST = 6;
 
 __device__ __forceinline__ float epi_apply(float acc, float bias, int epi, float aux) {
@@ -42,7 +43,7 @@ __device__ __forceinline__ float epi_apply(float acc, float bias, int epi, float
 // stage ring, the MMA warp alternates between two TMEM accumulator sets (each = 4 parity classes in
 // 2-D), the epilogue warps drain one set while the next is being computed.
 template <int DIM, int NT, int KC>
-__global__ void __launch_bounds__(UP_THREADS, (DIM == 1 ? 3 : 2)) igemm_up_kernel(UpArgs a) {
+__global__ void __launch_bounds__(up_threads(DIM), (DIM == 1 ? 3 : 2)) igemm_up_kernel(UpArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[UP_MAXST], empty_bar[UP_MAXST], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base;
@@ -66,8 +67,9 @@ __global__ void __launch_bounds__(UP_THREADS, (DIM == 1 ? 3 : 2)) igemm_up_kerne
 
   if (warp == 8) tmem_alloc(&tmem_base, TMEM_COLS);
   if (tid == 0) {
-    for (int s = 0; s < UP_MAXST; ++s) { mbar_init(&full_bar[s], 5); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    // two MMA-issuing warps (each a serial one-thread chain) share the (class, tap) pairs of a stage
+    for (int s = 0; s < UP_MAXST; ++s) { mbar_init(&full_bar[s], 5); mbar_init(&empty_bar[s], DIM == 2 ? 2 : 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], DIM == 2 ? 2 : 1); mbar_init(&acc_empty[b], 4); }
     mbar_init_fence();
   }
   fence_before();
@@ -247,53 +249,50 @@ __global__ void __launch_bounds__(UP_THREADS, (DIM == 1 ? 3 : 2)) igemm_up_kerne
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
-  } else if (warp == 8) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(NT, 0, 0);
-      uint32_t it = 0, tc_ = 0;
-      // The issuing thread is a serial chain: descriptor offsets of the 16 (class, tap) pairs are
-      // computed once (16-byte units), per MMA only one 32-bit add per descriptor remains.
-      uint32_t aoff[COMBOS], boff[COMBOS];
-#pragma unroll
-      for (int cb = 0; cb < COMBOS; ++cb) {
-        if (DIM == 2) {
-          const int cls = cb >> 2, tap = cb & 3;
-          const int ry = cls >> 1, rx = cls & 1, d = tap >> 1, e = tap & 1;
-          const int dy = ry == 0 ? (d == 0 ? 0 : -1) : (d == 0 ? 1 : 0);
-          const int dx = rx == 0 ? (e == 0 ? 0 : -1) : (e == 0 ? 1 : 0);
-          aoff[cb] = (uint32_t)(halo + dy * PW + dx);
-          boff[cb] = (uint32_t)(cb * CC * NT);
-        } else {
-          aoff[cb] = 0; boff[cb] = 0;
-        }
-      }
-      for (int64_t item = blockIdx.x; item < total; item += gridDim.x, ++tc_) {
-        const uint32_t buf = tc_ & 1;
-        mbar_wait(&acc_empty[buf], ((tc_ >> 1) & 1) ^ 1);
+  } else if (warp == 8 || warp == 10) {
+    // ------------------------------------------------ MMA issuers.  The whole warp runs the (rolled)
+    // loop so every descriptor lives in uniform registers and lane 0 only predicates the tcgen05
+    // instructions: an unrolled single-lane version was 3800 SASS lines of waterfall loops that
+    // evicted the other roles' code from the instruction cache (33% of stall samples were
+    // "no instruction", profiles/r1_ncu_up2d_conv0.md).
+    const int mw = warp == 8 ? 0 : 1;               // 2-D: issuer 0 takes classes 0,1, issuer 1 classes 2,3
+    const bool leader = lane == 0;
+    const uint32_t idesc = make_idesc(NT, 0, 0);
+    const int cb0 = DIM == 2 ? mw * (COMBOS / 2) : 0, cb1 = DIM == 2 ? cb0 + COMBOS / 2 : COMBOS;
+    uint32_t it = 0, tc_ = 0;
+    for (int64_t item = blockIdx.x; item < total; item += gridDim.x, ++tc_) {
+      const uint32_t buf = tc_ & 1;
+      mbar_wait(&acc_empty[buf], ((tc_ >> 1) & 1) ^ 1);
+      fence_after();
+      const uint32_t tset = tmem + buf * TSET;
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int s = it % NS, ph = (it / NS) & 1;
+        mbar_wait(&full_bar[s], ph);
         fence_after();
-        const uint32_t tset = tmem + buf * TSET;
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % NS, ph = (it / NS) & 1;
-          mbar_wait(&full_bar[s], ph);
-          fence_after();
-          const uint32_t zhi = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint64_t dah = make_desc(zhi, SLOTS * 16, 128), dal = make_desc(zhi + zbytes, SLOTS * 16, 128);
-          const uint64_t dbh = make_desc(zhi + 2 * zbytes, NT * 16, 128), dbl = make_desc(zhi + 2 * zbytes + IMG / 2, NT * 16, 128);
-          const int ksteps = (min(KC, Apad - kb * KC)) >> 4;
-#pragma unroll
-          for (int cb = 0; cb < COMBOS; ++cb) {
-            const uint32_t td = DIM == 2 ? tset + (cb >> 2) * NT : tset;
-            const uint32_t first = DIM == 2 ? ((cb & 3) == 0 ? 1u : 0u) : 1u;   // first tap of a class
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint32_t ao = aoff[cb] + (uint32_t)(2 * ks) * SLOTS, bo = boff[cb] + (uint32_t)(2 * ks) * NT;
+        const uint32_t zhi = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint64_t dah = make_desc(zhi, SLOTS * 16, 128), dal = make_desc(zhi + zbytes, SLOTS * 16, 128);
+        const uint64_t dbh = make_desc(zhi + 2 * zbytes, NT * 16, 128), dbl = make_desc(zhi + 2 * zbytes + IMG / 2, NT * 16, 128);
+        const int ksteps = (min(KC, Apad - kb * KC)) >> 4;
+#pragma unroll 1
+        for (int cb = cb0; cb < cb1; ++cb) {
+          // class = (ry, rx), tap = (d, e): row shift ry - d, column shift rx - e (header comment)
+          const int cls = cb >> 2, tap = cb & 3;
+          const uint32_t abase = DIM == 2 ? (uint32_t)(halo + ((cls >> 1) - (tap >> 1)) * PW + ((cls & 1) - (tap & 1))) : 0u;
+          const uint32_t bbase = DIM == 2 ? (uint32_t)(cb * CC * NT) : 0u;
+          const uint32_t td = DIM == 2 ? tset + cls * NT : tset;
+          const bool first = DIM == 2 ? tap == 0 : true;                       // first tap of a class
+#pragma unroll 1
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t ao = abase + (uint32_t)(2 * ks) * SLOTS, bo = bbase + (uint32_t)(2 * ks) * NT;
+            if (leader)
               mma_split3(td, desc_off(dah, ao), desc_off(dal, ao), desc_off(dbh, bo), desc_off(dbl, bo), idesc,
                          (kb > 0 || !first || ks > 0) ? 1u : 0u);
-            }
           }
-          commit(&empty_bar[s]);
         }
-        commit(&acc_full[buf]);
+        __syncwarp();
+        if (leader) commit(&empty_bar[s]);
       }
+      if (leader) commit(&acc_full[buf]);
     }
   } else {
     if (lane == 0) {
@@ -332,7 +331,7 @@ int launch_up_t(UpArgs a, const UpGeom& g, cudaStream_t st) {
   const size_t smem = stage * a.nstage;
   LSHM_CUDA(cudaFuncSetAttribute(igemm_up_kernel<DIM, NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_up");
   const int64_t grid = std::min<int64_t>(a.mtiles * g.ntiles, (int64_t)sm_count() * per_sm);
-  igemm_up_kernel<DIM, NT, KC><<<(unsigned)grid, UP_THREADS, smem, st>>>(a);
+  igemm_up_kernel<DIM, NT, KC><<<(unsigned)grid, up_threads(DIM), smem, st>>>(a);
   LSHM_CHECK_LAUNCH("igemm_up");
   return LSHM_OK;
 }

@@ -232,10 +232,11 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
         const uint32_t slo = shi + SBYTES;
         const uint32_t zhi = slo + SBYTES;
         const uint32_t zlo = zhi + zbytes;
-#pragma unroll
+        // rolled on purpose: keeps the issuing lane's code small (instruction-cache footprint)
+#pragma unroll 1
         for (int tap = 0; tap < T; ++tap) {
           const uint32_t shift = DIM == 2 ? (uint32_t)((tap >> 1) * PW + (tap & 1)) : 0u;
-#pragma unroll
+#pragma unroll 1
           for (int ks = 0; ks < KP / 16; ++ks) {
             const uint32_t aoff = (uint32_t)ks * 256;
             const uint32_t boff = ((uint32_t)ks * 16 + shift) * 16;
