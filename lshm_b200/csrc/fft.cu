@@ -65,7 +65,14 @@ __device__ __forceinline__ constexpr int brev4(int v) { return ((v & 1) << 3) | 
 __device__ __forceinline__ float clampn(float a, float c) { return a != a ? a : fminf(fmaxf(a, -c), c); }
 
 constexpr int YS = 136;   // row stride (floats) of the per-warp stage-1 -> stage-2 exchange buffer
-constexpr int XS = 72;    // row stride (floats) of the half-spectrum X[128 rows][65 columns]
+constexpr int XS = 64;    // row stride (floats) of the half-spectrum X[128 rows][columns 0..63]; column 64 apart
+
+// X is addressed by lanes that differ in the column (8 consecutive) and in the row, where the row
+// step is 1 (first column stage: n2), 8 (second column stage: k1) or 2 (row-pass stores).  With any
+// padded row stride one of the three collides (a 72-float stride made every second-stage column load
+// a 4-way bank conflict: 37% extra shared-memory wavefronts in the ncu capture), so the 8-column
+// group is XOR-swizzled with two row bits taken from both the row's low and its /8 digits.
+__device__ __forceinline__ int xidx(int row, int col) { return row * XS + (col ^ (((row ^ (row >> 3)) & 3) << 3)); }
 
 // Real input: rows are transformed in PAIRS (z = a + i*b, one complex 128-point FFT, then
 // A[k] = (Z[k] + conj Z[-k])/2, B[k] = (Z[k] - conj Z[-k])/(2i)), and only columns k = 0..64 are kept:
@@ -75,10 +82,11 @@ __global__ void __launch_bounds__(FFT_THREADS, 2)
 fft2_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* __restrict__ out,
             int C, float clamp) {
   extern __shared__ __align__(16) float sm[];
-  float* xre = sm;                          // [128][XS]
+  float* xre = sm;                          // [128][XS] swizzled (xidx)
   float* xim = xre + FN * XS;               // [128][XS]
   float* ybase = xim + FN * XS;             // per warp: re[4][YS], im[4][YS]
   __shared__ float twr[FN], twi[FN];
+  __shared__ float nre[FN], nim[FN];        // the Nyquist column (k = 64) of the row transforms
   const int64_t plane = blockIdx.x;         // n*C + c
   const int64_t n = plane / C;
   const int c = (int)(plane - n * C);
@@ -124,10 +132,16 @@ fft2_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* 
       const int ra = 2 * (warp * 8 + half * 4 + pl);
       cpx v[8];
       {
-        const float4 a0 = *reinterpret_cast<const float4*>(yre + pl * YS + k1 * 8);
-        const float4 a1 = *reinterpret_cast<const float4*>(yre + pl * YS + k1 * 8 + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(yim + pl * YS + k1 * 8);
-        const float4 b1 = *reinterpret_cast<const float4*>(yim + pl * YS + k1 * 8 + 4);
+        // 16-byte loads at a 32-byte lane stride: lanes 4..7 of each quarter-warp fetch their upper
+        // half first so the eight lanes of a wavefront cover all 32 banks
+        const int sw = (k1 >> 2) & 1;
+        const float* yr_ = yre + pl * YS + k1 * 8;
+        const float* yi_ = yim + pl * YS + k1 * 8;
+        const float4 ra0 = *reinterpret_cast<const float4*>(yr_ + 4 * sw);
+        const float4 ra1 = *reinterpret_cast<const float4*>(yr_ + 4 * (sw ^ 1));
+        const float4 rb0 = *reinterpret_cast<const float4*>(yi_ + 4 * sw);
+        const float4 rb1 = *reinterpret_cast<const float4*>(yi_ + 4 * (sw ^ 1));
+        const float4 a0 = sw ? ra1 : ra0, a1 = sw ? ra0 : ra1, b0 = sw ? rb1 : rb0, b1 = sw ? rb0 : rb1;
         v[0] = {a0.x, b0.x}; v[1] = {a0.y, b0.y}; v[2] = {a0.z, b0.z}; v[3] = {a0.w, b0.w};
         v[4] = {a1.x, b1.x}; v[5] = {a1.y, b1.y}; v[6] = {a1.z, b1.z}; v[7] = {a1.w, b1.w};
       }
@@ -146,10 +160,14 @@ fft2_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* 
         if (k2 < 4 || k1 == 0) {
           const int k = k1 + 16 * k2;
           const float zr = v[jo].r, zi = v[jo].i;
-          xre[ra * XS + k] = 0.5f * (zr + pr);        // A[k] = (Z[k] + conj Zp)/2
-          xim[ra * XS + k] = 0.5f * (zi - pi);
-          xre[(ra + 1) * XS + k] = 0.5f * (zi + pi);  // B[k] = -i/2 (Z[k] - conj Zp)
-          xim[(ra + 1) * XS + k] = -0.5f * (zr - pr);
+          const float ar = 0.5f * (zr + pr), ai = 0.5f * (zi - pi);     // A[k] = (Z[k] + conj Zp)/2
+          const float br = 0.5f * (zi + pi), bi = -0.5f * (zr - pr);    // B[k] = -i/2 (Z[k] - conj Zp)
+          if (k2 < 4) {
+            xre[xidx(ra, k)] = ar; xim[xidx(ra, k)] = ai;
+            xre[xidx(ra + 1, k)] = br; xim[xidx(ra + 1, k)] = bi;
+          } else {
+            nre[ra] = ar; nim[ra] = ai; nre[ra + 1] = br; nim[ra + 1] = bi;
+          }
         }
       }
     }
@@ -175,15 +193,19 @@ fft2_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* 
       if (n2 < 8) {
         cpx v[16];
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) v[n1] = {xre[(n1 * 8 + n2) * XS + col], xim[(n1 * 8 + n2) * XS + col]};
+        for (int n1 = 0; n1 < 16; ++n1) {
+          const int r = n1 * 8 + n2;
+          v[n1] = grp == 0 ? cpx{xre[xidx(r, col)], xim[xidx(r, col)]} : cpx{nre[r], nim[r]};
+        }
         fft_dif<16>(v);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int k1 = brev4(j);
           const int t = k1 * n2;
           const cpx y = cmul(v[j], cpx{twr[t], twi[t]});
-          xre[(k1 * 8 + n2) * XS + col] = y.r;
-          xim[(k1 * 8 + n2) * XS + col] = y.i;
+          const int r = k1 * 8 + n2;
+          if (grp == 0) { xre[xidx(r, col)] = y.r; xim[xidx(r, col)] = y.i; }
+          else { nre[r] = y.r; nim[r] = y.i; }
         }
       }
     }
@@ -194,7 +216,10 @@ fft2_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* 
       if (k1 < 16) {
         cpx v[8];
 #pragma unroll
-        for (int n2 = 0; n2 < 8; ++n2) v[n2] = {xre[(k1 * 8 + n2) * XS + col], xim[(k1 * 8 + n2) * XS + col]};
+        for (int n2 = 0; n2 < 8; ++n2) {
+          const int r = k1 * 8 + n2;
+          v[n2] = grp == 0 ? cpx{xre[xidx(r, col)], xim[xidx(r, col)]} : cpx{nre[r], nim[r]};
+        }
         fft_dif<8>(v);
         const int vc = (col + 64) & 127;             // fftshift of column v = col
         const int vm = (128 - col + 64) & 127;       // ... and of the mirrored column -v

@@ -50,6 +50,10 @@ __device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64
 __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
+// 1/x to 1 ulp in one MUFU op (the IEEE-rounded division is ~12 instructions per (point, centre) pair,
+// a sixth of the K = 10 inner loop)
+__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 template <int TPP>
 __device__ __forceinline__ float lanes_sum(float v) {
 #pragma unroll
@@ -58,12 +62,12 @@ __device__ __forceinline__ float lanes_sum(float v) {
 }
 
 // squared distance between the lane's slice of x and the matching slice of centre row `mrow`
-template <int TPP>
+template <int TPP, int NCH>
 __device__ __forceinline__ float dist2(const float4 (&x4)[KHM_MAXCH], const float* mrow, int s, int nch) {
   f32x2 a0 = 0ull, a1 = 0ull;   // two packed accumulators = four independent chains
 #pragma unroll
   for (int c = 0; c < KHM_MAXCH; ++c) {
-    if (c < nch) {
+    if (NCH == KHM_MAXCH || c < nch) {
       const float4 m = *reinterpret_cast<const float4*>(mrow + ((c * TPP + s) << 2));
       const f32x2 d0 = sub2(pk2(x4[c].x, x4[c].y), pk2(m.x, m.y));
       const f32x2 d1 = sub2(pk2(x4[c].z, x4[c].w), pk2(m.z, m.w));
@@ -79,13 +83,13 @@ __device__ __forceinline__ float dist2(const float4 (&x4)[KHM_MAXCH], const floa
 // two points against one centre row: every broadcast LDS.128 of the centre feeds both points.  A warp-wide
 // 16-byte shared load costs 4 crossbar cycles even when it is a broadcast, so with one point per thread
 // the distance loop is shared-memory-bound at ~32 (point,k,l) elements per clock per SM (measured: 25).
-template <int TPP>
+template <int TPP, int NCH>
 __device__ __forceinline__ void dist2x2(const float4 (&xa)[KHM_MAXCH], const float4 (&xb)[KHM_MAXCH], const float* mrow,
                                         int s, int nch, float& da, float& db) {
   f32x2 a0 = 0ull, a1 = 0ull, b0 = 0ull, b1 = 0ull;
 #pragma unroll
   for (int c = 0; c < KHM_MAXCH; ++c) {
-    if (c < nch) {
+    if (NCH == KHM_MAXCH || c < nch) {
       const float4 m = *reinterpret_cast<const float4*>(mrow + ((c * TPP + s) << 2));
       const f32x2 m0 = pk2(m.x, m.y), m1 = pk2(m.z, m.w);
       const f32x2 p0 = sub2(pk2(xa[c].x, xa[c].y), m0), p1 = sub2(pk2(xa[c].z, xa[c].w), m1);
@@ -101,13 +105,13 @@ __device__ __forceinline__ void dist2x2(const float4 (&xa)[KHM_MAXCH], const flo
   db = lanes_sum<TPP>((p + q) + (r + t));
 }
 
-template <int TPP>
+template <int TPP, int NCH>
 __device__ __forceinline__ void load_point(float4 (&x4)[KHM_MAXCH], const float* X, int64_t ldx,
                                            int64_t i, bool valid, int s, int nch) {
 #pragma unroll
   for (int c = 0; c < KHM_MAXCH; ++c) {
     x4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < nch && valid) x4[c] = *reinterpret_cast<const float4*>(X + i * ldx + ((c * TPP + s) << 2));
+    if ((NCH == KHM_MAXCH || c < nch) && valid) x4[c] = *reinterpret_cast<const float4*>(X + i * ldx + ((c * TPP + s) << 2));
   }
 }
 
@@ -121,7 +125,10 @@ __device__ __forceinline__ void stage_centres(float* ms, const float* M, int k0,
 // ------------------------------------------------------------------------------------------
 // pass 1: e_i = sum_k 1/(d_ik^p + eps); loss, e_out, argmin ids, group distances
 // ------------------------------------------------------------------------------------------
-template <int TPP, bool RESIDENT>
+// NCH = KHM_MAXCH: every lane holds all eight float4 chunks (L = 32*TPP), the chunk loops carry no
+// guards (the guarded form cost a branch per chunk plus 8 accumulator moves: 36% useful FFMA2/FADD2 in
+// the K=10, L=64 capture); NCH = 0: chunk count known at run time only.
+template <int TPP, bool RESIDENT, int NCH>
 __global__ void __launch_bounds__(KHM_THREADS) khm_pass1_kernel(KhmArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* ms = smem;  // RESIDENT: K*L, else KC*L
@@ -138,8 +145,8 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass1_kernel(KhmArgs a) {
     const int64_t ia = t * 2 * PTS + pt, ib = ia + PTS;
     const bool va = ia < a.N, vb = ib < a.N;
     float4 xa[KHM_MAXCH], xb[KHM_MAXCH];
-    load_point<TPP>(xa, a.X, a.ldx, ia, va, s, nch);
-    load_point<TPP>(xb, a.X, a.ldx, ib, vb, s, nch);
+    load_point<TPP, NCH>(xa, a.X, a.ldx, ia, va, s, nch);
+    load_point<TPP, NCH>(xb, a.X, a.ldx, ib, vb, s, nch);
     float ea = 0.f, eb = 0.f, besta = 3.4e38f, bestb = 3.4e38f;
     int bia = 0, bib = 0;
     for (int k0 = 0; k0 < K; k0 += (RESIDENT ? K : KHM_KC)) {
@@ -148,10 +155,10 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass1_kernel(KhmArgs a) {
 #pragma unroll 2
       for (int kk = 0; kk < kc; ++kk) {
         float da, db;
-        dist2x2<TPP>(xa, xb, ms + kk * L, s, nch, da, db);
+        dist2x2<TPP, NCH>(xa, xb, ms + kk * L, s, nch, da, db);
         const float pa = pow_p(da, a.p, a.pmode), pb = pow_p(db, a.p, a.pmode);
-        ea += __frcp_rn(pa + KHM_EPS);
-        eb += __frcp_rn(pb + KHM_EPS);
+        ea += rcp_fast(pa + KHM_EPS);
+        eb += rcp_fast(pb + KHM_EPS);
         if (da < besta) { besta = da; bia = k0 + kk; }
         if (db < bestb) { bestb = db; bib = k0 + kk; }
         if (a.dist != nullptr && s == 0) {
@@ -175,7 +182,7 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass1_kernel(KhmArgs a) {
 // pass 2: weights w_ik (gradient) or Q_ik (centre update); gX in registers; [K,L] sums via a
 // shared-memory tile product
 // ------------------------------------------------------------------------------------------
-template <int TPP, bool RESIDENT, bool SUMS>
+template <int TPP, bool RESIDENT, bool SUMS, int NCH>
 __global__ void __launch_bounds__(KHM_THREADS) khm_pass2_kernel(KhmArgs a) {
   extern __shared__ __align__(16) float smem[];
   constexpr int PTS = KHM_THREADS / TPP;
@@ -201,15 +208,15 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass2_kernel(KhmArgs a) {
     const int64_t i = t * PTS + pt;
     const bool valid = i < a.N;
     float4 x4[KHM_MAXCH];
-    load_point<TPP>(x4, a.X, a.ldx, i, valid, s, nch);
+    load_point<TPP, NCH>(x4, a.X, a.ldx, i, valid, s, nch);
     // ---- harmonic sum e_i
     float e = 0.f;
     for (int k0 = 0; k0 < K; k0 += (RESIDENT ? K : KHM_KC)) {
       const int kc = RESIDENT ? K : min(KHM_KC, K - k0);
       if (!RESIDENT) { __syncthreads(); stage_centres(ms, a.M, k0, kc, L); __syncthreads(); }
       for (int kk = 0; kk < kc; ++kk) {
-        const float d2 = dist2<TPP>(x4, ms + kk * L, s, nch);
-        e += 1.0f / (pow_p(d2, a.p, a.pmode) + KHM_EPS);
+        const float d2 = dist2<TPP, NCH>(x4, ms + kk * L, s, nch);
+        e += rcp_fast(pow_p(d2, a.p, a.pmode) + KHM_EPS);
       }
     }
     if (valid && s == 0) lsum += (double)(Kf / (e + KHM_EPS));
@@ -218,7 +225,7 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass2_kernel(KhmArgs a) {
     // ---- x tile to shared memory for the [K x pts] x [pts x L] product
 #pragma unroll
     for (int c = 0; c < KHM_MAXCH; ++c)
-      if (c < nch) *reinterpret_cast<float4*>(xs + pt * L + ((c * TPP + s) << 2)) = x4[c];
+      if (NCH == KHM_MAXCH || c < nch) *reinterpret_cast<float4*>(xs + pt * L + ((c * TPP + s) << 2)) = x4[c];
     float4 g4[KHM_MAXCH];
 #pragma unroll
     for (int c = 0; c < KHM_MAXCH; ++c) g4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -228,20 +235,20 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass2_kernel(KhmArgs a) {
       const float* mbase = RESIDENT ? ms + k0 * L : ms;
       for (int kk = 0; kk < kc; ++kk) {
         const float* mrow = mbase + kk * L;
-        const float d2 = dist2<TPP>(x4, mrow, s, nch);
+        const float d2 = dist2<TPP, NCH>(x4, mrow, s, nch);
         const float dp = pow_p(d2, a.p, a.pmode);
         float w;
         if (SUMS) {
-          w = coef / (dp * d2 + KHM_EPS);                 // alpha_i / (d^(p+2) + eps)
+          w = coef * rcp_fast(dp * d2 + KHM_EPS);                 // alpha_i / (d^(p+2) + eps)
         } else {
           const float tt = dp + KHM_EPS;
-          w = d2 > 0.f ? coef * a.p * pow_pm2(d2, a.p, a.pmode) / (tt * tt) : 0.f;
+          w = d2 > 0.f ? coef * a.p * pow_pm2(d2, a.p, a.pmode) * rcp_fast(tt * tt) : 0.f;
         }
         if (!valid) w = 0.f;
         if (!SUMS) {
 #pragma unroll
           for (int c = 0; c < KHM_MAXCH; ++c) {
-            if (c < nch) {
+            if (NCH == KHM_MAXCH || c < nch) {
               const float4 m = *reinterpret_cast<const float4*>(mrow + ((c * TPP + s) << 2));
               const f32x2 w2 = pk2(w, w);
               const f32x2 r0 = fma2(w2, sub2(pk2(x4[c].x, x4[c].y), pk2(m.x, m.y)), pk2(g4[c].x, g4[c].y));
@@ -293,7 +300,7 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass2_kernel(KhmArgs a) {
     if (!SUMS && valid && a.gX != nullptr) {
 #pragma unroll
       for (int c = 0; c < KHM_MAXCH; ++c) {
-        if (c < nch) {
+        if (NCH == KHM_MAXCH || c < nch) {
           float4* dst = reinterpret_cast<float4*>(a.gX + i * a.ldg + ((c * TPP + s) << 2));
           float4 v = make_float4(a.gscale * g4[c].x, a.gscale * g4[c].y, a.gscale * g4[c].z, a.gscale * g4[c].w);
           if (a.accumulate_x) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
@@ -355,22 +362,34 @@ int check_common(const char* name, const float* X, int64_t ldx, const float* M, 
 
 int pmode_of(float p) { return p == 2.f ? 2 : (p == 4.f ? 4 : 0); }
 
+template <int TPP, bool RES, int NCH>
+int launch_pass1_n(const KhmArgs& a, size_t smem, int grid, cudaStream_t st) {
+  if (smem > 48 * 1024)
+    LSHM_CUDA(cudaFuncSetAttribute(khm_pass1_kernel<TPP, RES, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "khm_pass1");
+  khm_pass1_kernel<TPP, RES, NCH><<<grid, KHM_THREADS, smem, st>>>(a);
+  LSHM_CHECK_LAUNCH("khm_pass1");
+  return LSHM_OK;
+}
+
 template <int TPP, bool RES>
 int launch_pass1_t(const KhmArgs& a, size_t smem, int grid, cudaStream_t st) {
+  return a.L == 4 * TPP * KHM_MAXCH ? launch_pass1_n<TPP, RES, KHM_MAXCH>(a, smem, grid, st)
+                                    : launch_pass1_n<TPP, RES, 0>(a, smem, grid, st);
+}
+
+template <int TPP, bool RES, bool SUMS, int NCH>
+int launch_pass2_n(const KhmArgs& a, size_t smem, int grid, cudaStream_t st) {
   if (smem > 48 * 1024)
-    LSHM_CUDA(cudaFuncSetAttribute(khm_pass1_kernel<TPP, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "khm_pass1");
-  khm_pass1_kernel<TPP, RES><<<grid, KHM_THREADS, smem, st>>>(a);
-  LSHM_CHECK_LAUNCH("khm_pass1");
+    LSHM_CUDA(cudaFuncSetAttribute(khm_pass2_kernel<TPP, RES, SUMS, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "khm_pass2");
+  khm_pass2_kernel<TPP, RES, SUMS, NCH><<<grid, KHM_THREADS, smem, st>>>(a);
+  LSHM_CHECK_LAUNCH("khm_pass2");
   return LSHM_OK;
 }
 
 template <int TPP, bool RES, bool SUMS>
 int launch_pass2_t(const KhmArgs& a, size_t smem, int grid, cudaStream_t st) {
-  if (smem > 48 * 1024)
-    LSHM_CUDA(cudaFuncSetAttribute(khm_pass2_kernel<TPP, RES, SUMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "khm_pass2");
-  khm_pass2_kernel<TPP, RES, SUMS><<<grid, KHM_THREADS, smem, st>>>(a);
-  LSHM_CHECK_LAUNCH("khm_pass2");
-  return LSHM_OK;
+  return a.L == 4 * TPP * KHM_MAXCH ? launch_pass2_n<TPP, RES, SUMS, KHM_MAXCH>(a, smem, grid, st)
+                                    : launch_pass2_n<TPP, RES, SUMS, 0>(a, smem, grid, st);
 }
 
 int grid_for(int64_t N, int tpp, int blocks_per_sm, int ppt = 1) {

@@ -91,7 +91,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // Waiting warps must not steal issue slots from the producer warps (an ncu capture of the first
 // version showed 55% of all executed instructions were try_wait/branch spins): the retry path backs
 // off with a short nanosleep.  (A suspend-time hint on try_wait made every hand-off slower.)
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t backoff_ns = 20) {
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t backoff_ns = 32) {
   uint32_t done = 0;
   const uint32_t addr = smem_u32(bar);
   while (true) {
@@ -99,6 +99,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
                  : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     if (done) break;
     __nanosleep(backoff_ns);
+    // exponential back-off: with a fixed 20 ns the retry loops were still 30-45% of all executed
+    // instructions of the conv kernels, which are issue-bound (profiles/r1_ncu_conv_all.md)
+    backoff_ns = backoff_ns < 256 ? backoff_ns * 2 : backoff_ns;
   }
 }
 // 1-D bulk copy global -> shared, completion counted on `bar` (bytes multiple of 16, 16 B aligned)
