@@ -4,6 +4,19 @@
 
 namespace lshm {
 
+// Division of a 31-bit index by a launch-time constant: q = (mulhi(m, n) + n) >> l with
+// l = ceil(log2 d), m = floor(2^32 (2^l - d) / d) + 1 (Granlund-Montgomery; n < 2^31 keeps the sum in
+// 32 bits).  The compiler's generic 32-bit division is ~20 instructions and the position -> (image,
+// row, column) split is on every producer's and epilogue's critical path.
+struct FastDiv { uint32_t d, m, l; };
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f; f.d = d; f.l = 0;
+  while ((1ull << f.l) < d) ++f.l;
+  f.m = (uint32_t)((((1ull << f.l) - d) << 32) / d + 1);
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return (__umulhi(f.m, n) + n) >> f.l; }
+
 struct DownGeom { int NT, KC, ntiles, KB, T; size_t img; };
 struct UpGeom { int NT, KC, ntiles, KB, combos, ncols; size_t img; };
 

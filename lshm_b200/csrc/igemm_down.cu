@@ -28,6 +28,7 @@ struct DownArgs {
   float* small_; int64_t small_ns;
   int64_t N; int A; int Bc; int h; int w; int pad; int epi;
   int slots; int nstage; int64_t Q; int64_t mtiles; int ntn; int rawbytes; int rawG; int wres_on;
+  FastDiv d_pp, d_pw, d_w, d_ntn;   // divisors (h+1)(w+1), w+1, w, ntn
 };
 
 constexpr int DOWN_THREADS = 320;   // warps 0-3 epilogue, 4-7 producers, 8 MMA issuer, 9 weight loader
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(DOWN_THREADS, 3) igemm_down_kernel(DownArgs a)
 
   if (warp == 8) tmem_alloc(&tmem_base, TMEM_COLS);
   if (tid == 0) {
-    for (int s = 0; s < MAXST; ++s) { mbar_init(&full_bar[s], 5); mbar_init(&empty_bar[s], 1); mbar_init(&raw_bar[s], 128); }
+    for (int s = 0; s < MAXST; ++s) { mbar_init(&full_bar[s], wres ? 4 : 5); mbar_init(&empty_bar[s], 1); mbar_init(&raw_bar[s], 128); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
     mbar_init(&w_bar, 1);
     mbar_init_fence();
@@ -205,9 +206,9 @@ __global__ void __launch_bounds__(DOWN_THREADS, 3) igemm_down_kernel(DownArgs a)
     } else {
     // Register-staged path.  Per slot the source window is described once (base pointer of the first
     // channel, validity of the two rows / two columns); a chunk column is 8 loads at fixed offsets.
-    uint32_t it = 0;
+    Ring ring{0, 0};
     for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
-      const int64_t q0 = (item / a.ntn) * 128;
+      const int64_t q0 = (int64_t)fdiv((uint32_t)item, a.d_ntn) * 128;
       const float* sp[NSLOT]; bool sv[NSLOT], full[NSLOT], r0ok[NSLOT], r1ok[NSLOT], c0ok[NSLOT], c1ok[NSLOT]; int sj[NSLOT];
 #pragma unroll
       for (int i = 0; i < NSLOT; ++i) {
@@ -218,25 +219,25 @@ __global__ void __launch_bounds__(DOWN_THREADS, 3) igemm_down_kernel(DownArgs a)
         if (sv[i]) {
           const uint32_t uq = (uint32_t)q;            // Q < 2^31 (launcher): 32-bit divisions only
           if (DIM == 2) {
-            const uint32_t n = uq / (uint32_t)(PH * PW);
+            const uint32_t n = fdiv(uq, a.d_pp);
             const uint32_t r = uq - n * (uint32_t)(PH * PW);
-            const int by = (int)(r / (uint32_t)PW), bx = (int)(r - (r / (uint32_t)PW) * PW);
+            const int by = (int)fdiv(r, a.d_pw), bx = (int)r - by * PW;
             r0ok[i] = by > 0; r1ok[i] = by < a.h; c0ok[i] = bx > 0; c1ok[i] = bx < a.w;
             full[i] = r0ok[i] && r1ok[i] && c0ok[i] && c1ok[i];
             sp[i] = a.big + (int64_t)n * a.big_ns + (int64_t)(2 * by - 1) * W + (2 * bx - 1);
           } else {
-            const uint32_t n = uq / (uint32_t)a.w;    // 1-D: a.w holds the small length l
+            const uint32_t n = fdiv(uq, a.d_w);       // 1-D: a.w holds the small length l
             sj[i] = (int)(uq - n * (uint32_t)a.w);
             sp[i] = a.big + (int64_t)n * a.big_ns + 4 * (int64_t)sj[i] - a.pad;
           }
         }
       }
-      for (int kb = 0; kb < KB; ++kb, ++it) {
-        const int s = it % NS, ph = (it / NS) & 1;
+      for (int kb = 0; kb < KB; ++kb, ring.next(NS)) {
+        const int s = ring.s;
         uint8_t* zhi = smem + (size_t)s * stage_bytes + rawb;
         uint8_t* zlo = zhi + zbytes;
         const int ccb = (min(KC, Kc - kb * KC)) >> 3;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_wait(&empty_bar[s], ring.ph ^ 1);
         // per slot: fetch every chunk column, then convert (32 data registers -> 3 CTAs per SM)
 #pragma unroll
         for (int i = 0; i < NSLOT; ++i) {
@@ -299,20 +300,21 @@ __global__ void __launch_bounds__(DOWN_THREADS, 3) igemm_down_kernel(DownArgs a)
     const int64_t hw = DIM == 2 ? (int64_t)a.h * a.w : (int64_t)a.w;
     uint32_t tc_ = 0;
     for (int64_t item = blockIdx.x; item < total; item += gridDim.x, ++tc_) {
-      const int nt = (int)(item % a.ntn);
-      const int64_t q = (item / a.ntn) * 128 + tid;
+      const uint32_t mt = fdiv((uint32_t)item, a.d_ntn);
+      const int nt = (int)((uint32_t)item - mt * (uint32_t)a.ntn);
+      const int64_t q = (int64_t)mt * 128 + tid;
       bool ok = q < a.Q;
       int64_t n = 0, pos = 0;
       if (ok) {
         const uint32_t uq = (uint32_t)q;
         if (DIM == 2) {
-          const uint32_t un = uq / (uint32_t)(PH * PW);
+          const uint32_t un = fdiv(uq, a.d_pp);
           const uint32_t r = uq - un * (uint32_t)(PH * PW);
-          const int by = (int)(r / (uint32_t)PW), bx = (int)(r - (r / (uint32_t)PW) * PW);
+          const int by = (int)fdiv(r, a.d_pw), bx = (int)r - by * PW;
           ok = by < a.h && bx < a.w;
           n = un; pos = (int64_t)by * a.w + bx;
         } else {
-          const uint32_t un = uq / (uint32_t)a.w;
+          const uint32_t un = fdiv(uq, a.d_w);
           n = un; pos = uq - un * (uint32_t)a.w;
         }
       }
@@ -364,16 +366,17 @@ __global__ void __launch_bounds__(DOWN_THREADS, 3) igemm_down_kernel(DownArgs a)
     // ------------------------------------------------ MMA issuer (one elected lane)
     if (lane == 0) {
       const uint32_t idesc = make_idesc(NT, 0, 0);
-      uint32_t it = 0, tc_ = 0;
+      uint32_t tc_ = 0;
+      Ring ring{0, 0};
       if (wres) mbar_wait(&w_bar, 0);
       for (int64_t item = blockIdx.x; item < total; item += gridDim.x, ++tc_) {
         const uint32_t buf = tc_ & 1;
         mbar_wait(&acc_empty[buf], ((tc_ >> 1) & 1) ^ 1);
         fence_after();
         uint32_t acc = 0;
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % NS, ph = (it / NS) & 1;
-          mbar_wait(&full_bar[s], ph);
+        for (int kb = 0; kb < KB; ++kb, ring.next(NS)) {
+          const int s = ring.s;
+          mbar_wait(&full_bar[s], ring.ph);
           fence_after();
           const uint32_t zhi = smem_u32(smem + (size_t)s * stage_bytes) + rawb;
           const uint32_t bhi = wres ? smem_u32(wres_ptr) : zhi + 2 * zbytes;
@@ -398,22 +401,23 @@ __global__ void __launch_bounds__(DOWN_THREADS, 3) igemm_down_kernel(DownArgs a)
       }
     }
   } else {
-    // ------------------------------------------------ loader warp: weight images (+ raw input rows)
-    uint32_t it = 0;
-    if (wres && lane == 0) {
-      mbar_arrive_expect_tx(&w_bar, IMG);
-      bulk_g2s(wres_ptr, a.wimg, IMG, &w_bar);
-    }
-    for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
-      const int nt = (int)(item % a.ntn);
-      for (int kb = 0; kb < KB; ++kb, ++it) {
-        const int s = it % NS, ph = (it / NS) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* stage = smem + (size_t)s * stage_bytes;
-        if (lane == 0) {
-          if (wres) {
-            mbar_arrive(&full_bar[s]);
-          } else {
+    // ------------------------------------------------ loader warp: weight images
+    if (wres) {
+      // resident image: one fetch, the stage barriers then count the four producer warps only
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&w_bar, IMG);
+        bulk_g2s(wres_ptr, a.wimg, IMG, &w_bar);
+      }
+    } else {
+      Ring ring{0, 0};
+      for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+        const uint32_t mt = fdiv((uint32_t)item, a.d_ntn);
+        const int nt = (int)((uint32_t)item - mt * (uint32_t)a.ntn);
+        for (int kb = 0; kb < KB; ++kb, ring.next(NS)) {
+          const int s = ring.s;
+          mbar_wait(&empty_bar[s], ring.ph ^ 1);
+          uint8_t* stage = smem + (size_t)s * stage_bytes;
+          if (lane == 0) {
             mbar_arrive_expect_tx(&full_bar[s], IMG);
             bulk_g2s(stage + rawb + 2 * zbytes, a.wimg + ((size_t)nt * KB + kb) * IMG, IMG, &full_bar[s]);
           }
@@ -452,9 +456,11 @@ int launch_down(int dim, DownArgs a, cudaStream_t st) {
   const DownGeom g = down_geom(dim, a.A, a.Bc);
   a.slots = dim == 2 ? (128 + a.w + 2 + 7) / 8 * 8 : 128;
   a.Q = dim == 2 ? a.N * (int64_t)(a.h + 1) * (a.w + 1) : a.N * (int64_t)a.w;
+  a.d_pp = make_fastdiv((uint32_t)((a.h + 1) * (a.w + 1))); a.d_pw = make_fastdiv((uint32_t)(a.w + 1)); a.d_w = make_fastdiv((uint32_t)a.w);
   LSHM_REQUIRE(a.Q < (1LL << 31) - 4096, "lshm_down: too many positions (%lld) for one call; split the batch", (long long)a.Q);
   a.mtiles = ceil_div(a.Q, 128);
   a.ntn = g.ntiles;
+  a.d_ntn = make_fastdiv((uint32_t)a.ntn);
   const bool aligned = (reinterpret_cast<uintptr_t>(a.big) & 15) == 0 && (a.big_ns & 3) == 0;
   bool raw = false;
   static const bool wres_off = getenv("LSHM_DOWN_NOWRES") != nullptr;   // experiment switch

@@ -26,6 +26,7 @@ struct UpArgs {
   float* big; int64_t big_ns;
   int64_t N; int A; int Bc; int h; int w; int pad; int epi;
   int slots; int nstage; int64_t Q; int64_t mtiles; int ntn;
+  FastDiv d_pp, d_pw, d_w, d_ntn;   // divisors (h+1)(w+1), w+1, w, ntn
 };
 
 // warps 0-3 epilogue, 4-7 producers, 8 MMA issuer, 9 weight loader, (2-D only) 10 second MMA issuer
@@ -81,9 +82,9 @@ __global__ void __launch_bounds__(up_threads(DIM), (DIM == 1 ? 3 : 2)) igemm_up_
     // ------------------------------------------------ producers: stage S (hi/lo bf16), K = channels
     const int ptid = tid - 128;
     const int64_t hw = DIM == 2 ? (int64_t)a.h * a.w : (int64_t)a.w;
-    uint32_t it = 0;
+    Ring ring{0, 0};
     for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
-      const int64_t q0 = (item / a.ntn) * 128;
+      const int64_t q0 = (int64_t)fdiv((uint32_t)item, a.d_ntn) * 128;
       const float* sp[NSLOT]; bool sv[NSLOT];
 #pragma unroll
       for (int i = 0; i < NSLOT; ++i) {
@@ -94,20 +95,20 @@ __global__ void __launch_bounds__(up_threads(DIM), (DIM == 1 ? 3 : 2)) igemm_up_
         if (sv[i]) {
           const uint32_t uq = (uint32_t)q;              // Q < 2^31 (launcher): 32-bit divisions only
           if (DIM == 2) {
-            const uint32_t n = uq / (uint32_t)(PH * PW);
+            const uint32_t n = fdiv(uq, a.d_pp);
             const uint32_t r = uq - n * (uint32_t)(PH * PW);
-            const int m = (int)(r / (uint32_t)PW), x = (int)(r - (r / (uint32_t)PW) * PW);
+            const int m = (int)fdiv(r, a.d_pw), x = (int)r - m * PW;
             sv[i] = m < a.h && x < a.w;
             sp[i] = a.small_ + (int64_t)n * a.small_ns + (int64_t)m * a.w + x;
           } else {
-            const uint32_t n = uq / (uint32_t)a.w;
+            const uint32_t n = fdiv(uq, a.d_w);
             sp[i] = a.small_ + (int64_t)n * a.small_ns + (uq - n * (uint32_t)a.w);
           }
         }
       }
-      for (int kb = 0; kb < KB; ++kb, ++it) {
-        const int s = it % NS, ph = (it / NS) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+      for (int kb = 0; kb < KB; ++kb, ring.next(NS)) {
+        const int s = ring.s;
+        mbar_wait(&empty_bar[s], ring.ph ^ 1);
         uint8_t* zhi = smem + (size_t)s * stage_bytes;
         uint8_t* zlo = zhi + zbytes;
         const int ccb = (min(KC, Apad - kb * KC)) >> 3;
@@ -148,20 +149,21 @@ __global__ void __launch_bounds__(up_threads(DIM), (DIM == 1 ? 3 : 2)) igemm_up_
     // ------------------------------------------------ epilogue
     uint32_t tc_ = 0;
     for (int64_t item = blockIdx.x; item < total; item += gridDim.x, ++tc_) {
-      const int nt = (int)(item % a.ntn);
-      const int64_t q = (item / a.ntn) * 128 + tid;
+      const uint32_t mt = fdiv((uint32_t)item, a.d_ntn);
+      const int nt = (int)((uint32_t)item - mt * (uint32_t)a.ntn);
+      const int64_t q = (int64_t)mt * 128 + tid;
       bool ok = q < a.Q;
       int64_t n = 0; int m = 0, x = 0;
       if (ok) {
         const uint32_t uq = (uint32_t)q;
         if (DIM == 2) {
-          const uint32_t un = uq / (uint32_t)(PH * PW);
+          const uint32_t un = fdiv(uq, a.d_pp);
           const uint32_t r = uq - un * (uint32_t)(PH * PW);
-          m = (int)(r / (uint32_t)PW); x = (int)(r - (r / (uint32_t)PW) * PW);
+          m = (int)fdiv(r, a.d_pw); x = (int)r - m * PW;
           ok = m < a.h && x < a.w;
           n = un;
         } else {
-          const uint32_t un = uq / (uint32_t)a.w;
+          const uint32_t un = fdiv(uq, a.d_w);
           n = un; x = (int)(uq - un * (uint32_t)a.w);
         }
       }
@@ -259,15 +261,16 @@ __global__ void __launch_bounds__(up_threads(DIM), (DIM == 1 ? 3 : 2)) igemm_up_
     const bool leader = lane == 0;
     const uint32_t idesc = make_idesc(NT, 0, 0);
     const int cb0 = DIM == 2 ? mw * (COMBOS / 2) : 0, cb1 = DIM == 2 ? cb0 + COMBOS / 2 : COMBOS;
-    uint32_t it = 0, tc_ = 0;
+    uint32_t tc_ = 0;
+    Ring ring{0, 0};
     for (int64_t item = blockIdx.x; item < total; item += gridDim.x, ++tc_) {
       const uint32_t buf = tc_ & 1;
       mbar_wait(&acc_empty[buf], ((tc_ >> 1) & 1) ^ 1);
       fence_after();
       const uint32_t tset = tmem + buf * TSET;
-      for (int kb = 0; kb < KB; ++kb, ++it) {
-        const int s = it % NS, ph = (it / NS) & 1;
-        mbar_wait(&full_bar[s], ph);
+      for (int kb = 0; kb < KB; ++kb, ring.next(NS)) {
+        const int s = ring.s;
+        mbar_wait(&full_bar[s], ring.ph);
         fence_after();
         const uint32_t zhi = smem_u32(smem + (size_t)s * stage_bytes);
         const uint64_t dah = make_desc(zhi, SLOTS * 16, 128), dal = make_desc(zhi + zbytes, SLOTS * 16, 128);
@@ -296,12 +299,13 @@ __global__ void __launch_bounds__(up_threads(DIM), (DIM == 1 ? 3 : 2)) igemm_up_
     }
   } else {
     if (lane == 0) {
-      uint32_t it = 0;
+      Ring ring{0, 0};
       for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
-        const int nt = (int)(item % a.ntn);
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % NS, ph = (it / NS) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
+        const uint32_t mt = fdiv((uint32_t)item, a.d_ntn);
+        const int nt = (int)((uint32_t)item - mt * (uint32_t)a.ntn);
+        for (int kb = 0; kb < KB; ++kb, ring.next(NS)) {
+          const int s = ring.s;
+          mbar_wait(&empty_bar[s], ring.ph ^ 1);
           mbar_arrive_expect_tx(&full_bar[s], IMG);
           bulk_g2s(smem + (size_t)s * stage_bytes + 2 * zbytes, a.wimg + ((size_t)nt * KB + kb) * IMG, IMG, &full_bar[s]);
         }
@@ -340,9 +344,11 @@ int launch_up(int dim, UpArgs a, cudaStream_t st) {
   const UpGeom g = up_geom(dim, a.A, a.Bc);
   a.slots = dim == 2 ? (128 + 2 * (a.w + 2) + 7) / 8 * 8 : 128;
   a.Q = dim == 2 ? a.N * (int64_t)(a.h + 1) * (a.w + 1) : a.N * (int64_t)a.w;
+  a.d_pp = make_fastdiv((uint32_t)((a.h + 1) * (a.w + 1))); a.d_pw = make_fastdiv((uint32_t)(a.w + 1)); a.d_w = make_fastdiv((uint32_t)a.w);
   LSHM_REQUIRE(a.Q < (1LL << 31) - 4096, "lshm_up: too many positions (%lld) for one call; split the batch", (long long)a.Q);
   a.mtiles = ceil_div(a.Q, 128);
   a.ntn = g.ntiles;
+  a.d_ntn = make_fastdiv((uint32_t)a.ntn);
 #define LU(D, NTV, KCV) return launch_up_t<D, NTV, KCV>(a, g, st)
   if (dim == 2) {
     switch (g.NT) { case 16: LU(2, 16, 16); case 32: LU(2, 32, 16); default: LU(2, 48, 16); }

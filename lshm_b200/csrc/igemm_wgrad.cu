@@ -10,7 +10,7 @@
 // are again four descriptor start addresses into one Z tile and accumulate in four TMEM column
 // ranges.  The position range is split over CTAs (split-K); partial results are combined with
 // fp32 atomics into dW (zeroed first), already in the reference weight layout.
-#include "tc_common.cuh"
+#include "conv_geom.cuh"
 
 namespace lshm {
 namespace {
@@ -24,6 +24,7 @@ struct WgArgs {
   float* dw;
   int64_t N; int A; int Bc; int h; int w; int pad;
   int zslots; int nstage; int64_t Q; int64_t kblocks; int64_t kb_per_cta; int ntiles; int scols; int vec_ok;
+  FastDiv d_pp, d_pw, d_w, d_zs;   // divisors (h+1)(w+1), w+1, w, zslots
 };
 
 // KP = positions per K block: 128 for the shallow layers (fewer pipeline hand-offs per byte), 64 for the
@@ -68,10 +69,11 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
   if (warp < 4) {
     const int H = 2 * a.h, W = 2 * a.w;
     const int64_t hw = DIM == 2 ? (int64_t)a.h * a.w : (int64_t)a.w;
-    for (int it = 0; it < nkb; ++it) {
-      const int s = it % NS, ph = (it / NS) & 1;
+    Ring ring{0, 0};
+    for (int it = 0; it < nkb; ++it, ring.next(NS)) {
+      const int s = ring.s;
       const int64_t p0 = (kb0 + it) * KP;
-      mbar_wait(&empty_bar[s], ph ^ 1);
+      mbar_wait(&empty_bar[s], ring.ph ^ 1);
       uint8_t* shi = smem + (size_t)s * stage_bytes;
       uint8_t* slo = shi + SBYTES;
       uint8_t* zhi = slo + SBYTES;
@@ -92,11 +94,11 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
           if (item < KP * a.scols && ca < sch && q < uQ) {
             const float* sp = nullptr;
             if (DIM == 2) {
-              const uint32_t n = q / upp, r = q - n * upp;
-              const uint32_t m = r / uPW, x = r - m * uPW;
+              const uint32_t n = fdiv(q, a.d_pp), r = q - n * upp;
+              const uint32_t m = fdiv(r, a.d_pw), x = r - m * uPW;
               if (m < (uint32_t)a.h && x < uw) sp = a.small_ + (int64_t)n * a.small_ns + (int64_t)m * a.w + x;
             } else {
-              const uint32_t n = q / uw;
+              const uint32_t n = fdiv(q, a.d_w);
               sp = a.small_ + (int64_t)n * a.small_ns + (q - n * uw);
             }
             if (sp != nullptr) {
@@ -127,15 +129,15 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
 #pragma unroll
         for (int u = 0; u < UZ; ++u) {
           const int item = item0 + u * 128;
-          const int slot = item % ZS, cz = item / ZS;
+          const int cz = (int)fdiv((uint32_t)item, a.d_zs), slot = item - cz * ZS;
           const uint32_t q = up0 + slot;
           const int b0 = (c0 + cz * 8) >> 2;
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
           if (item < ZS * CZ && q < uQ) {
             if (DIM == 2) {
-              const uint32_t n = q / upp, r = q - n * upp;
-              const int by = (int)(r / uPW), bx = (int)(r - (r / uPW) * uPW);
+              const uint32_t n = fdiv(q, a.d_pp), r = q - n * upp;
+              const int by = (int)fdiv(r, a.d_pw), bx = (int)r - by * PW;
               const int r0 = 2 * by - 1, cc0 = 2 * bx - 1;
 #pragma unroll
               for (int bb = 0; bb < 2; ++bb) {
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
                 }
               }
             } else {
-              const uint32_t n = q / uw;
+              const uint32_t n = fdiv(q, a.d_w);
               const int j = (int)(q - n * uw);
               const int64_t Lb = 4 * (int64_t)a.w;
 #pragma unroll
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
         for (int u = 0; u < UZ; ++u) {
           const int item = item0 + u * 128;
           if (item < ZS * CZ) {
-            const int slot = item % ZS, cz = item / ZS;
+            const int cz = (int)fdiv((uint32_t)item, a.d_zs), slot = item - cz * ZS;
             uint4 hi, lo;
             split8(v[u], hi, lo);
             *reinterpret_cast<uint4*>(zhi + ((size_t)cz * ZS + slot) * 16) = hi;
@@ -224,9 +226,10 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
     // ------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc(NT, 1, 1);
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % NS, ph = (it / NS) & 1;
-        mbar_wait(&full_bar[s], ph);
+      Ring ring{0, 0};
+      for (int it = 0; it < nkb; ++it, ring.next(NS)) {
+        const int s = ring.s;
+        mbar_wait(&full_bar[s], ring.ph);
         fence_after();
         const uint32_t shi = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t slo = shi + SBYTES;
@@ -275,12 +278,14 @@ int launch_wgrad(int dim, WgArgs a, cudaStream_t st) {
   a.ntiles = (Kc + NT - 1) / NT;
   const int mtiles = (a.A + 127) / 128;
   a.Q = dim == 2 ? a.N * (int64_t)(a.h + 1) * (a.w + 1) : a.N * (int64_t)a.w;
+  a.d_pp = make_fastdiv((uint32_t)((a.h + 1) * (a.w + 1))); a.d_pw = make_fastdiv((uint32_t)(a.w + 1)); a.d_w = make_fastdiv((uint32_t)a.w);
   LSHM_REQUIRE(a.Q < (1LL << 31) - 4096, "lshm_wgrad: too many positions (%lld) for one call; split the batch", (long long)a.Q);
   a.scols = std::min(16, (std::min(a.A, 128) + 7) / 8);
   a.vec_ok = ((reinterpret_cast<uintptr_t>(a.big) & 15) == 0 && (a.big_ns & 3) == 0) ? 1 : 0;
   const int KP = (a.scols <= 2 && NT <= 32) ? 128 : 64;
   a.kblocks = ceil_div(a.Q, KP);
   a.zslots = dim == 2 ? (KP + a.w + 2 + 7) / 8 * 8 : KP;
+  a.d_zs = make_fastdiv((uint32_t)a.zslots);
   const size_t stage = (size_t)2 * a.scols * KP * 16 + (size_t)2 * (NT / 8) * a.zslots * 16;
   a.nstage = (int)std::min<size_t>(3, std::max<size_t>(2, (72 * 1024) / stage));
   const int64_t tiles = (int64_t)mtiles * a.ntiles;

@@ -104,6 +104,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
     backoff_ns = backoff_ns < 256 ? backoff_ns * 2 : backoff_ns;
   }
 }
+// position in a ring of `n` pipeline stages: stage index and phase bit, advanced without the
+// division/modulo by a run-time stage count (~40 instructions per hand-off in the first version)
+struct Ring {
+  int s; uint32_t ph;
+  __device__ __forceinline__ void next(int n) { if (++s == n) { s = 0; ph ^= 1u; } }
+};
+
 // 1-D bulk copy global -> shared, completion counted on `bar` (bytes multiple of 16, 16 B aligned)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
