@@ -38,6 +38,52 @@ constexpr int MAXST = 6;
 // producers run ahead through a ring of shared-memory stages, the MMA warp alternates between two
 // TMEM accumulators, the epilogue warps drain one while the next is being computed.
 //
+// One accumulator tile -> bias / activation -> global for the thread's output position.  Independent
+// loads first (bias, ELU' operand), then the accumulator, then math and stores, in halves of 8 channels
+// behind warp-uniform branches: the 8- and 12-channel layers (the two largest maps) skip the padding
+// half.  The first version went channel by channel with expm1f and 64-bit index math (~1500
+// instructions per tile for a lone warp, the bottleneck of the whole kernel); the epilogue mode is a
+// template parameter so no element carries the predicated-off instructions of the other modes.
+template <int NT, int EPI>
+__device__ __forceinline__ void down_epilogue_tile(const DownArgs& a, uint32_t trow, int nt, float* outp,
+                                                   const float* auxp, int64_t hw, bool ok) {
+#pragma unroll 1
+  for (int g = 0; g < NT / 16; ++g) {
+    const int ch0 = nt * NT + g * 16;
+    const int nch = min(16, a.A - ch0);
+    if (nch <= 0) break;                      // warp-uniform
+    float bs[16], ax[16];
+    const float* bp = a.bias + ch0;
+    const float* xp = auxp + (int64_t)ch0 * hw;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      if (hf * 8 < nch) {
+#pragma unroll
+        for (int j = hf * 8; j < hf * 8 + 8; ++j) {
+          bs[j] = (a.bias != nullptr && j < nch) ? __ldg(bp + j) : 0.f;
+          ax[j] = 0.f;
+          if (EPI == LSHM_EPI_DELU && ok && j < nch) ax[j] = __ldg(xp + (int64_t)j * hw);
+        }
+      }
+    }
+    float v[16];
+    tmem_ld16(trow + g * 16, v);
+    float* op = outp + (int64_t)ch0 * hw;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      if (hf * 8 < nch) {
+#pragma unroll
+        for (int j = hf * 8; j < hf * 8 + 8; ++j) {
+          float r = v[j] + bs[j];
+          if (EPI == LSHM_EPI_ELU) r = elu_fast(r);
+          else if (EPI == LSHM_EPI_DELU) r *= delu_from_out(ax[j]);
+          if (ok && j < nch) op[(int64_t)j * hw] = r;
+        }
+      }
+    }
+  }
+}
+
 // RAW = true (maps whose rows are >= 256 B): the input rows a tile needs are first copied as they are
 // (fp32) into shared memory by bulk async copies issued by the loader warp, several stages ahead,
 // and the producer warps only convert shared -> shared.  Registers then hold no in-flight HBM data,
@@ -323,41 +369,10 @@ __global__ void __launch_bounds__(DOWN_THREADS, 3) igemm_down_kernel(DownArgs a)
       const uint32_t buf = tc_ & 1;
       mbar_wait(&acc_full[buf], (tc_ >> 1) & 1);
       fence_after();
-#pragma unroll 1
-      for (int g = 0; g < NT / 16; ++g) {
-        // Independent loads first (bias, ELU' operand), then the accumulator, then math, then stores,
-        // only over the channels that exist.  The first version went channel by channel with expm1f
-        // and 64-bit index math: ~1500 instructions per tile for a lone warp, which made the four
-        // epilogue warps the bottleneck of the whole kernel (ncu source view).
-        const int ch0 = nt * NT + g * 16;
-        const int nch = min(16, a.A - ch0);
-        if (nch <= 0) break;                      // warp-uniform
-        float bs[16], ax[16];
-        const float* bp = a.bias + ch0;
-        const float* xp = auxp + (int64_t)ch0 * hw;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          bs[j] = (a.bias != nullptr && j < nch) ? __ldg(bp + j) : 0.f;
-          ax[j] = 0.f;
-          if (a.epi == LSHM_EPI_DELU && ok && j < nch) { ax[j] = __ldg(xp); xp += hw; }
-        }
-        float v[16];
-        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + buf * NT + g * 16, v);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float r = v[j] + bs[j];
-          if (a.epi == LSHM_EPI_ELU) r = elu_fast(r);
-          else if (a.epi == LSHM_EPI_DELU) r *= delu_from_out(ax[j]);
-          v[j] = r;
-        }
-        if (ok) {
-          float* op = outp + (int64_t)ch0 * hw;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (j < nch) { *op = v[j]; op += hw; }
-          }
-        }
-      }
+      const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16) + buf * NT;
+      if (a.epi == LSHM_EPI_ELU) down_epilogue_tile<NT, LSHM_EPI_ELU>(a, trow, nt, outp, auxp, hw, ok);
+      else if (a.epi == LSHM_EPI_DELU) down_epilogue_tile<NT, LSHM_EPI_DELU>(a, trow, nt, outp, auxp, hw, ok);
+      else down_epilogue_tile<NT, LSHM_EPI_NONE>(a, trow, nt, outp, auxp, hw, ok);
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);

@@ -33,11 +33,98 @@ struct UpArgs {
 constexpr int up_threads(int dim) { return dim == 2 ? 352 : 320; }
 constexpr int UP_MAXST = 6;
 
-__device__ __forceinline__ float epi_apply(float acc, float bias, int epi, float aux) {
+template <int EPI>
+__device__ __forceinline__ float epi_apply(float acc, float bias, float aux) {
   float r = acc + bias;
-  if (epi == LSHM_EPI_ELU) r = elu_fast(r);
-  else if (epi == LSHM_EPI_DELU) r *= delu_from_out(aux);
+  if (EPI == LSHM_EPI_ELU) r = elu_fast(r);
+  else if (EPI == LSHM_EPI_DELU) r *= delu_from_out(aux);
   return r;
+}
+
+// One accumulator set -> bias / activation -> global, for the thread's position (n, m, x).  The
+// epilogue mode is a template parameter (dispatched once per tile by a warp-uniform switch): with a
+// run-time mode every element carried the predicated-off instructions of the other two modes.
+template <int DIM, int NT, int EPI>
+__device__ __forceinline__ void up_epilogue_tile(const UpArgs& a, uint32_t trow, int nt, int64_t n, int m, int x, bool ok) {
+  if (DIM == 2) {
+    const int W = 2 * a.w;
+    const int64_t HW = 4 * (int64_t)a.h * a.w;
+    float* outp = a.big + n * a.big_ns + (int64_t)(2 * m) * W + 2 * x;
+    const float* auxp = EPI == LSHM_EPI_DELU ? a.aux + n * a.aux_ns + (int64_t)(2 * m) * W + 2 * x : nullptr;
+#pragma unroll 1
+    for (int g = 0; g < NT / 16; ++g) {
+      const int b0 = nt * NT + g * 16;
+      const int nch = min(16, a.Bc - b0);
+      if (nch <= 0) break;                       // warp-uniform
+      float v[4][16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld16(trow + c * NT + g * 16, v[c]);
+      if (ok) {
+        float* op = outp + (int64_t)b0 * HW;
+        const float* xp = EPI == LSHM_EPI_DELU ? auxp + (int64_t)b0 * HW : nullptr;
+        const float* bp = a.bias != nullptr ? a.bias + b0 : nullptr;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          if (hf * 8 < nch) {                    // warp-uniform: the padding half of 8/12-channel layers is skipped
+#pragma unroll
+            for (int j = hf * 8; j < hf * 8 + 8; ++j) {
+              if (j < nch) {
+                const float bs = bp != nullptr ? __ldg(bp + j) : 0.f;
+                float2 ax0 = make_float2(0.f, 0.f), ax1 = make_float2(0.f, 0.f);
+                if (EPI == LSHM_EPI_DELU) {
+                  ax0 = *reinterpret_cast<const float2*>(xp + (int64_t)j * HW);
+                  ax1 = *reinterpret_cast<const float2*>(xp + (int64_t)j * HW + W);
+                }
+                // class index = ry*2 + rx
+                const float2 o0 = make_float2(epi_apply<EPI>(v[0][j], bs, ax0.x), epi_apply<EPI>(v[1][j], bs, ax0.y));
+                const float2 o1 = make_float2(epi_apply<EPI>(v[2][j], bs, ax1.x), epi_apply<EPI>(v[3][j], bs, ax1.y));
+                *reinterpret_cast<float2*>(op + (int64_t)j * HW) = o0;
+                *reinterpret_cast<float2*>(op + (int64_t)j * HW + W) = o1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    const int64_t Lb = 4 * (int64_t)a.w;
+    float* outp = a.big + n * a.big_ns + 4 * (int64_t)x - a.pad;
+    const float* auxp = EPI == LSHM_EPI_DELU ? a.aux + n * a.aux_ns + 4 * (int64_t)x - a.pad : nullptr;
+#pragma unroll 1
+    for (int g = 0; g < NT / 16; ++g) {
+      const int bb0 = (nt * NT + g * 16) / 4;
+      if (bb0 >= a.Bc) break;                    // warp-uniform
+      float v[16];
+      tmem_ld16(trow + g * 16, v);
+      if (ok) {
+#pragma unroll
+        for (int jb = 0; jb < 4; ++jb) {
+          const int b = bb0 + jb;
+          if (b < a.Bc) {
+            const float bs = a.bias != nullptr ? __ldg(a.bias + b) : 0.f;
+            float* o = outp + b * Lb;
+            if (a.pad == 0 && EPI != LSHM_EPI_DELU) {
+              float4 r;
+              r.x = epi_apply<EPI>(v[jb * 4 + 0], bs, 0.f); r.y = epi_apply<EPI>(v[jb * 4 + 1], bs, 0.f);
+              r.z = epi_apply<EPI>(v[jb * 4 + 2], bs, 0.f); r.w = epi_apply<EPI>(v[jb * 4 + 3], bs, 0.f);
+              *reinterpret_cast<float4*>(o) = r;
+            } else {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                if (a.pad == 1 && x == 0 && t == 0) continue;        // position -1 does not exist
+                const float ax = EPI == LSHM_EPI_DELU ? auxp[b * Lb + t] : 0.f;
+                o[t] = epi_apply<EPI>(v[jb * 4 + t], bs, ax);
+              }
+              if (a.pad == 1 && x == a.w - 1) {                       // last position: no tap reaches it
+                const float ax = EPI == LSHM_EPI_DELU ? auxp[b * Lb + 4] : 0.f;
+                o[4] = epi_apply<EPI>(0.f, bs, ax);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
 }
 
 // Persistent, warp-specialised (same skeleton as igemm_down.cu): producers run ahead through the
@@ -171,82 +258,9 @@ __global__ void __launch_bounds__(up_threads(DIM), (DIM == 1 ? 3 : 2)) igemm_up_
       mbar_wait(&acc_full[buf], (tc_ >> 1) & 1);
       fence_after();
       const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16) + buf * TSET;
-      if (DIM == 2) {
-        const int W = 2 * a.w;
-        const int64_t HW = 4 * (int64_t)a.h * a.w;
-        float* outp = a.big + n * a.big_ns + (int64_t)(2 * m) * W + 2 * x;
-        const float* auxp = a.aux != nullptr ? a.aux + n * a.aux_ns + (int64_t)(2 * m) * W + 2 * x : nullptr;
-#pragma unroll 1
-        for (int g = 0; g < NT / 16; ++g) {
-          const int b0 = nt * NT + g * 16;
-          const int nch = min(16, a.Bc - b0);
-          if (nch <= 0) break;                       // warp-uniform
-          float v[4][16];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) tmem_ld16(trow + c * NT + g * 16, v[c]);
-          if (ok) {
-            float* op = outp + (int64_t)b0 * HW;
-            const float* xp = a.epi == LSHM_EPI_DELU ? auxp + (int64_t)b0 * HW : nullptr;
-            const float* bp = a.bias != nullptr ? a.bias + b0 : nullptr;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (j < nch) {
-                const float bs = bp != nullptr ? __ldg(bp + j) : 0.f;
-                float2 ax0 = make_float2(0.f, 0.f), ax1 = make_float2(0.f, 0.f);
-                if (a.epi == LSHM_EPI_DELU) {
-                  ax0 = *reinterpret_cast<const float2*>(xp);
-                  ax1 = *reinterpret_cast<const float2*>(xp + W);
-                  xp += HW;
-                }
-                // class index = ry*2 + rx
-                const float2 o0 = make_float2(epi_apply(v[0][j], bs, a.epi, ax0.x), epi_apply(v[1][j], bs, a.epi, ax0.y));
-                const float2 o1 = make_float2(epi_apply(v[2][j], bs, a.epi, ax1.x), epi_apply(v[3][j], bs, a.epi, ax1.y));
-                *reinterpret_cast<float2*>(op) = o0;
-                *reinterpret_cast<float2*>(op + W) = o1;
-                op += HW;
-              }
-            }
-          }
-        }
-      } else {
-        const int64_t Lb = 4 * (int64_t)a.w;
-        float* outp = a.big + n * a.big_ns + 4 * (int64_t)x - a.pad;
-        const float* auxp = a.aux != nullptr ? a.aux + n * a.aux_ns + 4 * (int64_t)x - a.pad : nullptr;
-#pragma unroll 1
-        for (int g = 0; g < NT / 16; ++g) {
-          const int bb0 = (nt * NT + g * 16) / 4;
-          if (bb0 >= a.Bc) break;                    // warp-uniform
-          float v[16];
-          tmem_ld16(trow + g * 16, v);
-          if (ok) {
-#pragma unroll
-            for (int jb = 0; jb < 4; ++jb) {
-              const int b = bb0 + jb;
-              if (b < a.Bc) {
-                const float bs = a.bias != nullptr ? __ldg(a.bias + b) : 0.f;
-                float* o = outp + b * Lb;
-                if (a.pad == 0 && a.epi != LSHM_EPI_DELU) {
-                  float4 r;
-                  r.x = epi_apply(v[jb * 4 + 0], bs, a.epi, 0.f); r.y = epi_apply(v[jb * 4 + 1], bs, a.epi, 0.f);
-                  r.z = epi_apply(v[jb * 4 + 2], bs, a.epi, 0.f); r.w = epi_apply(v[jb * 4 + 3], bs, a.epi, 0.f);
-                  *reinterpret_cast<float4*>(o) = r;
-                } else {
-#pragma unroll
-                  for (int t = 0; t < 4; ++t) {
-                    if (a.pad == 1 && x == 0 && t == 0) continue;        // position -1 does not exist
-                    const float ax = a.epi == LSHM_EPI_DELU ? auxp[b * Lb + t] : 0.f;
-                    o[t] = epi_apply(v[jb * 4 + t], bs, a.epi, ax);
-                  }
-                  if (a.pad == 1 && x == a.w - 1) {                       // last position: no tap reaches it
-                    const float ax = a.epi == LSHM_EPI_DELU ? auxp[b * Lb + 4] : 0.f;
-                    o[4] = epi_apply(0.f, bs, a.epi, ax);
-                  }
-                }
-              }
-            }
-          }
-        }
-      }
+      if (a.epi == LSHM_EPI_ELU) up_epilogue_tile<DIM, NT, LSHM_EPI_ELU>(a, trow, nt, n, m, x, ok);
+      else if (a.epi == LSHM_EPI_DELU) up_epilogue_tile<DIM, NT, LSHM_EPI_DELU>(a, trow, nt, n, m, x, ok);
+      else up_epilogue_tile<DIM, NT, LSHM_EPI_NONE>(a, trow, nt, n, m, x, ok);
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);

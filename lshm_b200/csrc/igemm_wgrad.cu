@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
   const uint32_t tmem = tmem_base;
 
   if (warp < 4) {
-    const int H = 2 * a.h, W = 2 * a.w;
+    const int W = 2 * a.w;
+    const int64_t HW2 = 4 * (int64_t)a.h * a.w;     // big-map plane size
     const int64_t hw = DIM == 2 ? (int64_t)a.h * a.w : (int64_t)a.w;
     Ring ring{0, 0};
     for (int it = 0; it < nkb; ++it, ring.next(NS)) {
@@ -138,23 +139,23 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
             if (DIM == 2) {
               const uint32_t n = fdiv(q, a.d_pp), r = q - n * upp;
               const int by = (int)fdiv(r, a.d_pw), bx = (int)r - by * PW;
-              const int r0 = 2 * by - 1, cc0 = 2 * bx - 1;
+              // one base pointer and four edge flags per slot; interior slots take the unpredicated path
+              const bool r0ok = by > 0, r1ok = by < a.h, c0ok = bx > 0, c1ok = bx < a.w;
+              const float* pb = a.big + (int64_t)n * a.big_ns + (int64_t)b0 * HW2 + (int64_t)(2 * by - 1) * W + (2 * bx - 1);
 #pragma unroll
               for (int bb = 0; bb < 2; ++bb) {
-                const int b = b0 + bb;
-                if (b < a.Bc) {
-                  const float* base = a.big + (int64_t)n * a.big_ns + (int64_t)b * H * W;
-#pragma unroll
-                  for (int yy = 0; yy < 2; ++yy) {
-                    const int rr = r0 + yy;
-                    const bool rin = rr >= 0 && rr < H;
-#pragma unroll
-                    for (int xx = 0; xx < 2; ++xx) {
-                      const int cx = cc0 + xx;
-                      if (rin && cx >= 0 && cx < W) v[u][bb * 4 + yy * 2 + xx] = __ldg(base + (int64_t)rr * W + cx);
-                    }
+                if (b0 + bb < a.Bc) {
+                  if (r0ok && r1ok && c0ok && c1ok) {
+                    v[u][bb * 4 + 0] = __ldg(pb); v[u][bb * 4 + 1] = __ldg(pb + 1);
+                    v[u][bb * 4 + 2] = __ldg(pb + W); v[u][bb * 4 + 3] = __ldg(pb + W + 1);
+                  } else {
+                    if (r0ok && c0ok) v[u][bb * 4 + 0] = __ldg(pb);
+                    if (r0ok && c1ok) v[u][bb * 4 + 1] = __ldg(pb + 1);
+                    if (r1ok && c0ok) v[u][bb * 4 + 2] = __ldg(pb + W);
+                    if (r1ok && c1ok) v[u][bb * 4 + 3] = __ldg(pb + W + 1);
                   }
                 }
+                pb += HW2;
               }
             } else {
               const uint32_t n = fdiv(q, a.d_w);
