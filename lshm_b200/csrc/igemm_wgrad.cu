@@ -224,35 +224,34 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
       }
     }
   } else {
-    // ------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(NT, 1, 1);
-      Ring ring{0, 0};
-      for (int it = 0; it < nkb; ++it, ring.next(NS)) {
-        const int s = ring.s;
-        mbar_wait(&full_bar[s], ring.ph);
-        fence_after();
-        const uint32_t shi = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t slo = shi + SBYTES;
-        const uint32_t zhi = slo + SBYTES;
-        const uint32_t zlo = zhi + zbytes;
-        // rolled on purpose: keeps the issuing lane's code small (instruction-cache footprint)
+    // ------------------------------------------------ MMA issuer: warp-uniform loop, one elected lane issues
+    const uint32_t idesc = make_idesc(NT, 1, 1);
+    Ring ring{0, 0};
+    for (int it = 0; it < nkb; ++it, ring.next(NS)) {
+      const int s = ring.s;
+      mbar_wait(&full_bar[s], ring.ph);
+      fence_after();
+      const uint32_t shi = smem_u32(smem + (size_t)s * stage_bytes);
+      const uint32_t slo = shi + SBYTES;
+      const uint32_t zhi = slo + SBYTES;
+      const uint32_t zlo = zhi + zbytes;
+      const uint64_t dsh = make_desc(shi, 128, KP * 16), dsl = make_desc(slo, 128, KP * 16);
+      const uint64_t dzh = make_desc(zhi, 128, ZS * 16), dzl = make_desc(zlo, 128, ZS * 16);
+      // rolled on purpose: keeps the issuing warp's code small (instruction-cache footprint)
 #pragma unroll 1
-        for (int tap = 0; tap < T; ++tap) {
-          const uint32_t shift = DIM == 2 ? (uint32_t)((tap >> 1) * PW + (tap & 1)) : 0u;
+      for (int tap = 0; tap < T; ++tap) {
+        const uint32_t shift = DIM == 2 ? (uint32_t)((tap >> 1) * PW + (tap & 1)) : 0u;
 #pragma unroll 1
-          for (int ks = 0; ks < KP / 16; ++ks) {
-            const uint32_t aoff = (uint32_t)ks * 256;
-            const uint32_t boff = ((uint32_t)ks * 16 + shift) * 16;
-            mma_split3(tmem + tap * NT, make_desc(shi + aoff, 128, KP * 16), make_desc(slo + aoff, 128, KP * 16),
-                       make_desc(zhi + boff, 128, ZS * 16), make_desc(zlo + boff, 128, ZS * 16), idesc,
-                       (it > 0 || ks > 0) ? 1u : 0u);
-          }
+        for (int ks = 0; ks < KP / 16; ++ks) {
+          const uint32_t ao = (uint32_t)ks * 16;                   // 16-byte units
+          const uint32_t bo = (uint32_t)ks * 16 + shift;
+          mma_split3_warp(tmem + tap * NT, desc_off(dsh, ao), desc_off(dsl, ao), desc_off(dzh, bo), desc_off(dzl, bo), idesc,
+                          (it > 0 || ks > 0) ? 1u : 0u);
         }
-        commit(&empty_bar[s]);
       }
-      commit(&acc_bar);
+      commit_warp(&empty_bar[s]);
     }
+    commit_warp(&acc_bar);
   }
   fence_before();
   __syncthreads();

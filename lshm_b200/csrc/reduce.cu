@@ -1,45 +1,54 @@
 // Bias gradients: db[c] = sum over samples and positions of g[n,c,:] (autograd of the bias add in
 // every conv / transposed conv, /root/reference/src/lofar_models.py:73-78,:93-98).
 //
-// One block per group of rows (n,c): rows are contiguous, read as float4 with many loads in flight,
-// no per-element index math; one atomic per (block, channel).
+// Rows (n,c) are contiguous and read as float4 with many loads in flight, no per-element index math.
+#include <algorithm>
 #include "common.cuh"
 
 namespace lshm {
 namespace {
 
-// long rows: one block per (n, c) row segment
+// long rows: persistent warps walk (row, 8 KB chunk) items, 16 independent 16-byte loads per lane in
+// flight, per-channel partial sums in shared memory, one global atomic per (block, channel).  The
+// first version ran one short-lived block per row (4-64 KB): block start-up, the two-barrier block
+// reduction and the atomic were a large part of every block's life (1.9 TB/s over the step's 36 calls).
+constexpr int CS_CHUNK = 2048;                  // floats per work item
 __global__ void __launch_bounds__(256)
-channel_sum_rows_kernel(const float* __restrict__ g, int64_t g_ns, float* __restrict__ db, int Cn, int64_t len,
-                        int vec_ok) {
-  __shared__ float red[32];
-  const int64_t row = blockIdx.x;             // n * Cn + c
-  const int64_t n = row / Cn;
-  const int c = (int)(row - n * Cn);
-  const float* p = g + n * g_ns + (int64_t)c * len;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  if (vec_ok) {
-    const float4* p4 = reinterpret_cast<const float4*>(p);
-    const int64_t n4 = len >> 2;
-    int64_t i = threadIdx.x;
-    for (; i + 3 * 256 < n4; i += 4 * 256) {
-      const float4 a = ld_nc_f4(reinterpret_cast<const float*>(p4 + i));
-      const float4 b = ld_nc_f4(reinterpret_cast<const float*>(p4 + i + 256));
-      const float4 cc = ld_nc_f4(reinterpret_cast<const float*>(p4 + i + 512));
-      const float4 d = ld_nc_f4(reinterpret_cast<const float*>(p4 + i + 768));
-      s0 += (a.x + a.y) + (a.z + a.w); s1 += (b.x + b.y) + (b.z + b.w);
-      s2 += (cc.x + cc.y) + (cc.z + cc.w); s3 += (d.x + d.y) + (d.z + d.w);
+channel_sum_rows_kernel(const float* __restrict__ g, int64_t g_ns, float* __restrict__ db, int64_t rows, int Cn,
+                        int64_t len, int chunks_per_row, int vec_ok) {
+  extern __shared__ float acc[];                // [Cn]
+  for (int c = threadIdx.x; c < Cn; c += blockDim.x) acc[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t items = rows * chunks_per_row;
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t item = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); item < items; item += nwarps) {
+    const int64_t row = item / chunks_per_row;
+    const int ck = (int)(item - row * chunks_per_row);
+    const int64_t n = row / Cn;
+    const int c = (int)(row - n * Cn);
+    const float* p = g + n * g_ns + (int64_t)c * len + (int64_t)ck * CS_CHUNK;
+    const int cnt = (int)min((int64_t)CS_CHUNK, len - (int64_t)ck * CS_CHUNK);
+    float s = 0.f;
+    if (vec_ok) {
+      const int n4 = cnt >> 2;
+      float4 v[CS_CHUNK / 128];
+#pragma unroll
+      for (int u = 0; u < CS_CHUNK / 128; ++u) {
+        const int i = lane + u * 32;
+        v[u] = i < n4 ? ld_nc_f4(p + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < CS_CHUNK / 128; ++u) s += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+      for (int j = (n4 << 2) + lane; j < cnt; j += 32) s += __ldg(p + j);
+    } else {
+      for (int j = lane; j < cnt; j += 32) s += __ldg(p + j);
     }
-    for (; i < n4; i += 256) {
-      const float4 a = ld_nc_f4(reinterpret_cast<const float*>(p4 + i));
-      s0 += (a.x + a.y) + (a.z + a.w);
-    }
-    for (int64_t j = (n4 << 2) + threadIdx.x; j < len; j += 256) s1 += p[j];
-  } else {
-    for (int64_t j = threadIdx.x; j < len; j += 256) s0 += p[j];
+    s = warp_sum(s);
+    if (lane == 0) atomicAdd(&acc[c], s);
   }
-  const float s = block_sum<float>((s0 + s1) + (s2 + s3), red);
-  if (threadIdx.x == 0) atomicAdd(db + c, s);
+  __syncthreads();
+  for (int c = threadIdx.x; c < Cn; c += blockDim.x) atomicAdd(db + c, acc[c]);
 }
 
 // short rows: one warp per (n, c) row, 8 rows per block
@@ -75,7 +84,11 @@ int lshm_channel_sum(const float* g, int64_t g_ns, float* db, int64_t N, int Cn,
   const int64_t rows = N * Cn;
   if (len >= 512) {
     const int vec_ok = ((reinterpret_cast<uintptr_t>(g) & 15) == 0 && (g_ns & 3) == 0 && (len & 3) == 0) ? 1 : 0;
-    channel_sum_rows_kernel<<<(unsigned)rows, 256, 0, st>>>(g, g_ns, db, Cn, len, vec_ok);
+    const int cpr = (int)ceil_div(len, (int64_t)CS_CHUNK);
+    const int64_t items = rows * cpr;
+    const int64_t want = ceil_div(items, (int64_t)8);
+    const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count() * 6);
+    channel_sum_rows_kernel<<<grid, 256, sizeof(float) * Cn, st>>>(g, g_ns, db, rows, Cn, len, cpr, vec_ok);
   } else {
     channel_sum_short_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(g, g_ns, db, rows, Cn, (int)len);
   }

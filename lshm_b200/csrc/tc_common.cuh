@@ -43,6 +43,26 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t 
                :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
 
+// Same instruction issued from warp-uniform code: every lane of the (converged) warp executes the call,
+// one elected lane issues.  The operands then stay in uniform registers; under `if (lane == 0)` the
+// compiler wraps every tcgen05.mma in a vote/broadcast "waterfall" (~16 instructions per MMA).
+__device__ __forceinline__ void mma_bf16_warp(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p, q;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|q, 0xffffffff;\n"
+               "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+               :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_split3_warp(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                                uint32_t idesc, uint32_t acc) {
+  mma_bf16_warp(tmem_d, a_hi, b_hi, idesc, acc);
+  mma_bf16_warp(tmem_d, a_lo, b_hi, idesc, 1u);
+  mma_bf16_warp(tmem_d, a_hi, b_lo, idesc, 1u);
+}
+__device__ __forceinline__ void commit_warp(uint64_t* bar) {     // warp-uniform call, one elected lane commits
+  asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
+               "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n"
+               :: "r"(smem_u32(bar)) : "memory");
+}
+
 // D += A*B with the 3-term bf16 split; *_hi / *_lo descriptors address the two halves
 __device__ __forceinline__ void mma_split3(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
                                            uint32_t idesc, uint32_t acc) {
