@@ -378,42 +378,44 @@ __global__ void __launch_bounds__(DOWN_THREADS, 3) igemm_down_kernel(DownArgs a)
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
   } else if (warp == 8) {
-    // ------------------------------------------------ MMA issuer (one elected lane)
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(NT, 0, 0);
-      uint32_t tc_ = 0;
-      Ring ring{0, 0};
-      if (wres) mbar_wait(&w_bar, 0);
-      for (int64_t item = blockIdx.x; item < total; item += gridDim.x, ++tc_) {
-        const uint32_t buf = tc_ & 1;
-        mbar_wait(&acc_empty[buf], ((tc_ >> 1) & 1) ^ 1);
+    // ------------------------------------------------ MMA issuer: warp-uniform loop, the elected lane issues
+    // (under `if (lane == 0)` every tcgen05.mma was wrapped in a vote/broadcast waterfall, ~16
+    // instructions per MMA; in uniform code the descriptors stay in uniform registers)
+    const uint32_t idesc = make_idesc(NT, 0, 0);
+    const uint32_t leader = elect_one();
+    uint32_t tc_ = 0;
+    Ring ring{0, 0};
+    if (wres) mbar_wait(&w_bar, 0);
+    for (int64_t item = blockIdx.x; item < total; item += gridDim.x, ++tc_) {
+      const uint32_t buf = tc_ & 1;
+      mbar_wait(&acc_empty[buf], ((tc_ >> 1) & 1) ^ 1);
+      fence_after();
+      uint32_t acc = 0;
+      for (int kb = 0; kb < KB; ++kb, ring.next(NS)) {
+        const int s = ring.s;
+        mbar_wait(&full_bar[s], ring.ph);
         fence_after();
-        uint32_t acc = 0;
-        for (int kb = 0; kb < KB; ++kb, ring.next(NS)) {
-          const int s = ring.s;
-          mbar_wait(&full_bar[s], ring.ph);
-          fence_after();
-          const uint32_t zhi = smem_u32(smem + (size_t)s * stage_bytes) + rawb;
-          const uint32_t bhi = wres ? smem_u32(wres_ptr) : zhi + 2 * zbytes;
-          const uint64_t dah = make_desc(zhi, SLOTS * 16, 128), dal = make_desc(zhi + zbytes, SLOTS * 16, 128);
-          const uint64_t dbh = make_desc(bhi, NT * 16, 128), dbl = make_desc(bhi + IMG / 2, NT * 16, 128);
-          const int ksteps = (min(KC, Kc - kb * KC)) >> 4;
-          // rolled on purpose: the issuing lane's code must stay small (instruction-cache footprint)
+        const uint32_t zhi = smem_u32(smem + (size_t)s * stage_bytes) + rawb;
+        const uint32_t bhi = wres ? smem_u32(wres_ptr) : zhi + 2 * zbytes;
+        const uint64_t dah = make_desc(zhi, SLOTS * 16, 128), dal = make_desc(zhi + zbytes, SLOTS * 16, 128);
+        const uint64_t dbh = make_desc(bhi, NT * 16, 128), dbl = make_desc(bhi + IMG / 2, NT * 16, 128);
+        const int ksteps = (min(KC, Kc - kb * KC)) >> 4;
+        // rolled on purpose: the issuing warp's code must stay small (instruction-cache footprint)
 #pragma unroll 1
-          for (int tap = 0; tap < T; ++tap) {
-            const uint32_t shift = DIM == 2 ? (uint32_t)((tap >> 1) * PW + (tap & 1)) : 0u;
+        for (int tap = 0; tap < T; ++tap) {
+          const uint32_t shift = DIM == 2 ? (uint32_t)((tap >> 1) * PW + (tap & 1)) : 0u;
 #pragma unroll 1
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint32_t ao = (uint32_t)(2 * ks) * SLOTS + shift;            // 16-byte units
-              const uint32_t bo = (uint32_t)(tap * CC + 2 * ks) * NT;
-              mma_split3(tmem + buf * NT, desc_off(dah, ao), desc_off(dal, ao), desc_off(dbh, bo), desc_off(dbl, bo), idesc, acc);
-              acc = 1;
-            }
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t ao = (uint32_t)(2 * ks) * SLOTS + shift;            // 16-byte units
+            const uint32_t bo = (uint32_t)(tap * CC + 2 * ks) * NT;
+            mma_split3_warp(tmem + buf * NT, desc_off(dah, ao), desc_off(dal, ao), desc_off(dbh, bo), desc_off(dbl, bo),
+                            idesc, acc, leader);
+            acc = 1;
           }
-          commit(&empty_bar[s]);
         }
-        commit(&acc_full[buf]);
+        commit_warp(&empty_bar[s], leader);
       }
+      commit_warp(&acc_full[buf], leader);
     }
   } else {
     // ------------------------------------------------ loader warp: weight images

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(up_threads(DIM), (DIM == 1 ? 3 : 2)) igemm_up_
     // evicted the other roles' code from the instruction cache (33% of stall samples were
     // "no instruction", profiles/r1_ncu_up2d_conv0.md).
     const int mw = warp == 8 ? 0 : 1;               // 2-D: issuer 0 takes classes 0,1, issuer 1 classes 2,3
-    const bool leader = lane == 0;
+    const uint32_t leader = elect_one();
     const uint32_t idesc = make_idesc(NT, 0, 0);
     const int cb0 = DIM == 2 ? mw * (COMBOS / 2) : 0, cb1 = DIM == 2 ? cb0 + COMBOS / 2 : COMBOS;
     uint32_t tc_ = 0;
@@ -301,15 +301,13 @@ __global__ void __launch_bounds__(up_threads(DIM), (DIM == 1 ? 3 : 2)) igemm_up_
 #pragma unroll 1
           for (int ks = 0; ks < ksteps; ++ks) {
             const uint32_t ao = abase + (uint32_t)(2 * ks) * SLOTS, bo = bbase + (uint32_t)(2 * ks) * NT;
-            if (leader)
-              mma_split3(td, desc_off(dah, ao), desc_off(dal, ao), desc_off(dbh, bo), desc_off(dbl, bo), idesc,
-                         (kb > 0 || !first || ks > 0) ? 1u : 0u);
+            mma_split3_warp(td, desc_off(dah, ao), desc_off(dal, ao), desc_off(dbh, bo), desc_off(dbl, bo), idesc,
+                            (kb > 0 || !first || ks > 0) ? 1u : 0u, leader);
           }
         }
-        __syncwarp();
-        if (leader) commit(&empty_bar[s]);
+        commit_warp(&empty_bar[s], leader);
       }
-      if (leader) commit(&acc_full[buf]);
+      commit_warp(&acc_full[buf], leader);
     }
   } else {
     if (lane == 0) {

@@ -29,8 +29,13 @@ struct WgArgs {
 
 // KP = positions per K block: 128 for the shallow layers (fewer pipeline hand-offs per byte), 64 for the
 // deep ones (their two tiles are wide and would not fit twice in shared memory).
+// Eight producer warps: the kernel is bound by the latency of the gathering loads (38% of the stall
+// samples with four), so the bytes in flight per CTA are what matters; warps 0-3 also run the epilogue.
+constexpr int WG_NPW = 8;
+constexpr int WG_PT = WG_NPW * 32;                 // producer threads
+constexpr int WG_THREADS = WG_PT + 32;             // + the MMA warp
 template <int DIM, int NT, int KP>
-__global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
+__global__ void __launch_bounds__(WG_THREADS) igemm_wgrad_kernel(WgArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], acc_bar;
   __shared__ uint32_t tmem_base;
@@ -54,9 +59,9 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
   const int a0 = mt * 128, c0 = nt * NT;
   const int sch = min(a.scols, (a.A - a0 + 7) / 8);     // S chunk columns that hold data in this M tile
 
-  if (warp == 4) tmem_alloc(&tmem_base, TMEM_COLS);
+  if (warp == WG_NPW) tmem_alloc(&tmem_base, TMEM_COLS);
   if (tid == 0) {
-    for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], 4); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], WG_NPW); mbar_init(&empty_bar[s], 1); }
     mbar_init(&acc_bar, 1);
     mbar_init_fence();
   }
@@ -66,7 +71,7 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
   fence_after();
   const uint32_t tmem = tmem_base;
 
-  if (warp < 4) {
+  if (warp < WG_NPW) {
     const int W = 2 * a.w;
     const int64_t HW2 = 4 * (int64_t)a.h * a.w;     // big-map plane size
     const int64_t hw = DIM == 2 ? (int64_t)a.h * a.w : (int64_t)a.w;
@@ -83,11 +88,11 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
       const uint32_t uQ = (uint32_t)a.Q, uPW = (uint32_t)PW, upp = (uint32_t)(PH * PW), uw = (uint32_t)a.w;
       // ---- S tile: item = (position, chunk of 8 channels); U items are fetched before any is converted
       constexpr int U = 2;
-      for (int item0 = tid; item0 < KP * a.scols; item0 += 128 * U) {
+      for (int item0 = tid; item0 < KP * a.scols; item0 += WG_PT * U) {
         float v[U][8];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int item = item0 + u * 128;
+          const int item = item0 + u * WG_PT;
           const int p = item % KP, ca = item / KP;
           const uint32_t q = up0 + p;
 #pragma unroll
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int item = item0 + u * 128;
+          const int item = item0 + u * WG_PT;
           if (item < KP * a.scols) {
             const int p = item % KP, ca = item / KP;
             uint4 hi, lo;
@@ -125,11 +130,11 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
       }
       // ---- Z tile: item = (slot, chunk of 8 s2d channels)
       constexpr int UZ = 4;
-      for (int item0 = tid; item0 < ZS * CZ; item0 += 128 * UZ) {
+      for (int item0 = tid; item0 < ZS * CZ; item0 += WG_PT * UZ) {
         float v[UZ][8];
 #pragma unroll
         for (int u = 0; u < UZ; ++u) {
-          const int item = item0 + u * 128;
+          const int item = item0 + u * WG_PT;
           const int cz = (int)fdiv((uint32_t)item, a.d_zs), slot = item - cz * ZS;
           const uint32_t q = up0 + slot;
           const int b0 = (c0 + cz * 8) >> 2;
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
         }
 #pragma unroll
         for (int u = 0; u < UZ; ++u) {
-          const int item = item0 + u * 128;
+          const int item = item0 + u * WG_PT;
           if (item < ZS * CZ) {
             const int cz = (int)fdiv((uint32_t)item, a.d_zs), slot = item - cz * ZS;
             uint4 hi, lo;
@@ -195,7 +200,8 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);
     }
-    // ------------------------------------------------ epilogue: scatter-add into dW
+    // ------------------------------------------------ epilogue: scatter-add into dW (TMEM lanes = warps 0-3)
+    if (warp < 4) {
     mbar_wait(&acc_bar, 0);
     fence_after();
     const int ch = a0 + tid;
@@ -223,9 +229,11 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
         }
       }
     }
+    }
   } else {
     // ------------------------------------------------ MMA issuer: warp-uniform loop, one elected lane issues
     const uint32_t idesc = make_idesc(NT, 1, 1);
+    const uint32_t leader = elect_one();
     Ring ring{0, 0};
     for (int it = 0; it < nkb; ++it, ring.next(NS)) {
       const int s = ring.s;
@@ -241,21 +249,23 @@ __global__ void __launch_bounds__(160) igemm_wgrad_kernel(WgArgs a) {
 #pragma unroll 1
       for (int tap = 0; tap < T; ++tap) {
         const uint32_t shift = DIM == 2 ? (uint32_t)((tap >> 1) * PW + (tap & 1)) : 0u;
-#pragma unroll 1
+        // the K steps are unrolled (offsets become immediates: ~6 instructions per MMA instead of 13; at
+        // 96 MMAs per 128 positions the issuing warp is what bounds the first 2-D layer), the taps are not
+#pragma unroll
         for (int ks = 0; ks < KP / 16; ++ks) {
           const uint32_t ao = (uint32_t)ks * 16;                   // 16-byte units
           const uint32_t bo = (uint32_t)ks * 16 + shift;
           mma_split3_warp(tmem + tap * NT, desc_off(dsh, ao), desc_off(dsl, ao), desc_off(dzh, bo), desc_off(dzl, bo), idesc,
-                          (it > 0 || ks > 0) ? 1u : 0u);
+                          (it > 0 || ks > 0) ? 1u : 0u, leader);
         }
       }
-      commit_warp(&empty_bar[s]);
+      commit_warp(&empty_bar[s], leader);
     }
-    commit_warp(&acc_bar);
+    commit_warp(&acc_bar, leader);
   }
   fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == WG_NPW) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 template <int DIM, int NT, int KP>
@@ -266,7 +276,7 @@ int launch_wgrad_t(const WgArgs& a, int64_t splits, int mtiles, cudaStream_t st)
   const size_t smem = stage * a.nstage + (reach > stage ? reach - stage : 0) + 256;
   LSHM_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<DIM, NT, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_wgrad");
   dim3 grid((unsigned)splits, (unsigned)(mtiles * a.ntiles));
-  igemm_wgrad_kernel<DIM, NT, KP><<<grid, 160, smem, st>>>(a);
+  igemm_wgrad_kernel<DIM, NT, KP><<<grid, WG_THREADS, smem, st>>>(a);
   LSHM_CHECK_LAUNCH("igemm_wgrad");
   return LSHM_OK;
 }

@@ -46,21 +46,27 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t 
 // Same instruction issued from warp-uniform code: every lane of the (converged) warp executes the call,
 // one elected lane issues.  The operands then stay in uniform registers; under `if (lane == 0)` the
 // compiler wraps every tcgen05.mma in a vote/broadcast "waterfall" (~16 instructions per MMA).
-__device__ __forceinline__ void mma_bf16_warp(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n.reg .pred p, q;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|q, 0xffffffff;\n"
+__device__ __forceinline__ uint32_t elect_one() {          // 1 in exactly one lane of the converged warp
+  uint32_t r;
+  asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\nselp.u32 %0, 1, 0, q;\n}\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void mma_bf16_warp(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc,
+                                              uint32_t leader) {
+  asm volatile("{\n.reg .pred p, q;\nsetp.ne.b32 p, %4, 0;\nsetp.ne.b32 q, %5, 0;\n"
                "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-               :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+               :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(leader) : "memory");
 }
 __device__ __forceinline__ void mma_split3_warp(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
-                                                uint32_t idesc, uint32_t acc) {
-  mma_bf16_warp(tmem_d, a_hi, b_hi, idesc, acc);
-  mma_bf16_warp(tmem_d, a_lo, b_hi, idesc, 1u);
-  mma_bf16_warp(tmem_d, a_hi, b_lo, idesc, 1u);
+                                                uint32_t idesc, uint32_t acc, uint32_t leader) {
+  mma_bf16_warp(tmem_d, a_hi, b_hi, idesc, acc, leader);
+  mma_bf16_warp(tmem_d, a_lo, b_hi, idesc, 1u, leader);
+  mma_bf16_warp(tmem_d, a_hi, b_lo, idesc, 1u, leader);
 }
-__device__ __forceinline__ void commit_warp(uint64_t* bar) {     // warp-uniform call, one elected lane commits
-  asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
+__device__ __forceinline__ void commit_warp(uint64_t* bar, uint32_t leader) {   // warp-uniform call, the leader commits
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n"
                "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n"
-               :: "r"(smem_u32(bar)) : "memory");
+               :: "r"(smem_u32(bar)), "r"(leader) : "memory");
 }
 
 // D += A*B with the 3-term bf16 split; *_hi / *_lo descriptors address the two halves
