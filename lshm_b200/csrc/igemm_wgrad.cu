@@ -232,7 +232,10 @@ __global__ void __launch_bounds__(WG_THREADS) igemm_wgrad_kernel(WgArgs a) {
     }
   } else {
     // ------------------------------------------------ MMA issuer: warp-uniform loop, one elected lane issues
-    const uint32_t idesc = make_idesc(NT, 1, 1);
+    // M = 64 when the layer has at most 16 output channels (rows 0-15 of the accumulator sit in TMEM lanes
+    // 0-15 for either M): the M-side operand fetch from shared memory (4 KB per MMA at M = 128, of which
+    // 8 rows are real in the first layer) is what bounds the wide first layers.
+    const uint32_t idesc = make_idesc(NT, 1, 1, a.A <= 16 ? 64 : 128);
     const uint32_t leader = elect_one();
     Ring ring{0, 0};
     for (int it = 0; it < nkb; ++it, ring.next(NS)) {

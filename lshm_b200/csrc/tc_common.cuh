@@ -32,9 +32,9 @@ __device__ __forceinline__ uint64_t desc_off(uint64_t d, uint32_t off16) {
 }
 
 // instruction descriptor: bf16 x bf16 -> fp32, M = 128
-__host__ __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+__host__ __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_major, int m = 128) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+         ((uint32_t)(n >> 3) << 17) | (((uint32_t)m >> 4) << 24);
 }
 
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
