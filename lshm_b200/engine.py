@@ -194,8 +194,9 @@ class AEEngine:
 
     def forward(self, x: torch.Tensor, uv: torch.Tensor, scales: torch.Tensor,
                 p: Dict[str, torch.Tensor], ws: Workspace, st: int,
-                mu_out: Optional[torch.Tensor] = None):
-        """Runs the network; returns (xhat [N,C*16384] in ws, mu view).
+                mu_out: Optional[torch.Tensor] = None, decode: bool = True):
+        """Runs the network; returns (xhat [N,C*16384] in ws, mu view); decode=False stops at the
+        latent (the 1-D nets of the clustering path, src/evaluate_clustering.py:86-89) and returns (None, mu).
 
         mu_out: optional [N,L] view (any row stride) that receives the returned latent
         (lets the three nets write straight into the concatenated Mu buffer).
@@ -212,6 +213,8 @@ class AEEngine:
         else:
             self.encode(x, ws.uvh, p, ws, st, out=ws.zcat[:, :L])
             mu_final.copy_(ws.zcat[:, :L])
+        if not decode:
+            return None, mu_final
         return self.decode(ws.uvh, p, ws, st), mu_final
 
     # ------------------------------------------------------------------ backward

@@ -39,8 +39,8 @@ def cascade_latents(net: AutoEncoderCNN2, net1D1: AutoEncoder1DCNN, net1D2: Auto
     lib().residual_split(x.data_ptr(), x1.data_ptr(), iy1.data_ptr(), iy2.data_ptr(), N, C, 128, st)
     del ws0
     ws1 = e1.workspace(N, x.device, False)
-    e1.forward(iy1, uv, scales, net1D1.named_param_dict(), ws1, st, mu_out=Mu[:, L:L + Lt])
-    e2.forward(iy2, uv, scales, net1D2.named_param_dict(), ws1, st, mu_out=Mu[:, L + Lt:])
+    e1.forward(iy1, uv, scales, net1D1.named_param_dict(), ws1, st, mu_out=Mu[:, L:L + Lt], decode=False)
+    e2.forward(iy2, uv, scales, net1D2.named_param_dict(), ws1, st, mu_out=Mu[:, L + Lt:], decode=False)
     return Mu
 
 
