@@ -76,22 +76,75 @@ def _to_device_i8(arr: np.ndarray, dev) -> torch.Tensor:
 
 
 def patchify_device(vis: torch.Tensor, scale: torch.Tensor, sel: torch.Tensor, patch_size: int,
-                    num_channels: int, clamp: float, normalize: bool):
+                    num_channels: int, clamp: float, normalize: bool, out: torch.Tensor = None,
+                    stats: torch.Tensor = None):
     """vis int8 [nbase,T,F,4,2], scale fp32 [nbase,F,4], sel int32 [nb] (all on device) ->
-    (patchx, patchy, y [nb*px*py, C, P, P])."""
+    (patchx, patchy, y [nb*px*py, C, P, P]).  `out` / `stats` (fp64 [2]): optional preallocated
+    destination and scratch, so a staging loop allocates nothing."""
     nbase, T, F = vis.shape[:3]
     nb, P = sel.numel(), patch_size
     s = P // 2
     px = (max(T, P) - P) // s + 1
     py = (max(F, P) - P) // s + 1
-    y = torch.empty(nb * px * py, num_channels, P, P, dtype=torch.float32, device=vis.device)
-    stats = torch.zeros(2, dtype=torch.float64, device=vis.device)
+    shape = (nb * px * py, num_channels, P, P)
+    if out is None:
+        y = torch.empty(shape, dtype=torch.float32, device=vis.device)
+    else:
+        if tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != vis.device:
+            raise ValueError(f"patchify_device: out must be a contiguous float32 {shape} tensor on {vis.device}")
+        y = out
+    if stats is None:
+        stats = torch.zeros(2, dtype=torch.float64, device=vis.device)
+    else:
+        stats.zero_()
     st = _stream()
     lib().patchify_scale_i8(vis.data_ptr(), scale.data_ptr(), sel.data_ptr(), nb, T, F, num_channels, P,
                             float(clamp), y.data_ptr(), stats.data_ptr(), st)
     if normalize:
         lib().normalise(y.data_ptr(), y.numel(), stats.data_ptr(), st)
     return px, py, y
+
+
+class DevicePrefetcher:
+    """Runs a batch loader (pinned-host -> device copies + the loader kernels) on a side stream so the
+    next minibatch is staged while the current closure / optimiser step computes.
+
+        pf = DevicePrefetcher(device); pf.submit(load)       # load() returns tensors / tuples of tensors
+        batch = pf.get(); pf.submit(load); ...train on batch...
+    """
+
+    def __init__(self, device, record_streams: bool = True):
+        # record_streams=False: the loader writes into caller-owned, preallocated buffers (no allocator
+        # hand-over between the two streams; the caller alternates buffer sets)
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.record_streams = record_streams
+        self._out, self._ev = None, None
+
+    def submit(self, load):
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))   # buffers the loader reuses are free
+        with torch.cuda.stream(self.stream):
+            self._out = load()
+            self._ev = torch.cuda.Event()
+            self._ev.record(self.stream)
+
+    def get(self):
+        if self._ev is None:
+            raise RuntimeError("DevicePrefetcher.get() before submit()")
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._ev)
+
+        def mark(o):
+            if isinstance(o, torch.Tensor):
+                if o.is_cuda:
+                    o.record_stream(cur)
+            elif isinstance(o, (tuple, list)):
+                for e in o:
+                    mark(e)
+        if self.record_streams:
+            mark(self._out)
+        out, self._out, self._ev = self._out, None, None
+        return out
 
 
 def _uv_rotation(f, SAP):
