@@ -35,7 +35,7 @@ constexpr int WG_NPW = 8;
 constexpr int WG_PT = WG_NPW * 32;                 // producer threads
 constexpr int WG_THREADS = WG_PT + 32;             // + the MMA warp
 template <int DIM, int NT, int KP>
-__global__ void __launch_bounds__(WG_THREADS) igemm_wgrad_kernel(WgArgs a) {
+__global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_kernel(WgArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], acc_bar;
   __shared__ uint32_t tmem_base;
@@ -206,23 +206,52 @@ __global__ void __launch_bounds__(WG_THREADS) igemm_wgrad_kernel(WgArgs a) {
     fence_after();
     const int ch = a0 + tid;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    // The split-K partial sums go to dW with 16-byte vector atomics: one per (channel pair row) instead
+    // of four scalar ones.  With scalar atomics the deep layers (few positions, 10^5 weights, 36 splits)
+    // spent most of their ~110 us in this epilogue, whatever their size.
+    const bool vec = (reinterpret_cast<uintptr_t>(a.dw) & 15) == 0;
 #pragma unroll 1
-    for (int tap = 0; tap < T; ++tap) {
+    for (int g = 0; g < NT / 16; ++g) {
+      if (DIM == 2) {
+        // one big-map channel at a time (4 taps x 4 sub-positions = its 4x4 kernel): 16 live registers,
+        // so the epilogue does not set the kernel's register count (3 CTAs per SM on the first layer)
 #pragma unroll 1
-      for (int g = 0; g < NT / 16; ++g) {
+        for (int jb = 0; jb < 4; ++jb) {
+          const int b = (c0 + g * 16) / 4 + jb;
+          if (b >= a.Bc) break;                             // warp-uniform
+          float v[4][4];                                    // [tap][sub-position]
+#pragma unroll
+          for (int tap = 0; tap < 4; ++tap) tmem_ld4(trow + tap * NT + g * 16 + jb * 4, v[tap]);
+          if (ch < a.A && nkb > 0) {
+            float* dst = a.dw + ((int64_t)ch * a.Bc + b) * 16;
+#pragma unroll
+            for (int ky = 0; ky < 4; ++ky) {
+              // kernel row ky = 2*ty + sy: taps (ty,0),(ty,1), sub-positions (sy,0),(sy,1)
+              const int ty = ky >> 1, sy = ky & 1;
+              const float4 r = make_float4(v[2 * ty][2 * sy], v[2 * ty][2 * sy + 1], v[2 * ty + 1][2 * sy], v[2 * ty + 1][2 * sy + 1]);
+              if (vec) {
+                atomicAdd(reinterpret_cast<float4*>(dst + ky * 4), r);
+              } else {
+                atomicAdd(dst + ky * 4 + 0, r.x); atomicAdd(dst + ky * 4 + 1, r.y);
+                atomicAdd(dst + ky * 4 + 2, r.z); atomicAdd(dst + ky * 4 + 3, r.w);
+              }
+            }
+          }
+        }
+      } else {
         float v[16];
-        tmem_ld16(trow + tap * NT + g * 16, v);
+        tmem_ld16(trow + g * 16, v);
         if (ch < a.A && nkb > 0) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int c = c0 + g * 16 + j;
-            const int b = c >> 2, sub = c & 3;
+          for (int jb = 0; jb < 4; ++jb) {
+            const int b = (c0 + g * 16) / 4 + jb;
             if (b < a.Bc) {
-              if (DIM == 2) {
-                const int ky = 2 * (tap >> 1) + (sub >> 1), kx = 2 * (tap & 1) + (sub & 1);
-                atomicAdd(a.dw + (((int64_t)ch * a.Bc + b) * 4 + ky) * 4 + kx, v[j]);
+              float* dst = a.dw + ((int64_t)ch * a.Bc + b) * 4;
+              if (vec) {
+                atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[jb * 4], v[jb * 4 + 1], v[jb * 4 + 2], v[jb * 4 + 3]));
               } else {
-                atomicAdd(a.dw + ((int64_t)ch * a.Bc + b) * 4 + sub, v[j]);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) atomicAdd(dst + t, v[jb * 4 + t]);
               }
             }
           }
