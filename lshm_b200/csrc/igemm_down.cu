@@ -27,11 +27,12 @@ struct DownArgs {
   const float* aux; int64_t aux_ns;
   float* small_; int64_t small_ns;
   int64_t N; int A; int Bc; int h; int w; int pad; int epi;
-  int slots; int nstage; int64_t Q; int64_t mtiles; int ntn; int rawbytes; int rawG; int wres_on;
+  int slots; int nstage; int64_t Q; int64_t mtiles; int ntn; int wres_on;
   FastDiv d_pp, d_pw, d_w, d_ntn;   // divisors (h+1)(w+1), w+1, w, ntn
 };
 
-constexpr int DOWN_THREADS = 320;   // warps 0-3 epilogue, 4-7 producers, 8 MMA issuer, 9 weight loader
+// warps 0-3 epilogue, 4-7 producers (group 0), 8 MMA issuer, 9 weight loader, 10-13 producers (group 1, G = 2)
+constexpr int down_threads(int g) { return 320 + 128 * (g - 1); }
 constexpr int MAXST = 6;
 
 // Persistent, warp-specialised: every CTA walks work items (position tile x channel tile); the
@@ -84,26 +85,23 @@ __device__ __forceinline__ void down_epilogue_tile(const DownArgs& a, uint32_t t
   }
 }
 
-// RAW = true (maps whose rows are >= 256 B): the input rows a tile needs are first copied as they are
-// (fp32) into shared memory by bulk async copies issued by the loader warp, several stages ahead,
-// and the producer warps only convert shared -> shared.  Registers then hold no in-flight HBM data,
-// so the bytes in flight per SM are set by the stage ring (tens of KB), not by the register file -
-// the register-staged path topped out near 25% of HBM bandwidth on the 16384-sample maps.
-template <int DIM, int NT, int KC, bool RAW>
-__global__ void __launch_bounds__(DOWN_THREADS, 3) igemm_down_kernel(DownArgs a) {
+// G = producer groups of four warps.  G = 2 (layers with more than one K block: the deep, small maps):
+// the groups fill alternate stages, so two gather -> convert -> hand-off chains are in flight per CTA; those
+// layers are bound by the latency of that chain (2-3.5 us per K block, one or two tiles per CTA), not by
+// bandwidth or issue slots.
+template <int DIM, int NT, int KC, int G>
+__global__ void __launch_bounds__(down_threads(G), (G == 1 ? 3 : 2)) igemm_down_kernel(DownArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t full_bar[MAXST], empty_bar[MAXST], raw_bar[MAXST], acc_full[2], acc_empty[2], w_bar;
+  __shared__ __align__(8) uint64_t full_bar[MAXST], empty_bar[MAXST], acc_full[2], acc_empty[2], w_bar;
   __shared__ uint32_t tmem_base;
   constexpr int T = DIM == 2 ? 4 : 1;
   constexpr int CC = KC / 8;
   constexpr uint32_t IMG = 2u * T * CC * NT * 16;
   constexpr uint32_t TMEM_COLS = 2 * NT <= 32 ? 32 : (2 * NT <= 64 ? 64 : (2 * NT <= 128 ? 128 : 256));
   const int SLOTS = a.slots, NS = a.nstage;
-  constexpr int BPB = KC / 4;                      // big-map channels per K block
   constexpr int NSLOT = DIM == 2 ? 2 : 1;          // staged slots per producer thread (1-D tiles: 128 slots)
   const uint32_t zbytes = (uint32_t)CC * SLOTS * 16;
-  const uint32_t rawb = RAW ? (uint32_t)a.rawbytes : 0u;
-  const uint32_t stage_bytes = rawb + 2 * zbytes + IMG;
+  const uint32_t stage_bytes = 2 * zbytes + IMG;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Kc = 4 * a.Bc;
   const int KB = (Kc + KC - 1) / KC;
@@ -116,7 +114,7 @@ __global__ void __launch_bounds__(DOWN_THREADS, 3) igemm_down_kernel(DownArgs a)
 
   if (warp == 8) tmem_alloc(&tmem_base, TMEM_COLS);
   if (tid == 0) {
-    for (int s = 0; s < MAXST; ++s) { mbar_init(&full_bar[s], wres ? 4 : 5); mbar_init(&empty_bar[s], 1); mbar_init(&raw_bar[s], 128); }
+    for (int s = 0; s < MAXST; ++s) { mbar_init(&full_bar[s], wres ? 4 : 5); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
     mbar_init(&w_bar, 1);
     mbar_init_fence();
@@ -126,133 +124,16 @@ __global__ void __launch_bounds__(DOWN_THREADS, 3) igemm_down_kernel(DownArgs a)
   fence_after();
   const uint32_t tmem = tmem_base;
 
-  if (warp >= 4 && warp < 8) {
+  if ((warp >= 4 && warp < 8) || warp >= 10) {
     // ------------------------------------------------ producers: stage the Z tile (hi/lo bf16)
-    const int ptid = tid - 128;
+    const int grp = warp >= 10 ? 1 : 0;                 // producer group
+    const int ptid = (tid & 127);                       // 0..127 within the group (warps 4-7 / 10-13... tid-128, tid-320)
     const int H = 2 * a.h, W = 2 * a.w;
     const int64_t HW = (int64_t)H * W;
-    const int64_t nitems = (total - blockIdx.x + gridDim.x - 1) / gridDim.x;
-    const int64_t nunits = nitems * KB;
-    if (RAW) {
-      // ---- RAW: async 16-byte copies of the needed input rows run `ahead` units in front of the
-      //      conversion, so the bytes in flight are bounded by the stage ring, not by registers
-      const int ahead = NS > 2 ? NS - 2 : 1;
-      auto issue = [&](int64_t u) {
-        const int s = (int)(u % NS), ph = (int)((u / NS) & 1);
-        const int kb = (int)(u % KB);
-        const int64_t item = blockIdx.x + (u / KB) * gridDim.x;
-        const int64_t q0 = (item / a.ntn) * 128;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* raw = smem + (size_t)s * stage_bytes;
-        if (DIM == 2) {
-          const int w4 = W >> 2;                               // 16-byte pieces per image row
-          const int64_t g0 = q0 / PW;
-          const int64_t glast = min(q0 + SLOTS - 1, a.Q - 1) / PW;
-          const int nops = a.rawG * 2 * BPB * w4;
-          for (int idx = ptid; idx < nops; idx += 128) {
-            const int rix = idx / w4, o = idx - rix * w4;
-            const int gi = rix / (2 * BPB), sy = (rix / BPB) & 1, bb = rix % BPB;
-            const int64_t g = g0 + gi;
-            const int64_t n = g / PH;
-            const int by = (int)(g - n * PH);
-            const int row = 2 * by - 1 + sy, b = kb * BPB + bb;
-            const bool ok = g <= glast && row >= 0 && row < H && b < a.Bc;
-            const float* src = ok ? a.big + n * a.big_ns + ((int64_t)b * H + row) * W + 4 * o : a.big;
-            cp_async16(raw + ((size_t)rix * W + 4 * o) * 4, src, ok ? 16u : 0u);
-          }
-        } else {
-          const int64_t n = q0 / a.w;
-          const int j0 = (int)(q0 - n * a.w);
-          const int nops = BPB * 129;                          // per channel: 4 floats in front + 512
-          for (int idx = ptid; idx < nops; idx += 128) {
-            const int bb = idx / 129, o = idx - bb * 129;
-            const int b = kb * BPB + bb;
-            const bool ok = b < a.Bc && !(o == 0 && j0 == 0);
-            const float* src = ok ? a.big + n * a.big_ns + (int64_t)b * 4 * a.w + 4 * (int64_t)j0 - 4 + 4 * o : a.big;
-            cp_async16(raw + (size_t)bb * 2064 + (size_t)o * 16, src, ok ? 16u : 0u);
-          }
-        }
-        cp_async_arrive(&raw_bar[s]);
-      };
-      for (int64_t u = 0; u < ahead && u < nunits; ++u) issue(u);
-      for (int64_t u = 0; u < nunits; ++u) {
-        if (u + ahead < nunits) issue(u + ahead);
-        const int s = (int)(u % NS), ph = (int)((u / NS) & 1);
-        const int kb = (int)(u % KB);
-        const int64_t item = blockIdx.x + (u / KB) * gridDim.x;
-        const int64_t q0 = (item / a.ntn) * 128;
-        uint8_t* zhi = smem + (size_t)s * stage_bytes + rawb;
-        uint8_t* zlo = zhi + zbytes;
-        const float* raw = reinterpret_cast<const float*>(smem + (size_t)s * stage_bytes);
-        const int ccb = (min(KC, Kc - kb * KC)) >> 3;
-        const int64_t g0 = DIM == 2 ? q0 / PW : 0;
-        mbar_wait(&raw_bar[s], ph);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int slot = ptid + i * 128;
-          if (slot >= SLOTS) continue;
-          const int64_t q = q0 + slot;
-          const bool valid = q < a.Q;
-          bool r0ok = false, r1ok = false, c0ok = false, c1ok = false;
-          int rloc = 0, cloc = 0, jj = 0;
-          if (valid) {
-            if (DIM == 2) {
-              const int64_t g = q / PW;
-              const int bx = (int)(q - g * PW);
-              const int by = (int)(g % PH);
-              r0ok = by > 0; r1ok = by < a.h; c0ok = bx > 0; c1ok = bx < a.w;
-              rloc = (int)(g - g0) * 2; cloc = 2 * bx - 1;
-            } else {
-              jj = (int)(q % a.w);
-            }
-          }
-#pragma unroll
-          for (int cc = 0; cc < CC; ++cc) {
-            if (cc >= ccb) continue;
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = 0.f;
-            if (valid && 2 * (kb * CC + cc) < a.Bc) {
-              if (DIM == 2) {
-                // raw layout: [block row gi][sy][channel bb][W]
-                const float* p0 = raw + ((size_t)(rloc * BPB + 2 * cc)) * W + cloc;
-                const float* p1 = p0 + W;                   // next channel
-                const float* q0p = p0 + (size_t)BPB * W;    // sy = 1
-                const float* q1p = q0p + W;
-                if (r0ok && c0ok) { v[0] = p0[0]; v[4] = p1[0]; }
-                if (r0ok && c1ok) { v[1] = p0[1]; v[5] = p1[1]; }
-                if (r1ok && c0ok) { v[2] = q0p[0]; v[6] = q1p[0]; }
-                if (r1ok && c1ok) { v[3] = q0p[1]; v[7] = q1p[1]; }
-              } else {
-                // raw layout: [channel bb][4 + 512]: window of slot j starts at 4 + 4*j - pad
-                const float* p0 = raw + (size_t)(2 * cc) * 516 + 4 + 4 * slot;
-                const float* p1 = p0 + 516;
-                const float4 x0 = *reinterpret_cast<const float4*>(p0);
-                const float4 x1 = *reinterpret_cast<const float4*>(p1);
-                if (a.pad == 0) {
-                  v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
-                  v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
-                } else {
-                  if (jj > 0) { v[0] = p0[-1]; v[4] = p1[-1]; }
-                  v[1] = x0.x; v[2] = x0.y; v[3] = x0.z;
-                  v[5] = x1.x; v[6] = x1.y; v[7] = x1.z;
-                }
-              }
-            }
-            uint4 hi, lo;
-            split8(v, hi, lo);
-            *reinterpret_cast<uint4*>(zhi + ((size_t)cc * SLOTS + slot) * 16) = hi;
-            *reinterpret_cast<uint4*>(zlo + ((size_t)cc * SLOTS + slot) * 16) = lo;
-          }
-        }
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[s]);
-      }
-    } else {
     // Register-staged path.  Per slot the source window is described once (base pointer of the first
     // channel, validity of the two rows / two columns); a chunk column is 8 loads at fixed offsets.
     Ring ring{0, 0};
+    uint32_t unit = 0;                                  // (item, K block) counter: group g fills units u % G == g
     for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
       const int64_t q0 = (int64_t)fdiv((uint32_t)item, a.d_ntn) * 128;
       const float* sp[NSLOT]; bool sv[NSLOT], full[NSLOT], r0ok[NSLOT], r1ok[NSLOT], c0ok[NSLOT], c1ok[NSLOT]; int sj[NSLOT];
@@ -278,9 +159,10 @@ __global__ void __launch_bounds__(DOWN_THREADS, 3) igemm_down_kernel(DownArgs a)
           }
         }
       }
-      for (int kb = 0; kb < KB; ++kb, ring.next(NS)) {
+      for (int kb = 0; kb < KB; ++kb, ring.next(NS), ++unit) {
+        if (G == 2 && (int)(unit & 1) != grp) continue;   // the other group's stage
         const int s = ring.s;
-        uint8_t* zhi = smem + (size_t)s * stage_bytes + rawb;
+        uint8_t* zhi = smem + (size_t)s * stage_bytes;
         uint8_t* zlo = zhi + zbytes;
         const int ccb = (min(KC, Kc - kb * KC)) >> 3;
         mbar_wait(&empty_bar[s], ring.ph ^ 1);
@@ -340,7 +222,6 @@ __global__ void __launch_bounds__(DOWN_THREADS, 3) igemm_down_kernel(DownArgs a)
         if (lane == 0) mbar_arrive(&full_bar[s]);
       }
     }
-    }
   } else if (warp < 4) {
     // ------------------------------------------------ epilogue: TMEM -> bias/act -> global
     const int64_t hw = DIM == 2 ? (int64_t)a.h * a.w : (int64_t)a.w;
@@ -395,7 +276,7 @@ __global__ void __launch_bounds__(DOWN_THREADS, 3) igemm_down_kernel(DownArgs a)
         const int s = ring.s;
         mbar_wait(&full_bar[s], ring.ph);
         fence_after();
-        const uint32_t zhi = smem_u32(smem + (size_t)s * stage_bytes) + rawb;
+        const uint32_t zhi = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t bhi = wres ? smem_u32(wres_ptr) : zhi + 2 * zbytes;
         const uint64_t dah = make_desc(zhi, SLOTS * 16, 128), dal = make_desc(zhi + zbytes, SLOTS * 16, 128);
         const uint64_t dbh = make_desc(bhi, NT * 16, 128), dbl = make_desc(bhi + IMG / 2, NT * 16, 128);
@@ -436,7 +317,7 @@ __global__ void __launch_bounds__(DOWN_THREADS, 3) igemm_down_kernel(DownArgs a)
           uint8_t* stage = smem + (size_t)s * stage_bytes;
           if (lane == 0) {
             mbar_arrive_expect_tx(&full_bar[s], IMG);
-            bulk_g2s(stage + rawb + 2 * zbytes, a.wimg + ((size_t)nt * KB + kb) * IMG, IMG, &full_bar[s]);
+            bulk_g2s(stage + 2 * zbytes, a.wimg + ((size_t)nt * KB + kb) * IMG, IMG, &full_bar[s]);
           }
         }
       }
@@ -447,24 +328,24 @@ __global__ void __launch_bounds__(DOWN_THREADS, 3) igemm_down_kernel(DownArgs a)
   if (warp == 8) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-template <int DIM, int NT, int KC, bool RAW>
+template <int DIM, int NT, int KC, int G>
 int launch_down_t(DownArgs a, const DownGeom& g, cudaStream_t st) {
-  const size_t stage = (size_t)(RAW ? a.rawbytes : 0) + (size_t)2 * (KC / 8) * a.slots * 16 + g.img;
+  const size_t stage = (size_t)2 * (KC / 8) * a.slots * 16 + g.img;
   const int64_t units = a.mtiles * g.ntiles * g.KB;
   // two CTAs per SM when the ring fits in ~110 KB each (227 KB per SM), else one CTA with a deep ring
   // three CTAs per SM when two stages fit in ~74 KB, else two, else one with a deep ring
   const size_t third_sm = 74 * 1024, half_sm = 110 * 1024, full_sm = 200 * 1024;
   int ns = (int)((third_sm - g.img) / stage);
   if (ns < 2) ns = (int)((half_sm - g.img) / stage);
-  if (RAW || ns < 2) ns = (int)((full_sm - g.img) / stage);
+  if (ns < 2) ns = (int)((full_sm - g.img) / stage);
   ns = std::min(ns, MAXST);
   LSHM_REQUIRE(ns >= 1, "igemm_down: tile does not fit in shared memory");
   a.nstage = (int)std::min<int64_t>(ns, std::max<int64_t>(1, units));
   const size_t smem = stage * a.nstage + g.img;   // + resident weight image (used when KB == ntiles == 1)
-  LSHM_CUDA(cudaFuncSetAttribute(igemm_down_kernel<DIM, NT, KC, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_down");
-  const int per_sm = smem <= 74 * 1024 ? 3 : (smem <= 112 * 1024 ? 2 : 1);
+  LSHM_CUDA(cudaFuncSetAttribute(igemm_down_kernel<DIM, NT, KC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_down");
+  const int per_sm = std::min(G == 1 ? 3 : 2, smem <= 74 * 1024 ? 3 : (smem <= 112 * 1024 ? 2 : 1));
   const int64_t grid = std::min<int64_t>(a.mtiles * g.ntiles, (int64_t)sm_count() * per_sm);
-  igemm_down_kernel<DIM, NT, KC, RAW><<<(unsigned)grid, DOWN_THREADS, smem, st>>>(a);
+  igemm_down_kernel<DIM, NT, KC, G><<<(unsigned)grid, down_threads(G), smem, st>>>(a);
   LSHM_CHECK_LAUNCH("igemm_down");
   return LSHM_OK;
 }
@@ -478,34 +359,24 @@ int launch_down(int dim, DownArgs a, cudaStream_t st) {
   a.mtiles = ceil_div(a.Q, 128);
   a.ntn = g.ntiles;
   a.d_ntn = make_fastdiv((uint32_t)a.ntn);
-  const bool aligned = (reinterpret_cast<uintptr_t>(a.big) & 15) == 0 && (a.big_ns & 3) == 0;
-  bool raw = false;
   static const bool wres_off = getenv("LSHM_DOWN_NOWRES") != nullptr;   // experiment switch
   a.wres_on = wres_off ? 0 : 1;
-  static const bool raw_off = getenv("LSHM_DOWN_RAW") == nullptr;   // experiment switch
-  const int bpb = g.KC / 4;
-  if (aligned && g.NT <= 32 && !raw_off) {
-    if (dim == 1 && a.w % 128 == 0) { raw = true; a.rawG = 1; a.rawbytes = bpb * 2064; }
-    if (dim == 2 && a.w >= 32 && (a.w & 1) == 0) {
-      raw = true;
-      a.rawG = (a.slots - 1) / (a.w + 1) + 2;
-      a.rawbytes = a.rawG * 2 * bpb * (2 * a.w) * 4;
-    }
-  }
-#define LD(D, NTV, KCV, R) return launch_down_t<D, NTV, KCV, R>(a, g, st)
+  static const bool one_group = getenv("LSHM_DOWN_G1") != nullptr;       // experiment switch
+  const bool two = g.KB >= 2 && !one_group;                              // two producer groups (see the kernel)
+#define LD(D, NTV, KCV) do { if (two) return launch_down_t<D, NTV, KCV, 2>(a, g, st); return launch_down_t<D, NTV, KCV, 1>(a, g, st); } while (0)
   if (dim == 2) {
     switch (g.NT) {
-      case 16: if (raw) LD(2, 16, 32, true); else LD(2, 16, 32, false);
-      case 32: if (raw) LD(2, 32, 32, true); else LD(2, 32, 32, false);
-      case 48: LD(2, 48, 32, false);
-      default: LD(2, 96, 16, false);
+      case 16: LD(2, 16, 32);
+      case 32: LD(2, 32, 32);
+      case 48: LD(2, 48, 32);
+      default: LD(2, 96, 16);
     }
   } else {
     switch (g.NT) {
-      case 16: if (raw) LD(1, 16, 32, true); else LD(1, 16, 32, false);
-      case 32: if (raw) LD(1, 32, 32, true); else LD(1, 32, 32, false);
-      case 48: LD(1, 48, 32, false);
-      default: LD(1, 96, 32, false);
+      case 16: LD(1, 16, 32);
+      case 32: LD(1, 32, 32);
+      case 48: LD(1, 48, 32);
+      default: LD(1, 96, 32);
     }
   }
 #undef LD
