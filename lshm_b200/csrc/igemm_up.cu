@@ -30,7 +30,8 @@ struct UpArgs {
 };
 
 // warps 0-3 epilogue, 4-7 producers, 8 MMA issuer, 9 weight loader, (2-D only) 10 second MMA issuer
-constexpr int up_threads(int dim) { return dim == 2 ? 352 : 320; }
+// G = 2 adds a second group of four producer warps after those (alternate stages, see igemm_down.cu)
+constexpr int up_threads(int dim, int g = 1) { return (dim == 2 ? 352 : 320) + 128 * (g - 1); }
 constexpr int UP_MAXST = 6;
 
 template <int EPI>
@@ -130,8 +131,8 @@ __device__ __forceinline__ void up_epilogue_tile(const UpArgs& a, uint32_t trow,
 // Persistent, warp-specialised (same skeleton as igemm_down.cu): producers run ahead through the
 // stage ring, the MMA warp alternates between two TMEM accumulator sets (each = 4 parity classes in
 // 2-D), the epilogue warps drain one set while the next is being computed.
-template <int DIM, int NT, int KC>
-__global__ void __launch_bounds__(up_threads(DIM), (DIM == 1 ? 3 : 2)) igemm_up_kernel(UpArgs a) {
+template <int DIM, int NT, int KC, int G>
+__global__ void __launch_bounds__(up_threads(DIM, G), (DIM == 1 && G == 1 ? 3 : 2)) igemm_up_kernel(UpArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[UP_MAXST], empty_bar[UP_MAXST], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base;
@@ -165,9 +166,12 @@ __global__ void __launch_bounds__(up_threads(DIM), (DIM == 1 ? 3 : 2)) igemm_up_
   fence_after();
   const uint32_t tmem = tmem_base;
 
-  if (warp >= 4 && warp < 8) {
+  constexpr int G1W = (DIM == 2 ? 352 : 320) / 32;   // first warp of producer group 1 (= up_threads(DIM) / 32)
+  if ((warp >= 4 && warp < 8) || warp >= G1W) {
     // ------------------------------------------------ producers: stage S (hi/lo bf16), K = channels
-    const int ptid = tid - 128;
+    const int grp = warp >= G1W ? 1 : 0;
+    const int ptid = grp == 0 ? tid - 128 : tid - G1W * 32;
+    uint32_t unit = 0;                                  // (item, K block) counter: group g fills units u % G == g
     const int64_t hw = DIM == 2 ? (int64_t)a.h * a.w : (int64_t)a.w;
     Ring ring{0, 0};
     for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
@@ -193,7 +197,8 @@ __global__ void __launch_bounds__(up_threads(DIM), (DIM == 1 ? 3 : 2)) igemm_up_
           }
         }
       }
-      for (int kb = 0; kb < KB; ++kb, ring.next(NS)) {
+      for (int kb = 0; kb < KB; ++kb, ring.next(NS), ++unit) {
+        if (G == 2 && (int)(unit & 1) != grp) continue;   // the other group's stage
         const int s = ring.s;
         mbar_wait(&empty_bar[s], ring.ph ^ 1);
         uint8_t* zhi = smem + (size_t)s * stage_bytes;
@@ -329,7 +334,7 @@ __global__ void __launch_bounds__(up_threads(DIM), (DIM == 1 ? 3 : 2)) igemm_up_
   if (warp == 8) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-template <int DIM, int NT, int KC>
+template <int DIM, int NT, int KC, int G>
 int launch_up_t(UpArgs a, const UpGeom& g, cudaStream_t st) {
   const size_t stage = (size_t)2 * (KC / 8) * a.slots * 16 + g.img;
   const int64_t units = a.mtiles * g.ntiles * g.KB;
@@ -337,7 +342,7 @@ int launch_up_t(UpArgs a, const UpGeom& g, cudaStream_t st) {
   const bool two = tcols <= 256;                       // TMEM allows two CTAs per SM
   int per_sm = 1;
   int ns = 0;
-  if (DIM == 1 && tcols <= 128) { ns = (int)((74 * 1024) / stage); if (ns >= 2) per_sm = 3; }
+  if (DIM == 1 && G == 1 && tcols <= 128) { ns = (int)((74 * 1024) / stage); if (ns >= 2) per_sm = 3; }
   if (per_sm == 1 && two) { ns = (int)((110 * 1024) / stage); if (ns >= 2) per_sm = 2; }
   bool pair = per_sm > 1;
   if (!pair) ns = (int)((200 * 1024) / stage);
@@ -345,9 +350,9 @@ int launch_up_t(UpArgs a, const UpGeom& g, cudaStream_t st) {
   LSHM_REQUIRE(ns >= 1, "igemm_up: tile does not fit in shared memory");
   a.nstage = (int)std::min<int64_t>(ns, std::max<int64_t>(1, units));
   const size_t smem = stage * a.nstage;
-  LSHM_CUDA(cudaFuncSetAttribute(igemm_up_kernel<DIM, NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_up");
+  LSHM_CUDA(cudaFuncSetAttribute(igemm_up_kernel<DIM, NT, KC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_up");
   const int64_t grid = std::min<int64_t>(a.mtiles * g.ntiles, (int64_t)sm_count() * per_sm);
-  igemm_up_kernel<DIM, NT, KC><<<(unsigned)grid, up_threads(DIM), smem, st>>>(a);
+  igemm_up_kernel<DIM, NT, KC, G><<<(unsigned)grid, up_threads(DIM, G), smem, st>>>(a);
   LSHM_CHECK_LAUNCH("igemm_up");
   return LSHM_OK;
 }
@@ -361,7 +366,10 @@ int launch_up(int dim, UpArgs a, cudaStream_t st) {
   a.mtiles = ceil_div(a.Q, 128);
   a.ntn = g.ntiles;
   a.d_ntn = make_fastdiv((uint32_t)a.ntn);
-#define LU(D, NTV, KCV) return launch_up_t<D, NTV, KCV>(a, g, st)
+  // two producer groups for the multi-K-block (deep) 1-D layers; in 2-D the 480-thread CTA would cap the
+  // kernel at 64 registers (it needs 80) and measured slower
+  const bool two = dim == 1 && g.KB >= 2;
+#define LU(D, NTV, KCV) do { if (two) return launch_up_t<D, NTV, KCV, 2>(a, g, st); return launch_up_t<D, NTV, KCV, 1>(a, g, st); } while (0)
   if (dim == 2) {
     switch (g.NT) { case 16: LU(2, 16, 16); case 32: LU(2, 32, 16); default: LU(2, 48, 16); }
   } else {
