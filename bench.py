@@ -257,9 +257,16 @@ def run_ours(args):
     bpb_, x, uv = load_from_host()
     step.set_batch(x, uv, bpb_, global_patches=Np * world)
 
-    def one_step():
+    def eager_step():
         opt.step(step.closure)
         step.update_multipliers()
+
+    # the step (closure fwd+bwd, Adam, multiplier-update forward: ~270 launches) is replayed from ONE CUDA graph
+    graphed = None
+    if args.graph == "on":
+        from lshm_b200.kharmonic_lofar import GraphedStep
+        graphed = GraphedStep(step, opt)
+    one_step = graphed.replay if graphed is not None else eager_step
 
     def barrier():
         if distributed:
@@ -292,13 +299,19 @@ def run_ours(args):
     # ---- end to end through the loader API from host memory
     # the next minibatch (H2D + loader kernels) is staged on a side stream while this step computes;
     # every step's copy and read-back are inside the timed region
+    def new_batch(x2, uv2, b):
+        if graphed is not None:
+            graphed.load(x2, uv2)            # into the static buffers the graph reads (also resets y1..y3)
+        else:
+            step.set_batch(x2, uv2, b, global_patches=Np * world)
+
     pf = T.DevicePrefetcher(dev, record_streams=False)
     sets = [(torch.empty_like(vis_h, device=dev), torch.empty_like(sc_h, device=dev), torch.empty_like(uv_h, device=dev),
              torch.empty(Np, CFG["channels"], 128, 128, device=dev), torch.zeros(2, dtype=torch.float64, device=dev))
             for _ in range(2)]
     for k in range(3):      # warm-up through the same path
         pf.submit(lambda: load_from_host(sets[k % 2]))
-        b, x2, uv2 = pf.get(); step.set_batch(x2, uv2, b, global_patches=Np * world); one_step(); step.loss_terms()
+        b, x2, uv2 = pf.get(); new_batch(x2, uv2, b); one_step(); step.loss_terms()
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(2, min(args.steps, 10))
@@ -308,7 +321,7 @@ def run_ours(args):
         if i + 1 < e2e_steps:
             nxt = sets[(i + 1) % 2]      # last used by step i-1, which has completed (loss read-back)
             pf.submit(lambda: load_from_host(nxt))
-        step.set_batch(x2, uv2, b, global_patches=Np * world)
+        new_batch(x2, uv2, b)
         one_step()
         terms = step.loss_terms()   # D2H of the 9 loss columns (synchronises)
     barrier()
@@ -328,11 +341,11 @@ def run_ours(args):
     if rank == 0:
         with KernelProfiler(L) as kp:
             for _ in range(prof_steps):
-                one_step()
+                eager_step()
             agg = kp.summary(prof_steps)
     else:
         for _ in range(prof_steps):
-            one_step()
+            eager_step()
     barrier()
     out = None
     if rank == 0:
@@ -364,7 +377,7 @@ def run_ours(args):
             "metric": "train patches/sec (fwd+bwd+K-harmonic)", "value": value, "unit": "patches/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(CFG, global_patches=Np * world, parallelism=f"dp{world}"),
+            "config": dict(CFG, global_patches=Np * world, parallelism=f"dp{world}", cuda_graph=graphed is not None),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "loss_terms_last": terms,
         }
@@ -473,6 +486,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-patches", type=int, default=64)
+    ap.add_argument("--graph", default="on", choices=["on", "off"],
+                    help="replay the step from one CUDA graph (default) or launch it kernel by kernel")
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel CUDA-event table (CSV) here")
     args = ap.parse_args()
     with StdoutToStderr():

@@ -226,6 +226,10 @@ LSHM_API int lshm_closure_total(const double* terms, float rho, double numel, do
  * torch.optim.Adam semantics (src/kharmonic_lofar.py:92) on one flat buffer. */
 LSHM_API int lshm_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,
                    float beta1, float beta2, float eps, int step, lshm_stream_t stream);
+/* Same update with the step count kept in device memory: *step_counter is incremented, then used for the
+ * bias corrections.  No argument changes from step to step, so the call can be captured in a CUDA graph. */
+LSHM_API int lshm_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr,
+                       float beta1, float beta2, float eps, int32_t* step_counter, lshm_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -293,6 +293,28 @@ __global__ void closure_total_kernel(const double* __restrict__ t, float rho, do
   out[5] = (float)kd; out[6] = (float)aug; out[7] = (float)sim; out[8] = (float)rica;
 }
 
+__global__ void counter_inc_kernel(int32_t* c) { *c += 1; }
+
+// Adam with the step count in device memory (incremented by counter_inc_kernel just before): nothing
+// step-dependent is a kernel argument, so the launch can be replayed from a CUDA graph.
+__global__ void __launch_bounds__(256)
+adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                const int32_t* __restrict__ step) {
+  const double t = (double)*step;
+  const float bc1 = (float)(1.0 - pow((double)b1, t));
+  const float bc2_sqrt = sqrtf((float)(1.0 - pow((double)b2, t)));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
@@ -432,6 +454,19 @@ int lshm_closure_total(const double* terms, float rho, double numel, double khm_
   LSHM_REQUIRE(terms && out && numel > 0, "lshm_closure_total: bad arguments");
   closure_total_kernel<<<1, 1, 0, as_stream(stream)>>>(terms, rho, numel, khm_scale, out);
   LSHM_CHECK_LAUNCH("lshm_closure_total");
+  return LSHM_OK;
+}
+
+int lshm_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr,
+                       float beta1, float beta2, float eps, int32_t* step_counter, lshm_stream_t stream) {
+  LSHM_REQUIRE(p && g && m && v && step_counter && n >= 0, "lshm_adam_step_dev: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  counter_inc_kernel<<<1, 1, 0, st>>>(step_counter);
+  LSHM_CHECK_LAUNCH("lshm_adam_step_dev");
+  if (n == 0) return LSHM_OK;
+  const int64_t blocks = std::min<int64_t>(ceil_div(n, 256), (int64_t)sm_count() * 8);
+  adam_dev_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_counter);
+  LSHM_CHECK_LAUNCH("lshm_adam_step_dev");
   return LSHM_OK;
 }
 

@@ -76,13 +76,18 @@ class FlatParams:
 
 class FlatAdam:
     """torch.optim.Adam semantics (src/kharmonic_lofar.py:92) as ONE kernel over the flat
-    buffer (lshm_adam_step)."""
+    buffer.  The step count lives in device memory (lshm_adam_step_dev), so a step can be
+    captured in a CUDA graph (GraphedStep)."""
 
     def __init__(self, flat: FlatParams, lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
         self.flat, self.lr, self.betas, self.eps = flat, lr, betas, eps
         self.m = torch.zeros_like(flat.flat)
         self.v = torch.zeros_like(flat.flat)
-        self.t = 0
+        self.t_dev = torch.zeros(1, dtype=torch.int32, device=flat.flat.device)
+
+    @property
+    def t(self) -> int:
+        return int(self.t_dev.item())
 
     def zero_grad(self):
         pass  # the fused closure overwrites every gradient
@@ -90,10 +95,68 @@ class FlatAdam:
     def step(self, closure):
         with torch.enable_grad():
             loss = closure()
-        self.t += 1
-        lib().adam_step(self.flat.flat.data_ptr(), self.flat.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-                        self.flat.numel, self.lr, self.betas[0], self.betas[1], self.eps, self.t, _stream())
+        lib().adam_step_dev(self.flat.flat.data_ptr(), self.flat.grad.data_ptr(), self.m.data_ptr(),
+                            self.v.data_ptr(), self.flat.numel, self.lr, self.betas[0], self.betas[1], self.eps,
+                            self.t_dev.data_ptr(), _stream())
         return loss
+
+
+class GraphedStep:
+    """`optimizer.step(step.closure); step.update_multipliers()` captured once as a CUDA graph and
+    replayed: ~270 kernel launches become one, which removes the launch gaps between the small kernels
+    of the deep layers and the host's launch lead after every loss read-back.
+
+    The minibatch lives in the static tensors `.x` [N,C,128,128] and `.uv` [N,2] (the ones given to
+    `step.set_batch` before construction): write the next minibatch into them (`load(x, uv)` copies, or
+    let `lofar_tools.patchify_device(..., out=graphed.x)` produce it in place), call `new_batch()` when
+    the multipliers must restart, then `replay()`.  Needs a FlatAdam optimiser (device-side step count).
+    """
+
+    def __init__(self, step: "DeepKHarmonicStep", optimizer: FlatAdam, warmup: int = 2):
+        if not isinstance(optimizer, FlatAdam):
+            raise RuntimeError("lshm_b200: GraphedStep needs a FlatAdam optimiser (device-side step count)")
+        if step.N == 0:
+            raise RuntimeError("lshm_b200: call step.set_batch(...) before capturing the step")
+        self.step, self.opt = step, optimizer
+        self.x, self.uv = step.x, step.uv
+        dev = step.device
+        # warm-up and capture must not change the training state: snapshot, run, restore
+        keep = [t.clone() for t in (step.flat.flat, optimizer.m, optimizer.v, optimizer.t_dev, step.y1, step.y2, step.y3)]
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._one()
+            side.synchronize()
+            l0 = lib().launches
+            with torch.cuda.graph(self.graph, stream=side):
+                self.loss = self._one()
+            self.launches_per_replay = lib().launches - l0
+        torch.cuda.current_stream(dev).wait_stream(side)
+        for dst, src in zip((step.flat.flat, optimizer.m, optimizer.v, optimizer.t_dev, step.y1, step.y2, step.y3), keep):
+            dst.copy_(src)
+
+    def _one(self):
+        loss = self.opt.step(self.step.closure)
+        self.step.update_multipliers()
+        return loss
+
+    def load(self, x: torch.Tensor, uv: torch.Tensor, reset_multipliers: bool = True):
+        self.x.copy_(x.view_as(self.x), non_blocking=True)
+        self.uv.copy_(uv.view_as(self.uv), non_blocking=True)
+        if reset_multipliers:
+            self.new_batch()
+
+    def new_batch(self):
+        """src/kharmonic_lofar.py:128-130: the multipliers restart with every minibatch."""
+        self.step.y1.zero_(); self.step.y2.zero_(); self.step.y3.zero_()
+
+    def replay(self) -> torch.Tensor:
+        """One optimiser step + multiplier update; returns the (static) total-loss tensor."""
+        self.graph.replay()
+        lib().launches += self.launches_per_replay     # kernels launched by the replay
+        return self.loss
 
 
 class DeepKHarmonicStep:

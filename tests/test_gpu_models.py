@@ -289,3 +289,44 @@ def test_closure_matches_golden_from_live_reference(cuda):
         gk = {"0": "n", "1": "T", "2": "F", "3": "k"}[tag] + "." + name
         ref_norm = float(g[gk + ":norm"])
         assert abs(p.grad.double().norm().item() - ref_norm) <= 1e-3 * ref_norm, nm
+
+
+def test_graphed_step_matches_eager_steps(cuda):
+    """optimizer.step(closure) + multiplier update replayed from one CUDA graph: same losses and parameters as
+    the eager loop (Adam's step count is device-side, so the bias corrections advance with every replay),
+    capture leaves the training state untouched, a new minibatch is picked up from the static buffers."""
+    from lshm_b200.kharmonic_lofar import DeepKHarmonicStep, FlatAdam, GraphedStep
+    case = closure_case(N=4, bpb=2)
+    x, uv = case["x"].to(cuda), case["uv"].to(cuda)
+
+    def fresh():
+        torch.manual_seed(3)
+        mods = build_modules(case, cuda)
+        step = DeepKHarmonicStep(*mods)
+        step.set_batch(x.clone(), uv.clone(), 2)
+        return step, FlatAdam(step.flat, lr=1e-3)
+
+    step_e, opt_e = fresh()
+    eager = []
+    for _ in range(4):
+        eager.append(float(opt_e.step(step_e.closure)))
+        step_e.update_multipliers()
+    step_g, opt_g = fresh()
+    before = step_g.flat.flat.clone()
+    gs = GraphedStep(step_g, opt_g)
+    assert torch.equal(step_g.flat.flat, before) and opt_g.t == 0 and float(step_g.y1.abs().max()) == 0.0
+    assert gs.launches_per_replay > 100
+    graphed = [float(gs.replay()) for _ in range(4)]
+    assert opt_g.t == 4
+    assert np.allclose(graphed, eager, rtol=2e-4), (graphed, eager)
+    assert rel_err(step_g.flat.flat, step_e.flat.flat) < 2e-4
+    assert rel_err(step_g.y1, step_e.y1) < 2e-3
+    # next minibatch through the static buffers
+    x2 = torch.roll(x, 1, 0) * 0.5
+    gs.load(x2, uv)
+    step_e.set_batch(x2.clone(), uv.clone(), 2)
+    le = float(opt_e.step(step_e.closure))
+    lg = float(gs.replay())
+    assert abs(lg - le) <= 2e-4 * abs(le)
+    with pytest.raises(RuntimeError):
+        GraphedStep(step_g, torch.optim.Adam(step_g.flat.params))
