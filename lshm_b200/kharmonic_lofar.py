@@ -95,10 +95,14 @@ class FlatAdam:
     def step(self, closure):
         with torch.enable_grad():
             loss = closure()
+        self.apply()
+        return loss
+
+    def apply(self):
+        """The parameter update alone, from the gradients already in the flat buffer."""
         lib().adam_step_dev(self.flat.flat.data_ptr(), self.flat.grad.data_ptr(), self.m.data_ptr(),
                             self.v.data_ptr(), self.flat.numel, self.lr, self.betas[0], self.betas[1], self.eps,
                             self.t_dev.data_ptr(), _stream())
-        return loss
 
 
 class GraphedStep:
@@ -124,14 +128,30 @@ class GraphedStep:
         keep = [t.clone() for t in (step.flat.flat, optimizer.m, optimizer.v, optimizer.t_dev, step.y1, step.y2, step.y3)]
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
+        # (thread-local capture mode: the NCCL watchdog thread polls events while we capture.)
+        # Data parallel: the NCCL all-reduce stays outside (collectives inside a capture are fragile), so the
+        # step is two graphs with the eager exchange between them: [closure] -> all-reduce -> [Adam, multipliers]
         self.graph = torch.cuda.CUDAGraph()
+        self.graph2 = torch.cuda.CUDAGraph() if step.distributed else None
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):
                 self._one()
             side.synchronize()
             l0 = lib().launches
-            with torch.cuda.graph(self.graph, stream=side):
-                self.loss = self._one()
+            if self.graph2 is None:
+                with torch.cuda.graph(self.graph, stream=side, capture_error_mode="thread_local"):
+                    self.loss = self._one()
+            else:
+                step._defer_exchange = True
+                try:
+                    with torch.cuda.graph(self.graph, stream=side, capture_error_mode="thread_local"):
+                        with torch.enable_grad():
+                            self.loss = step.closure()
+                    with torch.cuda.graph(self.graph2, stream=side, pool=self.graph.pool(), capture_error_mode="thread_local"):
+                        optimizer.apply()
+                        step.update_multipliers()
+                finally:
+                    step._defer_exchange = False
             self.launches_per_replay = lib().launches - l0
         torch.cuda.current_stream(dev).wait_stream(side)
         for dst, src in zip((step.flat.flat, optimizer.m, optimizer.v, optimizer.t_dev, step.y1, step.y2, step.y3), keep):
@@ -155,6 +175,9 @@ class GraphedStep:
     def replay(self) -> torch.Tensor:
         """One optimiser step + multiplier update; returns the (static) total-loss tensor."""
         self.graph.replay()
+        if self.graph2 is not None:
+            exchange(self.step.flat.grad, self.step.group)
+            self.graph2.replay()
         lib().launches += self.launches_per_replay     # kernels launched by the replay
         return self.loss
 
@@ -191,6 +214,7 @@ class DeepKHarmonicStep:
             self._gd.append({nm: views[f"{mi}.{nm}"] for nm in m._names})
         self._gM = views["3.M"]
         self.N = 0
+        self._defer_exchange = False     # GraphedStep runs the all-reduce itself, between its two graphs
         self.launches = 0
         if distributed:
             self.broadcast_parameters()
@@ -289,7 +313,7 @@ class DeepKHarmonicStep:
                           gMu[:, :L], Mu[:, :L], False)
         tail = self.flat.loss_tail
         lb.closure_total(tp, self.rho, numel_g, khm_scale, tail.data_ptr(), st)
-        if self.distributed:
+        if self.distributed and not self._defer_exchange:
             # ONE exchange per closure evaluation: gradients + loss scalars (forward-only: scalars)
             buf = self.flat.grad if grads else tail
             exchange(buf, self.group)
