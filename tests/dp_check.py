@@ -55,6 +55,29 @@ def main():
               f"identical loss on all ranks: {len(set(losses)) == 1} -> {'PASS' if ok else 'FAIL'}")
         if not ok:
             sys.exit(1)
+    # graphed data-parallel steps (two CUDA graphs around the eager all-reduce) against the eager loop
+    from lshm_b200.kharmonic_lofar import FlatAdam, GraphedStep
+    opt = FlatAdam(step.flat, lr=1e-3)
+    state = [t.clone() for t in (step.flat.flat, step.y1, step.y2, step.y3)]
+    eager = []
+    for _ in range(3):
+        eager.append(float(opt.step(step.closure)))
+        step.update_multipliers()
+    p_eager = step.flat.flat.clone()
+    for dst, src in zip((step.flat.flat, step.y1, step.y2, step.y3), state):
+        dst.copy_(src)
+    opt2 = FlatAdam(step.flat, lr=1e-3)
+    gs = GraphedStep(step, opt2)
+    graphed = [float(gs.replay()) for _ in range(3)]
+    err = rel_err(step.flat.flat, p_eager)
+    ok2 = all(abs(a - b) <= 2e-4 * abs(b) for a, b in zip(graphed, eager)) and err < 2e-4
+    flags = [None] * world
+    dist.all_gather_object(flags, ok2)
+    if rank == 0:
+        print(f"dp_check world={world}: graphed losses {graphed} eager {eager} param rel err {err:.2e} "
+              f"-> {'PASS' if all(flags) else 'FAIL'}")
+        if not all(flags):
+            sys.exit(1)
     dist.barrier()
     dist.destroy_process_group()
 
