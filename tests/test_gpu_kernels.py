@@ -346,3 +346,18 @@ def test_cascade_kernels(cuda):
     assert rel_err(g[4], y1 + rho * (x - x1).reshape(-1)) < 1e-6
     assert rel_err(g[5], y2 + rho * (x11 - x2).reshape(-1)) < 1e-6
     assert rel_err(g[6], y3 + rho * (x11 - x3).reshape(-1)) < 1e-6
+
+
+@pytest.mark.parametrize("Cn,ln,pad", [(192, 4, 0), (96, 16, 0), (24, 256, 0), (12, 1024, 0), (8, 16384, 0),
+                                        (48, 64, 8), (5, 37, 0), (8, 4100, 4), (3, 6, 2)])
+def test_channel_sum_all_row_lengths_and_strides(cuda, Cn, ln, pad):
+    """Bias-gradient reduction: long rows (persistent chunks), short contiguous rows (flat kernel), and the
+    strided / unaligned / odd-length fallbacks."""
+    torch.manual_seed(Cn * 7 + ln)
+    N = 37
+    buf = torch.randn(N, Cn * ln + pad, device=cuda)
+    g = buf[:, :Cn * ln]
+    db = torch.full((Cn,), 7.0, device=cuda)          # written, not accumulated
+    lib().channel_sum(g.data_ptr(), buf.stride(0), dp(db), N, Cn, ln, st())
+    ref = g.reshape(N, Cn, ln).double().sum(dim=(0, 2)).float()
+    assert rel_err(db, ref) < 1e-5
