@@ -7,6 +7,7 @@
 // One shared-memory tiled SGEMM with arbitrary element strides serves the three products
 // (y = x W^T, dx = dz W, dW = dz^T x); the weight-gradient product splits the long sample
 // dimension over blockIdx.z and combines with atomics.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace lshm {
@@ -89,7 +90,94 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_strided_kernel(GemmArgs g)
   }
 }
 
+// Narrow output (<= 32 columns): the 64x64 tiling leaves 16 blocks, and for the 784 -> 16/32 and
+// 768 -> 32/48 products of the dense head they walk ~49 K steps in sequence (47-66 us per call).  Here the
+// reduction is spread over the threads of a group (a warp for short reductions, the whole block for long
+// ones), each thread keeps NN column sums, the sums are reduced with shuffles (+ shared memory across warps).
+// B is read along whichever of its two strides is 1 (VECN: 16-byte loads over the columns).
+template <int NN, bool VECN>
+__device__ __forceinline__ void skinny_accumulate(const GemmArgs& g, const float* arow, int64_t k, float (&acc)[NN]) {
+  const float a = __ldg(arow + k * g.sak);
+  const float* bk = g.B + k * g.sbk;
+  if (VECN) {                                   // sbn == 1: the NN columns of row k are contiguous
+#pragma unroll
+    for (int n4 = 0; n4 < NN / 4; ++n4) {
+      if (n4 * 4 < g.N) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bk) + n4);
+        acc[n4 * 4 + 0] = fmaf(a, b.x, acc[n4 * 4 + 0]); acc[n4 * 4 + 1] = fmaf(a, b.y, acc[n4 * 4 + 1]);
+        acc[n4 * 4 + 2] = fmaf(a, b.z, acc[n4 * 4 + 2]); acc[n4 * 4 + 3] = fmaf(a, b.w, acc[n4 * 4 + 3]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int n = 0; n < NN; ++n)
+      if (n < g.N) acc[n] = fmaf(a, __ldg(bk + n * g.sbn), acc[n]);
+  }
+}
+
+__device__ __forceinline__ void skinny_store(const GemmArgs& g, int64_t m, int n, float v) {
+  if (g.bias) v += g.bias[n];
+  if (g.add) v += g.add[m * g.ldadd + n];
+  if (g.epi == LSHM_EPI_ELU) v = elu_f(v);
+  else if (g.epi == LSHM_EPI_DELU) v *= delu_from_out(g.aux[m * g.ldaux + n]);
+  g.C[m * g.ldc + n] = v;
+}
+
+// ROWBLOCK = false: a warp per output row (short reductions); true: a block per output row
+template <int NN, bool VECN, bool ROWBLOCK>
+__global__ void __launch_bounds__(256) sgemm_skinny_kernel(GemmArgs g) {
+  __shared__ float part[8][NN];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t mstep = ROWBLOCK ? (int64_t)gridDim.x : (int64_t)gridDim.x * 8;
+  for (int64_t m = ROWBLOCK ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * 8 + warp; m < g.M; m += mstep) {
+    float acc[NN];
+#pragma unroll
+    for (int n = 0; n < NN; ++n) acc[n] = 0.f;
+    const float* arow = g.A + m * g.sam;
+    for (int64_t k = ROWBLOCK ? threadIdx.x : lane; k < g.K; k += (ROWBLOCK ? 256 : 32))
+      skinny_accumulate<NN, VECN>(g, arow, k, acc);
+    float mine = 0.f;
+#pragma unroll
+    for (int n = 0; n < NN; ++n) {
+      const float t = warp_sum(acc[n]);
+      if (lane == n) mine = t;
+    }
+    if (ROWBLOCK) {
+      if (lane < NN) part[warp][lane] = mine;
+      __syncthreads();
+      if (threadIdx.x < g.N) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += part[w][threadIdx.x];
+        skinny_store(g, m, threadIdx.x, v);
+      }
+      __syncthreads();
+    } else if (lane < g.N) {
+      skinny_store(g, m, lane, mine);
+    }
+  }
+}
+
+template <int NN, bool VECN>
+void launch_skinny(const GemmArgs& g, cudaStream_t st) {
+  if (g.K >= 128) {
+    const int grid = (int)std::min<int64_t>(g.M, (int64_t)sm_count() * 8);
+    sgemm_skinny_kernel<NN, VECN, true><<<grid, 256, 0, st>>>(g);
+  } else {
+    const int grid = (int)std::min<int64_t>(ceil_div(g.M, 8), (int64_t)sm_count() * 8);
+    sgemm_skinny_kernel<NN, VECN, false><<<grid, 256, 0, st>>>(g);
+  }
+}
+
 int launch_gemm(GemmArgs g, int ksplit, cudaStream_t st, const char* name) {
+  static const bool no_skinny = getenv("LSHM_NO_SKINNY") != nullptr;   // experiment switch
+  if (!no_skinny && !g.atomic && ksplit == 1 && g.N <= 32 && g.K >= 16) {
+    const bool vecn = g.sbn == 1 && (g.sbk & 3) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0 && (g.N & 3) == 0;
+    if (g.N <= 16) { if (vecn) launch_skinny<16, true>(g, st); else launch_skinny<16, false>(g, st); }
+    else { if (vecn) launch_skinny<32, true>(g, st); else launch_skinny<32, false>(g, st); }
+    LSHM_CHECK_LAUNCH(name);
+    return LSHM_OK;
+  }
   g.kchunk = ceil_div(ceil_div(g.K, ksplit), BK) * BK;
   if (g.kchunk <= 0) g.kchunk = BK;
   const int zs = (int)std::max<int64_t>(1, ceil_div(g.K, g.kchunk));
