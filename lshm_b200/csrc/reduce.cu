@@ -51,20 +51,23 @@ channel_sum_rows_kernel(const float* __restrict__ g, int64_t g_ns, float* __rest
   for (int c = threadIdx.x; c < Cn; c += blockDim.x) atomicAdd(db + c, acc[c]);
 }
 
-// short rows (the deep layers: 4-256 values per row, 10^5 rows) of a contiguous tensor: the tensor is one flat
-// array, a thread sums 16 bytes and adds them to its row's channel in shared memory; persistent blocks, one
+// short rows (the deep layers: 4-256 values per row, 10^5 rows): every sample is one flat array (samples may
+// be strided), a thread sums 16 bytes and adds them to its row's channel in shared memory; persistent blocks, one
 // global atomic per (block, channel).  One warp per row in short-lived blocks (below, kept for strided or
 // unaligned input) was 44 us per call in the ncu launch list: 25k blocks of 8 nearly idle warps.
 __global__ void __launch_bounds__(256)
-channel_sum_flat_kernel(const float* __restrict__ g, float* __restrict__ db, int64_t n4, int Cn, int len4) {
+channel_sum_flat_kernel(const float* __restrict__ g, int64_t g_ns, float* __restrict__ db, int64_t n4, int Cn,
+                        int len4) {
   extern __shared__ float acc[];                // [Cn]
   for (int c = threadIdx.x; c < Cn; c += blockDim.x) acc[c] = 0.f;
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t per_n = (int64_t)Cn * len4;     // 16-byte pieces per sample (samples may be strided: g_ns)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const float4 v = ld_nc_f4(g + 4 * i);
-    const int64_t row = i / len4;               // n * Cn + c
-    atomicAdd(&acc[(int)(row % Cn)], (v.x + v.y) + (v.z + v.w));
+    const int64_t n = i / per_n;
+    const int rem = (int)(i - n * per_n);
+    const float4 v = ld_nc_f4(g + n * g_ns + 4 * (int64_t)rem);
+    atomicAdd(&acc[rem / len4], (v.x + v.y) + (v.z + v.w));
   }
   __syncthreads();
   for (int c = threadIdx.x; c < Cn; c += blockDim.x) atomicAdd(db + c, acc[c]);
@@ -108,10 +111,10 @@ int lshm_channel_sum(const float* g, int64_t g_ns, float* db, int64_t N, int Cn,
     const int64_t want = ceil_div(items, (int64_t)8);
     const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count() * 6);
     channel_sum_rows_kernel<<<grid, 256, sizeof(float) * Cn, st>>>(g, g_ns, db, rows, Cn, len, cpr, vec_ok);
-  } else if ((reinterpret_cast<uintptr_t>(g) & 15) == 0 && (len & 3) == 0 && g_ns == (int64_t)Cn * len) {
+  } else if ((reinterpret_cast<uintptr_t>(g) & 15) == 0 && (len & 3) == 0 && (g_ns & 3) == 0 && (int64_t)Cn * len < (1 << 30)) {
     const int64_t n4 = rows * (len >> 2);
     const int grid = (int)std::min<int64_t>(ceil_div(n4, (int64_t)256 * 4), (int64_t)sm_count() * 6);
-    channel_sum_flat_kernel<<<grid, 256, sizeof(float) * Cn, st>>>(g, db, n4, Cn, (int)(len >> 2));
+    channel_sum_flat_kernel<<<grid, 256, sizeof(float) * Cn, st>>>(g, g_ns, db, n4, Cn, (int)(len >> 2));
   } else {
     channel_sum_short_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(g, g_ns, db, rows, Cn, (int)len);
   }
