@@ -215,6 +215,7 @@ class DeepKHarmonicStep:
         self._gM = views["3.M"]
         self.N = 0
         self._defer_exchange = False     # GraphedStep runs the all-reduce itself, between its two graphs
+        self._side = None                # second stream for the frequency-axis net
         self.launches = 0
         if distributed:
             self.broadcast_parameters()
@@ -259,11 +260,30 @@ class DeepKHarmonicStep:
         xf = self.x.view(N, -1)
         x1, _ = e[0].forward(xf, self.uv, self.scales, self._pd[0], self.ws[0], st, mu_out=self.Mu[:, :L])
         lib().residual_split(self.x.data_ptr(), x1.data_ptr(), self.iyT.data_ptr(), self.iyF.data_ptr(), N, C, 128, st)
+        # The time-axis and frequency-axis nets are independent: they run on two streams (fork / join by
+        # events, also inside a graph capture), so the latency-bound deep layers of one overlap the other's.
+        side = self._fork()
+        with torch.cuda.stream(side):
+            x3f, _ = e[2].forward(self.iyF.view(N, -1), self.uv, self.scales, self._pd[2], self.ws[2],
+                                  side.cuda_stream, mu_out=self.Mu[:, L + Lt:])
         x2, _ = e[1].forward(self.iyT.view(N, -1), self.uv, self.scales, self._pd[1], self.ws[1], st,
                              mu_out=self.Mu[:, L:L + Lt])
-        x3f, _ = e[2].forward(self.iyF.view(N, -1), self.uv, self.scales, self._pd[2], self.ws[2], st,
-                              mu_out=self.Mu[:, L + Lt:])
+        self._join(side)
         return x1, x2, x3f
+
+    def _fork(self) -> torch.cuda.Stream:
+        """Side stream that starts after everything queued so far on the current stream."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._side.wait_event(ev)
+        return self._side
+
+    def _join(self, side: torch.cuda.Stream):
+        ev = torch.cuda.Event()
+        ev.record(side)
+        torch.cuda.current_stream(self.device).wait_event(ev)
 
     def closure(self) -> torch.Tensor:
         """src/kharmonic_lofar.py:132-182.  Returns the total loss (0-dim device tensor)."""
@@ -304,10 +324,13 @@ class DeepKHarmonicStep:
                            gMu.data_ptr() + 4 * off if grads else None, Ltot, st)
         if grads:
             e = self.net.engine(), self.netT.engine(), self.netF.engine()
+            side = self._fork()
+            with torch.cuda.stream(side):
+                dF = e[2].backward(self.iyF.view(N, -1), self._pd[2], self._gd[2], self.ws[2], side.cuda_stream,
+                                   self.g3f.view(N, -1), gMu[:, L + Lt:], Mu[:, L + Lt:], True)
             dT = e[1].backward(self.iyT.view(N, -1), self._pd[1], self._gd[1], self.ws[1], st, self.g2.view(N, -1),
                                gMu[:, L:L + Lt], Mu[:, L:L + Lt], True)
-            dF = e[2].backward(self.iyF.view(N, -1), self._pd[2], self._gd[2], self.ws[2], st, self.g3f.view(N, -1),
-                               gMu[:, L + Lt:], Mu[:, L + Lt:], True)
+            self._join(side)
             lb.cascade_combine(self.g1p.data_ptr(), dT.data_ptr(), dF.data_ptr(), self.gx1.data_ptr(), N, C, 128, st)
             e[0].backward(self.x.view(N, -1), self._pd[0], self._gd[0], self.ws[0], st, self.gx1.view(N, -1),
                           gMu[:, :L], Mu[:, :L], False)
