@@ -220,8 +220,14 @@ class AEEngine:
     # ------------------------------------------------------------------ backward
     def backward(self, x: torch.Tensor, p: Dict[str, torch.Tensor], g: Dict[str, torch.Tensor],
                  ws: Workspace, st: int, g_xhat: Optional[torch.Tensor],
-                 g_mu: Optional[torch.Tensor], mu: torch.Tensor, need_dx: bool):
+                 g_mu: Optional[torch.Tensor], mu: torch.Tensor, need_dx: bool,
+                 wstream: Optional[torch.cuda.Stream] = None):
         """Writes every parameter gradient into g[name] (overwrite) and returns dx or None.
+
+        wstream: optional second stream for the leaf work of the conv layers (weight and bias gradients).
+        The data-gradient chain stays on `st` (the current stream); each layer's wgrad / bias sum is forked
+        to `wstream` once its output gradient exists and everything is joined before returning, so the
+        latency-bound deep layers overlap instead of queueing behind each other.
 
         g_xhat: gradient w.r.t. the reconstruction ([N, C*16384] contiguous) or None;
         g_mu:   gradient w.r.t. the returned latent ([N,L] view, any row stride) or None;
@@ -230,6 +236,14 @@ class AEEngine:
         lb, N, L, H4, ch, sz = self.lib, ws.N, self.L, self.H4, self.ch, ws.sizes
         ld1, zc_ld = FLAT + H4, L + H4
         rch = ch[::-1]
+        main = torch.cuda.current_stream(x.device)
+        wst = st if wstream is None else wstream.cuda_stream
+
+        def fork():      # leaf work may start once everything queued so far on the main stream is done
+            if wstream is not None:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                wstream.wait_event(ev)
         if g_xhat is None:
             # no reconstruction gradient: decoder parameters get zero gradient
             for i in range(6):
@@ -245,8 +259,9 @@ class AEEngine:
             for i in range(5, -1, -1):
                 inp = ws.dec[i]                     # input of tconv_i (small map, level 6-i)
                 A, Bc, lvl = rch[i], rch[i + 1], 6 - i
-                self._wgrad(_p(inp), sz[lvl], _p(dz), sz[lvl - 1], _p(g[f"tconv{i}.weight"]), N, A, Bc, lvl, 0, st)
-                lb.channel_sum(_p(dz), sz[lvl - 1], _p(g[f"tconv{i}.bias"]), N, Bc, sz[lvl - 1] // Bc, st)
+                fork()
+                self._wgrad(_p(inp), sz[lvl], _p(dz), sz[lvl - 1], _p(g[f"tconv{i}.weight"]), N, A, Bc, lvl, 0, wst)
+                lb.channel_sum(_p(dz), sz[lvl - 1], _p(g[f"tconv{i}.bias"]), N, Bc, sz[lvl - 1] // Bc, wst)
                 nxt = ws.g_dec[i]
                 # dgrad of the transposed conv = "down"; ELU' of the producing layer unless it is fc3
                 self._down(_p(dz), sz[lvl - 1], _p(self.img[(f"tconv{i}.weight", 0)]), None,
@@ -280,8 +295,9 @@ class AEEngine:
         for i in range(5, -1, -1):
             inp, inp_ns = (x, sz[0]) if i == 0 else (ws.enc[i], sz[i])
             A, Bc, lvl = ch[i + 1], ch[i], i + 1
-            self._wgrad(_p(dz), dz_ns, _p(inp), inp_ns, _p(g[f"conv{i}.weight"]), N, A, Bc, lvl, 1, st)
-            lb.channel_sum(_p(dz), dz_ns, _p(g[f"conv{i}.bias"]), N, A, sz[lvl] // A, st)
+            fork()
+            self._wgrad(_p(dz), dz_ns, _p(inp), inp_ns, _p(g[f"conv{i}.weight"]), N, A, Bc, lvl, 1, wst)
+            lb.channel_sum(_p(dz), dz_ns, _p(g[f"conv{i}.bias"]), N, A, sz[lvl] // A, wst)
             if i > 0:
                 nxt = ws.g_enc[i]
                 self._up(_p(dz), dz_ns, _p(self.img[(f"conv{i}.weight", 1)]), None, _p(inp), inp_ns, _p(nxt), sz[i], N, A, Bc, lvl, 1, EPI_DELU, st)
@@ -292,4 +308,8 @@ class AEEngine:
                 elif not self.need_input_grad:
                     conv_image(p["conv0.weight"], self.ndim, 1, st, self.img[("conv0.weight", 1)])
                 self._up(_p(dz), dz_ns, _p(self.img[("conv0.weight", 1)]), None, None, 0, _p(ws.dx), sz[0], N, A, Bc, lvl, 1, EPI_NONE, st)
+        if wstream is not None:
+            ev = torch.cuda.Event()
+            ev.record(wstream)
+            main.wait_event(ev)
         return ws.dx if need_dx else None

@@ -216,6 +216,7 @@ class DeepKHarmonicStep:
         self.N = 0
         self._defer_exchange = False     # GraphedStep runs the all-reduce itself, between its two graphs
         self._side = None                # second stream for the frequency-axis net
+        self._wst = [None, None, None]   # per-net streams for the weight / bias gradients
         self.launches = 0
         if distributed:
             self.broadcast_parameters()
@@ -270,6 +271,12 @@ class DeepKHarmonicStep:
                              mu_out=self.Mu[:, L:L + Lt])
         self._join(side)
         return x1, x2, x3f
+
+    def _wstream(self, i: int) -> torch.cuda.Stream:
+        """Stream for the weight / bias gradients of net i (leaf work beside the data-gradient chain)."""
+        if self._wst[i] is None:
+            self._wst[i] = torch.cuda.Stream(self.device)
+        return self._wst[i]
 
     def _fork(self) -> torch.cuda.Stream:
         """Side stream that starts after everything queued so far on the current stream."""
@@ -327,13 +334,13 @@ class DeepKHarmonicStep:
             side = self._fork()
             with torch.cuda.stream(side):
                 dF = e[2].backward(self.iyF.view(N, -1), self._pd[2], self._gd[2], self.ws[2], side.cuda_stream,
-                                   self.g3f.view(N, -1), gMu[:, L + Lt:], Mu[:, L + Lt:], True)
+                                   self.g3f.view(N, -1), gMu[:, L + Lt:], Mu[:, L + Lt:], True, self._wstream(2))
             dT = e[1].backward(self.iyT.view(N, -1), self._pd[1], self._gd[1], self.ws[1], st, self.g2.view(N, -1),
-                               gMu[:, L:L + Lt], Mu[:, L:L + Lt], True)
+                               gMu[:, L:L + Lt], Mu[:, L:L + Lt], True, self._wstream(1))
             self._join(side)
             lb.cascade_combine(self.g1p.data_ptr(), dT.data_ptr(), dF.data_ptr(), self.gx1.data_ptr(), N, C, 128, st)
             e[0].backward(self.x.view(N, -1), self._pd[0], self._gd[0], self.ws[0], st, self.gx1.view(N, -1),
-                          gMu[:, :L], Mu[:, :L], False)
+                          gMu[:, :L], Mu[:, :L], False, self._wstream(0))
         tail = self.flat.loss_tail
         lb.closure_total(tp, self.rho, numel_g, khm_scale, tail.data_ptr(), st)
         if self.distributed and not self._defer_exchange:
