@@ -20,6 +20,16 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+_SIDE = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    key = torch.device(device).index
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device)
+    return _SIDE[key]
+
+
 @torch.no_grad()
 def cascade_latents(net: AutoEncoderCNN2, net1D1: AutoEncoder1DCNN, net1D2: AutoEncoder1DCNN,
                     x: torch.Tensor, uv: torch.Tensor) -> torch.Tensor:
@@ -38,9 +48,22 @@ def cascade_latents(net: AutoEncoderCNN2, net1D1: AutoEncoder1DCNN, net1D2: Auto
     iy2 = torch.empty_like(iy1)
     lib().residual_split(x.data_ptr(), x1.data_ptr(), iy1.data_ptr(), iy2.data_ptr(), N, C, 128, st)
     del ws0
+    # the two 1-D encoders are independent: second stream for the frequency-axis net (fork / join by events)
     ws1 = e1.workspace(N, x.device, False)
+    ws2 = e2.workspace(N, x.device, False)
+    cur = torch.cuda.current_stream(x.device)
+    side = _side_stream(x.device)
+    ev = torch.cuda.Event(); ev.record(cur); side.wait_event(ev)
+    with torch.cuda.stream(side):
+        e2.forward(iy2, uv, scales, net1D2.named_param_dict(), ws2, side.cuda_stream, mu_out=Mu[:, L + Lt:], decode=False)
+        ev2 = torch.cuda.Event(); ev2.record(side)
     e1.forward(iy1, uv, scales, net1D1.named_param_dict(), ws1, st, mu_out=Mu[:, L:L + Lt], decode=False)
-    e2.forward(iy2, uv, scales, net1D2.named_param_dict(), ws1, st, mu_out=Mu[:, L + Lt:], decode=False)
+    cur.wait_event(ev2)
+    iy2.record_stream(side)         # allocated on the current stream, last used on the side stream
+    for v in vars(ws2).values():
+        for t in (v if isinstance(v, (list, tuple)) else (v,)):
+            if isinstance(t, torch.Tensor):
+                t.record_stream(side)
     return Mu
 
 
