@@ -160,14 +160,18 @@ LSHM_API int lshm_residual_split(const float* x, const float* x1, float* iyT, fl
  * GLOBAL batch, so data-parallel shards divide by the same constant as the reference):
  *   g2  = d/dx2,  g3f = d/dx3 stored transposed like x3f,
  *   g1p = direct d/dx1 plus the x11 path of the direct terms (excludes the 1-D nets'
- *         input gradients, added by lshm_cascade_combine). */
+ *         input gradients, added by lshm_cascade_combine).
+ * db2 / db3 (both or neither, nullable, float[C], written): per-channel sums of g2 / g3f = the bias
+ * gradients of the last transposed conv of the two 1-D nets (saves their lshm_channel_sum passes). */
 LSHM_API int lshm_cascade_losses(const float* x, const float* x1, const float* x2, const float* x3f,
                         const float* y1, const float* y2, const float* y3, float rho,
                         int64_t N, int C, int P, float grad_scale, double* sums,
-                        float* g1p, float* g2, float* g3f, lshm_stream_t stream);
-/* gx1 = g1p - 0.5*(gT + transpose(gF)) : total gradient w.r.t. the 2-D net output. */
+                        float* g1p, float* g2, float* g3f, float* db2, float* db3, lshm_stream_t stream);
+/* gx1 = g1p - 0.5*(gT + transpose(gF)) : total gradient w.r.t. the 2-D net output.
+ * db1 (nullable, float[C], written): per-channel sums of gx1 = bias gradient of the 2-D net's last
+ * transposed conv. */
 LSHM_API int lshm_cascade_combine(const float* g1p, const float* gT, const float* gF, float* gx1,
-                         int64_t N, int C, int P, lshm_stream_t stream);
+                         int64_t N, int C, int P, float* db1, lshm_stream_t stream);
 /* src/kharmonic_lofar.py:200-202: y_i += rho * r_i. */
 LSHM_API int lshm_multiplier_update(const float* x, const float* x1, const float* x2, const float* x3f,
                            float rho, float* y1, float* y2, float* y3,

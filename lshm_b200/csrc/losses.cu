@@ -37,6 +37,8 @@ residual_split_kernel(const float* __restrict__ x, const float* __restrict__ x1,
 }
 
 // ------------------------------------------------------------------------------------------
+constexpr int CASCADE_MAXC = 64;   // channels whose bias-gradient sums can be fused
+
 template <bool GRADS>
 __global__ void __launch_bounds__(TILE * TROWS)
 cascade_losses_kernel(const float* __restrict__ x, const float* __restrict__ x1,
@@ -44,10 +46,17 @@ cascade_losses_kernel(const float* __restrict__ x, const float* __restrict__ x1,
                       const float* __restrict__ y1, const float* __restrict__ y2,
                       const float* __restrict__ y3, float rho, float inv_n, int P, int64_t ntiles,
                       double* __restrict__ sums, float* __restrict__ g1p, float* __restrict__ g2,
-                      float* __restrict__ g3f) {
+                      float* __restrict__ g3f, int C, float* __restrict__ db2, float* __restrict__ db3) {
   __shared__ float tile[TILE][TILE + 1];
   __shared__ float gt[TILE][TILE + 1];
   __shared__ double red[32];
+  // per-channel sums of g2 / g3f = bias gradients of the last transposed conv of the two 1-D nets
+  // (their channel_sum passes would re-read both tensors from HBM)
+  __shared__ float cacc[2][CASCADE_MAXC];
+  const bool chsum = GRADS && db2 != nullptr;
+  if (chsum) {
+    for (int c = threadIdx.y * TILE + threadIdx.x; c < 2 * CASCADE_MAXC; c += TILE * TROWS) (&cacc[0][0])[c] = 0.f;
+  }
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int tpr = P / TILE, tpp = tpr * tpr;     // tiles per row / per plane
   float s[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -56,6 +65,7 @@ cascade_losses_kernel(const float* __restrict__ x, const float* __restrict__ x1,
     const int64_t plane = (t / tpp) * (int64_t)P * P;
     const int tin = (int)(t % tpp);
     const int t0 = (tin / tpr) * TILE, f0 = (tin % tpr) * TILE;
+    float p2 = 0.f, p3 = 0.f;
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < TILE; i += TROWS)
@@ -76,9 +86,11 @@ cascade_losses_kernel(const float* __restrict__ x, const float* __restrict__ x1,
       s[5] = fmaf(m3, r3, s[5]); s[6] = fmaf(r3, r3, s[6]);
       if (GRADS) {
         const float e2 = m2 + rho * r2, e3 = m3 + rho * r3;
-        g2[off] = (2.f * r0 - e2) * inv_n;
-        gt[ty + i][tx] = (2.f * r0 - e3) * inv_n;
+        const float v2 = (2.f * r0 - e2) * inv_n, v3 = (2.f * r0 - e3) * inv_n;
+        g2[off] = v2;
+        gt[ty + i][tx] = v3;
         g1p[off] = (2.f * r0 - m1 - rho * r1 - 0.5f * (e2 + e3)) * inv_n;
+        p2 += v2; p3 += v3;
       }
     }
     if (GRADS) {
@@ -86,6 +98,17 @@ cascade_losses_kernel(const float* __restrict__ x, const float* __restrict__ x1,
 #pragma unroll
       for (int i = 0; i < TILE; i += TROWS)
         g3f[plane + (int64_t)(f0 + ty + i) * P + t0 + tx] = gt[tx][ty + i];
+      if (chsum) {                               // the whole tile belongs to one (sample, channel) plane
+        const int c = (int)((t / tpp) % C);
+        p2 = warp_sum(p2); p3 = warp_sum(p3);
+        if (tx == 0) { atomicAdd(&cacc[0][c], p2); atomicAdd(&cacc[1][c], p3); }
+      }
+    }
+  }
+  if (chsum) {
+    __syncthreads();
+    for (int c = threadIdx.y * TILE + threadIdx.x; c < C; c += TILE * TROWS) {
+      atomicAdd(db2 + c, cacc[0][c]); atomicAdd(db3 + c, cacc[1][c]);
     }
   }
   const int tid = ty * TILE + tx;
@@ -103,21 +126,43 @@ cascade_losses_kernel(const float* __restrict__ x, const float* __restrict__ x1,
   }
 }
 
+// persistent over a strided list of 32x32 tiles; optionally also the per-channel sums of gx1 (the bias
+// gradient of the 2-D net's last transposed conv)
 __global__ void __launch_bounds__(TILE * TROWS)
 cascade_combine_kernel(const float* __restrict__ g1p, const float* __restrict__ gT,
-                       const float* __restrict__ gF, float* __restrict__ gx1, int P) {
+                       const float* __restrict__ gF, float* __restrict__ gx1, int P, int64_t ntiles, int C,
+                       float* __restrict__ db1) {
   __shared__ float tile[TILE][TILE + 1];
-  const int64_t plane = (int64_t)blockIdx.z * P * P;
-  const int t0 = blockIdx.y * TILE, f0 = blockIdx.x * TILE;
+  __shared__ float cacc[CASCADE_MAXC];
   const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tpr = P / TILE, tpp = tpr * tpr;
+  if (db1 != nullptr)
+    for (int c = ty * TILE + tx; c < CASCADE_MAXC; c += TILE * TROWS) cacc[c] = 0.f;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t plane = (t / tpp) * (int64_t)P * P;
+    const int tin = (int)(t % tpp);
+    const int t0 = (tin / tpr) * TILE, f0 = (tin % tpr) * TILE;
+    __syncthreads();
 #pragma unroll
-  for (int i = 0; i < TILE; i += TROWS)
-    tile[ty + i][tx] = gF[plane + (int64_t)(f0 + ty + i) * P + t0 + tx];
-  __syncthreads();
+    for (int i = 0; i < TILE; i += TROWS)
+      tile[ty + i][tx] = gF[plane + (int64_t)(f0 + ty + i) * P + t0 + tx];
+    __syncthreads();
+    float p1 = 0.f;
 #pragma unroll
-  for (int i = 0; i < TILE; i += TROWS) {
-    const int64_t off = plane + (int64_t)(t0 + ty + i) * P + f0 + tx;
-    gx1[off] = g1p[off] - 0.5f * (gT[off] + tile[tx][ty + i]);
+    for (int i = 0; i < TILE; i += TROWS) {
+      const int64_t off = plane + (int64_t)(t0 + ty + i) * P + f0 + tx;
+      const float v = g1p[off] - 0.5f * (gT[off] + tile[tx][ty + i]);
+      gx1[off] = v;
+      p1 += v;
+    }
+    if (db1 != nullptr) {
+      p1 = warp_sum(p1);
+      if (tx == 0) atomicAdd(&cacc[(int)((t / tpp) % C)], p1);
+    }
+  }
+  if (db1 != nullptr) {
+    __syncthreads();
+    for (int c = ty * TILE + tx; c < C; c += TILE * TROWS) atomicAdd(db1 + c, cacc[c]);
   }
 }
 
@@ -362,8 +407,10 @@ int lshm_residual_split(const float* x, const float* x1, float* iyT, float* iyF,
 int lshm_cascade_losses(const float* x, const float* x1, const float* x2, const float* x3f,
                         const float* y1, const float* y2, const float* y3, float rho,
                         int64_t N, int C, int P, float grad_scale, double* sums,
-                        float* g1p, float* g2, float* g3f, lshm_stream_t stream) {
+                        float* g1p, float* g2, float* g3f, float* db2, float* db3, lshm_stream_t stream) {
   LSHM_REQUIRE(x && x1 && x2 && x3f && y1 && y2 && y3 && sums, "lshm_cascade_losses: null pointer");
+  LSHM_REQUIRE((db2 == nullptr) == (db3 == nullptr) && (db2 == nullptr || (g1p != nullptr && C <= CASCADE_MAXC)),
+               "lshm_cascade_losses: db2/db3 come together, need the gradient outputs and C <= %d", CASCADE_MAXC);
   LSHM_REQUIRE((g1p == nullptr) == (g2 == nullptr) && (g1p == nullptr) == (g3f == nullptr),
                "lshm_cascade_losses: give all three gradient outputs or none");
   if (int rc = check_cascade("lshm_cascade_losses", N, C, P)) return rc;
@@ -372,26 +419,29 @@ int lshm_cascade_losses(const float* x, const float* x1, const float* x2, const 
   const int64_t ntiles = N * C * (int64_t)(P / TILE) * (P / TILE);
   const int64_t blocks = std::min<int64_t>(ntiles, (int64_t)sm_count() * 16);
   dim3 block(TILE, TROWS);
+  if (db2) {
+    LSHM_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * C, as_stream(stream)), "lshm_cascade_losses");
+    LSHM_CUDA(cudaMemsetAsync(db3, 0, sizeof(float) * C, as_stream(stream)), "lshm_cascade_losses");
+  }
   if (g1p)
-    cascade_losses_kernel<true><<<(unsigned)blocks, block, 0, as_stream(stream)>>>(x, x1, x2, x3f, y1, y2, y3, rho, inv_n, P, ntiles, sums, g1p, g2, g3f);
+    cascade_losses_kernel<true><<<(unsigned)blocks, block, 0, as_stream(stream)>>>(x, x1, x2, x3f, y1, y2, y3, rho, inv_n, P, ntiles, sums, g1p, g2, g3f, C, db2, db3);
   else
-    cascade_losses_kernel<false><<<(unsigned)blocks, block, 0, as_stream(stream)>>>(x, x1, x2, x3f, y1, y2, y3, rho, inv_n, P, ntiles, sums, nullptr, nullptr, nullptr);
+    cascade_losses_kernel<false><<<(unsigned)blocks, block, 0, as_stream(stream)>>>(x, x1, x2, x3f, y1, y2, y3, rho, inv_n, P, ntiles, sums, nullptr, nullptr, nullptr, C, nullptr, nullptr);
   LSHM_CHECK_LAUNCH("lshm_cascade_losses");
   return LSHM_OK;
 }
 
 int lshm_cascade_combine(const float* g1p, const float* gT, const float* gF, float* gx1,
-                         int64_t N, int C, int P, lshm_stream_t stream) {
+                         int64_t N, int C, int P, float* db1, lshm_stream_t stream) {
   LSHM_REQUIRE(g1p && gT && gF && gx1, "lshm_cascade_combine: null pointer");
+  LSHM_REQUIRE(db1 == nullptr || C <= CASCADE_MAXC, "lshm_cascade_combine: db1 needs C <= %d", CASCADE_MAXC);
   if (int rc = check_cascade("lshm_cascade_combine", N, C, P)) return rc;
   if (N == 0) return LSHM_OK;
-  const int64_t planes = N * C;
-  for (int64_t z0 = 0; z0 < planes; z0 += 65535) {
-    const int64_t nz = planes - z0 < 65535 ? planes - z0 : 65535;
-    const int64_t o = z0 * P * P;
-    dim3 grid(P / TILE, P / TILE, (unsigned)nz), block(TILE, TROWS);
-    cascade_combine_kernel<<<grid, block, 0, as_stream(stream)>>>(g1p + o, gT + o, gF + o, gx1 + o, P);
-  }
+  if (db1) LSHM_CUDA(cudaMemsetAsync(db1, 0, sizeof(float) * C, as_stream(stream)), "lshm_cascade_combine");
+  const int64_t ntiles = N * C * (int64_t)(P / TILE) * (P / TILE);
+  const int64_t blocks = std::min<int64_t>(ntiles, (int64_t)sm_count() * 16);
+  dim3 block(TILE, TROWS);
+  cascade_combine_kernel<<<(unsigned)blocks, block, 0, as_stream(stream)>>>(g1p, gT, gF, gx1, P, ntiles, C, db1);
   LSHM_CHECK_LAUNCH("lshm_cascade_combine");
   return LSHM_OK;
 }

@@ -221,10 +221,12 @@ class AEEngine:
     def backward(self, x: torch.Tensor, p: Dict[str, torch.Tensor], g: Dict[str, torch.Tensor],
                  ws: Workspace, st: int, g_xhat: Optional[torch.Tensor],
                  g_mu: Optional[torch.Tensor], mu: torch.Tensor, need_dx: bool,
-                 wstream: Optional[torch.cuda.Stream] = None):
+                 wstream: Optional[torch.cuda.Stream] = None, out_bias_done: bool = False):
         """Writes every parameter gradient into g[name] (overwrite) and returns dx or None.
 
         wstream: optional second stream for the leaf work of the conv layers (weight and bias gradients).
+        out_bias_done: g["tconv5.bias"] (the per-channel sum of g_xhat) was already written by the kernel
+        that produced g_xhat (lshm_cascade_losses / lshm_cascade_combine).
         The data-gradient chain stays on `st` (the current stream); each layer's wgrad / bias sum is forked
         to `wstream` once its output gradient exists and everything is joined before returning, so the
         latency-bound deep layers overlap instead of queueing behind each other.
@@ -261,7 +263,8 @@ class AEEngine:
                 A, Bc, lvl = rch[i], rch[i + 1], 6 - i
                 fork()
                 self._wgrad(_p(inp), sz[lvl], _p(dz), sz[lvl - 1], _p(g[f"tconv{i}.weight"]), N, A, Bc, lvl, 0, wst)
-                lb.channel_sum(_p(dz), sz[lvl - 1], _p(g[f"tconv{i}.bias"]), N, Bc, sz[lvl - 1] // Bc, wst)
+                if not (i == 5 and out_bias_done):
+                    lb.channel_sum(_p(dz), sz[lvl - 1], _p(g[f"tconv{i}.bias"]), N, Bc, sz[lvl - 1] // Bc, wst)
                 nxt = ws.g_dec[i]
                 # dgrad of the transposed conv = "down"; ELU' of the producing layer unless it is fc3
                 self._down(_p(dz), sz[lvl - 1], _p(self.img[(f"tconv{i}.weight", 0)]), None,

@@ -305,9 +305,16 @@ class DeepKHarmonicStep:
         tp = self.terms.data_ptr()
         x1, x2, x3f = self._forward(st)
         g1p, g2, g3f = (self.g1p.data_ptr(), self.g2.data_ptr(), self.g3f.data_ptr()) if grads else (None, None, None)
+        # the bias gradients of the three last transposed convs (= channel sums of the reconstruction
+        # gradients) come out of the kernels that write those gradients
+        fuse_db = grads and C <= 64
+        if grads:
+            self.flat.attach_grads()
+        db2, db3 = ((self._gd[1]["tconv5.bias"].data_ptr(), self._gd[2]["tconv5.bias"].data_ptr()) if fuse_db
+                    else (None, None))
         lb.cascade_losses(self.x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(),
                           self.y1.data_ptr(), self.y2.data_ptr(), self.y3.data_ptr(), self.rho,
-                          N, C, 128, 1.0 / numel_g, tp, g1p, g2, g3f, st)
+                          N, C, 128, 1.0 / numel_g, tp, g1p, g2, g3f, db2, db3, st)
         khm_scale = plan.khm_scale(self.alpha)
         p = float(self.mod.p)
         aug_scale = plan.aug_scale(self.gamma)
@@ -334,13 +341,14 @@ class DeepKHarmonicStep:
             side = self._fork()
             with torch.cuda.stream(side):
                 dF = e[2].backward(self.iyF.view(N, -1), self._pd[2], self._gd[2], self.ws[2], side.cuda_stream,
-                                   self.g3f.view(N, -1), gMu[:, L + Lt:], Mu[:, L + Lt:], True, self._wstream(2))
+                                   self.g3f.view(N, -1), gMu[:, L + Lt:], Mu[:, L + Lt:], True, self._wstream(2), fuse_db)
             dT = e[1].backward(self.iyT.view(N, -1), self._pd[1], self._gd[1], self.ws[1], st, self.g2.view(N, -1),
-                               gMu[:, L:L + Lt], Mu[:, L:L + Lt], True, self._wstream(1))
+                               gMu[:, L:L + Lt], Mu[:, L:L + Lt], True, self._wstream(1), fuse_db)
             self._join(side)
-            lb.cascade_combine(self.g1p.data_ptr(), dT.data_ptr(), dF.data_ptr(), self.gx1.data_ptr(), N, C, 128, st)
+            lb.cascade_combine(self.g1p.data_ptr(), dT.data_ptr(), dF.data_ptr(), self.gx1.data_ptr(), N, C, 128,
+                               self._gd[0]["tconv5.bias"].data_ptr() if fuse_db else None, st)
             e[0].backward(self.x.view(N, -1), self._pd[0], self._gd[0], self.ws[0], st, self.gx1.view(N, -1),
-                          gMu[:, :L], Mu[:, :L], False, self._wstream(0))
+                          gMu[:, :L], Mu[:, :L], False, self._wstream(0), fuse_db)
         tail = self.flat.loss_tail
         lb.closure_total(tp, self.rho, numel_g, khm_scale, tail.data_ptr(), st)
         if self.distributed and not self._defer_exchange:

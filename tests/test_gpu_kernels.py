@@ -326,7 +326,7 @@ def test_cascade_kernels(cuda):
     (l0 + l1 + l2 + l3).backward()
     sums = torch.zeros(8, dtype=torch.float64, device=cuda)
     g1p, g2, g3f = (torch.empty_like(g[0]) for _ in range(3))
-    lib().cascade_losses(*(dp(t) for t in g), rho, N, C, P, 1.0 / n, dp(sums), dp(g1p), dp(g2), dp(g3f), st())
+    lib().cascade_losses(*(dp(t) for t in g), rho, N, C, P, 1.0 / n, dp(sums), dp(g1p), dp(g2), dp(g3f), None, None, st())
     s = sums.cpu()
     assert abs(float(s[0]) / n - float(l0)) < 1e-6 * float(l0)
     for (i, l) in ((1, l1), (3, l2), (5, l3)):
@@ -335,13 +335,23 @@ def test_cascade_kernels(cuda):
     assert rel_err(g1p, a1.grad) < 1e-5  # with no 1-D input gradients g1p is the whole d/dx1
     # forward-only variant gives the same sums
     sums2 = torch.zeros(8, dtype=torch.float64, device=cuda)
-    lib().cascade_losses(*(dp(t) for t in g), rho, N, C, P, 1.0 / n, dp(sums2), None, None, None, st())
+    lib().cascade_losses(*(dp(t) for t in g), rho, N, C, P, 1.0 / n, dp(sums2), None, None, None, None, None, st())
     assert torch.allclose(sums2, sums, rtol=1e-12)
+    # fused bias-gradient sums (per-channel sums of g2 / g3f), same sums and gradients otherwise
+    sums3 = torch.zeros(8, dtype=torch.float64, device=cuda)
+    h1, h2, h3 = (torch.empty_like(g[0]) for _ in range(3))
+    db2, db3 = torch.full((C,), 9.0, device=cuda), torch.full((C,), 9.0, device=cuda)
+    lib().cascade_losses(*(dp(t) for t in g), rho, N, C, P, 1.0 / n, dp(sums3), dp(h1), dp(h2), dp(h3), dp(db2), dp(db3), st())
+    assert torch.allclose(sums3, sums, rtol=1e-12) and torch.equal(h2, g2) and torch.equal(h3, g3f) and torch.equal(h1, g1p)
+    assert rel_err(db2, g2.sum(dim=(0, 2, 3))) < 1e-5 and rel_err(db3, g3f.sum(dim=(0, 2, 3))) < 1e-5
     gT, gF = torch.randn(N, C, P, P), torch.randn(N, C, P, P)
     gx1 = torch.empty_like(g[0])
     gTg, gFg = gT.to(cuda), gF.to(cuda)
-    lib().cascade_combine(dp(g1p), dp(gTg), dp(gFg), dp(gx1), N, C, P, st())
+    lib().cascade_combine(dp(g1p), dp(gTg), dp(gFg), dp(gx1), N, C, P, None, st())
     assert rel_err(gx1, g1p.cpu() - 0.5 * (gT + gF.transpose(2, 3))) < 1e-6
+    gx1b, db1 = torch.empty_like(g[0]), torch.full((C,), 9.0, device=cuda)
+    lib().cascade_combine(dp(g1p), dp(gTg), dp(gFg), dp(gx1b), N, C, P, dp(db1), st())
+    assert torch.equal(gx1b, gx1) and rel_err(db1, gx1.sum(dim=(0, 2, 3))) < 1e-5
     lib().multiplier_update(dp(g[0]), dp(g[1]), dp(g[2]), dp(g[3]), rho, dp(g[4]), dp(g[5]), dp(g[6]), N, C, P, st())
     assert rel_err(g[4], y1 + rho * (x - x1).reshape(-1)) < 1e-6
     assert rel_err(g[5], y2 + rho * (x11 - x2).reshape(-1)) < 1e-6
