@@ -338,6 +338,7 @@ def run_ours(args):
     #      Every rank runs the steps (the closure contains the all-reduce); rank 0 records.
     prof_steps = 2
     agg = None
+    step.overlap_streams = False     # one stream: the event pair around a call then times that kernel alone
     if rank == 0:
         with KernelProfiler(L) as kp:
             for _ in range(prof_steps):

@@ -8,6 +8,12 @@
 namespace lshm {
 namespace {
 
+__device__ __forceinline__ float warp_sum_active(float v) {   // all 32 lanes active
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // long rows: persistent warps walk (row, 8 KB chunk) items, 16 independent 16-byte loads per lane in
 // flight, per-channel partial sums in shared memory, one global atomic per (block, channel).  The
 // first version ran one short-lived block per row (4-64 KB): block start-up, the two-barrier block
@@ -59,6 +65,8 @@ __global__ void __launch_bounds__(256)
 channel_sum_flat_kernel(const float* __restrict__ g, int64_t g_ns, float* __restrict__ db, int64_t n4, int Cn,
                         int len4) {
   extern __shared__ float acc[];                // [Cn]
+  // (n4 is then a multiple of 32 too, so whole warps run every iteration)
+  const bool warp_rows = (len4 & 31) == 0;
   for (int c = threadIdx.x; c < Cn; c += blockDim.x) acc[c] = 0.f;
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -67,7 +75,13 @@ channel_sum_flat_kernel(const float* __restrict__ g, int64_t g_ns, float* __rest
     const int64_t n = i / per_n;
     const int rem = (int)(i - n * per_n);
     const float4 v = ld_nc_f4(g + n * g_ns + 4 * (int64_t)rem);
-    atomicAdd(&acc[rem / len4], (v.x + v.y) + (v.z + v.w));
+    float sv = (v.x + v.y) + (v.z + v.w);
+    if (warp_rows) {                            // rows of a multiple of 32 pieces: the warp's 32 pieces share a row
+      sv = warp_sum_active(sv);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&acc[rem / len4], sv);
+    } else {
+      atomicAdd(&acc[rem / len4], sv);
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < Cn; c += blockDim.x) atomicAdd(db + c, acc[c]);

@@ -216,6 +216,7 @@ class DeepKHarmonicStep:
         self.N = 0
         self._defer_exchange = False     # GraphedStep runs the all-reduce itself, between its two graphs
         self._side = None                # second stream for the frequency-axis net
+        self.overlap_streams = True      # False: everything on the current stream (per-kernel profiling)
         self._wst = [None, None, None]   # per-net streams for the weight / bias gradients
         self.launches = 0
         if distributed:
@@ -272,14 +273,18 @@ class DeepKHarmonicStep:
         self._join(side)
         return x1, x2, x3f
 
-    def _wstream(self, i: int) -> torch.cuda.Stream:
+    def _wstream(self, i: int) -> Optional[torch.cuda.Stream]:
         """Stream for the weight / bias gradients of net i (leaf work beside the data-gradient chain)."""
+        if not self.overlap_streams:
+            return None
         if self._wst[i] is None:
             self._wst[i] = torch.cuda.Stream(self.device)
         return self._wst[i]
 
     def _fork(self) -> torch.cuda.Stream:
         """Side stream that starts after everything queued so far on the current stream."""
+        if not self.overlap_streams:
+            return torch.cuda.current_stream(self.device)
         if self._side is None:
             self._side = torch.cuda.Stream(self.device)
         ev = torch.cuda.Event()
@@ -288,6 +293,8 @@ class DeepKHarmonicStep:
         return self._side
 
     def _join(self, side: torch.cuda.Stream):
+        if not self.overlap_streams:
+            return
         ev = torch.cuda.Event()
         ev.record(side)
         torch.cuda.current_stream(self.device).wait_event(ev)
