@@ -48,39 +48,31 @@ constexpr int MAXST = 6;
 template <int NT, int EPI>
 __device__ __forceinline__ void down_epilogue_tile(const DownArgs& a, uint32_t trow, int nt, float* outp,
                                                    const float* auxp, int64_t hw, bool ok) {
+  // eight channels at a time (24 live data registers: the kernel runs at a 64-register cap and the
+  // 16-wide version spilled)
 #pragma unroll 1
-  for (int g = 0; g < NT / 16; ++g) {
-    const int ch0 = nt * NT + g * 16;
-    const int nch = min(16, a.A - ch0);
+  for (int h8 = 0; h8 < NT / 8; ++h8) {
+    const int ch0 = nt * NT + h8 * 8;
+    const int nch = min(8, a.A - ch0);
     if (nch <= 0) break;                      // warp-uniform
-    float bs[16], ax[16];
+    float bs[8], ax[8];
     const float* bp = a.bias + ch0;
     const float* xp = auxp + (int64_t)ch0 * hw;
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      if (hf * 8 < nch) {
-#pragma unroll
-        for (int j = hf * 8; j < hf * 8 + 8; ++j) {
-          bs[j] = (a.bias != nullptr && j < nch) ? __ldg(bp + j) : 0.f;
-          ax[j] = 0.f;
-          if (EPI == LSHM_EPI_DELU && ok && j < nch) ax[j] = __ldg(xp + (int64_t)j * hw);
-        }
-      }
+    for (int j = 0; j < 8; ++j) {
+      bs[j] = (a.bias != nullptr && j < nch) ? __ldg(bp + j) : 0.f;
+      ax[j] = 0.f;
+      if (EPI == LSHM_EPI_DELU && ok && j < nch) ax[j] = __ldg(xp + (int64_t)j * hw);
     }
-    float v[16];
-    tmem_ld16(trow + g * 16, v);
+    float v[8];
+    tmem_ld8(trow + h8 * 8, v);
     float* op = outp + (int64_t)ch0 * hw;
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      if (hf * 8 < nch) {
-#pragma unroll
-        for (int j = hf * 8; j < hf * 8 + 8; ++j) {
-          float r = v[j] + bs[j];
-          if (EPI == LSHM_EPI_ELU) r = elu_fast(r);
-          else if (EPI == LSHM_EPI_DELU) r *= delu_from_out(ax[j]);
-          if (ok && j < nch) op[(int64_t)j * hw] = r;
-        }
-      }
+    for (int j = 0; j < 8; ++j) {
+      float r = v[j] + bs[j];
+      if (EPI == LSHM_EPI_ELU) r = elu_fast(r);
+      else if (EPI == LSHM_EPI_DELU) r *= delu_from_out(ax[j]);
+      if (ok && j < nch) op[(int64_t)j * hw] = r;
     }
   }
 }
