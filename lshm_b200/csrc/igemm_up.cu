@@ -52,37 +52,34 @@ __device__ __forceinline__ void up_epilogue_tile(const UpArgs& a, uint32_t trow,
     const int64_t HW = 4 * (int64_t)a.h * a.w;
     float* outp = a.big + n * a.big_ns + (int64_t)(2 * m) * W + 2 * x;
     const float* auxp = EPI == LSHM_EPI_DELU ? a.aux + n * a.aux_ns + (int64_t)(2 * m) * W + 2 * x : nullptr;
+    // eight channels (x four parity classes = 32 accumulator registers) at a time: the 16-wide version
+    // held 64 and spilled at the kernel's register cap
 #pragma unroll 1
-    for (int g = 0; g < NT / 16; ++g) {
-      const int b0 = nt * NT + g * 16;
-      const int nch = min(16, a.Bc - b0);
+    for (int h8 = 0; h8 < NT / 8; ++h8) {
+      const int b0 = nt * NT + h8 * 8;
+      const int nch = min(8, a.Bc - b0);
       if (nch <= 0) break;                       // warp-uniform
-      float v[4][16];
+      float v[4][8];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld16(trow + c * NT + g * 16, v[c]);
+      for (int c = 0; c < 4; ++c) tmem_ld8(trow + c * NT + h8 * 8, v[c]);
       if (ok) {
         float* op = outp + (int64_t)b0 * HW;
         const float* xp = EPI == LSHM_EPI_DELU ? auxp + (int64_t)b0 * HW : nullptr;
         const float* bp = a.bias != nullptr ? a.bias + b0 : nullptr;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          if (hf * 8 < nch) {                    // warp-uniform: the padding half of 8/12-channel layers is skipped
-#pragma unroll
-            for (int j = hf * 8; j < hf * 8 + 8; ++j) {
-              if (j < nch) {
-                const float bs = bp != nullptr ? __ldg(bp + j) : 0.f;
-                float2 ax0 = make_float2(0.f, 0.f), ax1 = make_float2(0.f, 0.f);
-                if (EPI == LSHM_EPI_DELU) {
-                  ax0 = *reinterpret_cast<const float2*>(xp + (int64_t)j * HW);
-                  ax1 = *reinterpret_cast<const float2*>(xp + (int64_t)j * HW + W);
-                }
-                // class index = ry*2 + rx
-                const float2 o0 = make_float2(epi_apply<EPI>(v[0][j], bs, ax0.x), epi_apply<EPI>(v[1][j], bs, ax0.y));
-                const float2 o1 = make_float2(epi_apply<EPI>(v[2][j], bs, ax1.x), epi_apply<EPI>(v[3][j], bs, ax1.y));
-                *reinterpret_cast<float2*>(op + (int64_t)j * HW) = o0;
-                *reinterpret_cast<float2*>(op + (int64_t)j * HW + W) = o1;
-              }
+        for (int j = 0; j < 8; ++j) {
+          if (j < nch) {
+            const float bs = bp != nullptr ? __ldg(bp + j) : 0.f;
+            float2 ax0 = make_float2(0.f, 0.f), ax1 = make_float2(0.f, 0.f);
+            if (EPI == LSHM_EPI_DELU) {
+              ax0 = *reinterpret_cast<const float2*>(xp + (int64_t)j * HW);
+              ax1 = *reinterpret_cast<const float2*>(xp + (int64_t)j * HW + W);
             }
+            // class index = ry*2 + rx
+            const float2 o0 = make_float2(epi_apply<EPI>(v[0][j], bs, ax0.x), epi_apply<EPI>(v[1][j], bs, ax0.y));
+            const float2 o1 = make_float2(epi_apply<EPI>(v[2][j], bs, ax1.x), epi_apply<EPI>(v[3][j], bs, ax1.y));
+            *reinterpret_cast<float2*>(op + (int64_t)j * HW) = o0;
+            *reinterpret_cast<float2*>(op + (int64_t)j * HW + W) = o1;
           }
         }
       }
