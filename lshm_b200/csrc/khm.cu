@@ -193,6 +193,10 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass2_kernel(KhmArgs a) {
   float* wsum_s = acc_s + (RESIDENT ? K * L : 0);         // RESIDENT: K
   float* xs = wsum_s + (RESIDENT ? ((K + 3) & ~3) : 0);   // PTS*L
   float* ws = xs + PTS * L;                               // PTS*KC
+  // K <= KHM_KC: the squared distances of the harmonic-sum loop are kept (one float per point and centre)
+  // for the weight loop instead of being recomputed - a quarter of the pass's arithmetic
+  const bool cache_d2 = K <= KHM_KC;
+  float* d2s = ws + PTS * KHM_KC;                         // [KC][PTS] when cache_d2
   __shared__ double red[32];
   const int pt = threadIdx.x / TPP, s = threadIdx.x % TPP;
   const int64_t ntiles = (a.N + PTS - 1) / PTS;
@@ -216,6 +220,7 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass2_kernel(KhmArgs a) {
       if (!RESIDENT) { __syncthreads(); stage_centres(ms, a.M, k0, kc, L); __syncthreads(); }
       for (int kk = 0; kk < kc; ++kk) {
         const float d2 = dist2<TPP, NCH>(x4, ms + kk * L, s, nch);
+        if (cache_d2) d2s[kk * PTS + pt] = d2;            // every lane of the point writes (and later reads) the same value
         e += rcp_fast(pow_p(d2, a.p, a.pmode) + KHM_EPS);
       }
     }
@@ -235,7 +240,7 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass2_kernel(KhmArgs a) {
       const float* mbase = RESIDENT ? ms + k0 * L : ms;
       for (int kk = 0; kk < kc; ++kk) {
         const float* mrow = mbase + kk * L;
-        const float d2 = dist2<TPP, NCH>(x4, mrow, s, nch);
+        const float d2 = cache_d2 ? d2s[kk * PTS + pt] : dist2<TPP, NCH>(x4, mrow, s, nch);
         const float dp = pow_p(d2, a.p, a.pmode);
         float w;
         if (SUMS) {
@@ -421,7 +426,7 @@ template <bool SUMS>
 int launch_pass2(const KhmArgs& a, cudaStream_t st) {
   const int tpp = pick_tpp(a.L);
   const int pts = KHM_THREADS / tpp;
-  const size_t tile = ((size_t)pts * a.L + (size_t)pts * KHM_KC) * sizeof(float);
+  const size_t tile = ((size_t)pts * a.L + (size_t)pts * KHM_KC + (a.K <= KHM_KC ? (size_t)pts * KHM_KC : 0)) * sizeof(float);
   const size_t res_bytes = ((size_t)2 * a.K * a.L + ((a.K + 3) & ~3)) * sizeof(float) + tile;
   const bool res = res_bytes <= RESIDENT_SMEM_LIMIT;
   const size_t smem = res ? res_bytes : (size_t)KHM_KC * a.L * sizeof(float) + tile;
