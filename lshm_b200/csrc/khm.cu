@@ -128,7 +128,10 @@ __device__ __forceinline__ void stage_centres(float* ms, const float* M, int k0,
 // NCH = KHM_MAXCH: every lane holds all eight float4 chunks (L = 32*TPP), the chunk loops carry no
 // guards (the guarded form cost a branch per chunk plus 8 accumulator moves: 36% useful FFMA2/FADD2 in
 // the K=10, L=64 capture); NCH = 0: chunk count known at run time only.
-template <int TPP, bool RESIDENT, int NCH>
+// MODE 0: harmonic sums only (forward loss); 1: nearest centre only (assignment); 2: everything (group
+// distances).  The per-centre tail is ~a third of the K = 10 inner loop, so the two hot entry points do not
+// carry each other's part.
+template <int TPP, bool RESIDENT, int NCH, int MODE>
 __global__ void __launch_bounds__(KHM_THREADS) khm_pass1_kernel(KhmArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* ms = smem;  // RESIDENT: K*L, else KC*L
@@ -156,12 +159,17 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass1_kernel(KhmArgs a) {
       for (int kk = 0; kk < kc; ++kk) {
         float da, db;
         dist2x2<TPP, NCH>(xa, xb, ms + kk * L, s, nch, da, db);
-        const float pa = pow_p(da, a.p, a.pmode), pb = pow_p(db, a.p, a.pmode);
-        ea += rcp_fast(pa + KHM_EPS);
-        eb += rcp_fast(pb + KHM_EPS);
-        if (da < besta) { besta = da; bia = k0 + kk; }
-        if (db < bestb) { bestb = db; bib = k0 + kk; }
-        if (a.dist != nullptr && s == 0) {
+        float pa = 0.f, pb = 0.f;
+        if (MODE != 1) {
+          pa = pow_p(da, a.p, a.pmode); pb = pow_p(db, a.p, a.pmode);
+          ea += rcp_fast(pa + KHM_EPS);
+          eb += rcp_fast(pb + KHM_EPS);
+        }
+        if (MODE != 0) {
+          if (da < besta) { besta = da; bia = k0 + kk; }
+          if (db < bestb) { bestb = db; bib = k0 + kk; }
+        }
+        if (MODE == 2 && a.dist != nullptr && s == 0) {
           if (va) atomicAdd(a.dist + (ia / a.group) * K + (k0 + kk), pa * inv_group);
           if (vb) atomicAdd(a.dist + (ib / a.group) * K + (k0 + kk), pb * inv_group);
         }
@@ -367,11 +375,24 @@ int check_common(const char* name, const float* X, int64_t ldx, const float* M, 
 
 int pmode_of(float p) { return p == 2.f ? 2 : (p == 4.f ? 4 : 0); }
 
+template <int TPP, bool RES, int NCH, int MODE>
+int launch_pass1_m(const KhmArgs& a, size_t smem, int grid, cudaStream_t st) {
+  if (smem > 48 * 1024)
+    LSHM_CUDA(cudaFuncSetAttribute(khm_pass1_kernel<TPP, RES, NCH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "khm_pass1");
+  khm_pass1_kernel<TPP, RES, NCH, MODE><<<grid, KHM_THREADS, smem, st>>>(a);
+  return LSHM_OK;
+}
+
 template <int TPP, bool RES, int NCH>
 int launch_pass1_n(const KhmArgs& a, size_t smem, int grid, cudaStream_t st) {
-  if (smem > 48 * 1024)
-    LSHM_CUDA(cudaFuncSetAttribute(khm_pass1_kernel<TPP, RES, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "khm_pass1");
-  khm_pass1_kernel<TPP, RES, NCH><<<grid, KHM_THREADS, smem, st>>>(a);
+  int rc;
+  if (a.dist != nullptr || (a.ids != nullptr && (a.loss_sum != nullptr || a.e_out != nullptr)))
+    rc = launch_pass1_m<TPP, RES, NCH, 2>(a, smem, grid, st);
+  else if (a.ids != nullptr)
+    rc = launch_pass1_m<TPP, RES, NCH, 1>(a, smem, grid, st);
+  else
+    rc = launch_pass1_m<TPP, RES, NCH, 0>(a, smem, grid, st);
+  if (rc) return rc;
   LSHM_CHECK_LAUNCH("khm_pass1");
   return LSHM_OK;
 }
