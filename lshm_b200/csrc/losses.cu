@@ -39,8 +39,10 @@ residual_split_kernel(const float* __restrict__ x, const float* __restrict__ x1,
 // ------------------------------------------------------------------------------------------
 constexpr int CASCADE_MAXC = 64;   // channels whose bias-gradient sums can be fused
 
+// 6 blocks per SM (<= 40 registers; 32 spills): at 48 registers the kernel ran at 55 % occupancy and 4.8 TB/s while the
+// 30-register multiplier kernel next to it reaches 5.35 TB/s (ncu, profiles/r1_ncu_dram_traffic.json)
 template <bool GRADS>
-__global__ void __launch_bounds__(TILE * TROWS)
+__global__ void __launch_bounds__(TILE * TROWS, 6)
 cascade_losses_kernel(const float* __restrict__ x, const float* __restrict__ x1,
                       const float* __restrict__ x2, const float* __restrict__ x3f,
                       const float* __restrict__ y1, const float* __restrict__ y2,
