@@ -319,6 +319,9 @@ class DeepKHarmonicStep:
             self.flat.attach_grads()
         db2, db3 = ((self._gd[1]["tconv5.bias"].data_ptr(), self._gd[2]["tconv5.bias"].data_ptr()) if fuse_db
                     else (None, None))
+        # the latent-space terms (a dozen small, latency-bound launches) run beside the HBM-bound cascade
+        # losses: forked here, joined before the backward passes
+        lside = self._fork()
         lb.cascade_losses(self.x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(),
                           self.y1.data_ptr(), self.y2.data_ptr(), self.y3.data_ptr(), self.rho,
                           N, C, 128, 1.0 / numel_g, tp, g1p, g2, g3f, db2, db3, st)
@@ -328,21 +331,23 @@ class DeepKHarmonicStep:
         sim_scale = plan.sim_scale(self.beta)        # M is replicated: count its penalty once
         rica_scale = plan.rica_scale(self.rica_lambda)  # the kernel divides by the LOCAL numel
         Mu, gMu = self.Mu, self.gMu
-        if grads:
-            self.flat.attach_grads()
-            self._gM.zero_()
-            lb.khm_fwd_bwd(Mu.data_ptr(), Ltot, M.data_ptr(), N, K, Ltot, p, khm_scale, tp + 8 * 8,
-                           gMu.data_ptr(), Ltot, 0, self._gM.data_ptr(), st)
-        else:
-            lb.khm_fwd(Mu.data_ptr(), Ltot, M.data_ptr(), N, K, Ltot, p, tp + 8 * 8, None, st)
-        lb.similarity(M.data_ptr(), K, Ltot, sim_scale, tp + 9 * 8, self._gM.data_ptr() if grads else None,
-                      self.simwork.data_ptr(), st)
-        lb.augment(Mu.data_ptr(), Ltot, N, Ltot, self.bpb, aug_scale, tp + 10 * 8,
-                   gMu.data_ptr() if grads else None, Ltot, st)
-        if self.use_rica:
-            for off, width in ((0, L), (L, Lt), (L + Lt, Lt)):
-                lb.logcosh(Mu.data_ptr() + 4 * off, Ltot, N, width, rica_scale, tp + 11 * 8,
-                           gMu.data_ptr() + 4 * off if grads else None, Ltot, st)
+        with torch.cuda.stream(lside):
+            sl = lside.cuda_stream
+            if grads:
+                self._gM.zero_()
+                lb.khm_fwd_bwd(Mu.data_ptr(), Ltot, M.data_ptr(), N, K, Ltot, p, khm_scale, tp + 8 * 8,
+                               gMu.data_ptr(), Ltot, 0, self._gM.data_ptr(), sl)
+            else:
+                lb.khm_fwd(Mu.data_ptr(), Ltot, M.data_ptr(), N, K, Ltot, p, tp + 8 * 8, None, sl)
+            lb.similarity(M.data_ptr(), K, Ltot, sim_scale, tp + 9 * 8, self._gM.data_ptr() if grads else None,
+                          self.simwork.data_ptr(), sl)
+            lb.augment(Mu.data_ptr(), Ltot, N, Ltot, self.bpb, aug_scale, tp + 10 * 8,
+                       gMu.data_ptr() if grads else None, Ltot, sl)
+            if self.use_rica:
+                for off, width in ((0, L), (L, Lt), (L + Lt, Lt)):
+                    lb.logcosh(Mu.data_ptr() + 4 * off, Ltot, N, width, rica_scale, tp + 11 * 8,
+                               gMu.data_ptr() + 4 * off if grads else None, Ltot, sl)
+        self._join(lside)
         if grads:
             e = self.net.engine(), self.netT.engine(), self.netF.engine()
             side = self._fork()
