@@ -101,6 +101,10 @@ LSHM_API int lshm_conv_prep(const float* w, int dim, int A, int Bc, void* down_i
  * lshm_conv_prep_batch re-makes all n images with a single launch. */
 LSHM_API int lshm_conv_prep_record(const float* w, int dim, int A, int Bc, int which, void* img, int64_t* record);
 LSHM_API int lshm_conv_prep_batch(const int64_t* table, int n, lshm_stream_t stream);
+/* Host-only self-check of the multiply-shift division the conv kernels use for their index math
+ * (conv_geom.cuh FastDiv: q = (mulhi(m, n) + n) >> l): *mismatches = how many of the `count` 31-bit values
+ * n[i] give a quotient different from n[i] / d.  Host pointers, no GPU needed. */
+LSHM_API int lshm_fastdiv_check(int64_t d, const int64_t* n, int count, int64_t* mismatches);
 
 /* Conv2d(k4,s2,p1) forward (src/lofar_models.py:73-78) and ConvTranspose2d dgrad.
  * wimg = "down" image of W (lshm_conv_prep). */

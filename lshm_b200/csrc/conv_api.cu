@@ -80,4 +80,19 @@ int lshm_conv_prep_batch(const int64_t* table, int n, lshm_stream_t stream) {
   return LSHM_OK;
 }
 
+int lshm_fastdiv_check(int64_t d, const int64_t* n, int count, int64_t* mismatches) {
+  LSHM_REQUIRE(d >= 1 && d < (1LL << 31) && n != nullptr && mismatches != nullptr && count >= 0,
+               "lshm_fastdiv_check: bad arguments");
+  const FastDiv f = make_fastdiv((uint32_t)d);
+  int bad = 0;
+  for (int i = 0; i < count; ++i) {
+    const uint32_t v = (uint32_t)n[i];
+    // host copy of fdiv(): __umulhi(m, v) = high word of the 64-bit product
+    const uint32_t q = (uint32_t)((((uint64_t)f.m * v) >> 32) + v) >> f.l;
+    if (n[i] < 0 || n[i] >= (1LL << 31) || q != v / (uint32_t)d) ++bad;
+  }
+  *mismatches = bad;
+  return LSHM_OK;
+}
+
 }  // extern "C"

@@ -9,9 +9,9 @@
 // Z tile in shared memory (rows at a uniform 16-byte pitch) and every tap is the same tile read
 // through a descriptor whose start address is shifted by the tap offset - no im2col duplication.
 // Weights arrive pre-split / pre-permuted ("image", lshm_conv_prep) by one bulk copy per K block.
-// Warp roles: 4 producer+epilogue warps, 1 MMA-issuing warp, 1 weight-loading warp; a ring of
-// shared-memory stages (mbarrier full/empty), fp32 accumulators in TMEM, bias/ELU/ELU' fused in
-// the epilogue which writes NCHW / NCL directly.
+// Warp roles: 4 epilogue warps, 4 (or 2 x 4) producer warps, 1 MMA-issuing warp, 1 weight-loading warp;
+// a ring of shared-memory stages (mbarrier full/empty), two fp32 accumulator sets in TMEM, bias / ELU /
+// ELU' fused in the epilogue which writes NCHW / NCL directly.
 #include <stdlib.h>
 #include "conv_geom.cuh"
 

@@ -70,3 +70,22 @@ def test_synthetic_measurement_layout():
     assert all(nm in sap["antenna_locations"]["XYZ"] for nm in sap["baselines"].reshape(-1))
     assert np.array_equal(S.make_measurement(5, 140, 130, seed=1)["measurement"]["saps"]["0"]["visibilities"],
                           sap["visibilities"])
+
+
+def test_fastdiv_constants_match_integer_division():
+    """The multiply-shift division of the conv kernels' index math (conv_geom.cuh), checked on the host through
+    the library: divisors that occur ((h+1)(w+1), w+1, w, tiles per row, slots) and random ones, dividends up to
+    the 2^31 limit the launchers enforce."""
+    import ctypes
+    from lshm_b200._lib import lib
+    rng = np.random.default_rng(7)
+    divisors = [1, 2, 3, 4, 5, 7, 9, 17, 33, 65, 129, 200, 328, 25, 81, 289, 1089, 4225, 16641, 4096, 16384,
+                (1 << 31) - 1] + [int(v) for v in rng.integers(1, 1 << 20, 200)]
+    for d in divisors:
+        n = np.concatenate([np.array([0, 1, d - 1, d, d + 1, 2 * d - 1, (1 << 31) - 1, (1 << 31) - 4097], np.int64),
+                            rng.integers(0, 1 << 31, 2000).astype(np.int64),
+                            (np.arange(1, 50, dtype=np.int64) * d - 1), np.arange(1, 50, dtype=np.int64) * d])
+        n = np.ascontiguousarray(n[(n >= 0) & (n < (1 << 31))])
+        bad = ctypes.c_int64(-1)
+        lib().fastdiv_check(d, n.ctypes.data, len(n), ctypes.addressof(bad))
+        assert bad.value == 0, (d, bad.value)
