@@ -77,6 +77,19 @@ def encode_assign(net, net1D1, net1D2, mod: Kmeans, x, uv, batch_per_bline: int)
 
 
 @torch.no_grad()
+def graph_features(net, net1D1, net1D2, mod: Kmeans, x, uv, batch_per_bline: int):
+    """Node features / labels of the graph classifiers (src/train_graph.py:137-158, src/train_graph_stat.py:
+    197-218) for many baselines at once: node_data[g] = mean of the baseline's latents, node_label[g,k] = mean
+    Euclidean distance of its patches to centre k.  x holds whole baselines, `batch_per_bline` patches each
+    (rows of one baseline consecutive)."""
+    Mu = cascade_latents(net, net1D1, net1D2, x, uv)
+    G = Mu.shape[0] // batch_per_bline
+    node_data = Mu.view(G, batch_per_bline, -1).mean(dim=1)
+    node_label, _ = mod.group_distances(Mu, batch_per_bline, power=1.0)
+    return node_data, node_label
+
+
+@torch.no_grad()
 def evaluate(net, net1D1, net1D2, mod: Kmeans, baseline_loader, nbase: int, log=None):
     """The per-baseline loop of src/evaluate_clustering.py:75-119.
 

@@ -284,14 +284,16 @@ class Kmeans(nn.Module):
         return ids
 
     @torch.no_grad()
-    def group_distances(self, X, group):
+    def group_distances(self, X, group, power=None):
         """src/evaluate_clustering.py:110-119 for every group of `group` consecutive rows:
-        dist[g,k] = mean_n ||x_n - m_k||^p and its argmin."""
+        dist[g,k] = mean_n ||x_n - m_k||^power and its argmin.  power defaults to the module's p;
+        power=1 gives the node labels of src/train_graph.py:152-157 (mean Euclidean distance)."""
         _require_cuda(X, "X")
         Xc = X.contiguous()
         G = X.shape[0] // group
         dist = torch.empty(G, self.K, dtype=torch.float32, device=X.device)
         gid = torch.empty(G, dtype=torch.int32, device=X.device)
         lib().khm_group_dist(Xc.data_ptr(), X.shape[1], self.M.data_ptr(), X.shape[0], self.K, X.shape[1],
-                             float(self.p), int(group), dist.data_ptr(), gid.data_ptr(), _stream())
+                             float(self.p if power is None else power), int(group), dist.data_ptr(), gid.data_ptr(),
+                             _stream())
         return dist, gid

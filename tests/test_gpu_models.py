@@ -268,6 +268,15 @@ def test_inference_loop(cuda):
     X, clusid = evaluate(net, netT, netF, mod, lambda nb: (2, 2, x[nb * 4:(nb + 1) * 4], uv[nb * 4:(nb + 1) * 4]), 2)
     assert X.shape == (case["K"], 2) and X.dtype == np.float64
     assert np.allclose(X[:, 0], dist[0].double().cpu().numpy(), rtol=1e-6) and clusid[0] == float(gid[0])
+    # graph-classifier features (src/train_graph.py:150-158): latent mean per baseline, mean Euclidean
+    # distance to every centre as the node label
+    from lshm_b200.evaluate_clustering import graph_features
+    node_data, node_label = graph_features(net, netT, netF, mod, x, uv, 4)
+    for g in range(2):
+        blk = Mu_ref[g * 4:(g + 1) * 4]
+        assert rel_err(node_data[g], blk.mean(0)) < ACT_TOL
+        ref_label = torch.stack([torch.linalg.norm(blk - case["M"][k], dim=1).mean() for k in range(case["K"])])
+        assert rel_err(node_label[g], ref_label) < 1e-4
 
 
 def test_closure_matches_golden_from_live_reference(cuda):
