@@ -12,9 +12,15 @@ all four modules, rho=1.  A "step" is one ADMM iteration o
 analytic backward, Adam] + the no-grad multiplier-update forward.  Weak scaling: every rank
 holds its own 1024 patches; one all-reduce of [gradients | loss scalars] per closure.
 
-`value` = patches/s with the batch resident in HBM.  `e2e` = the same step driven through the
-loader API from HOST memory: pinned int8 visibilities of the step's baselines -> H2D ->
-scale/patchify/z-score kernels -> step -> D2H of the loss columns, a fresh minibatch every step.
+`value` = patches/s with the batch resident in HBM: consecutive ADMM iterations on the same minibatch, as in
+the reference's `for admm` loop; the closure's forward is the multiplier-update forward of the previous
+iteration (same parameters, same x - computed once) and the multiplier update is applied inside the next loss
+pass (kharmonic_lofar.DeepKHarmonicStep).  `e2e` = the same iteration driven through the loader API from HOST
+memory: pinned int8 visibilities of the step's baselines -> H2D -> scale/patchify/z-score kernels -> full
+iteration (forward, backward, Adam, multiplier-update forward, multiplier update) -> D2H of the loss columns,
+a FRESH minibatch every step (nothing can be reused across steps there).
+
+The first closure of the run is checked against the CPU oracle on the same 1024 patches (`parity_check`).
 """
 from __future__ import annotations
 
@@ -35,7 +41,9 @@ import torch
 
 CFG = dict(workload="cfg2", baselines_per_gpu=256, patches_per_baseline=4, patches_per_gpu=1024, channels=8,
            patch=128, L=32, Lt=16, K=10, p=4, rica=True, optimizer="Adam(lr=1e-4) over net+netT+netF+mod",
-           admm_iterations_per_step=1, l2="inputs larger than L2 (x alone is 537 MB per GPU)")
+           admm_iterations_per_step=1, l2="inputs larger than L2 (x alone is 537 MB per GPU)",
+           reuse="value: closure forward = preceding multiplier-update forward (same params, same x), multiplier "
+                 "update fused into the next loss pass; e2e: fresh minibatch every step, nothing reused")
 SCALES = [1e-4, 1e-3, 1e-2, 1e-1]
 
 
@@ -122,6 +130,11 @@ def call_cost(name, a):
     if name in ("cascade_losses",):
         n = a[8] * a[9] * a[10] * a[10]
         return name, 4.0 * n * (7 + (3 if a[13] else 0)), 30.0 * n
+    if name == "cascade_losses_upd":
+        # reads x, x1, x2, x3, y1..y3; writes 3 gradients (grad closure) and 3 multipliers (deferred update)
+        n = a[9] * a[10] * a[11] * a[11]
+        tag = ("+grads" if a[14] else "") + ("+mult_update" if a[8] else "")
+        return f"cascade_losses{tag}", 4.0 * n * (7 + (3 if a[14] else 0) + (3 if a[8] else 0)), (30.0 + (6 if a[8] else 0)) * n
     if name in ("residual_split", "cascade_combine"):
         n = a[4] * a[5] * a[6] * a[6]
         return name, 4.0 * n * 4, 3.0 * n
@@ -149,12 +162,16 @@ def call_cost(name, a):
 
 def ncu_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/), or None."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_dram_traffic.json")
-    try:
-        with open(path) as fh:
-            return json.load(fh).get(kernel)
-    except Exception:
-        return None
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles")
+    for fn in ("r2_ncu_dram_traffic.json", "r1_ncu_dram_traffic.json"):
+        try:
+            with open(os.path.join(here, fn)) as fh:
+                v = json.load(fh).get(kernel)
+            if v is not None:
+                return v
+        except Exception:
+            pass
+    return None
 
 
 class KernelProfiler:
@@ -257,21 +274,29 @@ def run_ours(args):
     bpb_, x, uv = load_from_host()
     step.set_batch(x, uv, bpb_, global_patches=Np * world)
 
-    def eager_step():
-        opt.step(step.closure)
-        step.update_multipliers()
+    # ---- parity of the batch this run times: first closure (y = 0) against the CPU oracle on the SAME 1024 patches
+    parity = None
+    if rank == 0 and world == 1 and args.parity == "on":
+        parity = parity_check(step, x, uv, bpb_)
 
-    # the step (closure fwd+bwd, Adam, multiplier-update forward: ~270 launches) is replayed from ONE CUDA graph
-    graphed, graph_note = None, None
+    def one_step():
+        loss = opt.step(step.closure)
+        step.update_multipliers()
+        return loss
+
+    # every launch sequence (loss pass + backward, forward, ...) is replayed from a CUDA graph
+    graph_note = None
     if args.graph == "on":
-        from lshm_b200.kharmonic_lofar import GraphedStep
         try:
-            graphed = GraphedStep(step, opt)
+            step.enable_graphs()
+            one_step(); one_step()          # first use of each sequence: launched kernel by kernel, then captured
+            torch.cuda.synchronize()
         except Exception as exc:      # keep the benchmark alive: same kernels, launched one by one
             graph_note = f"graph capture failed ({type(exc).__name__}: {exc}); eager launches"
             print(graph_note, file=sys.stderr)
+            step.enable_graphs(False)
             torch.cuda.synchronize()
-    one_step = graphed.replay if graphed is not None else eager_step
+    graphed = step._graphs_on
 
     def barrier():
         if distributed:
@@ -303,12 +328,15 @@ def run_ours(args):
 
     # ---- end to end through the loader API from host memory
     # the next minibatch (H2D + loader kernels) is staged on a side stream while this step computes;
-    # every step's copy and read-back are inside the timed region
+    # every step's copy and read-back are inside the timed region.  A fresh minibatch every step: the
+    # closure runs its own forward, and the multiplier update of the iteration is applied (flush) although
+    # the next minibatch resets y1..y3 - the reference does that work too.
     def new_batch(x2, uv2, b):
-        if graphed is not None:
-            graphed.load(x2, uv2)            # into the static buffers the graph reads (also resets y1..y3)
-        else:
-            step.set_batch(x2, uv2, b, global_patches=Np * world)
+        step.set_batch(x2, uv2, b, global_patches=Np * world)
+
+    def e2e_step():
+        one_step()
+        step.flush_multipliers()
 
     pf = T.DevicePrefetcher(dev, record_streams=False)
     sets = [(torch.empty_like(vis_h, device=dev), torch.empty_like(sc_h, device=dev), torch.empty_like(uv_h, device=dev),
@@ -316,7 +344,7 @@ def run_ours(args):
             for _ in range(2)]
     for k in range(3):      # warm-up through the same path
         pf.submit(lambda: load_from_host(sets[k % 2]))
-        b, x2, uv2 = pf.get(); new_batch(x2, uv2, b); one_step(); step.loss_terms()
+        b, x2, uv2 = pf.get(); new_batch(x2, uv2, b); e2e_step(); step.loss_terms()
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(2, min(args.steps, 10))
@@ -327,7 +355,7 @@ def run_ours(args):
             nxt = sets[(i + 1) % 2]      # last used by step i-1, which has completed (loss read-back)
             pf.submit(lambda: load_from_host(nxt))
         new_batch(x2, uv2, b)
-        one_step()
+        e2e_step()
         terms = step.loss_terms()   # D2H of the 9 loss columns (synchronises)
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -337,21 +365,25 @@ def run_ours(args):
         e2e_s = float(t)
     e2e = dict(value=Np * world / (e2e_s / e2e_steps), unit="patches/s",
                h2d_bytes_per_step=int(vis_h.numel() + sc_h.numel() * 4 + uv_h.numel() * 4), d2h_bytes_per_step=9 * 4,
-               steps=e2e_steps, note="fresh minibatch from pinned host int8 every step (staged on a side stream) + loss read-back")
+               steps=e2e_steps, note="fresh minibatch from pinned host int8 every step (staged on a side stream): full "
+               "forward + backward + Adam + multiplier-update forward + multiplier update, then loss read-back")
 
     # ---- per-kernel device times (CUDA events) over two extra steps -> dominant kernel roofline.
     #      Every rank runs the steps (the closure contains the all-reduce); rank 0 records.
+    #      Same steady-state iteration as `value` (resident minibatch, reused forward), launched kernel by kernel.
     prof_steps = 2
     agg = None
+    step.enable_graphs(False)
     step.overlap_streams = False     # one stream: the event pair around a call then times that kernel alone
+    one_step()                       # settle into the steady state (forward held, multiplier update pending)
     if rank == 0:
         with KernelProfiler(L) as kp:
             for _ in range(prof_steps):
-                eager_step()
+                one_step()
             agg = kp.summary(prof_steps)
     else:
         for _ in range(prof_steps):
-            eager_step()
+            one_step()
     barrier()
     out = None
     if rank == 0:
@@ -378,14 +410,14 @@ def run_ours(args):
                              f"{v['bytes'] / s_ / 1e9 if s_ else 0:.1f},{v['flops'] / s_ / 1e12 if s_ else 0:.2f}\n")
                 fh.write(f"TOTAL,,{total_ms:.4f},1.0,,\n")
         # the CPU arm is timed on rank 0 at N=1 only (contract); other world sizes report null
-        cpu = cpu_baseline(sample_patches=args.cpu_patches, steps=1) if world == 1 else None
+        cpu = cpu_baseline(sample_patches=args.cpu_patches, steps=1) if (world == 1 and args.cpu == "on") else None
         out = {
             "metric": "train patches/sec (fwd+bwd+K-harmonic)", "value": value, "unit": "patches/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(CFG, global_patches=Np * world, parallelism=f"dp{world}", cuda_graph=graphed is not None, **({"graph_note": graph_note} if graph_note else {})),
+            "config": dict(CFG, global_patches=Np * world, parallelism=f"dp{world}", cuda_graph=bool(graphed), **({"graph_note": graph_note} if graph_note else {})),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-            "loss_terms_last": terms,
+            "parity_check": parity, "loss_terms_last": terms,
         }
     if distributed:
         torch.distributed.barrier()
@@ -394,13 +426,61 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path on the host cores
+# parity of the timed batch (oracle = checker)
 # ------------------------------------------------------------------------------------------
-def cpu_step_factory(n_patches):
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from lshm_b200 import synthetic as S
+def parity_check(step, x, uv, bpb):
+    """First closure of the run (y1..y3 = 0) on the GPU vs the CPU oracle on the SAME patches and parameters:
+    the nine loss columns and the argmin assignment of every latent.  Forward only (the gradients of this
+    batch size are compared in tests/test_gpu_sizes.py::test_fused_closure_at_benchmark_sizes)."""
     from oracle import lofar_oracle as O
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        step.closure()
+    got = step.loss_terms()
+    Mu_gpu = step.latents().detach().cpu()
+    ids_gpu = step.mod.assign(step.latents()).cpu().long()
+    cpu = lambda sd: {k: v.detach().cpu() for k, v in sd.items()}
+    pn, pT, pF = cpu(step.net.state_dict()), cpu(step.netT.state_dict()), cpu(step.netF.state_dict())
+    M = step.mod.M.detach().cpu()
+    xc, uvc = x.detach().cpu(), uv.detach().cpu()
+    N = xc.shape[0]
+    zeros = torch.zeros(xc.numel())
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        total, terms = O.closure_losses(pn, pT, pF, M, xc, uvc, torch.tensor(SCALES), zeros, zeros, zeros,
+                                        batch_per_bline=bpb, batch_size=N // bpb, Khp=CFG["p"])
+    ref = {k: float(v) for k, v in terms.items() if k != "Mu"}
+    ref["total"] = float(total)
+    errs = {k: abs(got[k] - ref[k]) / max(abs(ref[k]), 1e-30) for k in ref}
+    ids_ref = torch.cdist(terms["Mu"].double(), M.double()).argmin(dim=1)
+    agree = float((ids_gpu == ids_ref).double().mean())
+    mu_err = float((Mu_gpu.double() - terms["Mu"].double()).norm() / terms["Mu"].double().norm())
+    worst = max(errs.values())
+    step.invalidate()
+    return dict(patches=int(N), against="oracle/lofar_oracle.closure_losses (CPU fp32), same patches and parameters",
+                loss_terms_max_rel_err=worst, loss_terms_rel_err={k: float(f"{v:.3e}") for k, v in errs.items()},
+                latents_rel_err=mu_err, assignment_agreement=agree, tolerance=dict(loss=1e-3, assignment=0.999),
+                ok=bool(worst < 1e-3 and agree >= 0.999), seconds=round(time.perf_counter() - t0, 2))
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the reference's own modules (baseline/_ref) on the host cores; oracle port only if they are absent
+# ------------------------------------------------------------------------------------------
+def cpu_step_factory(n_patches, prefer_reference=True):
+    """Returns (one_step, kind, info): one ADMM iteration (closure + Adam + multiplier update) on `n_patches`
+    of the cfg2 batch.  kind "reference": the UNMODIFIED reference modules (lofar_models.py from baseline/_ref)
+    driven by the restated script loop (oracle/reference_loop.py); kind "port": the oracle port."""
+    from lshm_b200 import synthetic as S
     C, L, Lt, K, bpb = CFG["channels"], CFG["L"], CFG["Lt"], CFG["K"], CFG["patches_per_baseline"]
+    x = torch.from_numpy(S.make_patches(n_patches, C, seed=5))
+    uv = torch.from_numpy(S.make_uv(n_patches, seed=5, per_group=bpb))
+    if prefer_reference:
+        from oracle import reference_loop as RL
+        if RL.reference_dir() is not None:
+            R = RL.ReferenceLoop(L=L, Lt=Lt, C=C, K=K, Khp=CFG["p"], optimizer="adam", param_modules=(0, 1, 2, 3))
+            R.set_batch(x, uv, bpb)
+            return R.admm_iteration, "reference", R
+    from oracle import lofar_oracle as O
     hs = torch.tensor(SCALES)
     pn = O.make_ae_params(L, C, ndim=2, seed=1); pT = O.make_ae_params(Lt, C, ndim=1, seed=2)
     pF = O.make_ae_params(Lt, C, ndim=1, seed=3); M = O.make_centres(K, L + 2 * Lt, seed=4).requires_grad_()
@@ -410,8 +490,6 @@ def cpu_step_factory(n_patches):
             v.requires_grad_(); params.append(v)
     params.append(M)
     opt = torch.optim.Adam(params, lr=1e-4)
-    x = torch.from_numpy(S.make_patches(n_patches, C, seed=5))
-    uv = torch.from_numpy(S.make_uv(n_patches, seed=5, per_group=bpb))
     ys = [torch.zeros(x.numel()) for _ in range(3)]
 
     def closure():
@@ -424,49 +502,68 @@ def cpu_step_factory(n_patches):
     def one_step():
         opt.step(closure)
         ys[:] = O.multiplier_update(pn, pT, pF, x, uv, hs, *ys)
-    return one_step
+    return one_step, "port", None
 
 
-def cpu_baseline(sample_patches=64, steps=1):
+REF_NOTE = ("unmodified reference modules (lofar_models.py: AutoEncoderCNN2 / AutoEncoder1DCNN / Kmeans with its Python "
+            "N x K loop) from baseline/_ref + the script loop of src/kharmonic_lofar.py:84-202 restated in "
+            "oracle/reference_loop.py; torch CPU fp32, Adam over all four modules")
+PORT_NOTE = ("oracle port of /root/reference/src/kharmonic_lofar.py:131-202 (baseline/_ref absent: run "
+             "__graft_entry__.build() where /root/reference exists); vectorised K-harmonic")
+
+
+def timed_cpu_run(n_patches, warmup, steps, budget_s):
+    """W warm-up + K timed ADMM iterations on n_patches; if the first iteration shows that the whole run would not
+    fit in budget_s, the batch is halved (time is ~linear in patches) until it does - said in `sample`."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    one_step = cpu_step_factory(sample_patches)
-    one_step()  # warm-up
+    n = n_patches
+    while True:
+        one_step, kind, R = cpu_step_factory(n)
+        t0 = time.perf_counter()
+        one_step()
+        first = time.perf_counter() - t0
+        if first * (warmup + steps) <= budget_s or n <= 64:
+            break
+        n = max(64, n // 2)
+    for _ in range(max(0, warmup - 1)):
+        one_step()
+    if R is not None:
+        R.khm_seconds, R.closures = 0.0, 0
     t0 = time.perf_counter()
     for _ in range(steps):
         one_step()
     dt = (time.perf_counter() - t0) / steps
-    return dict(value=sample_patches / dt, unit="patches/s", cores=cores, kind="port",
-                sample=f"{steps} step(s) of the same closure+Adam+multiplier update on {sample_patches} patches "
-                       f"({sample_patches // 4} baselines x 4), torch CPU fp32, vectorised K-harmonic "
-                       "(the reference's Python N x K loop would be slower)")
+    extra = {}
+    if R is not None:
+        extra = dict(khm_python_loop_forward_ms_per_step=1e3 * R.khm_seconds / steps,
+                     khm_python_loop_share_of_step=R.khm_seconds / steps / dt, closures_per_step=R.closures / steps)
+    sample = (f"{warmup} warm-up + {steps} timed ADMM iteration(s) (closure + Adam + multiplier update) on {n} of the "
+              f"{n_patches} patches of the cfg2 batch" + ("" if n == n_patches else f" (batch reduced so that the run fits in {budget_s:.0f} s)")
+              + "; " + (REF_NOTE if kind == "reference" else PORT_NOTE))
+    return dict(value=n / dt, unit="patches/s", cores=cores, kind=kind, sample=sample, sample_patches=n,
+                ms_per_step=dt * 1e3, **extra)
+
+
+def cpu_baseline(sample_patches=1024, steps=1):
+    """Rank-0 CPU baseline of the `ours` arm: one warm-up + `steps` timed iterations, bounded to ~40 s."""
+    return timed_cpu_run(sample_patches, 1, steps, budget_s=40.0)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    n = args.cpu_patches
-    one_step = cpu_step_factory(n)
-    for _ in range(min(args.warmup, 1)):
-        one_step()
-    steps = max(1, min(args.steps, 3))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        one_step()
-    dt = (time.perf_counter() - t0) / steps
-    value = n / dt
-    sample = (f"each step = closure+Adam+multiplier update on a {n}-patch sample of the cfg2 batch; oracle port of "
-              "/root/reference/src/kharmonic_lofar.py:131-202 (the Python reference cannot travel to the GPU box)")
+    warmup, steps = max(args.warmup, 0), max(args.steps, 1)
+    r = timed_cpu_run(args.cpu_patches, warmup, steps, budget_s=args.cpu_budget)
+    n = r["sample_patches"]
     return json.dumps({
-        "impl": "reference", "metric": "train patches/sec (fwd+bwd+K-harmonic)", "value": value, "unit": "patches/s",
-        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": min(args.warmup, 1),
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": dict(CFG, sample_patches=n),
-        "cpu_baseline": dict(value=value, unit="patches/s", cores=cores, kind="port", sample=sample),
-        "e2e": dict(value=value, unit="patches/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)})
+        "impl": "reference", "metric": "train patches/sec (fwd+bwd+K-harmonic)", "value": r["value"], "unit": "patches/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": dict(CFG, sample_patches=n, reuse="none (reference loop as written)"),
+        "cpu_baseline": {k: v for k, v in r.items() if k != "ms_per_step"},
+        "e2e": dict(value=r["value"], unit="patches/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)})
 
 
 class StdoutToStderr:
@@ -491,7 +588,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-patches", type=int, default=64)
+    ap.add_argument("--cpu-patches", type=int, default=CFG["patches_per_gpu"],
+                    help="patches per CPU step (default: the full cfg2 batch; reduced automatically if too slow)")
+    ap.add_argument("--cpu-budget", type=float, default=270.0, help="wall-time budget (s) of the --impl reference run")
+    ap.add_argument("--cpu", default="on", choices=["on", "off"], help="time the CPU baseline in the `ours` arm")
+    ap.add_argument("--parity", default="on", choices=["on", "off"], help="check the first closure against the CPU oracle")
     ap.add_argument("--graph", default="on", choices=["on", "off"],
                     help="replay the step from one CUDA graph (default) or launch it kernel by kernel")
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel CUDA-event table (CSV) here")

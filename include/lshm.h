@@ -75,6 +75,9 @@ LSHM_API int lshm_patchify_scale_i8(const int8_t* vis, const float* scale, const
                            float* y, double* stats, lshm_stream_t stream);
 /* y = (y - mean) / std, UNBIASED std (torch.Tensor.std), from stats of n elements. */
 LSHM_API int lshm_normalise(float* y, int64_t n, const double* stats, lshm_stream_t stream);
+/* Same for a SHARD of the minibatch: y holds n of the n_stats elements the (all-reduced) stats describe, so
+ * every data-parallel rank z-scores with the statistics of the whole minibatch. */
+LSHM_API int lshm_normalise_n(float* y, int64_t n, const double* stats, int64_t n_stats, lshm_stream_t stream);
 
 /* ------------------------------------------------------------- FFT features -----
  * Replaces Demo.ipynb:169-174 + torch_fftshift (src/lofar_tools.py:24-30):
@@ -101,10 +104,6 @@ LSHM_API int lshm_conv_prep(const float* w, int dim, int A, int Bc, void* down_i
  * lshm_conv_prep_batch re-makes all n images with a single launch. */
 LSHM_API int lshm_conv_prep_record(const float* w, int dim, int A, int Bc, int which, void* img, int64_t* record);
 LSHM_API int lshm_conv_prep_batch(const int64_t* table, int n, lshm_stream_t stream);
-/* Host-only self-check of the multiply-shift division the conv kernels use for their index math
- * (conv_geom.cuh FastDiv: q = (mulhi(m, n) + n) >> l): *mismatches = how many of the `count` 31-bit values
- * n[i] give a quotient different from n[i] / d.  Host pointers, no GPU needed. */
-LSHM_API int lshm_fastdiv_check(int64_t d, const int64_t* n, int count, int64_t* mismatches);
 
 /* Conv2d(k4,s2,p1) forward (src/lofar_models.py:73-78) and ConvTranspose2d dgrad.
  * wimg = "down" image of W (lshm_conv_prep). */
@@ -171,6 +170,14 @@ LSHM_API int lshm_cascade_losses(const float* x, const float* x1, const float* x
                         const float* y1, const float* y2, const float* y3, float rho,
                         int64_t N, int C, int P, float grad_scale, double* sums,
                         float* g1p, float* g2, float* g3f, float* db2, float* db3, lshm_stream_t stream);
+/* Same pass with the DEFERRED multiplier update of the previous ADMM iteration folded in
+ * (src/kharmonic_lofar.py:187-202 followed by :150-158 on the same minibatch and parameters): when
+ * update_y != 0 the kernel first does y_i += rho * r_i with the residuals it computes anyway, stores the
+ * new multipliers, and evaluates the loss terms / gradients with them.  update_y == 0 is lshm_cascade_losses. */
+LSHM_API int lshm_cascade_losses_upd(const float* x, const float* x1, const float* x2, const float* x3f,
+                            float* y1, float* y2, float* y3, float rho, int update_y,
+                            int64_t N, int C, int P, float grad_scale, double* sums,
+                            float* g1p, float* g2, float* g3f, float* db2, float* db3, lshm_stream_t stream);
 /* gx1 = g1p - 0.5*(gT + transpose(gF)) : total gradient w.r.t. the 2-D net output.
  * db1 (nullable, float[C], written): per-channel sums of gx1 = bias gradient of the 2-D net's last
  * transposed conv. */

@@ -72,7 +72,7 @@ class _Library:
             setattr(self, name[len("lshm_"):], self._wrap(name, fn))
 
     def _wrap(self, name, fn):
-        host_only = name in ("lshm_conv_prep_record", "lshm_fastdiv_check")
+        host_only = name in ("lshm_conv_prep_record",)
 
         def call(*args):
             rc = fn(*args)

@@ -1,5 +1,6 @@
 // Weight-image management for the tensor-core conv kernels (see include/lshm.h).
 #include "conv_geom.cuh"
+#include "../../include/lshm_selftest.h"
 
 namespace lshm {
 namespace {

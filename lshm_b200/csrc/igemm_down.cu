@@ -389,7 +389,8 @@ int lshm_down2d(const float* big, int64_t big_ns, const void* wimg, const float*
   LSHM_REQUIRE(N >= 0 && A > 0 && Bc > 0 && (Bc & 3) == 0 && h > 0 && w_ > 0, "lshm_down2d: bad sizes (Bc must be a multiple of 4)");
   LSHM_REQUIRE(epilogue >= 0 && epilogue <= 2, "lshm_down2d: bad epilogue %d", epilogue);
   LSHM_REQUIRE(epilogue != LSHM_EPI_DELU || aux != nullptr, "lshm_down2d: DELU epilogue needs aux");
-  LSHM_REQUIRE(w_ <= 512, "lshm_down2d: small-map width %d too large", w_);
+  // the producers stage 2 x 128 slots per tile (tile + one halo row): 128 + w + 2 <= 256
+  LSHM_REQUIRE(w_ <= 126, "lshm_down2d: small-map width %d too large (max 126)", w_);
   LSHM_REQUIRE((reinterpret_cast<uintptr_t>(wimg) & 15) == 0, "lshm_down2d: weight image must be 16-byte aligned");
   if (N == 0) return LSHM_OK;
   DownArgs a{};

@@ -387,7 +387,9 @@ int lshm_up2d(const float* small_, int64_t small_ns, const void* wimg, const flo
               const float* aux, int64_t aux_ns, float* big, int64_t big_ns,
               int64_t N, int A, int Bc, int h, int w_, int epilogue, lshm_stream_t stream) {
   LSHM_REQUIRE(small_ && wimg && big, "lshm_up2d: null pointer");
-  LSHM_REQUIRE(N >= 0 && A > 0 && Bc > 0 && h > 0 && w_ > 0 && w_ <= 512, "lshm_up2d: bad sizes");
+  LSHM_REQUIRE(N >= 0 && A > 0 && Bc > 0 && h > 0 && w_ > 0, "lshm_up2d: bad sizes");
+  // the producers stage 3 x 128 slots per tile (tile + two halo rows): 128 + 2 (w + 2) <= 384
+  LSHM_REQUIRE(w_ <= 126, "lshm_up2d: small-map width %d too large (max 126)", w_);
   LSHM_REQUIRE(epilogue >= 0 && epilogue <= 2, "lshm_up2d: bad epilogue %d", epilogue);
   LSHM_REQUIRE(epilogue != LSHM_EPI_DELU || aux != nullptr, "lshm_up2d: DELU epilogue needs aux");
   LSHM_REQUIRE((reinterpret_cast<uintptr_t>(wimg) & 15) == 0 && (reinterpret_cast<uintptr_t>(big) & 7) == 0 &&

@@ -41,12 +41,16 @@ constexpr int CASCADE_MAXC = 64;   // channels whose bias-gradient sums can be f
 
 // 6 blocks per SM (<= 40 registers; 32 spills): at 48 registers the kernel ran at 55 % occupancy and 4.8 TB/s while the
 // 30-register multiplier kernel next to it reaches 5.35 TB/s (ncu, profiles/r1_ncu_dram_traffic.json)
-template <bool GRADS>
+// UPD: the deferred multiplier update of the previous ADMM iteration (y_i += rho * r_i,
+// src/kharmonic_lofar.py:200-202) is applied on the fly - the residuals r_i are exactly the ones this
+// pass computes anyway (same parameters, same minibatch), so the stand-alone 10-pass update kernel and its
+// re-read of x, x1, x2, x3 disappear; the loss terms and gradients then use the UPDATED multipliers.
+template <bool GRADS, bool UPD>
 __global__ void __launch_bounds__(TILE * TROWS, 6)
 cascade_losses_kernel(const float* __restrict__ x, const float* __restrict__ x1,
                       const float* __restrict__ x2, const float* __restrict__ x3f,
-                      const float* __restrict__ y1, const float* __restrict__ y2,
-                      const float* __restrict__ y3, float rho, float inv_n, int P, int64_t ntiles,
+                      float* __restrict__ y1, float* __restrict__ y2,
+                      float* __restrict__ y3, float rho, float inv_n, int P, int64_t ntiles,
                       double* __restrict__ sums, float* __restrict__ g1p, float* __restrict__ g2,
                       float* __restrict__ g3f, int C, float* __restrict__ db2, float* __restrict__ db3) {
   __shared__ float tile[TILE][TILE + 1];
@@ -77,11 +81,15 @@ cascade_losses_kernel(const float* __restrict__ x, const float* __restrict__ x1,
     for (int i = 0; i < TILE; i += TROWS) {
       const int64_t off = plane + (int64_t)(t0 + ty + i) * P + f0 + tx;
       const float xv = x[off], a1 = x1[off], a2 = x2[off], a3 = tile[tx][ty + i];
-      const float m1 = y1[off], m2 = y2[off], m3 = y3[off];
+      float m1 = y1[off], m2 = y2[off], m3 = y3[off];
       const float r0 = a1 + a2 + a3 - xv;
       const float r1 = xv - a1;
       const float x11 = 0.5f * r1;
       const float r2 = x11 - a2, r3 = x11 - a3;
+      if (UPD) {
+        m1 = fmaf(rho, r1, m1); m2 = fmaf(rho, r2, m2); m3 = fmaf(rho, r3, m3);
+        y1[off] = m1; y2[off] = m2; y3[off] = m3;
+      }
       s[0] = fmaf(r0, r0, s[0]);
       s[1] = fmaf(m1, r1, s[1]); s[2] = fmaf(r1, r1, s[2]);
       s[3] = fmaf(m2, r2, s[3]); s[4] = fmaf(r2, r2, s[4]);
@@ -410,6 +418,14 @@ int lshm_cascade_losses(const float* x, const float* x1, const float* x2, const 
                         const float* y1, const float* y2, const float* y3, float rho,
                         int64_t N, int C, int P, float grad_scale, double* sums,
                         float* g1p, float* g2, float* g3f, float* db2, float* db3, lshm_stream_t stream) {
+  return lshm_cascade_losses_upd(x, x1, x2, x3f, const_cast<float*>(y1), const_cast<float*>(y2), const_cast<float*>(y3),
+                                 rho, 0, N, C, P, grad_scale, sums, g1p, g2, g3f, db2, db3, stream);
+}
+
+int lshm_cascade_losses_upd(const float* x, const float* x1, const float* x2, const float* x3f,
+                            float* y1, float* y2, float* y3, float rho, int update_y,
+                            int64_t N, int C, int P, float grad_scale, double* sums,
+                            float* g1p, float* g2, float* g3f, float* db2, float* db3, lshm_stream_t stream) {
   LSHM_REQUIRE(x && x1 && x2 && x3f && y1 && y2 && y3 && sums, "lshm_cascade_losses: null pointer");
   LSHM_REQUIRE((db2 == nullptr) == (db3 == nullptr) && (db2 == nullptr || (g1p != nullptr && C <= CASCADE_MAXC)),
                "lshm_cascade_losses: db2/db3 come together, need the gradient outputs and C <= %d", CASCADE_MAXC);
@@ -425,10 +441,11 @@ int lshm_cascade_losses(const float* x, const float* x1, const float* x2, const 
     LSHM_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * C, as_stream(stream)), "lshm_cascade_losses");
     LSHM_CUDA(cudaMemsetAsync(db3, 0, sizeof(float) * C, as_stream(stream)), "lshm_cascade_losses");
   }
-  if (g1p)
-    cascade_losses_kernel<true><<<(unsigned)blocks, block, 0, as_stream(stream)>>>(x, x1, x2, x3f, y1, y2, y3, rho, inv_n, P, ntiles, sums, g1p, g2, g3f, C, db2, db3);
-  else
-    cascade_losses_kernel<false><<<(unsigned)blocks, block, 0, as_stream(stream)>>>(x, x1, x2, x3f, y1, y2, y3, rho, inv_n, P, ntiles, sums, nullptr, nullptr, nullptr, C, nullptr, nullptr);
+#define LSHM_CL(G, U) cascade_losses_kernel<G, U><<<(unsigned)blocks, block, 0, as_stream(stream)>>>( \
+      x, x1, x2, x3f, y1, y2, y3, rho, inv_n, P, ntiles, sums, g1p, g2, g3f, C, db2, db3)
+  if (g1p) { if (update_y) LSHM_CL(true, true); else LSHM_CL(true, false); }
+  else { if (update_y) LSHM_CL(false, true); else LSHM_CL(false, false); }
+#undef LSHM_CL
   LSHM_CHECK_LAUNCH("lshm_cascade_losses");
   return LSHM_OK;
 }

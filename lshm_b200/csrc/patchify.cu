@@ -83,8 +83,8 @@ patchify_kernel(const int8_t* __restrict__ vis, const float* __restrict__ scale,
 }
 
 __global__ void __launch_bounds__(256)
-normalise_kernel(float* __restrict__ y, int64_t n, const double* __restrict__ stats) {
-  const double cnt = (double)n;
+normalise_kernel(float* __restrict__ y, int64_t n, const double* __restrict__ stats, int64_t n_stats) {
+  const double cnt = (double)n_stats;
   const double mean_d = stats[0] / cnt;
   const double var_d = (stats[1] - stats[0] * stats[0] / cnt) / (cnt - 1.0);
   const float mean = (float)mean_d, sd = (float)sqrt(var_d);
@@ -129,10 +129,15 @@ int lshm_patchify_scale_i8(const int8_t* vis, const float* scale, const int32_t*
 }
 
 int lshm_normalise(float* y, int64_t n, const double* stats, lshm_stream_t stream) {
-  LSHM_REQUIRE(y && stats && n >= 2, "lshm_normalise: bad arguments");
+  return lshm_normalise_n(y, n, stats, n, stream);
+}
+
+int lshm_normalise_n(float* y, int64_t n, const double* stats, int64_t n_stats, lshm_stream_t stream) {
+  LSHM_REQUIRE(y && stats && n >= 0 && n_stats >= 2 && n_stats >= n, "lshm_normalise: bad arguments");
+  if (n == 0) return LSHM_OK;
   LSHM_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0, "lshm_normalise: y must be 16-byte aligned");
   const int64_t blocks = std::min<int64_t>(ceil_div(n >> 2, 256) + 1, (int64_t)sm_count() * 16);
-  normalise_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(y, n, stats);
+  normalise_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(y, n, stats, n_stats);
   LSHM_CHECK_LAUNCH("lshm_normalise");
   return LSHM_OK;
 }

@@ -90,6 +90,19 @@ def graph_features(net, net1D1, net1D2, mod: Kmeans, x, uv, batch_per_bline: int
 
 
 @torch.no_grad()
+def graph_stat_features(net, net1D1, net1D2, mod: Kmeans, x, uv):
+    """Station-graph features of src/train_graph_stat.py:197-218 for every patch given (the script picks ONE random
+    patch per baseline, :191-194, and calls the nets on it): attr[n] = Mu_n (node attribute of an autocorrelation,
+    edge attribute of a cross-correlation) and label[n] = softmax_k(-d_nk / mean_k d_nk) with
+    d_nk = ||Mu_n - M_k||^p (:207-210, 'smallest dist ~ highest prob').  The distances come from the grouped
+    distance kernel with groups of one patch; the K-wide softmax is a torch op on the [N,K] result."""
+    Mu = cascade_latents(net, net1D1, net1D2, x, uv)
+    dist, _ = mod.group_distances(Mu, 1)
+    label = torch.softmax(-dist / dist.mean(dim=1, keepdim=True), dim=1)
+    return Mu, label
+
+
+@torch.no_grad()
 def evaluate(net, net1D1, net1D2, mod: Kmeans, baseline_loader, nbase: int, log=None):
     """The per-baseline loop of src/evaluate_clustering.py:75-119.
 

@@ -18,7 +18,7 @@ identical on every rank.
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -39,24 +39,35 @@ class FlatParams:
     """Re-homes every Parameter of `modules` into one flat fp32 buffer (and `.grad` into a
     second one).  Parameters stay ordinary dense leaf tensors (views), so ``torch.optim.Adam``,
     ``LBFGSNew`` (``p.data.add_``, ``p.copy_``, ``p.grad.data`` - src/lbfgsnew.py:84-112) and
-    ``state_dict`` keep working; the flat layout makes the data-parallel exchange one call."""
+    ``state_dict`` keep working; the flat layout makes the data-parallel exchange one call.
+
+    `extra_tail` floats follow the 16 loss scalars in the gradient buffer (the K x L centre numerator and
+    K denominator sums of Kmeans.offline_update ride in the same all-reduce).
+
+    `version` / `tracked`: an optimiser that owns every parameter update (FlatAdam, lbfgsnew.LBFGSNew on
+    a FlatParams) sets `tracked` and calls `bump()` after each change; the step then knows when the
+    activations it already holds belong to the current parameters and reuses them.  Untracked
+    parameters (torch.optim.*, the unmodified reference LBFGSNew with its `p.data.add_`) are never
+    assumed unchanged."""
 
     ALIGN = 64  # floats: every tensor starts 256-byte aligned
 
-    def __init__(self, modules, device):
+    def __init__(self, modules, device, extra_tail: int = 0):
         self.params: List[torch.nn.Parameter] = []
         self.names: List[str] = []
+        self.module_of: List[int] = []
         for mi, m in enumerate(modules):
             for nm, p in m.named_parameters():
                 self.params.append(p)
                 self.names.append(f"{mi}.{nm}")
+                self.module_of.append(mi)
         offs, off = [], 0
         for p in self.params:
             offs.append(off)
             off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.offsets, self.numel = offs, off
         self.flat = torch.zeros(off, dtype=torch.float32, device=device)
-        self.grad = torch.zeros(off + LOSS_TAIL, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(off + LOSS_TAIL + extra_tail, dtype=torch.float32, device=device)
         self.grad_views = []
         with torch.no_grad():
             for p, o in zip(self.params, offs):
@@ -67,23 +78,49 @@ class FlatParams:
                 p.grad = gv
                 self.grad_views.append(gv)
         self.loss_tail = self.grad[off:off + LOSS_TAIL]
+        self.extra_tail = self.grad[off + LOSS_TAIL:]
+        self.version = 0
+        self.tracked = False
+
+    def bump(self):
+        """The parameters changed (called by the optimiser that owns the updates)."""
+        self.version += 1
 
     def attach_grads(self):
         for p, gv in zip(self.params, self.grad_views):
             if p.grad is not gv:
                 p.grad = gv
 
+    def range_of(self, modules) -> Tuple[int, int]:
+        """[start, stop) of the flat buffer that holds the parameters of the given module indices
+        (they must be adjacent in the construction order)."""
+        ids = sorted(set(int(m) for m in modules))
+        if ids != list(range(ids[0], ids[-1] + 1)):
+            raise ValueError("FlatParams.range_of: module indices must be adjacent")
+        sel = [i for i, m in enumerate(self.module_of) if m in ids]
+        if not sel:
+            raise ValueError("FlatParams.range_of: no parameters selected")
+        last = sel[-1]
+        stop = self.offsets[last + 1] if last + 1 < len(self.offsets) else self.numel
+        return self.offsets[sel[0]], stop
+
 
 class FlatAdam:
-    """torch.optim.Adam semantics (src/kharmonic_lofar.py:92) as ONE kernel over the flat
-    buffer.  The step count lives in device memory (lshm_adam_step_dev), so a step can be
-    captured in a CUDA graph (GraphedStep)."""
+    """torch.optim.Adam semantics as ONE kernel over (a range of) the flat buffer.  The step count lives
+    in device memory (lshm_adam_step_dev), so a step can be replayed from a CUDA graph.
 
-    def __init__(self, flat: FlatParams, lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
+    `modules`: indices into the step's module list (0 net, 1 netT, 2 netF, 3 mod) whose parameters are
+    updated; None = all four.  The reference script as shipped optimises `net.parameters()` only
+    (src/kharmonic_lofar.py:84-92, the other three `params.extend` lines are commented out):
+    that is ``modules=(0,)``; BASELINE's configs train all four."""
+
+    def __init__(self, flat: FlatParams, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, modules=None):
         self.flat, self.lr, self.betas, self.eps = flat, lr, betas, eps
+        self.start, self.stop = (0, flat.numel) if modules is None else flat.range_of(modules)
         self.m = torch.zeros_like(flat.flat)
         self.v = torch.zeros_like(flat.flat)
         self.t_dev = torch.zeros(1, dtype=torch.int32, device=flat.flat.device)
+        flat.tracked = True
 
     @property
     def t(self) -> int:
@@ -100,86 +137,54 @@ class FlatAdam:
 
     def apply(self):
         """The parameter update alone, from the gradients already in the flat buffer."""
-        lib().adam_step_dev(self.flat.flat.data_ptr(), self.flat.grad.data_ptr(), self.m.data_ptr(),
-                            self.v.data_ptr(), self.flat.numel, self.lr, self.betas[0], self.betas[1], self.eps,
-                            self.t_dev.data_ptr(), _stream())
+        o = 4 * self.start
+        lib().adam_step_dev(self.flat.flat.data_ptr() + o, self.flat.grad.data_ptr() + o, self.m.data_ptr() + o,
+                            self.v.data_ptr() + o, self.stop - self.start, self.lr, self.betas[0], self.betas[1],
+                            self.eps, self.t_dev.data_ptr(), _stream())
+        self.flat.bump()
 
 
 class GraphedStep:
-    """`optimizer.step(step.closure); step.update_multipliers()` captured once as a CUDA graph and
-    replayed: ~270 kernel launches become one, which removes the launch gaps between the small kernels
-    of the deep layers and the host's launch lead after every loss read-back.
+    """`optimizer.step(step.closure); step.update_multipliers()` with every launch sequence replayed from CUDA
+    graphs (`DeepKHarmonicStep.enable_graphs`): the ~270 kernel launches of an ADMM iteration become three graph
+    launches, which removes the launch gaps between the small kernels of the deep layers.
 
     The minibatch lives in the static tensors `.x` [N,C,128,128] and `.uv` [N,2] (the ones given to
     `step.set_batch` before construction): write the next minibatch into them (`load(x, uv)` copies, or
     let `lofar_tools.patchify_device(..., out=graphed.x)` produce it in place), call `new_batch()` when
-    the multipliers must restart, then `replay()`.  Needs a FlatAdam optimiser (device-side step count).
+    the multipliers must restart, then `replay()`.  Any optimiser works (the graphs belong to the closure);
+    with FlatAdam the parameter update is a fixed launch too.
     """
 
-    def __init__(self, step: "DeepKHarmonicStep", optimizer: FlatAdam, warmup: int = 2):
-        if not isinstance(optimizer, FlatAdam):
-            raise RuntimeError("lshm_b200: GraphedStep needs a FlatAdam optimiser (device-side step count)")
+    def __init__(self, step: "DeepKHarmonicStep", optimizer, warmup: int = 0):
         if step.N == 0:
             raise RuntimeError("lshm_b200: call step.set_batch(...) before capturing the step")
         self.step, self.opt = step, optimizer
         self.x, self.uv = step.x, step.uv
-        dev = step.device
-        # warm-up and capture must not change the training state: snapshot, run, restore
-        keep = [t.clone() for t in (step.flat.flat, optimizer.m, optimizer.v, optimizer.t_dev, step.y1, step.y2, step.y3)]
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        # (thread-local capture mode: the NCCL watchdog thread polls events while we capture.)
-        # Data parallel: the NCCL all-reduce stays outside (collectives inside a capture are fragile), so the
-        # step is two graphs with the eager exchange between them: [closure] -> all-reduce -> [Adam, multipliers]
-        self.graph = torch.cuda.CUDAGraph()
-        self.graph2 = torch.cuda.CUDAGraph() if step.distributed else None
-        with torch.cuda.stream(side):
-            for _ in range(max(1, warmup)):
-                self._one()
-            side.synchronize()
-            l0 = lib().launches
-            if self.graph2 is None:
-                with torch.cuda.graph(self.graph, stream=side, capture_error_mode="thread_local"):
-                    self.loss = self._one()
-            else:
-                step._defer_exchange = True
-                try:
-                    with torch.cuda.graph(self.graph, stream=side, capture_error_mode="thread_local"):
-                        with torch.enable_grad():
-                            self.loss = step.closure()
-                    with torch.cuda.graph(self.graph2, stream=side, pool=self.graph.pool(), capture_error_mode="thread_local"):
-                        optimizer.apply()
-                        step.update_multipliers()
-                finally:
-                    step._defer_exchange = False
-            self.launches_per_replay = lib().launches - l0
-        torch.cuda.current_stream(dev).wait_stream(side)
-        for dst, src in zip((step.flat.flat, optimizer.m, optimizer.v, optimizer.t_dev, step.y1, step.y2, step.y3), keep):
-            dst.copy_(src)
+        step.enable_graphs()
 
-    def _one(self):
-        loss = self.opt.step(self.step.closure)
-        self.step.update_multipliers()
-        return loss
+    @property
+    def launches_per_replay(self) -> int:
+        return self.step.launches_last_iteration
 
     def load(self, x: torch.Tensor, uv: torch.Tensor, reset_multipliers: bool = True):
         self.x.copy_(x.view_as(self.x), non_blocking=True)
         self.uv.copy_(uv.view_as(self.uv), non_blocking=True)
+        self.step.invalidate()
         if reset_multipliers:
             self.new_batch()
 
     def new_batch(self):
         """src/kharmonic_lofar.py:128-130: the multipliers restart with every minibatch."""
-        self.step.y1.zero_(); self.step.y2.zero_(); self.step.y3.zero_()
+        self.step.reset_multipliers()
 
     def replay(self) -> torch.Tensor:
-        """One optimiser step + multiplier update; returns the (static) total-loss tensor."""
-        self.graph.replay()
-        if self.graph2 is not None:
-            exchange(self.step.flat.grad, self.step.group)
-            self.graph2.replay()
-        lib().launches += self.launches_per_replay     # kernels launched by the replay
-        return self.loss
+        """One optimiser step + multiplier update; returns the total loss of the closure."""
+        l0 = lib().launches
+        loss = self.opt.step(self.step.closure)
+        self.step.update_multipliers()
+        self.step.launches_last_iteration = lib().launches - l0
+        return loss
 
 
 class DeepKHarmonicStep:
@@ -188,11 +193,24 @@ class DeepKHarmonicStep:
     Hyper-parameter names and defaults follow src/kharmonic_lofar.py:37-48.
     `group` is an optional torch.distributed process group: each rank then holds a shard of
     whole baseline groups (rows [g*bpb,(g+1)*bpb)) and `global_patches` is the global N.
+
+    Work that the reference repeats is done once (only when the optimiser tracks its updates, see
+    FlatParams): the no-grad forward of the multiplier update (:187-198) IS the forward of the next
+    closure on the same minibatch (same parameters, same x; only y1..y3 differ), so `update_multipliers`
+    runs the forward, leaves the update y_i += rho r_i pending, and the next closure applies it inside the
+    loss pass that reads x, x1, x2, x3 anyway (lshm_cascade_losses_upd) and goes straight to the backward.
+    `y1`, `y2`, `y3` read through properties that apply a pending update first, so observable state always
+    equals the reference's.  A closure evaluated again at unchanged parameters and multipliers (the f_old
+    probe of the LBFGSNew line search, src/lbfgsnew.py:140) returns the loss already computed.
+
+    `centre_sums=True` adds the K x L numerator / K denominator of Kmeans.offline_update
+    (src/lofar_models.py:231-261) to every gradient closure; they travel in the same all-reduce as the
+    gradients and `apply_centre_update()` sets M = num / den from the reduced sums.
     """
 
     def __init__(self, net: AutoEncoderCNN2, netT: AutoEncoder1DCNN, netF: AutoEncoder1DCNN, mod: Kmeans, *,
                  alpha=0.01, beta=0.01, gamma=0.01, rho=1.0, use_rica=True, rica_lambda=0.01,
-                 group: Optional[dist.ProcessGroup] = None, distributed: bool = False):
+                 group: Optional[dist.ProcessGroup] = None, distributed: bool = False, centre_sums: bool = False):
         self.net, self.netT, self.netF, self.mod = net, netT, netF, mod
         self.alpha, self.beta, self.gamma, self.rho = alpha, beta, gamma, rho
         self.use_rica, self.rica_lambda = use_rica, rica_lambda
@@ -202,11 +220,13 @@ class DeepKHarmonicStep:
         if dev.type != "cuda":
             raise RuntimeError("lshm_b200: DeepKHarmonicStep needs CUDA modules (no CPU path)")
         self.device = dev
-        self.flat = FlatParams([net, netT, netF, mod], dev)
         self.L, self.Lt = net.latent_dim, netT.latent_dim
         self.Ltot = self.L + 2 * self.Lt
         if mod.latent_dim != self.Ltot:
             raise RuntimeError("lshm_b200: Kmeans.latent_dim must equal L + 2*Lt")
+        self.centre_sums = bool(centre_sums)
+        K = mod.K
+        self.flat = FlatParams([net, netT, netF, mod], dev, extra_tail=(K * self.Ltot + K) if centre_sums else 0)
         self._pd = [m.named_param_dict() for m in (net, netT, netF)]
         self._gd = []
         views = dict(zip(self.flat.names, self.flat.grad_views))
@@ -214,17 +234,25 @@ class DeepKHarmonicStep:
             self._gd.append({nm: views[f"{mi}.{nm}"] for nm in m._names})
         self._gM = views["3.M"]
         self.N = 0
-        self._defer_exchange = False     # GraphedStep runs the all-reduce itself, between its two graphs
         self._side = None                # second stream for the frequency-axis net
         self.overlap_streams = True      # False: everything on the current stream (per-kernel profiling)
         self._wst = [None, None, None]   # per-net streams for the weight / bias gradients
         self.launches = 0
+        self.launches_last_iteration = 0
+        self.reuse = True                # reuse activations / losses when the optimiser tracks its updates
+        self._graphs_on = False
+        self._graphs = {}                # launch-sequence key -> (CUDAGraph, launches)
+        self._fwd_key = None             # (flat.version, batch id) the held activations belong to
+        self._loss_key = None            # same for the loss scalars in the tail (+ multiplier state)
+        self._batch_id = 0
+        self._pending = False            # multiplier update deferred into the next loss pass
         if distributed:
             self.broadcast_parameters()
 
     # ------------------------------------------------------------------ data parallel
     def broadcast_parameters(self, src: int = 0):
         dist.broadcast(self.flat.flat, src=src, group=self.group)
+        self.invalidate()
 
     # ------------------------------------------------------------------ batch
     def set_batch(self, x: torch.Tensor, uv: torch.Tensor, batch_per_bline: int,
@@ -233,11 +261,24 @@ class DeepKHarmonicStep:
         N, C = x.shape[0], x.shape[1]
         if N % batch_per_bline:
             raise RuntimeError("lshm_b200: shard must hold whole baseline groups")
-        self.x = x.contiguous()
-        self.uv = uv.contiguous()
+        same_shape = N == self.N and getattr(self, "C", None) == C
+        if self._graphs_on and same_shape:
+            # the captured graphs read the static buffers: copy instead of re-binding
+            if x.data_ptr() != self.x.data_ptr():
+                self.x.copy_(x.view_as(self.x), non_blocking=True)
+            if uv.data_ptr() != self.uv.data_ptr():
+                self.uv.copy_(uv.view_as(self.uv), non_blocking=True)
+        else:
+            self.x = x.contiguous()
+            self.uv = uv.contiguous()
+        if self._graphs_on and (not same_shape or batch_per_bline != self.bpb):
+            self._graphs = {}
         self.bpb = batch_per_bline
-        self.Nglobal = int(global_patches) if global_patches is not None else N * self.world
-        if N != self.N or getattr(self, "C", None) != C:
+        Ng = int(global_patches) if global_patches is not None else N * self.world
+        if self._graphs_on and getattr(self, "Nglobal", Ng) != Ng:
+            self._graphs = {}
+        self.Nglobal = Ng
+        if not same_shape:
             dev, f = self.device, dict(device=self.device, dtype=torch.float32)
             self.N, self.C = N, C
             e = self.net.engine(), self.netT.engine(), self.netF.engine()
@@ -246,16 +287,59 @@ class DeepKHarmonicStep:
             n = N * C * 16384
             self.iyT, self.iyF = torch.empty(n, **f), torch.empty(n, **f)
             self.g1p, self.g2, self.g3f, self.gx1 = (torch.empty(n, **f) for _ in range(4))
-            self.y1, self.y2, self.y3 = (torch.empty(n, **f) for _ in range(3))
+            self._y = [torch.empty(n, **f) for _ in range(3)]
             self.Mu = torch.empty(N, self.Ltot, **f)
             self.gMu = torch.empty(N, self.Ltot, **f)
             self.terms = torch.zeros(16, dtype=torch.float64, device=dev)
             K = self.mod.K
             self.simwork = torch.empty(2 * K * K, **f)
             self.scales = self.net.harmonic_scales.to(dev).float().contiguous()
-        self.y1.zero_(); self.y2.zero_(); self.y3.zero_()
+        self.invalidate()
+        self.reset_multipliers()
 
-    # ------------------------------------------------------------------ forward pieces
+    def reset_multipliers(self):
+        """y1 = y2 = y3 = 0 (a new minibatch); a deferred update of the previous minibatch is dropped, as the
+        reference drops the multipliers themselves (src/kharmonic_lofar.py:128-130)."""
+        for y in self._y:
+            y.zero_()
+        self._pending = False
+        self._loss_key = None
+
+    def invalidate(self):
+        """The minibatch or the parameters were changed behind the step's back: recompute everything."""
+        self._batch_id += 1
+        self._fwd_key = None
+        self._loss_key = None
+
+    # multipliers: reading them applies a deferred update first, so they always hold the reference's values
+    @property
+    def y1(self) -> torch.Tensor:
+        self.flush_multipliers()
+        self._loss_key = None        # the caller may write into the returned tensor
+        return self._y[0]
+
+    @property
+    def y2(self) -> torch.Tensor:
+        self.flush_multipliers()
+        self._loss_key = None        # the caller may write into the returned tensor
+        return self._y[1]
+
+    @property
+    def y3(self) -> torch.Tensor:
+        self.flush_multipliers()
+        self._loss_key = None        # the caller may write into the returned tensor
+        return self._y[2]
+
+    # ------------------------------------------------------------------ launch sequences
+    def _state_key(self):
+        return (self.flat.version, self._batch_id)
+
+    def _forward_is_current(self) -> bool:
+        return self.reuse and self.flat.tracked and self._fwd_key == self._state_key()
+
+    def _outputs(self):
+        return self.ws[0].xhat, self.ws[1].xhat, self.ws[2].xhat
+
     def _forward(self, st):
         L, Lt, N, C = self.L, self.Lt, self.N, self.C
         e = self.net.engine(), self.netT.engine(), self.netF.engine()
@@ -299,32 +383,31 @@ class DeepKHarmonicStep:
         ev.record(side)
         torch.cuda.current_stream(self.device).wait_event(ev)
 
-    def closure(self) -> torch.Tensor:
-        """src/kharmonic_lofar.py:132-182.  Returns the total loss (0-dim device tensor)."""
+    def _seq_closure(self, grads: bool, forward: bool, upd: bool):
+        """The launch sequence of one closure evaluation (no host decisions inside: it can be captured)."""
         lb, st = lib(), _stream()
-        grads = torch.is_grad_enabled()
-        start = lb.launches
         N, C, L, Lt, Ltot, K = self.N, self.C, self.L, self.Lt, self.Ltot, self.mod.K
         M = self.mod.M
         plan = ShardPlan(N, self.Nglobal, self.world, self.bpb, C, K, Ltot)
         numel_g = plan.numel_global
         self.terms.zero_()
         tp = self.terms.data_ptr()
-        x1, x2, x3f = self._forward(st)
+        if forward:
+            self._forward(st)
+        x1, x2, x3f = self._outputs()
         g1p, g2, g3f = (self.g1p.data_ptr(), self.g2.data_ptr(), self.g3f.data_ptr()) if grads else (None, None, None)
         # the bias gradients of the three last transposed convs (= channel sums of the reconstruction
         # gradients) come out of the kernels that write those gradients
         fuse_db = grads and C <= 64
-        if grads:
-            self.flat.attach_grads()
         db2, db3 = ((self._gd[1]["tconv5.bias"].data_ptr(), self._gd[2]["tconv5.bias"].data_ptr()) if fuse_db
                     else (None, None))
         # the latent-space terms (a dozen small, latency-bound launches) run beside the HBM-bound cascade
         # losses: forked here, joined before the backward passes
         lside = self._fork()
-        lb.cascade_losses(self.x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(),
-                          self.y1.data_ptr(), self.y2.data_ptr(), self.y3.data_ptr(), self.rho,
-                          N, C, 128, 1.0 / numel_g, tp, g1p, g2, g3f, db2, db3, st)
+        y = self._y
+        lb.cascade_losses_upd(self.x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(),
+                              y[0].data_ptr(), y[1].data_ptr(), y[2].data_ptr(), self.rho, 1 if upd else 0,
+                              N, C, 128, 1.0 / numel_g, tp, g1p, g2, g3f, db2, db3, st)
         khm_scale = plan.khm_scale(self.alpha)
         p = float(self.mod.p)
         aug_scale = plan.aug_scale(self.gamma)
@@ -337,6 +420,11 @@ class DeepKHarmonicStep:
                 self._gM.zero_()
                 lb.khm_fwd_bwd(Mu.data_ptr(), Ltot, M.data_ptr(), N, K, Ltot, p, khm_scale, tp + 8 * 8,
                                gMu.data_ptr(), Ltot, 0, self._gM.data_ptr(), sl)
+                if self.centre_sums:
+                    ex = self.flat.extra_tail
+                    ex.zero_()
+                    lb.khm_center_sums(Mu.data_ptr(), Ltot, M.data_ptr(), N, K, Ltot, p, ex.data_ptr(),
+                                       ex.data_ptr() + 4 * K * Ltot, sl)
             else:
                 lb.khm_fwd(Mu.data_ptr(), Ltot, M.data_ptr(), N, K, Ltot, p, tp + 8 * 8, None, sl)
             lb.similarity(M.data_ptr(), K, Ltot, sim_scale, tp + 9 * 8, self._gM.data_ptr() if grads else None,
@@ -361,14 +449,82 @@ class DeepKHarmonicStep:
                                self._gd[0]["tconv5.bias"].data_ptr() if fuse_db else None, st)
             e[0].backward(self.x.view(N, -1), self._pd[0], self._gd[0], self.ws[0], st, self.gx1.view(N, -1),
                           gMu[:, :L], Mu[:, :L], False, self._wstream(0), fuse_db)
+        lb.closure_total(tp, self.rho, numel_g, khm_scale, self.flat.loss_tail.data_ptr(), st)
+
+    def _seq_forward(self):
+        self._forward(_stream())
+
+    def _seq_flush(self):
+        x1, x2, x3f = self._outputs()
+        y = self._y
+        lib().multiplier_update(self.x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(), self.rho,
+                                y[0].data_ptr(), y[1].data_ptr(), y[2].data_ptr(), self.N, self.C, 128, _stream())
+
+    # ------------------------------------------------------------------ CUDA graphs
+    def enable_graphs(self, on: bool = True):
+        """Replay every launch sequence (closure variants, forward, multiplier update) from a CUDA graph.
+        A sequence is launched kernel by kernel the first time it is needed and captured right after
+        (capturing executes nothing), so no state has to be saved and restored.  The minibatch then lives
+        in the static tensors `x` / `uv` given to the first `set_batch` (later calls copy into them)."""
+        if self.N == 0 and on:
+            raise RuntimeError("lshm_b200: call step.set_batch(...) before enabling graphs")
+        self._graphs_on = bool(on)
+        if not on:
+            self._graphs = {}
+
+    def _run(self, key, fn):
+        lb = lib()
+        if not self._graphs_on:
+            fn()
+            return
+        hit = self._graphs.get(key)
+        if hit is not None:
+            hit[0].replay()
+            lb.launches += hit[1]
+            return
+        fn()                                    # this call's real execution (also warms up lazy state)
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(cur)
+        g = torch.cuda.CUDAGraph()
+        l0 = lb.launches
+        # (thread-local capture mode: the NCCL watchdog thread polls events while we capture.)
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                fn()
+        n = lb.launches - l0
+        lb.launches = l0                        # the capture launched nothing
+        cur.wait_stream(side)
+        self._graphs[key] = (g, n)
+
+    # ------------------------------------------------------------------ public: closure
+    def closure(self) -> torch.Tensor:
+        """src/kharmonic_lofar.py:132-182.  Returns the total loss (0-dim device tensor)."""
+        lb = lib()
+        grads = torch.is_grad_enabled()
+        start = lb.launches
         tail = self.flat.loss_tail
-        lb.closure_total(tp, self.rho, numel_g, khm_scale, tail.data_ptr(), st)
-        if self.distributed and not self._defer_exchange:
-            # ONE exchange per closure evaluation: gradients + loss scalars (forward-only: scalars)
-            buf = self.flat.grad if grads else tail
-            exchange(buf, self.group)
+        tracked = self.reuse and self.flat.tracked
+        # nothing changed since these loss scalars were computed (LBFGSNew's f_old probe): no launch at all
+        if tracked and not grads and not self._pending and self._loss_key == self._state_key():
+            self.launches = 0
+            return tail[0].clone()
+        fresh = self._forward_is_current()
+        if self._pending and not fresh:
+            self.flush_multipliers()            # the deferred update belongs to the activations still held
+        upd = self._pending
+        if grads:
+            self.flat.attach_grads()
+        self._run(("closure", grads, not fresh, upd), lambda: self._seq_closure(grads, not fresh, upd))
+        self._pending = False
+        if tracked:
+            self._fwd_key = self._state_key()
+            self._loss_key = self._state_key()
+        if self.distributed:
+            # ONE exchange per closure evaluation: gradients + loss scalars (+ centre sums); forward-only: scalars
+            exchange(self.flat.grad if grads else tail, self.group)
         self.launches = lb.launches - start
-        return tail[0]
+        return tail[0].clone()
 
     def loss_terms(self) -> dict:
         """The columns printed at src/kharmonic_lofar.py:179 (one device->host copy)."""
@@ -377,14 +533,48 @@ class DeepKHarmonicStep:
         d.update(zip(TERM_NAMES, v[1:]))
         return d
 
+    # ------------------------------------------------------------------ public: multipliers
     def update_multipliers(self):
-        """src/kharmonic_lofar.py:187-202: no-grad forward of the cascade, then y_i += rho*r_i."""
-        st = _stream()
+        """src/kharmonic_lofar.py:187-202: no-grad forward of the cascade, then y_i += rho*r_i.
+        With a tracking optimiser the update itself is deferred into the next loss pass (class docstring)."""
         with torch.no_grad():
-            x1, x2, x3f = self._forward(st)
-            lib().multiplier_update(self.x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(), self.rho,
-                                    self.y1.data_ptr(), self.y2.data_ptr(), self.y3.data_ptr(),
-                                    self.N, self.C, 128, st)
+            if self._pending:
+                self.flush_multipliers()
+            if not self._forward_is_current():
+                self._run(("forward",), self._seq_forward)
+                if self.reuse and self.flat.tracked:
+                    self._fwd_key = self._state_key()
+            self._pending = True
+            self._loss_key = None
+            if not (self.reuse and self.flat.tracked):
+                self.flush_multipliers()
+
+    def flush_multipliers(self):
+        """Apply a deferred multiplier update now (stand-alone pass over x, x1, x2, x3, y1..y3)."""
+        if self._pending:
+            self._pending = False
+            self._loss_key = None
+            with torch.no_grad():
+                self._run(("flush",), self._seq_flush)
+
+    # ------------------------------------------------------------------ public: centre update
+    def centre_sums_view(self):
+        """(num [K,Ltot], den [K]) views of the exchange buffer (valid after a gradient closure; already
+        summed over ranks under data parallelism)."""
+        if not self.centre_sums:
+            raise RuntimeError("lshm_b200: construct the step with centre_sums=True")
+        K, Lt = self.mod.K, self.Ltot
+        ex = self.flat.extra_tail
+        return ex[:K * Lt].view(K, Lt), ex[K * Lt:K * Lt + K]
+
+    def apply_centre_update(self):
+        """Kmeans.offline_update (src/lofar_models.py:231-261, Zhang GKHM 7.1-7.5) from the sums the last
+        gradient closure left in the exchange buffer: M_k = num_k / den_k."""
+        num, den = self.centre_sums_view()
+        lib().khm_center_apply(num.data_ptr(), den.data_ptr(), self.mod.M.data_ptr(), self.mod.K, self.Ltot, _stream())
+        self.flat.bump()
+        self._fwd_key = None      # centres do not enter the activations, but keep the bookkeeping simple
+        self._loss_key = None
 
     def latents(self) -> torch.Tensor:
         return self.Mu

@@ -77,10 +77,15 @@ def _to_device_i8(arr: np.ndarray, dev) -> torch.Tensor:
 
 def patchify_device(vis: torch.Tensor, scale: torch.Tensor, sel: torch.Tensor, patch_size: int,
                     num_channels: int, clamp: float, normalize: bool, out: torch.Tensor = None,
-                    stats: torch.Tensor = None):
+                    stats: torch.Tensor = None, group=None, n_global: int = None):
     """vis int8 [nbase,T,F,4,2], scale fp32 [nbase,F,4], sel int32 [nb] (all on device) ->
     (patchx, patchy, y [nb*px*py, C, P, P]).  `out` / `stats` (fp64 [2]): optional preallocated
-    destination and scratch, so a staging loop allocates nothing."""
+    destination and scratch, so a staging loop allocates nothing.
+
+    `group` + `n_global`: the minibatch is sharded over the ranks of a torch.distributed group; the z-score
+    (src/lofar_tools.py:190-193: mean / unbiased std over the WHOLE minibatch) then uses the all-reduced
+    (sum, sum of squares) of all `n_global` elements.  Without a group every rank normalises its own shard
+    with its own statistics (N independent reference loaders)."""
     nbase, T, F = vis.shape[:3]
     nb, P = sel.numel(), patch_size
     s = P // 2
@@ -101,7 +106,12 @@ def patchify_device(vis: torch.Tensor, scale: torch.Tensor, sel: torch.Tensor, p
     lib().patchify_scale_i8(vis.data_ptr(), scale.data_ptr(), sel.data_ptr(), nb, T, F, num_channels, P,
                             float(clamp), y.data_ptr(), stats.data_ptr(), st)
     if normalize:
-        lib().normalise(y.data_ptr(), y.numel(), stats.data_ptr(), st)
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+            lib().normalise_n(y.data_ptr(), y.numel(), stats.data_ptr(), int(n_global), st)
+        else:
+            lib().normalise(y.data_ptr(), y.numel(), stats.data_ptr(), st)
     return px, py, y
 
 

@@ -277,6 +277,13 @@ def test_inference_loop(cuda):
         assert rel_err(node_data[g], blk.mean(0)) < ACT_TOL
         ref_label = torch.stack([torch.linalg.norm(blk - case["M"][k], dim=1).mean() for k in range(case["K"])])
         assert rel_err(node_label[g], ref_label) < 1e-4
+    # station-graph labels (src/train_graph_stat.py:205-210): softmax(-dist/dist.mean()) of ||Mu_n - M_k||^p per patch
+    from lshm_b200.evaluate_clustering import graph_stat_features
+    attr, label = graph_stat_features(net, netT, netF, mod, x, uv)
+    assert rel_err(attr, Mu_ref) < ACT_TOL
+    for n in range(case["N"]):
+        d = torch.stack([torch.sum(torch.pow(torch.linalg.norm(Mu_ref[n, :] - case["M"][k, :], 2), 4)) for k in range(case["K"])])
+        assert max_abs(label[n], torch.softmax(-d / d.mean(), 0)) < 2e-5
 
 
 def test_closure_matches_golden_from_live_reference(cuda):
@@ -324,8 +331,8 @@ def test_graphed_step_matches_eager_steps(cuda):
     before = step_g.flat.flat.clone()
     gs = GraphedStep(step_g, opt_g)
     assert torch.equal(step_g.flat.flat, before) and opt_g.t == 0 and float(step_g.y1.abs().max()) == 0.0
-    assert gs.launches_per_replay > 100
     graphed = [float(gs.replay()) for _ in range(4)]
+    assert gs.launches_per_replay > 100 and len(step_g._graphs) >= 2
     assert opt_g.t == 4
     assert np.allclose(graphed, eager, rtol=2e-4), (graphed, eager)
     assert rel_err(step_g.flat.flat, step_e.flat.flat) < 2e-4
@@ -337,5 +344,11 @@ def test_graphed_step_matches_eager_steps(cuda):
     le = float(opt_e.step(step_e.closure))
     lg = float(gs.replay())
     assert abs(lg - le) <= 2e-4 * abs(le)
-    with pytest.raises(RuntimeError):
-        GraphedStep(step_g, torch.optim.Adam(step_g.flat.params))
+    # the graphs belong to the closure: any optimiser can drive them (torch.optim.Adam does not track its
+    # updates, so nothing is reused: every closure replays the full forward + backward graph)
+    step_t, _ = fresh()
+    step_t.flat.tracked = False
+    topt = torch.optim.Adam(step_t.flat.params, lr=1e-3)
+    gt = GraphedStep(step_t, topt)
+    torch_losses = [float(gt.replay()) for _ in range(4)]
+    assert np.allclose(torch_losses, eager, rtol=2e-4), (torch_losses, eager)

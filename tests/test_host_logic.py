@@ -77,7 +77,12 @@ def test_fastdiv_constants_match_integer_division():
     the library: divisors that occur ((h+1)(w+1), w+1, w, tiles per row, slots) and random ones, dividends up to
     the 2^31 limit the launchers enforce."""
     import ctypes
-    from lshm_b200._lib import lib
+    from lshm_b200 import _lib
+    # self-test hook declared in include/lshm_selftest.h (not part of the product ABI, include/lshm.h)
+    check = ctypes.CDLL(_lib.LIBRARY).lshm_fastdiv_check
+    check.argtypes = [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    check.restype = ctypes.c_int
+    assert "lshm_fastdiv_check" not in _lib.parse_header()
     rng = np.random.default_rng(7)
     divisors = [1, 2, 3, 4, 5, 7, 9, 17, 33, 65, 129, 200, 328, 25, 81, 289, 1089, 4225, 16641, 4096, 16384,
                 (1 << 31) - 1] + [int(v) for v in rng.integers(1, 1 << 20, 200)]
@@ -87,5 +92,5 @@ def test_fastdiv_constants_match_integer_division():
                             (np.arange(1, 50, dtype=np.int64) * d - 1), np.arange(1, 50, dtype=np.int64) * d])
         n = np.ascontiguousarray(n[(n >= 0) & (n < (1 << 31))])
         bad = ctypes.c_int64(-1)
-        lib().fastdiv_check(d, n.ctypes.data, len(n), ctypes.addressof(bad))
+        assert check(d, n.ctypes.data, len(n), ctypes.addressof(bad)) == 0
         assert bad.value == 0, (d, bad.value)
