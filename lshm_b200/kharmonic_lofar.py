@@ -18,6 +18,7 @@ identical on every rank.
 """
 from __future__ import annotations
 
+import contextlib
 from typing import List, Optional, Tuple
 
 import torch
@@ -44,11 +45,11 @@ class FlatParams:
     `extra_tail` floats follow the 16 loss scalars in the gradient buffer (the K x L centre numerator and
     K denominator sums of Kmeans.offline_update ride in the same all-reduce).
 
-    `version` / `tracked`: an optimiser that owns every parameter update (FlatAdam, lbfgsnew.LBFGSNew on
-    a FlatParams) sets `tracked` and calls `bump()` after each change; the step then knows when the
-    activations it already holds belong to the current parameters and reuses them.  Untracked
-    parameters (torch.optim.*, the unmodified reference LBFGSNew with its `p.data.add_`) are never
-    assumed unchanged."""
+    `version` / `tracked` / `owning()`: an optimiser that owns every parameter update (FlatAdam,
+    lbfgsnew.LBFGSNew on a FlatParams) sets `tracked`, calls `bump()` after each change and evaluates its
+    closures inside `with flat.owning():`; the step then knows when the activations it already holds belong
+    to the current parameters and reuses them.  A closure called from anywhere else (a hand-written client,
+    torch.optim.*, the unmodified reference LBFGSNew with its `p.data.add_`) is always computed in full."""
 
     ALIGN = 64  # floats: every tensor starts 256-byte aligned
 
@@ -81,6 +82,20 @@ class FlatParams:
         self.extra_tail = self.grad[off + LOSS_TAIL:]
         self.version = 0
         self.tracked = False
+        self._owner_depth = 0
+
+    @property
+    def in_owner_step(self) -> bool:
+        return self._owner_depth > 0
+
+    @contextlib.contextmanager
+    def owning(self):
+        """Entered by the tracking optimiser around the closure calls of its step()."""
+        self._owner_depth += 1
+        try:
+            yield self
+        finally:
+            self._owner_depth -= 1
 
     def bump(self):
         """The parameters changed (called by the optimiser that owns the updates)."""
@@ -130,7 +145,7 @@ class FlatAdam:
         pass  # the fused closure overwrites every gradient
 
     def step(self, closure):
-        with torch.enable_grad():
+        with torch.enable_grad(), self.flat.owning():
             loss = closure()
         self.apply()
         return loss
@@ -334,6 +349,10 @@ class DeepKHarmonicStep:
     def _state_key(self):
         return (self.flat.version, self._batch_id)
 
+    def _trusted(self) -> bool:
+        """The caller is the optimiser that tracks every parameter change (see FlatParams)."""
+        return self.reuse and self.flat.tracked and self.flat.in_owner_step
+
     def _forward_is_current(self) -> bool:
         return self.reuse and self.flat.tracked and self._fwd_key == self._state_key()
 
@@ -504,12 +523,12 @@ class DeepKHarmonicStep:
         grads = torch.is_grad_enabled()
         start = lb.launches
         tail = self.flat.loss_tail
-        tracked = self.reuse and self.flat.tracked
+        tracked = self._trusted()
         # nothing changed since these loss scalars were computed (LBFGSNew's f_old probe): no launch at all
         if tracked and not grads and not self._pending and self._loss_key == self._state_key():
             self.launches = 0
             return tail[0].clone()
-        fresh = self._forward_is_current()
+        fresh = tracked and self._forward_is_current()
         if self._pending and not fresh:
             self.flush_multipliers()            # the deferred update belongs to the activations still held
         upd = self._pending
@@ -517,9 +536,8 @@ class DeepKHarmonicStep:
             self.flat.attach_grads()
         self._run(("closure", grads, not fresh, upd), lambda: self._seq_closure(grads, not fresh, upd))
         self._pending = False
-        if tracked:
-            self._fwd_key = self._state_key()
-            self._loss_key = self._state_key()
+        self._fwd_key = self._state_key() if tracked else None
+        self._loss_key = self._state_key() if tracked else None
         if self.distributed:
             # ONE exchange per closure evaluation: gradients + loss scalars (+ centre sums); forward-only: scalars
             exchange(self.flat.grad if grads else tail, self.group)
