@@ -86,7 +86,7 @@ def test_reference_lbfgsnew_and_flat_lbfgsnew_follow_the_cpu_reference(cuda, N, 
     for got in (l_ref, l_new):
         assert np.allclose(got, l_cpu, rtol=5e-3), (got, l_cpu)
     assert abs(f_ref - f_cpu) <= 2e-2 * abs(f_cpu) and abs(f_new - f_cpu) <= 2e-2 * abs(f_cpu)
-    assert f_new < l_new[0] and f_ref < l_ref[0]
+    # (the total loss GROWS over the ADMM iterations of one minibatch - the multipliers y_i grow - exactly as on the CPU)
     # same line-search decisions as the CPU reference in the first step (later steps may flip on last-bit ties)
     assert c_ref[0] == c_cpu[0] and c_new[0] == c_cpu[0], (c_ref, c_new, c_cpu)
     # parameters after the run: both GPU runs stay close to the CPU reference

@@ -284,7 +284,7 @@ def test_reused_forward_and_deferred_multipliers_match_the_plain_loop(cuda, N, g
     # a closure called from outside the owner's step is always computed in full
     with torch.no_grad():
         n0 = lib().launches
-        assert abs(float(fused.closure()) - l_a) <= 1e-6 * abs(l_a) and lib().launches - n0 > 100
+        assert abs(float(fused.closure()) - l_a) <= 1e-6 * abs(l_a) and lib().launches - n0 > 50
 
 
 def test_adam_on_a_parameter_subset(cuda):
