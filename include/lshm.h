@@ -129,6 +129,33 @@ LSHM_API int lshm_up1d(const float* small_, int64_t small_ns, const void* wimg, 
               int64_t N, int A, int Bc, int l, int pad, int epilogue, lshm_stream_t stream);
 LSHM_API int lshm_wgrad1d(const float* small_, int64_t small_ns, const float* big, int64_t big_ns,
                  float* dw, int64_t N, int A, int Bc, int l, int pad, lshm_stream_t stream);
+/* ---- operand planes -----------------------------------------------------------------------------
+ * An input-sized tensor ("big" map B of the geometry above) stored the way the tensor-core kernels consume
+ * it: the space-to-depth operand Z[q, c = 4*b + sub] (2-D: q over the (h+1) x (w+1) grid of 2x2 pixel blocks
+ * at rows 2by-1, 2by / columns 2bx-1, 2bx incl. the zero halo, sub = 2*sy + sx; 1-D: q = window j,
+ * sub = t, sample 4j - pad + t) split into bf16 hi = bf16(v), lo = bf16(v - hi):
+ *     planes = [half hi|lo][chunk c/8][position q][8 x bf16]          (lshm_planes_bytes bytes)
+ * lshm_down*_planes / lshm_wgrad*_planes fetch their tiles from it with tensor-TMA box loads
+ * (cp.async.bulk.tensor.3d) instead of gathering + converting fp32 in producer warps.  Supported for the
+ * first layers (A <= 16 output channels, Bc = 8 / Bc <= 16 input channels), whose inputs are what the
+ * loader / the loss kernels produce. */
+LSHM_API int lshm_planes_bytes(int dim, int64_t N, int Bc, int h, int w_or_l, int64_t* bytes);
+/* planes <- fp32 big map [N,Bc,2h,2w] (sample stride big_ns) / [N,Bc,4l] with the 1-D padding baked in. */
+LSHM_API int lshm_stage_planes2d(const float* big, int64_t big_ns, void* planes, int64_t N, int Bc, int h, int w_,
+                        lshm_stream_t stream);
+LSHM_API int lshm_stage_planes1d(const float* big, int64_t big_ns, void* planes, int64_t N, int Bc, int l, int pad,
+                        lshm_stream_t stream);
+/* lshm_down2d / lshm_down1d / lshm_wgrad2d / lshm_wgrad1d with the big map given as planes. */
+LSHM_API int lshm_down2d_planes(const void* planes, const void* wimg, const float* bias,
+                       const float* aux, int64_t aux_ns, float* small_, int64_t small_ns,
+                       int64_t N, int A, int Bc, int h, int w_, int epilogue, lshm_stream_t stream);
+LSHM_API int lshm_down1d_planes(const void* planes, const void* wimg, const float* bias,
+                       const float* aux, int64_t aux_ns, float* small_, int64_t small_ns,
+                       int64_t N, int A, int Bc, int l, int epilogue, lshm_stream_t stream);
+LSHM_API int lshm_wgrad2d_planes(const float* small_, int64_t small_ns, const void* planes,
+                        float* dw, int64_t N, int A, int Bc, int h, int w_, lshm_stream_t stream);
+LSHM_API int lshm_wgrad1d_planes(const float* small_, int64_t small_ns, const void* planes,
+                        float* dw, int64_t N, int A, int Bc, int l, lshm_stream_t stream);
 /* db[c] = sum over n and positions of g[n,c,:]  (bias gradients). g [N,Cn,len]. */
 LSHM_API int lshm_channel_sum(const float* g, int64_t g_ns, float* db, int64_t N, int Cn, int64_t len,
                      lshm_stream_t stream);
@@ -155,6 +182,10 @@ LSHM_API int lshm_delu(const float* g, int64_t ldg, const float* aux, int64_t ld
  * iyT[n,c,t*P+f] and iyF[n,c,f*P+t]. */
 LSHM_API int lshm_residual_split(const float* x, const float* x1, float* iyT, float* iyF,
                         int64_t N, int C, int P, lshm_stream_t stream);
+/* lshm_residual_split writing the two 1-D inputs as pad-1 operand planes (Conv1d(k4,s4,p1): window j covers
+ * samples [4j-1, 4j+2] of the flattened map) instead of fp32 tensors. */
+LSHM_API int lshm_residual_split_planes(const float* x, const float* x1, void* planesT, void* planesF,
+                               int64_t N, int C, int P, lshm_stream_t stream);
 /* src/kharmonic_lofar.py:150-158.  x,x1 [N,C,P,P]; x2 = netT output viewed [N,C,P,P];
  * x3f = netF output (still transposed: x3[n,c,t,f] = x3f[n,c,f,t]); y1..y3 multipliers
  * in x's flat order.  sums (double[8], caller-zeroed) += { |x1+x2+x3-x|^2, <y1,x-x1>,
@@ -183,6 +214,9 @@ LSHM_API int lshm_cascade_losses_upd(const float* x, const float* x1, const floa
  * transposed conv. */
 LSHM_API int lshm_cascade_combine(const float* g1p, const float* gT, const float* gF, float* gx1,
                          int64_t N, int C, int P, float* db1, lshm_stream_t stream);
+/* lshm_cascade_combine writing gx1 as the 2-D operand planes of the 2-D net's last transposed conv. */
+LSHM_API int lshm_cascade_combine_planes(const float* g1p, const float* gT, const float* gF, void* planes,
+                                int64_t N, int C, int P, float* db1, lshm_stream_t stream);
 /* src/kharmonic_lofar.py:200-202: y_i += rho * r_i. */
 LSHM_API int lshm_multiplier_update(const float* x, const float* x1, const float* x2, const float* x3f,
                            float rho, float* y1, float* y2, float* y3,

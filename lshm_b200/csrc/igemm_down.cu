@@ -14,6 +14,7 @@
 // ELU' fused in the epilogue which writes NCHW / NCL directly.
 #include <stdlib.h>
 #include "conv_geom.cuh"
+#include "tma.cuh"
 
 namespace lshm {
 namespace {
@@ -21,6 +22,9 @@ namespace {
 using namespace tc;
 
 struct DownArgs {
+  // operand planes (tma.cuh): tensor maps over the hi / lo halves; used by the PRE instances only
+  alignas(64) CUtensorMap tm_hi;
+  alignas(64) CUtensorMap tm_lo;
   const float* big; int64_t big_ns;
   const uint8_t* wimg;
   const float* bias;
@@ -81,8 +85,10 @@ __device__ __forceinline__ void down_epilogue_tile(const DownArgs& a, uint32_t t
 // the groups fill alternate stages, so two gather -> convert -> hand-off chains are in flight per CTA; those
 // layers are bound by the latency of that chain (2-3.5 us per K block, one or two tiles per CTA), not by
 // bandwidth or issue slots.
-template <int DIM, int NT, int KC, int G>
-__global__ void __launch_bounds__(down_threads(G), (G == 1 ? 3 : 2)) igemm_down_kernel(DownArgs a) {
+// PRE: the input arrives as operand planes (already space-to-depth, already split into bf16 hi / lo): the producer
+// warps are replaced by ONE thread that issues two tensor-TMA box loads per stage (cp.async.bulk.tensor.3d).
+template <int DIM, int NT, int KC, int G, bool PRE>
+__global__ void __launch_bounds__(down_threads(G), (G == 1 ? 3 : 2)) igemm_down_kernel(const __grid_constant__ DownArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[MAXST], empty_bar[MAXST], acc_full[2], acc_empty[2], w_bar;
   __shared__ uint32_t tmem_base;
@@ -106,7 +112,9 @@ __global__ void __launch_bounds__(down_threads(G), (G == 1 ? 3 : 2)) igemm_down_
 
   if (warp == 8) tmem_alloc(&tmem_base, TMEM_COLS);
   if (tid == 0) {
-    for (int s = 0; s < MAXST; ++s) { mbar_init(&full_bar[s], wres ? 4 : 5); mbar_init(&empty_bar[s], 1); }
+    // arrivals per stage: the four producer warps (or the one TMA-issuing thread) + the weight loader unless resident
+    const uint32_t nprod = PRE ? 1u : 4u;
+    for (int s = 0; s < MAXST; ++s) { mbar_init(&full_bar[s], wres ? nprod : nprod + 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
     mbar_init(&w_bar, 1);
     mbar_init_fence();
@@ -116,7 +124,25 @@ __global__ void __launch_bounds__(down_threads(G), (G == 1 ? 3 : 2)) igemm_down_
   fence_after();
   const uint32_t tmem = tmem_base;
 
-  if ((warp >= 4 && warp < 8) || warp >= 10) {
+  if (PRE && ((warp >= 4 && warp < 8) || warp >= 10)) {
+    // ------------------------------------------------ producer = the copy engine: one box per half and stage
+    if (warp == 4 && lane == 0) {
+      tma_prefetch_desc(&a.tm_hi);
+      tma_prefetch_desc(&a.tm_lo);
+      Ring ring{0, 0};
+      for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+        const int q0 = (int)(fdiv((uint32_t)item, a.d_ntn) * 128u);
+        for (int kb = 0; kb < KB; ++kb, ring.next(NS)) {
+          const int s = ring.s;
+          uint8_t* zhi = smem + (size_t)s * stage_bytes;
+          mbar_wait(&empty_bar[s], ring.ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], 2 * zbytes);
+          tma_load_3d(zhi, &a.tm_hi, 0, q0, kb * CC, &full_bar[s]);
+          tma_load_3d(zhi + zbytes, &a.tm_lo, 0, q0, kb * CC, &full_bar[s]);
+        }
+      }
+    }
+  } else if ((warp >= 4 && warp < 8) || warp >= 10) {
     // ------------------------------------------------ producers: stage the Z tile (hi/lo bf16)
     const int grp = warp >= 10 ? 1 : 0;                 // producer group
     const int ptid = (tid & 127);                       // 0..127 within the group (warps 4-7 / 10-13... tid-128, tid-320)
@@ -320,7 +346,7 @@ __global__ void __launch_bounds__(down_threads(G), (G == 1 ? 3 : 2)) igemm_down_
   if (warp == 8) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-template <int DIM, int NT, int KC, int G>
+template <int DIM, int NT, int KC, int G, bool PRE = false>
 int launch_down_t(DownArgs a, const DownGeom& g, cudaStream_t st) {
   const size_t stage = (size_t)2 * (KC / 8) * a.slots * 16 + g.img;
   const int64_t units = a.mtiles * g.ntiles * g.KB;
@@ -334,15 +360,21 @@ int launch_down_t(DownArgs a, const DownGeom& g, cudaStream_t st) {
   LSHM_REQUIRE(ns >= 1, "igemm_down: tile does not fit in shared memory");
   a.nstage = (int)std::min<int64_t>(ns, std::max<int64_t>(1, units));
   const size_t smem = stage * a.nstage + g.img;   // + resident weight image (used when KB == ntiles == 1)
-  LSHM_CUDA(cudaFuncSetAttribute(igemm_down_kernel<DIM, NT, KC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_down");
+  if (PRE) {
+    const PlaneGeom pg = plane_geom(DIM, a.N, a.Bc, a.h, a.w);
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(a.big);
+    if (int rc = make_plane_tmap(&a.tm_hi, base, pg.Q, pg.chunks, a.slots, KC / 8)) return rc;
+    if (int rc = make_plane_tmap(&a.tm_lo, base + pg.half_bytes, pg.Q, pg.chunks, a.slots, KC / 8)) return rc;
+  }
+  LSHM_CUDA(cudaFuncSetAttribute(igemm_down_kernel<DIM, NT, KC, G, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_down");
   const int per_sm = std::min(G == 1 ? 3 : 2, smem <= 74 * 1024 ? 3 : (smem <= 112 * 1024 ? 2 : 1));
   const int64_t grid = std::min<int64_t>(a.mtiles * g.ntiles, (int64_t)sm_count() * per_sm);
-  igemm_down_kernel<DIM, NT, KC, G><<<(unsigned)grid, down_threads(G), smem, st>>>(a);
+  igemm_down_kernel<DIM, NT, KC, G, PRE><<<(unsigned)grid, down_threads(G), smem, st>>>(a);
   LSHM_CHECK_LAUNCH("igemm_down");
   return LSHM_OK;
 }
 
-int launch_down(int dim, DownArgs a, cudaStream_t st) {
+int launch_down(int dim, DownArgs a, cudaStream_t st, bool planes = false) {
   const DownGeom g = down_geom(dim, a.A, a.Bc);
   a.slots = dim == 2 ? (128 + a.w + 2 + 7) / 8 * 8 : 128;
   a.Q = dim == 2 ? a.N * (int64_t)(a.h + 1) * (a.w + 1) : a.N * (int64_t)a.w;
@@ -355,6 +387,12 @@ int launch_down(int dim, DownArgs a, cudaStream_t st) {
   a.wres_on = wres_off ? 0 : 1;
   static const bool one_group = getenv("LSHM_DOWN_G1") != nullptr;       // experiment switch
   const bool two = g.KB >= 2 && !one_group;                              // two producer groups (see the kernel)
+  if (planes) {
+    // operand planes exist for the input-sized tensors only: the 8- and 12-channel first layers (NT = 16)
+    LSHM_REQUIRE(g.NT == 16 && a.Bc <= 16, "lshm_down*_planes: operand planes serve layers with <= 16 output and <= 16 input channels");
+    if (dim == 2) return launch_down_t<2, 16, 32, 1, true>(a, g, st);
+    return launch_down_t<1, 16, 32, 1, true>(a, g, st);
+  }
 #define LD(D, NTV, KCV) do { if (two) return launch_down_t<D, NTV, KCV, 2>(a, g, st); return launch_down_t<D, NTV, KCV, 1>(a, g, st); } while (0)
   if (dim == 2) {
     switch (g.NT) {
@@ -416,6 +454,41 @@ int lshm_down1d(const float* big, int64_t big_ns, const void* wimg, const float*
   a.aux = epilogue == LSHM_EPI_DELU ? aux : nullptr; a.aux_ns = aux_ns;
   a.small_ = small_; a.small_ns = small_ns; a.N = N; a.A = A; a.Bc = Bc; a.h = 1; a.w = l; a.pad = pad; a.epi = epilogue;
   return launch_down(1, a, as_stream(stream));
+}
+
+// Same kernels with the input given as operand planes (lshm_stage_planes*, lshm_cascade_combine_planes,
+// lshm_residual_split_planes): the tiles are fetched by tensor-TMA box loads instead of producer warps.
+int lshm_down2d_planes(const void* planes, const void* wimg, const float* bias,
+                       const float* aux, int64_t aux_ns, float* small_, int64_t small_ns,
+                       int64_t N, int A, int Bc, int h, int w_, int epilogue, lshm_stream_t stream) {
+  LSHM_REQUIRE(planes && wimg && small_, "lshm_down2d_planes: null pointer");
+  LSHM_REQUIRE(N >= 0 && A > 0 && Bc > 0 && (Bc & 3) == 0 && h > 0 && w_ > 0, "lshm_down2d_planes: bad sizes (Bc must be a multiple of 4)");
+  LSHM_REQUIRE(epilogue >= 0 && epilogue <= 2, "lshm_down2d_planes: bad epilogue %d", epilogue);
+  LSHM_REQUIRE(epilogue != LSHM_EPI_DELU || aux != nullptr, "lshm_down2d_planes: DELU epilogue needs aux");
+  LSHM_REQUIRE(w_ <= 126, "lshm_down2d_planes: small-map width %d too large (max 126)", w_);
+  LSHM_REQUIRE((reinterpret_cast<uintptr_t>(wimg) & 15) == 0, "lshm_down2d_planes: weight image must be 16-byte aligned");
+  if (N == 0) return LSHM_OK;
+  DownArgs a{};
+  a.big = reinterpret_cast<const float*>(planes); a.big_ns = 0; a.wimg = reinterpret_cast<const uint8_t*>(wimg); a.bias = bias;
+  a.aux = epilogue == LSHM_EPI_DELU ? aux : nullptr; a.aux_ns = aux_ns;
+  a.small_ = small_; a.small_ns = small_ns; a.N = N; a.A = A; a.Bc = Bc; a.h = h; a.w = w_; a.pad = 0; a.epi = epilogue;
+  return launch_down(2, a, as_stream(stream), true);
+}
+
+int lshm_down1d_planes(const void* planes, const void* wimg, const float* bias,
+                       const float* aux, int64_t aux_ns, float* small_, int64_t small_ns,
+                       int64_t N, int A, int Bc, int l, int epilogue, lshm_stream_t stream) {
+  LSHM_REQUIRE(planes && wimg && small_, "lshm_down1d_planes: null pointer");
+  LSHM_REQUIRE(N >= 0 && A > 0 && Bc > 0 && (Bc & 3) == 0 && l > 0, "lshm_down1d_planes: bad sizes (Bc must be a multiple of 4)");
+  LSHM_REQUIRE(epilogue >= 0 && epilogue <= 2, "lshm_down1d_planes: bad epilogue %d", epilogue);
+  LSHM_REQUIRE(epilogue != LSHM_EPI_DELU || aux != nullptr, "lshm_down1d_planes: DELU epilogue needs aux");
+  LSHM_REQUIRE((reinterpret_cast<uintptr_t>(wimg) & 15) == 0, "lshm_down1d_planes: weight image must be 16-byte aligned");
+  if (N == 0) return LSHM_OK;
+  DownArgs a{};
+  a.big = reinterpret_cast<const float*>(planes); a.big_ns = 0; a.wimg = reinterpret_cast<const uint8_t*>(wimg); a.bias = bias;
+  a.aux = epilogue == LSHM_EPI_DELU ? aux : nullptr; a.aux_ns = aux_ns;
+  a.small_ = small_; a.small_ns = small_ns; a.N = N; a.A = A; a.Bc = Bc; a.h = 1; a.w = l; a.pad = 0; a.epi = epilogue;
+  return launch_down(1, a, as_stream(stream), true);
 }
 
 }  // extern "C"

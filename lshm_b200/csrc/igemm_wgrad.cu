@@ -11,6 +11,7 @@
 // ranges.  The position range is split over CTAs (split-K); partial results are combined with
 // fp32 atomics into dW (zeroed first), already in the reference weight layout.
 #include "conv_geom.cuh"
+#include "tma.cuh"
 
 namespace lshm {
 namespace {
@@ -19,6 +20,9 @@ using namespace tc;
 
 
 struct WgArgs {
+  // operand planes of the big map (tma.cuh): tensor maps over the hi / lo halves; PRE instances only
+  alignas(64) CUtensorMap tm_hi;
+  alignas(64) CUtensorMap tm_lo;
   const float* small_; int64_t small_ns;
   const float* big; int64_t big_ns;
   float* dw;
@@ -34,8 +38,10 @@ struct WgArgs {
 constexpr int WG_NPW = 8;
 constexpr int WG_PT = WG_NPW * 32;                 // producer threads
 constexpr int WG_THREADS = WG_PT + 32;             // + the MMA warp
-template <int DIM, int NT, int KP>
-__global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_kernel(WgArgs a) {
+// PRE: the big map arrives as operand planes; its tile is one tensor-TMA box per half (issued by thread 0),
+// the producer warps stage the (8x smaller) small-map tile only.
+template <int DIM, int NT, int KP, bool PRE>
+__global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_kernel(const __grid_constant__ WgArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], acc_bar;
   __shared__ uint32_t tmem_base;
@@ -61,7 +67,7 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
 
   if (warp == WG_NPW) tmem_alloc(&tmem_base, TMEM_COLS);
   if (tid == 0) {
-    for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], WG_NPW); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], WG_NPW + (PRE ? 1 : 0)); mbar_init(&empty_bar[s], 1); }
     mbar_init(&acc_bar, 1);
     mbar_init_fence();
   }
@@ -84,6 +90,11 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
       uint8_t* slo = shi + SBYTES;
       uint8_t* zhi = slo + SBYTES;
       uint8_t* zlo = zhi + zbytes;
+      if (PRE && tid == 0) {
+        mbar_arrive_expect_tx(&full_bar[s], 2 * zbytes);
+        tma_load_3d(zhi, &a.tm_hi, 0, (int)p0, c0 >> 3, &full_bar[s]);
+        tma_load_3d(zlo, &a.tm_lo, 0, (int)p0, c0 >> 3, &full_bar[s]);
+      }
       const uint32_t up0 = (uint32_t)p0;              // Q < 2^31 (checked by the launcher): 32-bit index math
       const uint32_t uQ = (uint32_t)a.Q, uPW = (uint32_t)PW, upp = (uint32_t)(PH * PW), uw = (uint32_t)a.w;
       // ---- S tile: item = (position, chunk of 8 channels); U items are fetched before any is converted
@@ -130,7 +141,7 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
       }
       // ---- Z tile: item = (slot, chunk of 8 s2d channels)
       constexpr int UZ = 4;
-      for (int item0 = tid; item0 < ZS * CZ; item0 += WG_PT * UZ) {
+      for (int item0 = tid; !PRE && item0 < ZS * CZ; item0 += WG_PT * UZ) {
         float v[UZ][8];
 #pragma unroll
         for (int u = 0; u < UZ; ++u) {
@@ -300,20 +311,26 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
   if (warp == WG_NPW) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-template <int DIM, int NT, int KP>
-int launch_wgrad_t(const WgArgs& a, int64_t splits, int mtiles, cudaStream_t st) {
+template <int DIM, int NT, int KP, bool PRE = false>
+int launch_wgrad_t(WgArgs a, int64_t splits, int mtiles, cudaStream_t st) {
+  if (PRE) {
+    const PlaneGeom pg = plane_geom(DIM, a.N, a.Bc, a.h, a.w);
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(a.big);
+    if (int rc = make_plane_tmap(&a.tm_hi, base, pg.Q, pg.chunks, a.zslots, NT / 8)) return rc;
+    if (int rc = make_plane_tmap(&a.tm_lo, base + pg.half_bytes, pg.Q, pg.chunks, a.zslots, NT / 8)) return rc;
+  }
   const size_t stage = (size_t)2 * a.scols * KP * 16 + (size_t)2 * (NT / 8) * a.zslots * 16;
   // slack: the padding row groups of the last stage's S tiles are read (and ignored) up to 16 groups
   const size_t reach = (size_t)a.scols * KP * 16 + (size_t)16 * KP * 16;     // from the stage start
   const size_t smem = stage * a.nstage + (reach > stage ? reach - stage : 0) + 256;
-  LSHM_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<DIM, NT, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_wgrad");
+  LSHM_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<DIM, NT, KP, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_wgrad");
   dim3 grid((unsigned)splits, (unsigned)(mtiles * a.ntiles));
-  igemm_wgrad_kernel<DIM, NT, KP><<<grid, WG_THREADS, smem, st>>>(a);
+  igemm_wgrad_kernel<DIM, NT, KP, PRE><<<grid, WG_THREADS, smem, st>>>(a);
   LSHM_CHECK_LAUNCH("igemm_wgrad");
   return LSHM_OK;
 }
 
-int launch_wgrad(int dim, WgArgs a, cudaStream_t st) {
+int launch_wgrad(int dim, WgArgs a, cudaStream_t st, bool planes = false) {
   const int Kc = 4 * a.Bc;
   const int k16 = (Kc + 15) / 16 * 16;
   const int NT = k16 <= 16 ? 16 : (k16 <= 32 ? 32 : (k16 <= 48 ? 48 : 96));
@@ -336,6 +353,11 @@ int launch_wgrad(int dim, WgArgs a, cudaStream_t st) {
   a.kb_per_cta = ceil_div(a.kblocks, splits);
   splits = ceil_div(a.kblocks, a.kb_per_cta);
   a.nstage = (int)std::min<int64_t>(a.nstage, std::max<int64_t>(1, a.kb_per_cta));
+  if (planes) {
+    LSHM_REQUIRE(NT == 32 && KP == 128 && a.zslots <= 256, "lshm_wgrad*_planes: operand planes serve the 8-channel first layers (A <= 16, Bc = 8)");
+    if (dim == 2) return launch_wgrad_t<2, 32, 128, true>(a, splits, mtiles, st);
+    return launch_wgrad_t<1, 32, 128, true>(a, splits, mtiles, st);
+  }
 #define LW(D, NTV, KPV) return launch_wgrad_t<D, NTV, KPV>(a, splits, mtiles, st)
   if (dim == 2) {
     switch (NT) {
@@ -386,6 +408,33 @@ int lshm_wgrad1d(const float* small_, int64_t small_ns, const float* big, int64_
   a.small_ = small_; a.small_ns = small_ns; a.big = big; a.big_ns = big_ns; a.dw = dw;
   a.N = N; a.A = A; a.Bc = Bc; a.h = 1; a.w = l; a.pad = pad;
   return launch_wgrad(1, a, st);
+}
+
+// Same kernels with the big map given as operand planes (see lshm_down*_planes).
+int lshm_wgrad2d_planes(const float* small_, int64_t small_ns, const void* planes,
+                        float* dw, int64_t N, int A, int Bc, int h, int w_, lshm_stream_t stream) {
+  LSHM_REQUIRE(small_ && planes && dw, "lshm_wgrad2d_planes: null pointer");
+  LSHM_REQUIRE(N >= 0 && A > 0 && Bc > 0 && (Bc & 3) == 0 && h > 0 && w_ > 0 && w_ <= 118, "lshm_wgrad2d_planes: bad sizes");
+  cudaStream_t st = as_stream(stream);
+  LSHM_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)A * Bc * 16, st), "lshm_wgrad2d_planes");
+  if (N == 0) return LSHM_OK;
+  WgArgs a{};
+  a.small_ = small_; a.small_ns = small_ns; a.big = reinterpret_cast<const float*>(planes); a.big_ns = 0; a.dw = dw;
+  a.N = N; a.A = A; a.Bc = Bc; a.h = h; a.w = w_; a.pad = 0;
+  return launch_wgrad(2, a, st, true);
+}
+
+int lshm_wgrad1d_planes(const float* small_, int64_t small_ns, const void* planes,
+                        float* dw, int64_t N, int A, int Bc, int l, lshm_stream_t stream) {
+  LSHM_REQUIRE(small_ && planes && dw, "lshm_wgrad1d_planes: null pointer");
+  LSHM_REQUIRE(N >= 0 && A > 0 && Bc > 0 && (Bc & 3) == 0 && l > 0, "lshm_wgrad1d_planes: bad sizes");
+  cudaStream_t st = as_stream(stream);
+  LSHM_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)A * Bc * 4, st), "lshm_wgrad1d_planes");
+  if (N == 0) return LSHM_OK;
+  WgArgs a{};
+  a.small_ = small_; a.small_ns = small_ns; a.big = reinterpret_cast<const float*>(planes); a.big_ns = 0; a.dw = dw;
+  a.N = N; a.A = A; a.Bc = Bc; a.h = 1; a.w = l; a.pad = 0;
+  return launch_wgrad(1, a, st, true);
 }
 
 }  // extern "C"

@@ -1,0 +1,169 @@
+"""Operand planes (include/lshm.h "operand planes", csrc/tma.cuh): the staging kernels against a CPU restatement of
+the layout, the tensor-TMA instances of the first-layer conv kernels against the fp32-input instances (same bf16
+hi/lo values, same MMA order: identical results) and against PyTorch, and the fused writers (residual split,
+gradient combine) against staging their fp32 outputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from common import rel_err
+from lshm_b200._lib import lib
+
+pytestmark = pytest.mark.gpu
+TC_TOL = 2e-5
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dp(t):
+    return None if t is None else t.data_ptr()
+
+
+def image(w, dim, which=0):
+    from lshm_b200.engine import conv_image
+    return conv_image(w, dim, which, st())
+
+
+def planes_buffer(dim, N, Bc, h, w, dev):
+    import ctypes
+    n = ctypes.c_int64()
+    assert lib().cdll.lshm_planes_bytes(dim, N, Bc, h, w, ctypes.byref(n)) == 0
+    return torch.empty(n.value // 2, dtype=torch.bfloat16, device=dev)
+
+
+def split_ref(v):
+    hi = v.bfloat16()
+    lo = (v - hi.float()).bfloat16()
+    return hi, lo
+
+
+def planes_ref_2d(big):
+    """[half][chunk][q][8] from big [N,Bc,2h,2w]: q over the (h+1)x(w+1) block grid, block (by,bx) = rows 2by-1,2by x cols
+    2bx-1,2bx (zero outside), chunk = channel pair, element = (b&1)*4 + sy*2 + sx."""
+    N, Bc, H, W = big.shape
+    pad = F.pad(big, (1, 1, 1, 1))                       # pixel (r, c) at [r+1, c+1]
+    blocks = pad.unfold(2, 2, 2).unfold(3, 2, 2)         # [N,Bc,h+1,w+1,2(sy),2(sx)]
+    z = blocks.reshape(N, Bc // 2, 2, H // 2 + 1, W // 2 + 1, 4)      # [N,cc,bb,by,bx,sub]
+    z = z.permute(1, 0, 3, 4, 2, 5).reshape(Bc // 2, -1, 8)           # [cc, q, 8]
+    hi, lo = split_ref(z.contiguous())
+    return torch.stack((hi, lo))
+
+
+def planes_ref_1d(big, pad):
+    N, Bc, Lb = big.shape
+    src = F.pad(big, (pad, 0))[:, :, :Lb]                # sample s at index s + pad  -> window j = [4j, 4j+3] of src
+    z = src.reshape(N, Bc // 2, 2, Lb // 4, 4).permute(1, 0, 3, 2, 4).reshape(Bc // 2, -1, 8)
+    hi, lo = split_ref(z.contiguous())
+    return torch.stack((hi, lo))
+
+
+@pytest.mark.parametrize("N,Bc,s", [(3, 8, 64), (2, 4, 16), (2, 12, 8)])
+def test_stage_planes2d_layout(cuda, N, Bc, s):
+    torch.manual_seed(N + Bc)
+    big = torch.randn(N, Bc, 2 * s, 2 * s)
+    bg = big.to(cuda)
+    pl = planes_buffer(2, N, Bc, s, s, cuda)
+    lib().stage_planes2d(dp(bg), Bc * 4 * s * s, dp(pl), N, Bc, s, s, st())
+    ref = planes_ref_2d(big)
+    assert torch.equal(pl.cpu().view(torch.int16), ref.reshape(-1).view(torch.int16))
+
+
+@pytest.mark.parametrize("N,Bc,l,pad", [(3, 8, 4096, 1), (2, 8, 4096, 0), (2, 4, 64, 1)])
+def test_stage_planes1d_layout(cuda, N, Bc, l, pad):
+    torch.manual_seed(N + l)
+    big = torch.randn(N, Bc, 4 * l)
+    bg = big.to(cuda)
+    pl = planes_buffer(1, N, Bc, 1, l, cuda)
+    lib().stage_planes1d(dp(bg), Bc * 4 * l, dp(pl), N, Bc, l, pad, st())
+    ref = planes_ref_1d(big, pad)
+    assert torch.equal(pl.cpu().view(torch.int16), ref.reshape(-1).view(torch.int16))
+
+
+@pytest.mark.parametrize("N,A", [(2, 8), (64, 8), (5, 12)])
+def test_down2d_and_wgrad2d_from_planes(cuda, N, A):
+    torch.manual_seed(N)
+    Bc, s = 8, 64
+    big = torch.randn(N, Bc, 2 * s, 2 * s)
+    w = torch.randn(A, Bc, 4, 4) * 0.1
+    bias = torch.randn(A)
+    bg, wg, bsg = big.to(cuda), w.to(cuda), bias.to(cuda)
+    wdn = image(wg, 2)
+    pl = planes_buffer(2, N, Bc, s, s, cuda)
+    lib().stage_planes2d(dp(bg), Bc * 4 * s * s, dp(pl), N, Bc, s, s, st())
+    out_f = torch.empty(N, A, s, s, device=cuda)
+    out_p = torch.empty(N, A, s, s, device=cuda)
+    lib().down2d(dp(bg), Bc * 4 * s * s, dp(wdn), dp(bsg), None, 0, dp(out_f), A * s * s, N, A, Bc, s, s, 1, st())
+    lib().down2d_planes(dp(pl), dp(wdn), dp(bsg), None, 0, dp(out_p), A * s * s, N, A, Bc, s, s, 1, st())
+    assert torch.equal(out_p, out_f)
+    assert rel_err(out_p, F.elu(F.conv2d(big, w, bias, stride=2, padding=1))) < TC_TOL
+    # dgrad of the transposed conv with ELU'
+    act = F.elu(torch.randn(N, A, s, s))
+    ag = act.to(cuda)
+    lib().down2d_planes(dp(pl), dp(wdn), None, dp(ag), A * s * s, dp(out_p), A * s * s, N, A, Bc, s, s, 2, st())
+    ref = F.conv2d(big, w, None, stride=2, padding=1) * torch.where(act > 0, torch.ones_like(act), act + 1)
+    assert rel_err(out_p, ref) < TC_TOL
+    # weight gradient
+    small = torch.randn(N, A, s, s)
+    sg = small.to(cuda)
+    wr = w.clone().requires_grad_()
+    F.conv2d(big, wr, None, stride=2, padding=1).backward(small)
+    dw = torch.empty(A, Bc, 4, 4, device=cuda)
+    lib().wgrad2d_planes(dp(sg), A * s * s, dp(pl), dp(dw), N, A, Bc, s, s, st())
+    assert rel_err(dw, wr.grad) < 2e-5
+
+
+@pytest.mark.parametrize("N,A,pad", [(2, 8, 1), (64, 8, 0), (3, 12, 1)])
+def test_down1d_and_wgrad1d_from_planes(cuda, N, A, pad):
+    torch.manual_seed(N + 7)
+    Bc, l = 8, 4096
+    big = torch.randn(N, Bc, 4 * l)
+    w = torch.randn(A, Bc, 4) * 0.1
+    bias = torch.randn(A)
+    bg, wg, bsg = big.to(cuda), w.to(cuda), bias.to(cuda)
+    wdn = image(wg, 1)
+    pl = planes_buffer(1, N, Bc, 1, l, cuda)
+    lib().stage_planes1d(dp(bg), Bc * 4 * l, dp(pl), N, Bc, l, pad, st())
+    out_f = torch.empty(N, A, l, device=cuda)
+    out_p = torch.empty(N, A, l, device=cuda)
+    lib().down1d(dp(bg), Bc * 4 * l, dp(wdn), dp(bsg), None, 0, dp(out_f), A * l, N, A, Bc, l, pad, 1, st())
+    lib().down1d_planes(dp(pl), dp(wdn), dp(bsg), None, 0, dp(out_p), A * l, N, A, Bc, l, 1, st())
+    assert torch.equal(out_p, out_f)
+    assert rel_err(out_p, F.elu(F.conv1d(big, w, bias, stride=4, padding=pad))) < TC_TOL
+    small = torch.randn(N, A, l)
+    sg = small.to(cuda)
+    wr = w.clone().requires_grad_()
+    F.conv1d(big, wr, None, stride=4, padding=pad).backward(small)
+    dw = torch.empty(A, Bc, 4, device=cuda)
+    lib().wgrad1d_planes(dp(sg), A * l, dp(pl), dp(dw), N, A, Bc, l, st())
+    assert rel_err(dw, wr.grad) < 2e-5
+
+
+@pytest.mark.parametrize("N,C", [(3, 8), (2, 4)])
+def test_fused_plane_writers(cuda, N, C):
+    torch.manual_seed(N * C)
+    P = 128
+    x, x1 = torch.randn(N, C, P, P, device=cuda), torch.randn(N, C, P, P, device=cuda)
+    iyT, iyF = torch.empty_like(x), torch.empty_like(x)
+    lib().residual_split(dp(x), dp(x1), dp(iyT), dp(iyF), N, C, P, st())
+    l = P * P // 4
+    refT, refF = planes_buffer(1, N, C, 1, l, cuda), planes_buffer(1, N, C, 1, l, cuda)
+    lib().stage_planes1d(dp(iyT), C * P * P, dp(refT), N, C, l, 1, st())
+    lib().stage_planes1d(dp(iyF), C * P * P, dp(refF), N, C, l, 1, st())
+    pT, pF = torch.zeros_like(refT), torch.zeros_like(refF)
+    lib().residual_split_planes(dp(x), dp(x1), dp(pT), dp(pF), N, C, P, st())
+    assert torch.equal(pT.view(torch.int16), refT.view(torch.int16))
+    assert torch.equal(pF.view(torch.int16), refF.view(torch.int16))
+    # gradient combine -> 2-D planes (+ bias-gradient sums)
+    g1p, gT, gF = (torch.randn(N, C, P, P, device=cuda) for _ in range(3))
+    gx1 = torch.empty_like(g1p)
+    db_ref = torch.empty(C, device=cuda)
+    lib().cascade_combine(dp(g1p), dp(gT), dp(gF), dp(gx1), N, C, P, dp(db_ref), st())
+    ref = planes_buffer(2, N, C, P // 2, P // 2, cuda)
+    lib().stage_planes2d(dp(gx1), C * P * P, dp(ref), N, C, P // 2, P // 2, st())
+    got = torch.zeros_like(ref)
+    db = torch.full((C,), 3.0, device=cuda)
+    lib().cascade_combine_planes(dp(g1p), dp(gT), dp(gF), dp(got), N, C, P, dp(db), st())
+    assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
+    assert rel_err(db, db_ref) < 1e-5
