@@ -35,9 +35,9 @@ def main():
     dw2, dw1 = torch.empty_like(w2), torch.empty_like(w1)
     i2, i1 = conv_image(w2, 2, 0, st), conv_image(w1, 1, 0, st)
     nb = ctypes.c_int64()
-    L.cdll.lshm_planes_bytes(2, N, Bc, s, s, ctypes.byref(nb)); p2 = torch.empty(nb.value, dtype=torch.uint8, device=dev)
-    L.cdll.lshm_planes_bytes(1, N, Bc, 1, l, ctypes.byref(nb)); p1 = torch.empty(nb.value, dtype=torch.uint8, device=dev)
-    p1b = torch.empty_like(p1)
+    L.cdll.lshm_planes_bytes(2, N, Bc, s, s, ctypes.byref(nb)); p2 = torch.zeros(nb.value, dtype=torch.uint8, device=dev)
+    L.cdll.lshm_planes_bytes(1, N, Bc, 1, l, ctypes.byref(nb)); p1 = torch.zeros(nb.value, dtype=torch.uint8, device=dev)
+    p1b = torch.zeros_like(p1)
     x1 = torch.randn_like(big); g3 = torch.randn_like(big)
     db = torch.empty(Bc, device=dev)
     f32 = 4.0 * big.numel()

@@ -99,7 +99,9 @@ __global__ void __launch_bounds__(down_threads(G), (G == 1 ? 3 : 2)) igemm_down_
   const int SLOTS = a.slots, NS = a.nstage;
   constexpr int NSLOT = DIM == 2 ? 2 : 1;          // staged slots per producer thread (1-D tiles: 128 slots)
   const uint32_t zbytes = (uint32_t)CC * SLOTS * 16;
-  const uint32_t stage_bytes = 2 * zbytes + IMG;
+  // (operand-plane instances with a resident weight image keep no image slot in the stages)
+  const bool wres_early = ((4 * a.Bc + KC - 1) / KC) == 1 && a.ntn == 1 && a.wres_on;
+  const uint32_t stage_bytes = 2 * zbytes + ((PRE && wres_early) ? 0u : IMG);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Kc = 4 * a.Bc;
   const int KB = (Kc + KC - 1) / KC;
@@ -137,8 +139,8 @@ __global__ void __launch_bounds__(down_threads(G), (G == 1 ? 3 : 2)) igemm_down_
           uint8_t* zhi = smem + (size_t)s * stage_bytes;
           mbar_wait(&empty_bar[s], ring.ph ^ 1);
           mbar_arrive_expect_tx(&full_bar[s], 2 * zbytes);
-          tma_load_3d(zhi, &a.tm_hi, 0, q0, kb * CC, &full_bar[s]);
-          tma_load_3d(zhi + zbytes, &a.tm_lo, 0, q0, kb * CC, &full_bar[s]);
+          tma_load_3d(zhi, &a.tm_hi, 0, q0 / PLANE_ROW, kb * CC, &full_bar[s]);
+          tma_load_3d(zhi + zbytes, &a.tm_lo, 0, q0 / PLANE_ROW, kb * CC, &full_bar[s]);
         }
       }
     }
@@ -348,7 +350,8 @@ __global__ void __launch_bounds__(down_threads(G), (G == 1 ? 3 : 2)) igemm_down_
 
 template <int DIM, int NT, int KC, int G, bool PRE = false>
 int launch_down_t(DownArgs a, const DownGeom& g, cudaStream_t st) {
-  const size_t stage = (size_t)2 * (KC / 8) * a.slots * 16 + g.img;
+  const bool wres = g.KB == 1 && g.ntiles == 1 && a.wres_on;
+  const size_t stage = (size_t)2 * (KC / 8) * a.slots * 16 + ((PRE && wres) ? 0 : g.img);
   const int64_t units = a.mtiles * g.ntiles * g.KB;
   // two CTAs per SM when the ring fits in ~110 KB each (227 KB per SM), else one CTA with a deep ring
   // three CTAs per SM when two stages fit in ~74 KB, else two, else one with a deep ring
@@ -363,8 +366,8 @@ int launch_down_t(DownArgs a, const DownGeom& g, cudaStream_t st) {
   if (PRE) {
     const PlaneGeom pg = plane_geom(DIM, a.N, a.Bc, a.h, a.w);
     const uint8_t* base = reinterpret_cast<const uint8_t*>(a.big);
-    if (int rc = make_plane_tmap(&a.tm_hi, base, pg.Q, pg.chunks, a.slots, KC / 8)) return rc;
-    if (int rc = make_plane_tmap(&a.tm_lo, base + pg.half_bytes, pg.Q, pg.chunks, a.slots, KC / 8)) return rc;
+    if (int rc = make_plane_tmap(&a.tm_hi, base, pg.Qs, pg.chunks, a.slots, KC / 8)) return rc;
+    if (int rc = make_plane_tmap(&a.tm_lo, base + pg.half_bytes, pg.Qs, pg.chunks, a.slots, KC / 8)) return rc;
   }
   LSHM_CUDA(cudaFuncSetAttribute(igemm_down_kernel<DIM, NT, KC, G, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_down");
   const int per_sm = std::min(G == 1 ? 3 : 2, smem <= 74 * 1024 ? 3 : (smem <= 112 * 1024 ? 2 : 1));
@@ -377,6 +380,7 @@ int launch_down_t(DownArgs a, const DownGeom& g, cudaStream_t st) {
 int launch_down(int dim, DownArgs a, cudaStream_t st, bool planes = false) {
   const DownGeom g = down_geom(dim, a.A, a.Bc);
   a.slots = dim == 2 ? (128 + a.w + 2 + 7) / 8 * 8 : 128;
+  if (planes) a.slots = (a.slots + PLANE_ROW - 1) / PLANE_ROW * PLANE_ROW;   // whole 512-byte rows of the tensor map
   a.Q = dim == 2 ? a.N * (int64_t)(a.h + 1) * (a.w + 1) : a.N * (int64_t)a.w;
   a.d_pp = make_fastdiv((uint32_t)((a.h + 1) * (a.w + 1))); a.d_pw = make_fastdiv((uint32_t)(a.w + 1)); a.d_w = make_fastdiv((uint32_t)a.w);
   LSHM_REQUIRE(a.Q < (1LL << 31) - 4096, "lshm_down: too many positions (%lld) for one call; split the batch", (long long)a.Q);

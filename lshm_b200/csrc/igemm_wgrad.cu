@@ -92,8 +92,8 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
       uint8_t* zlo = zhi + zbytes;
       if (PRE && tid == 0) {
         mbar_arrive_expect_tx(&full_bar[s], 2 * zbytes);
-        tma_load_3d(zhi, &a.tm_hi, 0, (int)p0, c0 >> 3, &full_bar[s]);
-        tma_load_3d(zlo, &a.tm_lo, 0, (int)p0, c0 >> 3, &full_bar[s]);
+        tma_load_3d(zhi, &a.tm_hi, 0, (int)(p0 / PLANE_ROW), c0 >> 3, &full_bar[s]);
+        tma_load_3d(zlo, &a.tm_lo, 0, (int)(p0 / PLANE_ROW), c0 >> 3, &full_bar[s]);
       }
       const uint32_t up0 = (uint32_t)p0;              // Q < 2^31 (checked by the launcher): 32-bit index math
       const uint32_t uQ = (uint32_t)a.Q, uPW = (uint32_t)PW, upp = (uint32_t)(PH * PW), uw = (uint32_t)a.w;
@@ -316,8 +316,8 @@ int launch_wgrad_t(WgArgs a, int64_t splits, int mtiles, cudaStream_t st) {
   if (PRE) {
     const PlaneGeom pg = plane_geom(DIM, a.N, a.Bc, a.h, a.w);
     const uint8_t* base = reinterpret_cast<const uint8_t*>(a.big);
-    if (int rc = make_plane_tmap(&a.tm_hi, base, pg.Q, pg.chunks, a.zslots, NT / 8)) return rc;
-    if (int rc = make_plane_tmap(&a.tm_lo, base + pg.half_bytes, pg.Q, pg.chunks, a.zslots, NT / 8)) return rc;
+    if (int rc = make_plane_tmap(&a.tm_hi, base, pg.Qs, pg.chunks, a.zslots, NT / 8)) return rc;
+    if (int rc = make_plane_tmap(&a.tm_lo, base + pg.half_bytes, pg.Qs, pg.chunks, a.zslots, NT / 8)) return rc;
   }
   const size_t stage = (size_t)2 * a.scols * KP * 16 + (size_t)2 * (NT / 8) * a.zslots * 16;
   // slack: the padding row groups of the last stage's S tiles are read (and ignored) up to 16 groups
@@ -344,6 +344,7 @@ int launch_wgrad(int dim, WgArgs a, cudaStream_t st, bool planes = false) {
   const int KP = (a.scols <= 2 && NT <= 32) ? 128 : 64;
   a.kblocks = ceil_div(a.Q, KP);
   a.zslots = dim == 2 ? (KP + a.w + 2 + 7) / 8 * 8 : KP;
+  if (planes) a.zslots = (a.zslots + PLANE_ROW - 1) / PLANE_ROW * PLANE_ROW;   // whole 512-byte rows of the tensor map
   a.d_zs = make_fastdiv((uint32_t)a.zslots);
   const size_t stage = (size_t)2 * a.scols * KP * 16 + (size_t)2 * (NT / 8) * a.zslots * 16;
   a.nstage = (int)std::min<size_t>(3, std::max<size_t>(2, (72 * 1024) / stage));

@@ -27,17 +27,18 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-int make_plane_tmap(CUtensorMap* m, const void* half_base, int64_t Q, int chunks, int slots, int box_chunks) {
+int make_plane_tmap(CUtensorMap* m, const void* half_base, int64_t Qs, int chunks, int slots, int box_chunks) {
   EncodeTiledFn fn = encode_tiled_fn();
   LSHM_REQUIRE(fn != nullptr, "operand planes: cuTensorMapEncodeTiled is not available from this driver");
-  LSHM_REQUIRE(slots >= 1 && slots <= 256 && box_chunks >= 1 && box_chunks <= 256, "operand planes: box too large");
+  LSHM_REQUIRE(slots >= PLANE_ROW && slots % PLANE_ROW == 0 && slots / PLANE_ROW <= 256 && box_chunks >= 1 && box_chunks <= 256 &&
+               Qs % PLANE_ROW == 0, "operand planes: bad box");
   LSHM_REQUIRE((reinterpret_cast<uintptr_t>(half_base) & 15) == 0, "operand planes: buffer must be 16-byte aligned");
-  const cuuint64_t gdim[3] = {8, (cuuint64_t)Q, (cuuint64_t)chunks};
-  const cuuint64_t gstr[2] = {16, (cuuint64_t)Q * 16};          // bytes, dims 1 and 2
-  const cuuint32_t box[3] = {8, (cuuint32_t)slots, (cuuint32_t)box_chunks};
+  const cuuint64_t gdim[3] = {64, (cuuint64_t)(Qs / PLANE_ROW), (cuuint64_t)chunks};
+  const cuuint64_t gstr[2] = {512, (cuuint64_t)Qs * 16};          // bytes, dims 1 and 2
+  const cuuint32_t box[3] = {64, (cuuint32_t)(slots / PLANE_ROW), (cuuint32_t)box_chunks};
   const cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(half_base), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(half_base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LSHM_REQUIRE(r == CUDA_SUCCESS, "operand planes: cuTensorMapEncodeTiled failed (%d)", (int)r);
   return LSHM_OK;
@@ -47,6 +48,7 @@ namespace {
 
 using namespace tc;
 
+// Q here is the chunk stride in positions (PlaneGeom::Qs)
 __device__ __forceinline__ void store_chunk(uint8_t* __restrict__ hi, size_t half_bytes, int64_t Q, int cc, int64_t q,
                                             const float (&v)[8]) {
   uint4 h, l;
@@ -59,7 +61,7 @@ __device__ __forceinline__ void store_chunk(uint8_t* __restrict__ hi, size_t hal
 // one thread per (chunk, block position): 2 channels x the 2x2 pixel block at rows 2by-1, 2by / columns 2bx-1, 2bx
 __global__ void __launch_bounds__(256)
 stage2d_kernel(const float* __restrict__ big, int64_t big_ns, uint8_t* __restrict__ planes, size_t half_bytes,
-               int Bc, int h, int w, int64_t Q, int chunks, FastDiv d_pp, FastDiv d_pw) {
+               int Bc, int h, int w, int64_t Q, int64_t Qs, int chunks, FastDiv d_pp, FastDiv d_pw) {
   const int PW = w + 1, PH = h + 1, W = 2 * w;
   const int64_t HW = 4 * (int64_t)h * w;
   const int64_t total = Q * chunks;
@@ -83,14 +85,14 @@ stage2d_kernel(const float* __restrict__ big, int64_t big_ns, uint8_t* __restric
         if (r1 && c1) v[bb * 4 + 3] = __ldg(p + W + 1);
       }
     }
-    store_chunk(planes, half_bytes, Q, cc, q, v);
+    store_chunk(planes, half_bytes, Qs, cc, q, v);
   }
 }
 
 // one thread per (chunk, window j): 2 channels x samples [4j - pad, 4j - pad + 3]
 __global__ void __launch_bounds__(256)
 stage1d_kernel(const float* __restrict__ big, int64_t big_ns, uint8_t* __restrict__ planes, size_t half_bytes,
-               int Bc, int l, int pad, int64_t Q, int chunks, FastDiv d_l) {
+               int Bc, int l, int pad, int64_t Q, int64_t Qs, int chunks, FastDiv d_l) {
   const int64_t total = Q * chunks;
   const int64_t Lb = 4 * (int64_t)l;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -111,7 +113,7 @@ stage1d_kernel(const float* __restrict__ big, int64_t big_ns, uint8_t* __restric
           if (pad == 0 || t > 0 || j > 0) v[bb * 4 + t] = __ldg(p + t);
       }
     }
-    store_chunk(planes, half_bytes, Q, cc, q, v);
+    store_chunk(planes, half_bytes, Qs, cc, q, v);
   }
 }
 
@@ -294,7 +296,7 @@ int lshm_stage_planes2d(const float* big, int64_t big_ns, void* planes, int64_t 
   const int64_t total = g.Q * g.chunks;
   const int64_t blocks = std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
   stage2d_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(big, big_ns, reinterpret_cast<uint8_t*>(planes), g.half_bytes,
-      Bc, h, w_, g.Q, g.chunks, make_fastdiv((uint32_t)((h + 1) * (w_ + 1))), make_fastdiv((uint32_t)(w_ + 1)));
+      Bc, h, w_, g.Q, g.Qs, g.chunks, make_fastdiv((uint32_t)((h + 1) * (w_ + 1))), make_fastdiv((uint32_t)(w_ + 1)));
   LSHM_CHECK_LAUNCH("lshm_stage_planes2d");
   return LSHM_OK;
 }
@@ -309,7 +311,7 @@ int lshm_stage_planes1d(const float* big, int64_t big_ns, void* planes, int64_t 
   const int64_t total = g.Q * g.chunks;
   const int64_t blocks = std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
   stage1d_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(big, big_ns, reinterpret_cast<uint8_t*>(planes), g.half_bytes,
-      Bc, l, pad, g.Q, g.chunks, make_fastdiv((uint32_t)l));
+      Bc, l, pad, g.Q, g.Qs, g.chunks, make_fastdiv((uint32_t)l));
   LSHM_CHECK_LAUNCH("lshm_stage_planes1d");
   return LSHM_OK;
 }
@@ -323,7 +325,7 @@ int lshm_residual_split_planes(const float* x, const float* x1, void* planesT, v
   const int64_t blocks = N * (C / 2) * (int64_t)(P / PT) * (P / PT);
   LSHM_REQUIRE(blocks < (1LL << 31), "lshm_residual_split_planes: batch too large for one call");
   residual_split_planes_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
-      x, x1, reinterpret_cast<uint8_t*>(planesT), reinterpret_cast<uint8_t*>(planesF), g.half_bytes, C, P, g.Q, g.chunks);
+      x, x1, reinterpret_cast<uint8_t*>(planesT), reinterpret_cast<uint8_t*>(planesF), g.half_bytes, C, P, g.Qs, g.chunks);
   LSHM_CHECK_LAUNCH("lshm_residual_split_planes");
   return LSHM_OK;
 }
@@ -339,7 +341,7 @@ int lshm_cascade_combine_planes(const float* g1p, const float* gT, const float* 
   const int64_t items = N * (C / 2) * (int64_t)tpr * tpr;
   const int64_t blocks = std::min<int64_t>(items, (int64_t)sm_count() * 8);
   combine_planes_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(g1p, gT, gF, reinterpret_cast<uint8_t*>(planes),
-                                                                          g.half_bytes, C, P, g.Q, items, db1);
+                                                                          g.half_bytes, C, P, g.Qs, items, db1);
   LSHM_CHECK_LAUNCH("lshm_cascade_combine_planes");
   return LSHM_OK;
 }

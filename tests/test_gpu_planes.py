@@ -30,7 +30,17 @@ def planes_buffer(dim, N, Bc, h, w, dev):
     import ctypes
     n = ctypes.c_int64()
     assert lib().cdll.lshm_planes_bytes(dim, N, Bc, h, w, ctypes.byref(n)) == 0
-    return torch.empty(n.value // 2, dtype=torch.bfloat16, device=dev)
+    # zero-filled: the <= 31 padding positions per chunk (chunk stride = positions rounded up to 32) are never written
+    return torch.zeros(n.value // 2, dtype=torch.bfloat16, device=dev)
+
+
+def pad_positions(z):
+    """[cc, Q, 8] -> [cc, Qs, 8] with Qs = Q rounded up to 32 (zero padding)."""
+    cc, Q, _ = z.shape
+    Qs = (Q + 31) // 32 * 32
+    out = torch.zeros(cc, Qs, 8, dtype=z.dtype)
+    out[:, :Q] = z
+    return out
 
 
 def split_ref(v):
@@ -47,7 +57,7 @@ def planes_ref_2d(big):
     blocks = pad.unfold(2, 2, 2).unfold(3, 2, 2)         # [N,Bc,h+1,w+1,2(sy),2(sx)]
     z = blocks.reshape(N, Bc // 2, 2, H // 2 + 1, W // 2 + 1, 4)      # [N,cc,bb,by,bx,sub]
     z = z.permute(1, 0, 3, 4, 2, 5).reshape(Bc // 2, -1, 8)           # [cc, q, 8]
-    hi, lo = split_ref(z.contiguous())
+    hi, lo = split_ref(pad_positions(z.contiguous()))
     return torch.stack((hi, lo))
 
 
@@ -55,7 +65,7 @@ def planes_ref_1d(big, pad):
     N, Bc, Lb = big.shape
     src = F.pad(big, (pad, 0))[:, :, :Lb]                # sample s at index s + pad  -> window j = [4j, 4j+3] of src
     z = src.reshape(N, Bc // 2, 2, Lb // 4, 4).permute(1, 0, 3, 2, 4).reshape(Bc // 2, -1, 8)
-    hi, lo = split_ref(z.contiguous())
+    hi, lo = split_ref(pad_positions(z.contiguous()))
     return torch.stack((hi, lo))
 
 
