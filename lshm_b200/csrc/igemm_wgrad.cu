@@ -355,8 +355,9 @@ int launch_wgrad(int dim, WgArgs a, cudaStream_t st, bool planes = false) {
   splits = ceil_div(a.kblocks, a.kb_per_cta);
   a.nstage = (int)std::min<int64_t>(a.nstage, std::max<int64_t>(1, a.kb_per_cta));
   if (planes) {
-    LSHM_REQUIRE(NT == 32 && KP == 128 && a.zslots <= 256, "lshm_wgrad*_planes: operand planes serve the 8-channel first layers (A <= 16, Bc = 8)");
-    if (dim == 2) return launch_wgrad_t<2, 32, 128, true>(a, splits, mtiles, st);
+    LSHM_REQUIRE(NT <= 32 && KP == 128 && a.zslots <= 256, "lshm_wgrad*_planes: operand planes serve the first layers (A <= 16, Bc <= 8)");
+    if (dim == 2) { if (NT == 16) return launch_wgrad_t<2, 16, 128, true>(a, splits, mtiles, st); return launch_wgrad_t<2, 32, 128, true>(a, splits, mtiles, st); }
+    if (NT == 16) return launch_wgrad_t<1, 16, 128, true>(a, splits, mtiles, st);
     return launch_wgrad_t<1, 32, 128, true>(a, splits, mtiles, st);
   }
 #define LW(D, NTV, KPV) return launch_wgrad_t<D, NTV, KPV>(a, splits, mtiles, st)

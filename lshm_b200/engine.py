@@ -68,6 +68,16 @@ class Workspace:
             self.dx = torch.empty(N, sz[0], **f) if need_dx else None
 
 
+def planes_buffer(dim: int, N: int, Bc: int, h: int, w: int, device) -> torch.Tensor:
+    """Zero-filled operand-plane buffer (include/lshm.h "operand planes") for a big map [N,Bc,2h,2w] (dim 2) or
+    [N,Bc,4w] (dim 1).  Zero-filled once: the <= 31 padding positions per chunk are never written."""
+    import ctypes
+    n = ctypes.c_int64()
+    if lib().cdll.lshm_planes_bytes(dim, N, Bc, h, w, ctypes.byref(n)) != 0:
+        raise RuntimeError("lshm_planes_bytes failed")
+    return torch.zeros(n.value, dtype=torch.uint8, device=device)
+
+
 def conv_image(w: torch.Tensor, dim: int, which: int, st: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """bf16 hi/lo operand image of a conv / transposed-conv weight W[A,Bc,4(,4)] for the tensor-core
     kernels (which: 0 = lshm_down*, 1 = lshm_up*); lshm_conv_prep."""
@@ -137,6 +147,20 @@ class AEEngine:
             self.lib.down1d(big, big_ns, w, bias, aux, aux_ns, small, small_ns, N, A, Bc,
                             INPUT_ELEMS >> (2 * lvl), pad, epi, st)
 
+    def _down_planes(self, planes, w, bias, aux, aux_ns, small, small_ns, N, A, Bc, lvl, epi, st):
+        if self.ndim == 2:
+            s = 128 >> lvl
+            self.lib.down2d_planes(planes, w, bias, aux, aux_ns, small, small_ns, N, A, Bc, s, s, epi, st)
+        else:
+            self.lib.down1d_planes(planes, w, bias, aux, aux_ns, small, small_ns, N, A, Bc, INPUT_ELEMS >> (2 * lvl), epi, st)
+
+    def _wgrad_planes(self, small, small_ns, planes, dw, N, A, Bc, lvl, st):
+        if self.ndim == 2:
+            s = 128 >> lvl
+            self.lib.wgrad2d_planes(small, small_ns, planes, dw, N, A, Bc, s, s, st)
+        else:
+            self.lib.wgrad1d_planes(small, small_ns, planes, dw, N, A, Bc, INPUT_ELEMS >> (2 * lvl), st)
+
     def _up(self, small, small_ns, w, bias, aux, aux_ns, big, big_ns, N, A, Bc, lvl, pad, epi, st):
         if self.ndim == 2:
             s = 128 >> lvl
@@ -153,10 +177,11 @@ class AEEngine:
             self.lib.wgrad1d(small, small_ns, big, big_ns, dw, N, A, Bc, INPUT_ELEMS >> (2 * lvl), pad, st)
 
     # ------------------------------------------------------------------ forward
-    def encode(self, x, uvh, p, ws: Workspace, st: int, out=None):
+    def encode(self, x, uvh, p, ws: Workspace, st: int, out=None, x_planes=None):
         """ELU(fc1(cat(flatten(conv stack(x)), ELU(fcuv1(uvh))))) -> `out` (default ws.mu0).
 
         src/lofar_models.py:71-84 / :156-169.  uvh is the [N,4H] harmonic vector.
+        x_planes: the input as operand planes (then `x` is not read: the first conv fetches its tiles by TMA).
         """
         lb, N, L, H4, ch, sz = self.lib, ws.N, self.L, self.H4, self.ch, ws.sizes
         ld1 = FLAT + H4
@@ -166,8 +191,12 @@ class AEEngine:
                 dst, dst_ns = ws.enc[i + 1], sz[i + 1]
             else:
                 dst, dst_ns = ws.cat1, ld1
-            self._down(_p(src), src_ns, _p(self.img[(f"conv{i}.weight", 0)]), _p(p[f"conv{i}.bias"]), None, 0,
-                       _p(dst), dst_ns, N, ch[i + 1], ch[i], i + 1, 1, EPI_ELU, st)
+            if i == 0 and x_planes is not None:
+                self._down_planes(_p(x_planes), _p(self.img[("conv0.weight", 0)]), _p(p["conv0.bias"]), None, 0,
+                                  _p(dst), dst_ns, N, ch[1], ch[0], 1, EPI_ELU, st)
+            else:
+                self._down(_p(src), src_ns, _p(self.img[(f"conv{i}.weight", 0)]), _p(p[f"conv{i}.bias"]), None, 0,
+                           _p(dst), dst_ns, N, ch[i + 1], ch[i], i + 1, 1, EPI_ELU, st)
             src, src_ns = dst, dst_ns
         lb.linear_fwd(_p(uvh), uvh.stride(0), _p(p["fcuv1.weight"]), _p(p["fcuv1.bias"]),
                       ws.cat1.data_ptr() + 4 * FLAT, ld1, N, H4, H4, EPI_ELU, st)
@@ -194,7 +223,7 @@ class AEEngine:
 
     def forward(self, x: torch.Tensor, uv: torch.Tensor, scales: torch.Tensor,
                 p: Dict[str, torch.Tensor], ws: Workspace, st: int,
-                mu_out: Optional[torch.Tensor] = None, decode: bool = True):
+                mu_out: Optional[torch.Tensor] = None, decode: bool = True, x_planes: Optional[torch.Tensor] = None):
         """Runs the network; returns (xhat [N,C*16384] in ws, mu view); decode=False stops at the
         latent (the 1-D nets of the clustering path, src/evaluate_clustering.py:86-89) and returns (None, mu).
 
@@ -207,11 +236,11 @@ class AEEngine:
         mu_final = mu_out if mu_out is not None else ws.mu
         mu_ld, zc_ld = mu_final.stride(0), L + H4
         if self.rica:
-            self.encode(x, ws.uvh, p, ws, st)
+            self.encode(x, ws.uvh, p, ws, st, x_planes=x_planes)
             lb.linear_fwd(_p(ws.mu0), L, _p(p["fc2in.weight"]), _p(p["fc2in.bias"]), _p(mu_final), mu_ld, N, L, L, EPI_ELU, st)
             lb.linear_fwd(_p(mu_final), mu_ld, _p(p["fc2out.weight"]), _p(p["fc2out.bias"]), _p(ws.zcat), zc_ld, N, L, L, EPI_ELU, st)
         else:
-            self.encode(x, ws.uvh, p, ws, st, out=ws.zcat[:, :L])
+            self.encode(x, ws.uvh, p, ws, st, out=ws.zcat[:, :L], x_planes=x_planes)
             mu_final.copy_(ws.zcat[:, :L])
         if not decode:
             return None, mu_final
@@ -221,7 +250,8 @@ class AEEngine:
     def backward(self, x: torch.Tensor, p: Dict[str, torch.Tensor], g: Dict[str, torch.Tensor],
                  ws: Workspace, st: int, g_xhat: Optional[torch.Tensor],
                  g_mu: Optional[torch.Tensor], mu: torch.Tensor, need_dx: bool,
-                 wstream: Optional[torch.cuda.Stream] = None, out_bias_done: bool = False):
+                 wstream: Optional[torch.cuda.Stream] = None, out_bias_done: bool = False,
+                 x_planes: Optional[torch.Tensor] = None, g_xhat_planes: Optional[torch.Tensor] = None):
         """Writes every parameter gradient into g[name] (overwrite) and returns dx or None.
 
         wstream: optional second stream for the leaf work of the conv layers (weight and bias gradients).
@@ -231,6 +261,8 @@ class AEEngine:
         to `wstream` once its output gradient exists and everything is joined before returning, so the
         latency-bound deep layers overlap instead of queueing behind each other.
 
+        x_planes / g_xhat_planes: the network input / the reconstruction gradient as operand planes (then the fp32
+        tensors `x` / `g_xhat` are not read; g_xhat_planes needs out_bias_done, the bias sum has no fp32 source);
         g_xhat: gradient w.r.t. the reconstruction ([N, C*16384] contiguous) or None;
         g_mu:   gradient w.r.t. the returned latent ([N,L] view, any row stride) or None;
         mu:     the latent view returned by forward (post-fc2in activation when rica).
@@ -246,7 +278,9 @@ class AEEngine:
                 ev = torch.cuda.Event()
                 ev.record(main)
                 wstream.wait_event(ev)
-        if g_xhat is None:
+        if g_xhat_planes is not None and not out_bias_done:
+            raise RuntimeError("lshm_b200: g_xhat_planes needs the output-bias gradient from the producing kernel")
+        if g_xhat is None and g_xhat_planes is None:
             # no reconstruction gradient: decoder parameters get zero gradient
             for i in range(6):
                 g[f"tconv{i}.weight"].zero_(); g[f"tconv{i}.bias"].zero_()
@@ -262,10 +296,16 @@ class AEEngine:
                 inp = ws.dec[i]                     # input of tconv_i (small map, level 6-i)
                 A, Bc, lvl = rch[i], rch[i + 1], 6 - i
                 fork()
+                nxt = ws.g_dec[i]
+                if i == 5 and g_xhat_planes is not None:
+                    self._wgrad_planes(_p(inp), sz[lvl], _p(g_xhat_planes), _p(g["tconv5.weight"]), N, A, Bc, lvl, wst)
+                    self._down_planes(_p(g_xhat_planes), _p(self.img[("tconv5.weight", 0)]), None, _p(inp), sz[lvl],
+                                      _p(nxt), sz[lvl], N, A, Bc, lvl, EPI_DELU, st)
+                    dz = nxt
+                    continue
                 self._wgrad(_p(inp), sz[lvl], _p(dz), sz[lvl - 1], _p(g[f"tconv{i}.weight"]), N, A, Bc, lvl, 0, wst)
                 if not (i == 5 and out_bias_done):
                     lb.channel_sum(_p(dz), sz[lvl - 1], _p(g[f"tconv{i}.bias"]), N, Bc, sz[lvl - 1] // Bc, wst)
-                nxt = ws.g_dec[i]
                 # dgrad of the transposed conv = "down"; ELU' of the producing layer unless it is fc3
                 self._down(_p(dz), sz[lvl - 1], _p(self.img[(f"tconv{i}.weight", 0)]), None,
                            _p(inp) if i > 0 else None, sz[lvl], _p(nxt), sz[lvl], N, A, Bc, lvl, 0,
@@ -278,7 +318,7 @@ class AEEngine:
         mu_ld = mu.stride(0)
         gmu_p, gmu_ld = (_p(g_mu), g_mu.stride(0)) if g_mu is not None else (None, 0)
         if self.rica:
-            if g_xhat is not None:
+            if g_xhat is not None or g_xhat_planes is not None:
                 lb.linear_bwd_weight(_p(mu), mu_ld, _p(ws.g_zcat), zc_ld, _p(g["fc2out.weight"]), _p(g["fc2out.bias"]), N, L, L, st)
             # dz(fc2in) = (dz(fc2out) W2out + g_mu) * ELU'(mu)
             lb.linear_bwd_data(_p(ws.g_zcat), zc_ld, _p(p["fc2out.weight"]), gmu_p, gmu_ld, _p(mu), mu_ld, _p(ws.g_mu), L, N, L, L, st)
@@ -299,7 +339,10 @@ class AEEngine:
             inp, inp_ns = (x, sz[0]) if i == 0 else (ws.enc[i], sz[i])
             A, Bc, lvl = ch[i + 1], ch[i], i + 1
             fork()
-            self._wgrad(_p(dz), dz_ns, _p(inp), inp_ns, _p(g[f"conv{i}.weight"]), N, A, Bc, lvl, 1, wst)
+            if i == 0 and x_planes is not None:
+                self._wgrad_planes(_p(dz), dz_ns, _p(x_planes), _p(g["conv0.weight"]), N, A, Bc, lvl, wst)
+            else:
+                self._wgrad(_p(dz), dz_ns, _p(inp), inp_ns, _p(g[f"conv{i}.weight"]), N, A, Bc, lvl, 1, wst)
             lb.channel_sum(_p(dz), dz_ns, _p(g[f"conv{i}.bias"]), N, A, sz[lvl] // A, wst)
             if i > 0:
                 nxt = ws.g_enc[i]

@@ -225,7 +225,8 @@ class DeepKHarmonicStep:
 
     def __init__(self, net: AutoEncoderCNN2, netT: AutoEncoder1DCNN, netF: AutoEncoder1DCNN, mod: Kmeans, *,
                  alpha=0.01, beta=0.01, gamma=0.01, rho=1.0, use_rica=True, rica_lambda=0.01,
-                 group: Optional[dist.ProcessGroup] = None, distributed: bool = False, centre_sums: bool = False):
+                 group: Optional[dist.ProcessGroup] = None, distributed: bool = False, centre_sums: bool = False,
+                 use_planes: bool = True):
         self.net, self.netT, self.netF, self.mod = net, netT, netF, mod
         self.alpha, self.beta, self.gamma, self.rho = alpha, beta, gamma, rho
         self.use_rica, self.rica_lambda = use_rica, rica_lambda
@@ -240,6 +241,9 @@ class DeepKHarmonicStep:
         if mod.latent_dim != self.Ltot:
             raise RuntimeError("lshm_b200: Kmeans.latent_dim must equal L + 2*Lt")
         self.centre_sums = bool(centre_sums)
+        # input-sized tensors that feed the first conv layers (x, x11, x11^T, the gradient of x1) live as operand
+        # planes (include/lshm.h): those kernels fetch their tiles by tensor-TMA instead of gathering fp32
+        self.use_planes = bool(use_planes)
         K = mod.K
         self.flat = FlatParams([net, netT, netF, mod], dev, extra_tail=(K * self.Ltot + K) if centre_sums else 0)
         self._pd = [m.named_param_dict() for m in (net, netT, netF)]
@@ -300,8 +304,15 @@ class DeepKHarmonicStep:
             self.ws = [e[0].workspace(N, dev, True, False), e[1].workspace(N, dev, True, True),
                        e[2].workspace(N, dev, True, True)]
             n = N * C * 16384
-            self.iyT, self.iyF = torch.empty(n, **f), torch.empty(n, **f)
-            self.g1p, self.g2, self.g3f, self.gx1 = (torch.empty(n, **f) for _ in range(4))
+            if self.use_planes:
+                from .engine import planes_buffer
+                self.xp, self.gx1p = planes_buffer(2, N, C, 64, 64, dev), planes_buffer(2, N, C, 64, 64, dev)
+                self.pT, self.pF = planes_buffer(1, N, C, 1, 4096, dev), planes_buffer(1, N, C, 1, 4096, dev)
+                self.iyT = self.iyF = self.gx1 = None
+            else:
+                self.xp = self.gx1p = self.pT = self.pF = None
+                self.iyT, self.iyF, self.gx1 = torch.empty(n, **f), torch.empty(n, **f), torch.empty(n, **f)
+            self.g1p, self.g2, self.g3f = (torch.empty(n, **f) for _ in range(3))
             self._y = [torch.empty(n, **f) for _ in range(3)]
             self.Mu = torch.empty(N, self.Ltot, **f)
             self.gMu = torch.empty(N, self.Ltot, **f)
@@ -325,6 +336,12 @@ class DeepKHarmonicStep:
         self._batch_id += 1
         self._fwd_key = None
         self._loss_key = None
+        self.stage_input()
+
+    def stage_input(self):
+        """x -> operand planes for the 2-D net's first conv (forward and weight gradient); once per minibatch."""
+        if self.use_planes and self.N:
+            lib().stage_planes2d(self.x.data_ptr(), self.C * 16384, self.xp.data_ptr(), self.N, self.C, 64, 64, _stream())
 
     # multipliers: reading them applies a deferred update first, so they always hold the reference's values
     @property
@@ -363,16 +380,21 @@ class DeepKHarmonicStep:
         L, Lt, N, C = self.L, self.Lt, self.N, self.C
         e = self.net.engine(), self.netT.engine(), self.netF.engine()
         xf = self.x.view(N, -1)
-        x1, _ = e[0].forward(xf, self.uv, self.scales, self._pd[0], self.ws[0], st, mu_out=self.Mu[:, :L])
-        lib().residual_split(self.x.data_ptr(), x1.data_ptr(), self.iyT.data_ptr(), self.iyF.data_ptr(), N, C, 128, st)
+        x1, _ = e[0].forward(xf, self.uv, self.scales, self._pd[0], self.ws[0], st, mu_out=self.Mu[:, :L], x_planes=self.xp)
+        if self.use_planes:
+            lib().residual_split_planes(self.x.data_ptr(), x1.data_ptr(), self.pT.data_ptr(), self.pF.data_ptr(), N, C, 128, st)
+            inT = inF = xf          # not read: the first conv of the 1-D nets takes the planes
+        else:
+            lib().residual_split(self.x.data_ptr(), x1.data_ptr(), self.iyT.data_ptr(), self.iyF.data_ptr(), N, C, 128, st)
+            inT, inF = self.iyT.view(N, -1), self.iyF.view(N, -1)
         # The time-axis and frequency-axis nets are independent: they run on two streams (fork / join by
         # events, also inside a graph capture), so the latency-bound deep layers of one overlap the other's.
         side = self._fork()
         with torch.cuda.stream(side):
-            x3f, _ = e[2].forward(self.iyF.view(N, -1), self.uv, self.scales, self._pd[2], self.ws[2],
-                                  side.cuda_stream, mu_out=self.Mu[:, L + Lt:])
-        x2, _ = e[1].forward(self.iyT.view(N, -1), self.uv, self.scales, self._pd[1], self.ws[1], st,
-                             mu_out=self.Mu[:, L:L + Lt])
+            x3f, _ = e[2].forward(inF, self.uv, self.scales, self._pd[2], self.ws[2],
+                                  side.cuda_stream, mu_out=self.Mu[:, L + Lt:], x_planes=self.pF)
+        x2, _ = e[1].forward(inT, self.uv, self.scales, self._pd[1], self.ws[1], st,
+                             mu_out=self.Mu[:, L:L + Lt], x_planes=self.pT)
         self._join(side)
         return x1, x2, x3f
 
@@ -457,17 +479,27 @@ class DeepKHarmonicStep:
         self._join(lside)
         if grads:
             e = self.net.engine(), self.netT.engine(), self.netF.engine()
+            xf = self.x.view(N, -1)
+            inT, inF = (xf, xf) if self.use_planes else (self.iyT.view(N, -1), self.iyF.view(N, -1))
             side = self._fork()
             with torch.cuda.stream(side):
-                dF = e[2].backward(self.iyF.view(N, -1), self._pd[2], self._gd[2], self.ws[2], side.cuda_stream,
-                                   self.g3f.view(N, -1), gMu[:, L + Lt:], Mu[:, L + Lt:], True, self._wstream(2), fuse_db)
-            dT = e[1].backward(self.iyT.view(N, -1), self._pd[1], self._gd[1], self.ws[1], st, self.g2.view(N, -1),
-                               gMu[:, L:L + Lt], Mu[:, L:L + Lt], True, self._wstream(1), fuse_db)
+                dF = e[2].backward(inF, self._pd[2], self._gd[2], self.ws[2], side.cuda_stream,
+                                   self.g3f.view(N, -1), gMu[:, L + Lt:], Mu[:, L + Lt:], True, self._wstream(2), fuse_db,
+                                   x_planes=self.pF)
+            dT = e[1].backward(inT, self._pd[1], self._gd[1], self.ws[1], st, self.g2.view(N, -1),
+                               gMu[:, L:L + Lt], Mu[:, L:L + Lt], True, self._wstream(1), fuse_db, x_planes=self.pT)
             self._join(side)
-            lb.cascade_combine(self.g1p.data_ptr(), dT.data_ptr(), dF.data_ptr(), self.gx1.data_ptr(), N, C, 128,
-                               self._gd[0]["tconv5.bias"].data_ptr() if fuse_db else None, st)
-            e[0].backward(self.x.view(N, -1), self._pd[0], self._gd[0], self.ws[0], st, self.gx1.view(N, -1),
-                          gMu[:, :L], Mu[:, :L], False, self._wstream(0), fuse_db)
+            db1 = self._gd[0]["tconv5.bias"].data_ptr() if fuse_db else None
+            if self.use_planes and fuse_db:
+                lb.cascade_combine_planes(self.g1p.data_ptr(), dT.data_ptr(), dF.data_ptr(), self.gx1p.data_ptr(), N, C, 128, db1, st)
+                e[0].backward(xf, self._pd[0], self._gd[0], self.ws[0], st, None, gMu[:, :L], Mu[:, :L], False,
+                              self._wstream(0), True, x_planes=self.xp, g_xhat_planes=self.gx1p)
+            else:
+                if self.gx1 is None:
+                    self.gx1 = torch.empty(N * C * 16384, dtype=torch.float32, device=self.device)
+                lb.cascade_combine(self.g1p.data_ptr(), dT.data_ptr(), dF.data_ptr(), self.gx1.data_ptr(), N, C, 128, db1, st)
+                e[0].backward(xf, self._pd[0], self._gd[0], self.ws[0], st, self.gx1.view(N, -1),
+                              gMu[:, :L], Mu[:, :L], False, self._wstream(0), fuse_db, x_planes=self.xp)
         lb.closure_total(tp, self.rho, numel_g, khm_scale, self.flat.loss_tail.data_ptr(), st)
 
     def _seq_forward(self):

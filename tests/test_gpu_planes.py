@@ -177,3 +177,36 @@ def test_fused_plane_writers(cuda, N, C):
     lib().cascade_combine_planes(dp(g1p), dp(gT), dp(gF), dp(got), N, C, P, dp(db), st())
     assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
     assert rel_err(db, db_ref) < 1e-5
+
+
+@pytest.mark.parametrize("C,N", [(8, 8), (4, 6)])
+def test_training_closure_with_and_without_operand_planes(cuda, C, N):
+    """The fused closure with the input-sized tensors as operand planes (default) against the same closure on fp32
+    tensors: identical loss columns and latents (the first-layer forward results are bit-identical), gradients equal
+    up to the order of the split-K atomics."""
+    from common import SCALES, closure_case
+    from lshm_b200.kharmonic_lofar import DeepKHarmonicStep
+    from lshm_b200.lofar_models import AutoEncoder1DCNN, AutoEncoderCNN2, Kmeans
+    case = closure_case(C=C, L=32, Lt=16, N=N, bpb=2, seed=31)
+
+    def run(use_planes):
+        hs = torch.tensor(SCALES).to(cuda)
+        net = AutoEncoderCNN2(32, C, hs, True); netT = AutoEncoder1DCNN(16, C, hs, True); netF = AutoEncoder1DCNN(16, C, hs, True)
+        mod = Kmeans(64, case["K"], 4)
+        net.load_state_dict(case["pn"]); netT.load_state_dict(case["pT"]); netF.load_state_dict(case["pF"])
+        mod.load_state_dict({"M": case["M"]})
+        step = DeepKHarmonicStep(net.to(cuda), netT.to(cuda), netF.to(cuda), mod.to(cuda), use_planes=use_planes)
+        step.set_batch(case["x"].to(cuda), case["uv"].to(cuda), 2)
+        for dst, src in zip((step.y1, step.y2, step.y3), case["ys"]):
+            dst.copy_(src.to(cuda))
+        step.closure()
+        return step
+
+    a, b = run(True), run(False)
+    assert a.xp is not None and b.xp is None
+    ta, tb = a.loss_terms(), b.loss_terms()
+    for k in ta:
+        assert abs(ta[k] - tb[k]) <= 1e-6 * abs(tb[k]) + 1e-12, (k, ta[k], tb[k])
+    assert torch.equal(a.latents(), b.latents())
+    for nm, pa, pb in zip(a.flat.names, a.flat.params, b.flat.params):
+        assert rel_err(pa.grad, pb.grad) < 2e-5, nm
