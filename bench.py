@@ -135,6 +135,32 @@ def call_cost(name, a):
         n = a[9] * a[10] * a[11] * a[11]
         tag = ("+grads" if a[14] else "") + ("+mult_update" if a[8] else "")
         return f"cascade_losses{tag}", 4.0 * n * (7 + (3 if a[14] else 0) + (3 if a[8] else 0)), (30.0 + (6 if a[8] else 0)) * n
+    if name in ("down2d_planes", "down1d_planes"):
+        two_d = name.startswith("down2d")
+        N, A, B = a[7], a[8], a[9]
+        small_px = a[10] * a[11] if two_d else a[10]
+        epi = a[-2]
+        small, big = N * A * small_px, N * B * small_px * 4
+        return f"{name}[A={A},B={B},px={small_px}]", 4.0 * (small + big) + (4.0 * small if epi == 2 else 0.0), 2.0 * N * small_px * A * B * (16 if two_d else 4)
+    if name in ("wgrad2d_planes", "wgrad1d_planes"):
+        two_d = name.startswith("wgrad2d")
+        N, A, B = a[4], a[5], a[6]
+        small_px = a[7] * a[8] if two_d else a[7]
+        return f"{name}[A={A},B={B},px={small_px}]", 4.0 * (N * A * small_px + N * B * small_px * 4), 2.0 * N * small_px * A * B * (16 if two_d else 4)
+    if name == "stage_planes2d":
+        n = a[3] * a[4] * a[5] * a[6] * 4
+        return name, 8.0 * n, 3.0 * n
+    if name == "residual_split_planes":
+        n = a[4] * a[5] * a[6] * a[6]
+        return name, 4.0 * n * 4, 9.0 * n
+    if name == "cascade_combine_planes":
+        n = a[4] * a[5] * a[6] * a[6]
+        return name, 4.0 * n * 4, 6.0 * n
+    if name == "cascade_losses_planes":
+        # reads x, x1, x2, x3, y1..y3; writes g1p + two gradient planes (and 3 multipliers with the deferred update)
+        n = a[9] * a[10] * a[11] * a[11]
+        tag = "+grads(planes)" + ("+mult_update" if a[8] else "")
+        return f"cascade_losses{tag}", 4.0 * n * (10 + (3 if a[8] else 0)), (36.0 + (6 if a[8] else 0)) * n
     if name in ("residual_split", "cascade_combine"):
         n = a[4] * a[5] * a[6] * a[6]
         return name, 4.0 * n * 4, 3.0 * n

@@ -209,6 +209,12 @@ LSHM_API int lshm_cascade_losses_upd(const float* x, const float* x1, const floa
                             float* y1, float* y2, float* y3, float rho, int update_y,
                             int64_t N, int C, int P, float grad_scale, double* sums,
                             float* g1p, float* g2, float* g3f, float* db2, float* db3, lshm_stream_t stream);
+/* lshm_cascade_losses_upd (gradient form) writing g2 / g3 as the pad-0 operand planes of the two 1-D nets' last
+ * transposed convs (their dgrad and weight gradient then fetch tiles by TMA); g1p stays fp32. */
+LSHM_API int lshm_cascade_losses_planes(const float* x, const float* x1, const float* x2, const float* x3f,
+                               float* y1, float* y2, float* y3, float rho, int update_y,
+                               int64_t N, int C, int P, float grad_scale, double* sums,
+                               float* g1p, void* planes2, void* planes3, float* db2, float* db3, lshm_stream_t stream);
 /* gx1 = g1p - 0.5*(gT + transpose(gF)) : total gradient w.r.t. the 2-D net output.
  * db1 (nullable, float[C], written): per-channel sums of gx1 = bias gradient of the 2-D net's last
  * transposed conv. */

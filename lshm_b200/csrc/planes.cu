@@ -119,156 +119,291 @@ stage1d_kernel(const float* __restrict__ big, int64_t big_ns, uint8_t* __restric
 
 // ------------------------------------------------------------------------------------------------
 // Fused writers.  Both work on 32 x 32 pixel tiles of a PAIR of channel planes (a chunk holds two channels).
-constexpr int PT = 32;
+constexpr int PT = 32;     // P must be a multiple of the 32-row strips
+
+// ---- micro-tile scheme of the fused writers ------------------------------------------------------------
+// A thread owns a 4 x 4 (t x f) block of a PAIR of channel planes; a warp covers 32 t x 16 f (lane = 4*tg + fg:
+// 8 row groups x 4 column groups), a 256-thread block a strip of 32 rows x 128 columns.  Row-major tensors are
+// read as float4 along f (a warp touches 64 contiguous bytes in each of 8 rows), transposed tensors as float4
+// along t (128 contiguous bytes per column): every 32-byte sector is used whole in both layouts, no shared
+// memory, no barriers.  A chunk of the time-axis planes is 4 consecutive f of one row, a chunk of the
+// frequency-axis planes 4 consecutive t of one column - both are rows / columns of the thread's own block.
 
 // x11 = (x - x1) / 2 written as the 1-D pad-1 planes of the time-axis net (flattened s = t*P + f) and of the
-// frequency-axis net (flattened s = f*P + t): window j of a flattened map covers samples [4j-1, 4j+2].
-// Block: (tile, channel pair); 256 threads.  The tile is extended by one leading column (time net) / one
-// leading row (frequency net) so that every window that STARTS in the tile is complete.
+// frequency-axis net (flattened s = f*P + t): window j of a flattened map covers samples [4j-1, 4j+2], i.e. the
+// element BEFORE the block's row / column and its first three elements (one halo row + one halo column per thread;
+// the flattened predecessor of (t, f=0) is (t-1, P-1), of (f, t=0) it is (f-1, P-1)).
 __global__ void __launch_bounds__(256)
 residual_split_planes_kernel(const float* __restrict__ x, const float* __restrict__ x1, uint8_t* __restrict__ pT,
-                             uint8_t* __restrict__ pF, size_t half_bytes, int C, int P, int64_t Q, int chunks) {
-  __shared__ float s[2][PT + 1][PT + 2];     // [channel][row t (+1 halo row above)][col f (+1 halo col left)]
-  const int tpr = P / PT;
-  const int tile = blockIdx.x % (tpr * tpr), pair = blockIdx.x / (tpr * tpr);
+                             uint8_t* __restrict__ pF, size_t half_bytes, int C, int P, int64_t Qs) {
+  const int strips = P / 32;
+  const int strip = blockIdx.x % strips;
+  const int64_t pair = blockIdx.x / strips;
   const int ccn = C / 2;
-  const int n = pair / ccn, cc = pair % ccn;
-  const int t0 = (tile / tpr) * PT, f0 = (tile % tpr) * PT;
-  const int tid = threadIdx.x;
-  // load (PT+1) x (PT+1) values per channel: rows t0-1 .. t0+PT-1, cols f0-1 .. f0+PT-1.  The flattened
-  // predecessor of (t, f=0) is (t-1, P-1) for the time net and of (f, t=0) is (f-1, P-1) for the frequency net:
-  // those wrap-around values are fetched separately below, the halo here serves the in-row windows.
-  for (int i = tid; i < 2 * (PT + 1) * (PT + 1); i += 256) {
-    const int ch = i / ((PT + 1) * (PT + 1)), r = (i / (PT + 1)) % (PT + 1), c = i % (PT + 1);
-    const int t = t0 - 1 + r, f = f0 - 1 + c;
-    float v = 0.f;
-    if (t >= 0 && f >= 0) {
-      const int64_t off = (((int64_t)n * C + 2 * cc + ch) * P + t) * P + f;
-      v = 0.5f * (__ldg(x + off) - __ldg(x1 + off));
-    }
-    s[ch][r][c] = v;
-  }
-  __syncthreads();
-  const int64_t plane0 = ((int64_t)n * C + 2 * cc) * P * (int64_t)P;
-  const int wpr = PT / 4;                    // windows per tile row
-  // ---- time net: windows along f.  Window starting at sample s0 = t*P + 4m - 1 (m = window index in the row).
-  for (int i = tid; i < PT * wpr; i += 256) {
-    const int r = i / wpr, m = i % wpr;
-    const int t = t0 + r, fw = f0 + 4 * m;   // window covers f = fw-1 .. fw+2
-    float v[8];
+  const int n = (int)(pair / ccn), cc = (int)(pair % ccn);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t4 = strip * 32 + (lane >> 2) * 4;
+  const int f4 = warp * 16 + (lane & 3) * 4;
+  if (f4 >= P) return;
+  float v[2][4][4], left[2][4], up[2][4];
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      float first = s[ch][r + 1][4 * m];     // (t, fw-1); for fw == 0 the predecessor is (t-1, P-1)
-      if (fw == 0) {
-        first = 0.f;
-        if (t > 0) {
-          const int64_t off = plane0 + (int64_t)ch * P * P + (int64_t)(t - 1) * P + (P - 1);
-          first = 0.5f * (__ldg(x + off) - __ldg(x1 + off));
-        }
-      }
-      v[ch * 4 + 0] = first;
-      v[ch * 4 + 1] = s[ch][r + 1][4 * m + 1];
-      v[ch * 4 + 2] = s[ch][r + 1][4 * m + 2];
-      v[ch * 4 + 3] = s[ch][r + 1][4 * m + 3];
-    }
-    const int64_t q = (int64_t)n * (P * P / 4) + ((int64_t)t * P + fw) / 4;
-    store_chunk(pT, half_bytes, Q, cc, q, v);
-  }
-  // ---- frequency net: flattened s = f*P + t, windows along t at fixed f.
-  for (int i = tid; i < PT * wpr; i += 256) {
-    const int c = i / wpr, m = i % wpr;      // consecutive threads -> consecutive windows of one f (contiguous stores)
-    const int f = f0 + c, tw = t0 + 4 * m;   // window covers t = tw-1 .. tw+2
-    float v[8];
+  for (int ch = 0; ch < 2; ++ch) {
+    const int64_t plane = ((int64_t)n * C + 2 * cc + ch) * P * (int64_t)P;
+    const float* xp = x + plane;
+    const float* x1p = x1 + plane;
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      float first = s[ch][4 * m][c + 1];     // (tw-1, f); for tw == 0 the predecessor is (P-1, f-1)
-      if (tw == 0) {
-        first = 0.f;
-        if (f > 0) {
-          const int64_t off = plane0 + (int64_t)ch * P * P + (int64_t)(P - 1) * P + (f - 1);
-          first = 0.5f * (__ldg(x + off) - __ldg(x1 + off));
-        }
-      }
-      v[ch * 4 + 0] = first;
-      v[ch * 4 + 1] = s[ch][4 * m + 1][c + 1];
-      v[ch * 4 + 2] = s[ch][4 * m + 2][c + 1];
-      v[ch * 4 + 3] = s[ch][4 * m + 3][c + 1];
+    for (int j = 0; j < 4; ++j) {
+      const int64_t off = (int64_t)(t4 + j) * P + f4;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(xp + off));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(x1p + off));
+      v[ch][j][0] = 0.5f * (a.x - b.x); v[ch][j][1] = 0.5f * (a.y - b.y);
+      v[ch][j][2] = 0.5f * (a.z - b.z); v[ch][j][3] = 0.5f * (a.w - b.w);
+      // element before (t, f4) in the flattened time-axis map
+      const int64_t lo = f4 > 0 ? off - 1 : off - 1;       // (t, f4-1), or (t-1, P-1) when f4 == 0: both are off-1
+      left[ch][j] = (f4 > 0 || t4 + j > 0) ? 0.5f * (__ldg(xp + lo) - __ldg(x1p + lo)) : 0.f;
     }
-    const int64_t q = (int64_t)n * (P * P / 4) + ((int64_t)f * P + tw) / 4;
-    store_chunk(pF, half_bytes, Q, cc, q, v);
+    // elements before (f, t4) in the flattened frequency-axis map: (t4-1, f), or (P-1, f-1) when t4 == 0
+    if (t4 > 0) {
+      const int64_t off = (int64_t)(t4 - 1) * P + f4;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(xp + off));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(x1p + off));
+      up[ch][0] = 0.5f * (a.x - b.x); up[ch][1] = 0.5f * (a.y - b.y);
+      up[ch][2] = 0.5f * (a.z - b.z); up[ch][3] = 0.5f * (a.w - b.w);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int f = f4 + k;
+        const int64_t off = (int64_t)(P - 1) * P + (f - 1);
+        up[ch][k] = f > 0 ? 0.5f * (__ldg(xp + off) - __ldg(x1p + off)) : 0.f;
+      }
+    }
+  }
+  const int64_t l = (int64_t)P * P / 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float c[8] = {left[0][j], v[0][j][0], v[0][j][1], v[0][j][2], left[1][j], v[1][j][0], v[1][j][1], v[1][j][2]};
+    store_chunk(pT, half_bytes, Qs, cc, (int64_t)n * l + ((int64_t)(t4 + j) * P + f4) / 4, c);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float c[8] = {up[0][k], v[0][0][k], v[0][1][k], v[0][2][k], up[1][k], v[1][0][k], v[1][1][k], v[1][2][k]};
+    store_chunk(pF, half_bytes, Qs, cc, (int64_t)n * l + ((int64_t)(f4 + k) * P + t4) / 4, c);
   }
 }
 
 // gx1 = g1p - 0.5 (gT + transpose(gF)) written as the 2-D planes of the 2-D net's last transposed conv
 // (block (by,bx) = pixel rows 2by-1, 2by x columns 2bx-1, 2bx), plus the per-channel sums (bias gradient).
-// Tiles are shifted by (-1,-1) so that they hold whole 2x2 blocks: tile (i,j) covers pixel rows 32i-1 .. 32i+30;
-// a fifth tile row / column holds the last halo blocks (pixel row / column P-1 only).
+// Micro-tile scheme: the thread of the aligned block (t4, f4) evaluates gx1 on rows t4-1 .. t4+3 x columns
+// f4-1 .. f4+3 (row-major inputs: float4 + one scalar per row; the transposed input gF: float4 along t + one scalar
+// per column) and owns the 2 x 2 pixel blocks by = t4/2, t4/2+1, bx = f4/2, f4/2+1 - plus the last halo block row /
+// column (pixel row / column P-1 and the zero beyond it) when it sits on the bottom / right edge.
 __global__ void __launch_bounds__(256)
 combine_planes_kernel(const float* __restrict__ g1p, const float* __restrict__ gT, const float* __restrict__ gF,
-                      uint8_t* __restrict__ planes, size_t half_bytes, int C, int P, int64_t Q, int64_t items,
+                      uint8_t* __restrict__ planes, size_t half_bytes, int C, int P, int64_t Qs, int64_t items,
                       float* __restrict__ db1) {
-  __shared__ float s[2][PT][PT + 1];
-  __shared__ float tr[PT][PT + 1];
-  __shared__ float cacc[64];                 // per-channel partial sums of this (persistent) block
-  const int tpr = P / PT + 1;                // tiles per row incl. the halo tile
+  __shared__ float cacc[64];                 // per-channel sums of this (persistent) block
+  const int strips = P / 32;
   const int ccn = C / 2;
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  const int PW = P / 2 + 1;
-  if (tid < 64) cacc[tid] = 0.f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 64) cacc[threadIdx.x] = 0.f;
+  __syncthreads();
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-    const int tile = (int)(item % (tpr * tpr));
-    const int64_t pair = item / (tpr * tpr);
-    const int n = (int)(pair / ccn), cc = (int)(pair % ccn);
-    const int ti = tile / tpr, tj = tile % tpr;
-    const int r0 = ti * PT - 1, c0 = tj * PT - 1;      // first pixel row / column of the tile
+  const int strip = (int)(item % strips);
+  const int64_t pair = item / strips;
+  const int n = (int)(pair / ccn), cc = (int)(pair % ccn);
+  const int t4 = strip * 32 + (lane >> 2) * 4;
+  const int f4 = warp * 16 + (lane & 3) * 4;
+  float v[2][5][5];
+  float part[2] = {0.f, 0.f};
+  const bool active = f4 < P;
+  if (active) {
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
       const int64_t plane = ((int64_t)n * C + 2 * cc + ch) * P * (int64_t)P;
-      __syncthreads();
-      // transposed input: tr[a][b] = gF[f = c0 + a][t = r0 + b]
+      const float* ap = g1p + plane;
+      const float* bp = gT + plane;
+      const float* cp = gF + plane;
+      // transposed input first: w[c][r] = gF[f4-1+c][t4-1+r]
+      float w[5][5];
 #pragma unroll
-      for (int i = 0; i < PT; i += 8) {
-        const int f = c0 + ty + i, t = r0 + tx;
-        tr[ty + i][tx] = (f >= 0 && f < P && t >= 0 && t < P) ? __ldg(gF + plane + (int64_t)f * P + t) : 0.f;
-      }
-      __syncthreads();
-      float part = 0.f;
+      for (int c = 0; c < 5; ++c) {
+        const int f = f4 - 1 + c;
+        if (f >= 0) {
+          const float* q = cp + (int64_t)f * P + t4;
+          const float4 d = __ldg(reinterpret_cast<const float4*>(q));
+          w[c][1] = d.x; w[c][2] = d.y; w[c][3] = d.z; w[c][4] = d.w;
+          w[c][0] = t4 > 0 ? __ldg(q - 1) : 0.f;
+        } else {
 #pragma unroll
-      for (int i = 0; i < PT; i += 8) {
-        const int t = r0 + ty + i, f = c0 + tx;
-        float v = 0.f;
-        if (t >= 0 && t < P && f >= 0 && f < P) {
-          const int64_t off = plane + (int64_t)t * P + f;
-          v = __ldg(g1p + off) - 0.5f * (__ldg(gT + off) + tr[tx][ty + i]);
+          for (int r = 0; r < 5; ++r) w[c][r] = 0.f;
         }
-        s[ch][ty + i][tx] = v;
-        part += v;
       }
-      if (db1 != nullptr) {
-        part = warp_sum(part);
-        if (tx == 0) atomicAdd(&cacc[2 * cc + ch], part);
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {
+        const int t = t4 - 1 + r;
+        if (t >= 0) {
+          const int64_t off = (int64_t)t * P + f4;
+          const float4 a = __ldg(reinterpret_cast<const float4*>(ap + off));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(bp + off));
+          v[ch][r][1] = a.x - 0.5f * (b.x + w[1][r]); v[ch][r][2] = a.y - 0.5f * (b.y + w[2][r]);
+          v[ch][r][3] = a.z - 0.5f * (b.z + w[3][r]); v[ch][r][4] = a.w - 0.5f * (b.w + w[4][r]);
+          v[ch][r][0] = f4 > 0 ? __ldg(ap + off - 1) - 0.5f * (__ldg(bp + off - 1) + w[0][r]) : 0.f;
+          if (r > 0) part[ch] += (v[ch][r][1] + v[ch][r][2]) + (v[ch][r][3] + v[ch][r][4]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 5; ++c) v[ch][r][c] = 0.f;
+        }
       }
     }
-    __syncthreads();
-    // 16 x 16 blocks per tile, one per thread
-    const int byl = tid >> 4, bxl = tid & 15;
-    const int by = ti * (PT / 2) + byl, bx = tj * (PT / 2) + bxl;
-    if (by < PW && bx < PW) {
-      float v[8];
+    const int PW = P / 2 + 1;
+    const int nbi = (t4 == P - 4) ? 3 : 2, nbj = (f4 == P - 4) ? 3 : 2;
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        v[ch * 4 + 0] = s[ch][2 * byl][2 * bxl];
-        v[ch * 4 + 1] = s[ch][2 * byl][2 * bxl + 1];
-        v[ch * 4 + 2] = s[ch][2 * byl + 1][2 * bxl];
-        v[ch * 4 + 3] = s[ch][2 * byl + 1][2 * bxl + 1];
+    for (int bi = 0; bi < 3; ++bi) {
+      if (bi >= nbi) break;
+#pragma unroll
+      for (int bj = 0; bj < 3; ++bj) {
+        if (bj >= nbj) break;
+        float c[8];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          // rows 2bi, 2bi+1 / columns 2bj, 2bj+1 of the 5 x 5 grid; index 5 is beyond the map (zero)
+          c[ch * 4 + 0] = v[ch][2 * bi][2 * bj];
+          c[ch * 4 + 1] = (2 * bj + 1 < 5) ? v[ch][2 * bi][(2 * bj + 1) % 5] : 0.f;
+          c[ch * 4 + 2] = (2 * bi + 1 < 5) ? v[ch][(2 * bi + 1) % 5][2 * bj] : 0.f;
+          c[ch * 4 + 3] = (2 * bi + 1 < 5 && 2 * bj + 1 < 5) ? v[ch][(2 * bi + 1) % 5][(2 * bj + 1) % 5] : 0.f;
+        }
+        const int64_t q = ((int64_t)n * PW + (t4 / 2 + bi)) * PW + (f4 / 2 + bj);
+        store_chunk(planes, half_bytes, Qs, cc, q, c);
       }
-      const int64_t q = ((int64_t)n * PW + by) * PW + bx;
-      store_chunk(planes, half_bytes, Q, cc, q, v);
     }
   }
   if (db1 != nullptr) {
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      const float p = warp_sum(part[ch]);
+      if (lane == 0) atomicAdd(&cacc[2 * cc + ch], p);
+    }
+  }
+  }
+  if (db1 != nullptr) {
     __syncthreads();
-    if (tid < C) atomicAdd(db1 + tid, cacc[tid]);
+    if (threadIdx.x < C) atomicAdd(db1 + threadIdx.x, cacc[threadIdx.x]);
+  }
+}
+
+// src/kharmonic_lofar.py:150-158 + its gradient (lshm_cascade_losses_upd), writing the gradients w.r.t. the two 1-D
+// reconstructions as the pad-0 operand planes their nets' last transposed convs consume (window j = samples
+// [4j, 4j+3] of the flattened map: a row of the thread's 4 x 4 block for the time-axis net, a column for the
+// frequency-axis net).  Same micro-tile scheme; x3f is read along t (it is stored transposed), nothing goes through
+// shared memory.  Persistent blocks: the seven loss sums and the bias-gradient sums are flushed once per block.
+template <bool UPD>
+__global__ void __launch_bounds__(256, 2)
+cascade_losses_planes_kernel(const float* __restrict__ x, const float* __restrict__ x1, const float* __restrict__ x2,
+                             const float* __restrict__ x3f, float* __restrict__ y1, float* __restrict__ y2,
+                             float* __restrict__ y3, float rho, float inv_n, int C, int P, int64_t items,
+                             double* __restrict__ sums, float* __restrict__ g1p, uint8_t* __restrict__ p2,
+                             uint8_t* __restrict__ p3, size_t half_bytes, int64_t Qs, float* __restrict__ db2,
+                             float* __restrict__ db3) {
+  __shared__ float cacc[2][64];
+  __shared__ double red[8];
+  const int strips = P / 32;
+  const int ccn = C / 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 128) (&cacc[0][0])[threadIdx.x] = 0.f;
+  __syncthreads();
+  float s[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int64_t l = (int64_t)P * P / 4;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int strip = (int)(item % strips);
+    const int64_t pair = item / strips;
+    const int n = (int)(pair / ccn), cc = (int)(pair % ccn);
+    const int t4 = strip * 32 + (lane >> 2) * 4;
+    const int f4 = warp * 16 + (lane & 3) * 4;
+    if (f4 >= P) continue;
+    float g3v[2][4][4];                      // d/dx3 of the block, [channel][t][f]
+    float xt[2][4][4];                       // x3 of the block read from the transposed tensor: [channel][f][t]
+    float sb2[2] = {0.f, 0.f}, sb3[2] = {0.f, 0.f};
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      const float* q = x3f + ((int64_t)n * C + 2 * cc + ch) * P * (int64_t)P + (int64_t)f4 * P + t4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 d = __ldg(reinterpret_cast<const float4*>(q + (int64_t)k * P));
+        xt[ch][k][0] = d.x; xt[ch][k][1] = d.y; xt[ch][k][2] = d.z; xt[ch][k][3] = d.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float g2row[8];
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const int64_t off = (((int64_t)n * C + 2 * cc + ch) * P + (t4 + j)) * (int64_t)P + f4;
+        const float4 X = __ldg(reinterpret_cast<const float4*>(x + off));
+        const float4 A1 = __ldg(reinterpret_cast<const float4*>(x1 + off));
+        const float4 A2 = __ldg(reinterpret_cast<const float4*>(x2 + off));
+        float4 M1 = *reinterpret_cast<const float4*>(y1 + off);
+        float4 M2 = *reinterpret_cast<const float4*>(y2 + off);
+        float4 M3 = *reinterpret_cast<const float4*>(y3 + off);
+        const float xv[4] = {X.x, X.y, X.z, X.w}, a1[4] = {A1.x, A1.y, A1.z, A1.w}, a2[4] = {A2.x, A2.y, A2.z, A2.w};
+        float m1[4] = {M1.x, M1.y, M1.z, M1.w}, m2[4] = {M2.x, M2.y, M2.z, M2.w}, m3[4] = {M3.x, M3.y, M3.z, M3.w};
+        float g1[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float a3 = xt[ch][k][j];
+          const float r0 = a1[k] + a2[k] + a3 - xv[k];
+          const float r1 = xv[k] - a1[k];
+          const float x11 = 0.5f * r1;
+          const float r2 = x11 - a2[k], r3 = x11 - a3;
+          if (UPD) { m1[k] = fmaf(rho, r1, m1[k]); m2[k] = fmaf(rho, r2, m2[k]); m3[k] = fmaf(rho, r3, m3[k]); }
+          s[0] = fmaf(r0, r0, s[0]);
+          s[1] = fmaf(m1[k], r1, s[1]); s[2] = fmaf(r1, r1, s[2]);
+          s[3] = fmaf(m2[k], r2, s[3]); s[4] = fmaf(r2, r2, s[4]);
+          s[5] = fmaf(m3[k], r3, s[5]); s[6] = fmaf(r3, r3, s[6]);
+          const float e2 = m2[k] + rho * r2, e3 = m3[k] + rho * r3;
+          const float v2 = (2.f * r0 - e2) * inv_n, v3 = (2.f * r0 - e3) * inv_n;
+          g2row[ch * 4 + k] = v2;
+          g3v[ch][j][k] = v3;
+          g1[k] = (2.f * r0 - m1[k] - rho * r1 - 0.5f * (e2 + e3)) * inv_n;
+          sb2[ch] += v2; sb3[ch] += v3;
+        }
+        if (UPD) {
+          *reinterpret_cast<float4*>(y1 + off) = make_float4(m1[0], m1[1], m1[2], m1[3]);
+          *reinterpret_cast<float4*>(y2 + off) = make_float4(m2[0], m2[1], m2[2], m2[3]);
+          *reinterpret_cast<float4*>(y3 + off) = make_float4(m3[0], m3[1], m3[2], m3[3]);
+        }
+        *reinterpret_cast<float4*>(g1p + off) = make_float4(g1[0], g1[1], g1[2], g1[3]);
+      }
+      store_chunk(p2, half_bytes, Qs, cc, (int64_t)n * l + ((int64_t)(t4 + j) * P + f4) / 4, g2row);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float c[8] = {g3v[0][0][k], g3v[0][1][k], g3v[0][2][k], g3v[0][3][k],
+                          g3v[1][0][k], g3v[1][1][k], g3v[1][2][k], g3v[1][3][k]};
+      store_chunk(p3, half_bytes, Qs, cc, (int64_t)n * l + ((int64_t)(f4 + k) * P + t4) / 4, c);
+    }
+    if (db2 != nullptr) {
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const float a = warp_sum(sb2[ch]), b = warp_sum(sb3[ch]);
+        if (lane == 0) { atomicAdd(&cacc[0][2 * cc + ch], a); atomicAdd(&cacc[1][2 * cc + ch], b); }
+      }
+    }
+  }
+  __syncthreads();
+  if (db2 != nullptr && threadIdx.x < C) {
+    atomicAdd(db2 + threadIdx.x, cacc[0][threadIdx.x]); atomicAdd(db3 + threadIdx.x, cacc[1][threadIdx.x]);
+  }
+#pragma unroll
+  for (int q = 0; q < 7; ++q) {
+    const double v = warp_sum((double)s[q]);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += red[w];
+      atomicAdd(sums + q, t);
+    }
   }
 }
 
@@ -322,10 +457,11 @@ int lshm_residual_split_planes(const float* x, const float* x1, void* planesT, v
   LSHM_REQUIRE(N >= 0 && C > 0 && (C & 3) == 0 && P > 0 && P % PT == 0, "lshm_residual_split_planes: need C%%4==0 and P%%32==0");
   if (N == 0) return LSHM_OK;
   const PlaneGeom g = plane_geom(1, N, C, 1, P * P / 4);
-  const int64_t blocks = N * (C / 2) * (int64_t)(P / PT) * (P / PT);
+  LSHM_REQUIRE(P <= 128, "lshm_residual_split_planes: P > 128 is not supported");
+  const int64_t blocks = N * (C / 2) * (int64_t)(P / 32);
   LSHM_REQUIRE(blocks < (1LL << 31), "lshm_residual_split_planes: batch too large for one call");
   residual_split_planes_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
-      x, x1, reinterpret_cast<uint8_t*>(planesT), reinterpret_cast<uint8_t*>(planesF), g.half_bytes, C, P, g.Qs, g.chunks);
+      x, x1, reinterpret_cast<uint8_t*>(planesT), reinterpret_cast<uint8_t*>(planesF), g.half_bytes, C, P, g.Qs);
   LSHM_CHECK_LAUNCH("lshm_residual_split_planes");
   return LSHM_OK;
 }
@@ -337,12 +473,37 @@ int lshm_cascade_combine_planes(const float* g1p, const float* gT, const float* 
   if (N == 0) return LSHM_OK;
   if (db1) LSHM_CUDA(cudaMemsetAsync(db1, 0, sizeof(float) * C, as_stream(stream)), "lshm_cascade_combine_planes");
   const PlaneGeom g = plane_geom(2, N, C, P / 2, P / 2);
-  const int tpr = P / PT + 1;
-  const int64_t items = N * (C / 2) * (int64_t)tpr * tpr;
+  LSHM_REQUIRE(P <= 128, "lshm_cascade_combine_planes: P > 128 is not supported");
+  const int64_t items = N * (C / 2) * (int64_t)(P / 32);
   const int64_t blocks = std::min<int64_t>(items, (int64_t)sm_count() * 8);
   combine_planes_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(g1p, gT, gF, reinterpret_cast<uint8_t*>(planes),
                                                                           g.half_bytes, C, P, g.Qs, items, db1);
   LSHM_CHECK_LAUNCH("lshm_cascade_combine_planes");
+  return LSHM_OK;
+}
+
+int lshm_cascade_losses_planes(const float* x, const float* x1, const float* x2, const float* x3f,
+                               float* y1, float* y2, float* y3, float rho, int update_y,
+                               int64_t N, int C, int P, float grad_scale, double* sums,
+                               float* g1p, void* planes2, void* planes3, float* db2, float* db3, lshm_stream_t stream) {
+  LSHM_REQUIRE(x && x1 && x2 && x3f && y1 && y2 && y3 && sums && g1p && planes2 && planes3, "lshm_cascade_losses_planes: null pointer");
+  LSHM_REQUIRE((db2 == nullptr) == (db3 == nullptr), "lshm_cascade_losses_planes: db2/db3 come together");
+  LSHM_REQUIRE(N >= 0 && C > 0 && (C & 3) == 0 && C <= 64 && P > 0 && P % PT == 0 && P <= 128,
+               "lshm_cascade_losses_planes: need C%%4==0, C<=64, P%%32==0, P<=128");
+  if (N == 0) return LSHM_OK;
+  cudaStream_t st = as_stream(stream);
+  if (db2) {
+    LSHM_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * C, st), "lshm_cascade_losses_planes");
+    LSHM_CUDA(cudaMemsetAsync(db3, 0, sizeof(float) * C, st), "lshm_cascade_losses_planes");
+  }
+  const PlaneGeom g = plane_geom(1, N, C, 1, P * P / 4);
+  const int64_t items = N * (C / 2) * (int64_t)(P / 32);
+  const int64_t blocks = std::min<int64_t>(items, (int64_t)sm_count() * 2);
+#define LSHM_CLP(U) cascade_losses_planes_kernel<U><<<(unsigned)blocks, 256, 0, st>>>(x, x1, x2, x3f, y1, y2, y3, rho, grad_scale, \
+      C, P, items, sums, g1p, reinterpret_cast<uint8_t*>(planes2), reinterpret_cast<uint8_t*>(planes3), g.half_bytes, g.Qs, db2, db3)
+  if (update_y) LSHM_CLP(true); else LSHM_CLP(false);
+#undef LSHM_CLP
+  LSHM_CHECK_LAUNCH("lshm_cascade_losses_planes");
   return LSHM_OK;
 }
 

@@ -308,11 +308,13 @@ class DeepKHarmonicStep:
                 from .engine import planes_buffer
                 self.xp, self.gx1p = planes_buffer(2, N, C, 64, 64, dev), planes_buffer(2, N, C, 64, 64, dev)
                 self.pT, self.pF = planes_buffer(1, N, C, 1, 4096, dev), planes_buffer(1, N, C, 1, 4096, dev)
-                self.iyT = self.iyF = self.gx1 = None
+                self.p2, self.p3 = planes_buffer(1, N, C, 1, 4096, dev), planes_buffer(1, N, C, 1, 4096, dev)
+                self.iyT = self.iyF = self.gx1 = self.g2 = self.g3f = None
             else:
-                self.xp = self.gx1p = self.pT = self.pF = None
+                self.xp = self.gx1p = self.pT = self.pF = self.p2 = self.p3 = None
                 self.iyT, self.iyF, self.gx1 = torch.empty(n, **f), torch.empty(n, **f), torch.empty(n, **f)
-            self.g1p, self.g2, self.g3f = (torch.empty(n, **f) for _ in range(3))
+                self.g2, self.g3f = torch.empty(n, **f), torch.empty(n, **f)
+            self.g1p = torch.empty(n, **f)
             self._y = [torch.empty(n, **f) for _ in range(3)]
             self.Mu = torch.empty(N, self.Ltot, **f)
             self.gMu = torch.empty(N, self.Ltot, **f)
@@ -436,19 +438,28 @@ class DeepKHarmonicStep:
         if forward:
             self._forward(st)
         x1, x2, x3f = self._outputs()
-        g1p, g2, g3f = (self.g1p.data_ptr(), self.g2.data_ptr(), self.g3f.data_ptr()) if grads else (None, None, None)
         # the bias gradients of the three last transposed convs (= channel sums of the reconstruction
         # gradients) come out of the kernels that write those gradients
         fuse_db = grads and C <= 64
+        planes = self.use_planes and fuse_db
+        g1p, g2, g3f = ((self.g1p.data_ptr(), self.g2.data_ptr(), self.g3f.data_ptr()) if (grads and not planes)
+                        else (None, None, None))
         db2, db3 = ((self._gd[1]["tconv5.bias"].data_ptr(), self._gd[2]["tconv5.bias"].data_ptr()) if fuse_db
                     else (None, None))
         # the latent-space terms (a dozen small, latency-bound launches) run beside the HBM-bound cascade
         # losses: forked here, joined before the backward passes
         lside = self._fork()
         y = self._y
-        lb.cascade_losses_upd(self.x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(),
-                              y[0].data_ptr(), y[1].data_ptr(), y[2].data_ptr(), self.rho, 1 if upd else 0,
-                              N, C, 128, 1.0 / numel_g, tp, g1p, g2, g3f, db2, db3, st)
+        if planes:
+            # gradient closure: d/dx2 and d/dx3 leave the loss pass as the operand planes of the 1-D nets' last layers
+            lb.cascade_losses_planes(self.x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(),
+                                     y[0].data_ptr(), y[1].data_ptr(), y[2].data_ptr(), self.rho, 1 if upd else 0,
+                                     N, C, 128, 1.0 / numel_g, tp, self.g1p.data_ptr(), self.p2.data_ptr(),
+                                     self.p3.data_ptr(), db2, db3, st)
+        else:
+            lb.cascade_losses_upd(self.x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(),
+                                  y[0].data_ptr(), y[1].data_ptr(), y[2].data_ptr(), self.rho, 1 if upd else 0,
+                                  N, C, 128, 1.0 / numel_g, tp, g1p, g2, g3f, db2, db3, st)
         khm_scale = plan.khm_scale(self.alpha)
         p = float(self.mod.p)
         aug_scale = plan.aug_scale(self.gamma)
@@ -482,15 +493,17 @@ class DeepKHarmonicStep:
             xf = self.x.view(N, -1)
             inT, inF = (xf, xf) if self.use_planes else (self.iyT.view(N, -1), self.iyF.view(N, -1))
             side = self._fork()
+            g2v, g3v = (None, None) if planes else (self.g2.view(N, -1), self.g3f.view(N, -1))
             with torch.cuda.stream(side):
                 dF = e[2].backward(inF, self._pd[2], self._gd[2], self.ws[2], side.cuda_stream,
-                                   self.g3f.view(N, -1), gMu[:, L + Lt:], Mu[:, L + Lt:], True, self._wstream(2), fuse_db,
-                                   x_planes=self.pF)
-            dT = e[1].backward(inT, self._pd[1], self._gd[1], self.ws[1], st, self.g2.view(N, -1),
-                               gMu[:, L:L + Lt], Mu[:, L:L + Lt], True, self._wstream(1), fuse_db, x_planes=self.pT)
+                                   g3v, gMu[:, L + Lt:], Mu[:, L + Lt:], True, self._wstream(2), fuse_db,
+                                   x_planes=self.pF, g_xhat_planes=self.p3 if planes else None)
+            dT = e[1].backward(inT, self._pd[1], self._gd[1], self.ws[1], st, g2v,
+                               gMu[:, L:L + Lt], Mu[:, L:L + Lt], True, self._wstream(1), fuse_db, x_planes=self.pT,
+                               g_xhat_planes=self.p2 if planes else None)
             self._join(side)
             db1 = self._gd[0]["tconv5.bias"].data_ptr() if fuse_db else None
-            if self.use_planes and fuse_db:
+            if planes:
                 lb.cascade_combine_planes(self.g1p.data_ptr(), dT.data_ptr(), dF.data_ptr(), self.gx1p.data_ptr(), N, C, 128, db1, st)
                 e[0].backward(xf, self._pd[0], self._gd[0], self.ws[0], st, None, gMu[:, :L], Mu[:, :L], False,
                               self._wstream(0), True, x_planes=self.xp, g_xhat_planes=self.gx1p)

@@ -210,3 +210,42 @@ def test_training_closure_with_and_without_operand_planes(cuda, C, N):
     assert torch.equal(a.latents(), b.latents())
     for nm, pa, pb in zip(a.flat.names, a.flat.params, b.flat.params):
         assert rel_err(pa.grad, pb.grad) < 2e-5, nm
+
+
+@pytest.mark.parametrize("N,C,upd", [(3, 8, 1), (2, 4, 0)])
+def test_loss_pass_with_plane_outputs(cuda, N, C, upd):
+    """lshm_cascade_losses_planes against lshm_cascade_losses_upd (fp32 gradients) + staging: same sums, same g1p, same
+    multipliers, same bias-gradient sums, and the two gradient planes equal the staged fp32 gradients."""
+    torch.manual_seed(N * 10 + C)
+    P, rho = 128, 0.7
+    x, x1, x2, x3f = (torch.randn(N, C, P, P, device=cuda) for _ in range(4))
+    ys = [torch.randn(N * C * P * P, device=cuda) for _ in range(3)]
+    n = x.numel()
+    ya = [t.clone() for t in ys]
+    sums_a = torch.zeros(8, dtype=torch.float64, device=cuda)
+    g1a, g2a, g3a = (torch.empty_like(x) for _ in range(3))
+    db2a, db3a = torch.empty(C, device=cuda), torch.empty(C, device=cuda)
+    lib().cascade_losses_upd(dp(x), dp(x1), dp(x2), dp(x3f), dp(ya[0]), dp(ya[1]), dp(ya[2]), rho, upd, N, C, P, 1.0 / n,
+                             dp(sums_a), dp(g1a), dp(g2a), dp(g3a), dp(db2a), dp(db3a), st())
+    l = P * P // 4
+    ref2, ref3 = planes_buffer(1, N, C, 1, l, cuda), planes_buffer(1, N, C, 1, l, cuda)
+    lib().stage_planes1d(dp(g2a), C * P * P, dp(ref2), N, C, l, 0, st())
+    lib().stage_planes1d(dp(g3a), C * P * P, dp(ref3), N, C, l, 0, st())
+    yb = [t.clone() for t in ys]
+    sums_b = torch.zeros(8, dtype=torch.float64, device=cuda)
+    g1b = torch.empty_like(x)
+    p2, p3 = planes_buffer(1, N, C, 1, l, cuda), planes_buffer(1, N, C, 1, l, cuda)
+    db2b, db3b = torch.full((C,), 5.0, device=cuda), torch.full((C,), 5.0, device=cuda)
+    lib().cascade_losses_planes(dp(x), dp(x1), dp(x2), dp(x3f), dp(yb[0]), dp(yb[1]), dp(yb[2]), rho, upd, N, C, P, 1.0 / n,
+                                dp(sums_b), dp(g1b), dp(p2), dp(p3), dp(db2b), dp(db3b), st())
+    assert torch.allclose(sums_b, sums_a, rtol=1e-6)
+    for a, b in zip(ya, yb):
+        assert torch.equal(a, b)
+    assert rel_err(g1b, g1a) < 1e-7
+    # the planes hold bf16 hi/lo of the same fp32 values: decode and compare (a last-bit fp32 difference from a
+    # different multiply-add contraction would flip low bits of lo, so compare values, not bit patterns)
+    def decode(pl):
+        h = pl.view(2, -1).float()
+        return h[0] + h[1]
+    assert rel_err(decode(p2), decode(ref2)) < 1e-6 and rel_err(decode(p3), decode(ref3)) < 1e-6
+    assert rel_err(db2b, db2a) < 1e-5 and rel_err(db3b, db3a) < 1e-5
