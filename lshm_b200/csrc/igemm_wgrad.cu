@@ -10,6 +10,7 @@
 // are again four descriptor start addresses into one Z tile and accumulate in four TMEM column
 // ranges.  The position range is split over CTAs (split-K); partial results are combined with
 // fp32 atomics into dW (zeroed first), already in the reference weight layout.
+#include <stdlib.h>
 #include "conv_geom.cuh"
 #include "tma.cuh"
 
@@ -28,6 +29,7 @@ struct WgArgs {
   float* dw;
   int64_t N; int A; int Bc; int h; int w; int pad;
   int zslots; int nstage; int64_t Q; int64_t kblocks; int64_t kb_per_cta; int ntiles; int scols; int vec_ok;
+  int acols;                        // FOLD: chunk columns (8 channels each) per tap, scols = 4 * acols
   FastDiv d_pp, d_pw, d_w, d_zs;   // divisors (h+1)(w+1), w+1, w, zslots
 };
 
@@ -40,12 +42,17 @@ constexpr int WG_PT = WG_NPW * 32;                 // producer threads
 constexpr int WG_THREADS = WG_PT + 32;             // + the MMA warp
 // PRE: the big map arrives as operand planes; its tile is one tensor-TMA box per half (issued by thread 0),
 // the producer warps stage the (8x smaller) small-map tile only.
-template <int DIM, int NT, int KP, bool PRE>
+// FOLD (2-D, A <= 32): the four taps are folded into the M dimension.  D_tap[a,c] = sum_q S[q,a] Z[q+shift_tap,c]
+// = sum_q' S[q'-shift_tap, a] Z[q', c]: the small-map tile is staged FOUR times, shifted by the tap offsets, as four
+// groups of chunk columns, and one accumulator [(tap,a), c] replaces the four per-tap ones - 24 instead of 96 MMAs
+// per 128 positions (the un-folded first layer ran the tensor pipe at 98 %: every MMA costs max(M,128)*N/256 cycles
+// whatever the number of real rows, profiles/r2_ncu_planes.md), and the big-map tile needs no halo.
+template <int DIM, int NT, int KP, bool PRE, bool FOLD>
 __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_kernel(const __grid_constant__ WgArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], acc_bar;
   __shared__ uint32_t tmem_base;
-  constexpr int T = DIM == 2 ? 4 : 1;
+  constexpr int T = (DIM == 2 && !FOLD) ? 4 : 1;      // accumulators / descriptor shifts per K block
   constexpr int CZ = NT / 8;
   constexpr uint32_t TCOLS = T * NT;
   constexpr uint32_t TMEM_COLS = TCOLS <= 32 ? 32 : (TCOLS <= 64 ? 64 : (TCOLS <= 128 ? 128 : (TCOLS <= 256 ? 256 : 512)));
@@ -63,7 +70,7 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
   const int nkb = (int)(kb1 - kb0);
   const int PW = a.w + 1, PH = a.h + 1;
   const int a0 = mt * 128, c0 = nt * NT;
-  const int sch = min(a.scols, (a.A - a0 + 7) / 8);     // S chunk columns that hold data in this M tile
+  const int sch = FOLD ? a.scols : min(a.scols, (a.A - a0 + 7) / 8);     // S chunk columns that hold data in this M tile
 
   if (warp == WG_NPW) tmem_alloc(&tmem_base, TMEM_COLS);
   if (tid == 0) {
@@ -105,10 +112,14 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
         for (int u = 0; u < U; ++u) {
           const int item = item0 + u * WG_PT;
           const int p = item % KP, ca = item / KP;
-          const uint32_t q = up0 + p;
+          // FOLD: chunk column ca = tap * acols + channel chunk; this copy is shifted by the tap offset
+          const int tap = FOLD ? ca / a.acols : 0;
+          const int cch = FOLD ? ca - tap * a.acols : ca;
+          const uint32_t shift = FOLD ? (uint32_t)((tap >> 1) * PW + (tap & 1)) : 0u;
+          const uint32_t q = up0 + p - shift;             // wraps for the first positions of the map: q >= uQ below
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
-          if (item < KP * a.scols && ca < sch && q < uQ) {
+          if (item < KP * a.scols && ca < sch && up0 + p >= shift && q < uQ) {
             const float* sp = nullptr;
             if (DIM == 2) {
               const uint32_t n = fdiv(q, a.d_pp), r = q - n * upp;
@@ -121,7 +132,7 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
             if (sp != nullptr) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                const int ch = a0 + ca * 8 + e;
+                const int ch = a0 + cch * 8 + e;
                 if (ch < a.A) v[u][e] = __ldg(sp + (int64_t)ch * hw);
               }
             }
@@ -215,8 +226,40 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
     if (warp < 4) {
     mbar_wait(&acc_bar, 0);
     fence_after();
-    const int ch = a0 + tid;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    if (FOLD) {
+      // accumulator row = tap * 8 acols + channel.  M = 64: row 16 j + i sits in TMEM lane 32 j + i (i < 16); M = 128: row = lane
+      const int rows = 32 * a.acols;
+      const bool m64 = rows <= 64;
+      const int row = m64 ? (warp * 16 + lane) : tid;
+      const bool rok = (m64 ? lane < 16 : true) && row < rows && nkb > 0;
+      const int tapr = row / (8 * a.acols), chn = row - tapr * 8 * a.acols;
+      const int ty = tapr >> 1, tx = tapr & 1;
+      const bool v2ok = (reinterpret_cast<uintptr_t>(a.dw) & 7) == 0;
+#pragma unroll 1
+      for (int g = 0; g < NT / 16; ++g) {
+        float v[16];
+        tmem_ld16(trow + g * 16, v);
+        if (rok && chn < a.A) {
+#pragma unroll
+          for (int jb = 0; jb < 4; ++jb) {
+            const int b = (c0 + g * 16) / 4 + jb;
+            if (b < a.Bc) {
+              // columns 4 b + (sy, sx): kernel element (2 ty + sy, 2 tx + sx)
+              float* dst = a.dw + ((int64_t)chn * a.Bc + b) * 16 + (2 * ty) * 4 + 2 * tx;
+              if (v2ok) {
+                atomicAdd(reinterpret_cast<float2*>(dst), make_float2(v[jb * 4 + 0], v[jb * 4 + 1]));
+                atomicAdd(reinterpret_cast<float2*>(dst + 4), make_float2(v[jb * 4 + 2], v[jb * 4 + 3]));
+              } else {
+                atomicAdd(dst, v[jb * 4 + 0]); atomicAdd(dst + 1, v[jb * 4 + 1]);
+                atomicAdd(dst + 4, v[jb * 4 + 2]); atomicAdd(dst + 5, v[jb * 4 + 3]);
+              }
+            }
+          }
+        }
+      }
+    } else {
+    const int ch = a0 + tid;
     // The split-K partial sums go to dW with 16-byte vector atomics: one per (channel pair row) instead
     // of four scalar ones.  With scalar atomics the deep layers (few positions, 10^5 weights, 36 splits)
     // spent most of their ~110 us in this epilogue, whatever their size.
@@ -270,12 +313,13 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
       }
     }
     }
+    }
   } else {
     // ------------------------------------------------ MMA issuer: warp-uniform loop, one elected lane issues
     // M = 64 when the layer has at most 16 output channels (rows 0-15 of the accumulator sit in TMEM lanes
     // 0-15 for either M): the M-side operand fetch from shared memory (4 KB per MMA at M = 128, of which
     // 8 rows are real in the first layer) is what bounds the wide first layers.
-    const uint32_t idesc = make_idesc(NT, 1, 1, a.A <= 16 ? 64 : 128);
+    const uint32_t idesc = make_idesc(NT, 1, 1, FOLD ? (32 * a.acols <= 64 ? 64 : 128) : (a.A <= 16 ? 64 : 128));
     const uint32_t leader = elect_one();
     Ring ring{0, 0};
     for (int it = 0; it < nkb; ++it, ring.next(NS)) {
@@ -311,7 +355,7 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
   if (warp == WG_NPW) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-template <int DIM, int NT, int KP, bool PRE = false>
+template <int DIM, int NT, int KP, bool PRE = false, bool FOLD = false>
 int launch_wgrad_t(WgArgs a, int64_t splits, int mtiles, cudaStream_t st) {
   if (PRE) {
     const PlaneGeom pg = plane_geom(DIM, a.N, a.Bc, a.h, a.w);
@@ -323,9 +367,9 @@ int launch_wgrad_t(WgArgs a, int64_t splits, int mtiles, cudaStream_t st) {
   // slack: the padding row groups of the last stage's S tiles are read (and ignored) up to 16 groups
   const size_t reach = (size_t)a.scols * KP * 16 + (size_t)16 * KP * 16;     // from the stage start
   const size_t smem = stage * a.nstage + (reach > stage ? reach - stage : 0) + 256;
-  LSHM_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<DIM, NT, KP, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_wgrad");
+  LSHM_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<DIM, NT, KP, PRE, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_wgrad");
   dim3 grid((unsigned)splits, (unsigned)(mtiles * a.ntiles));
-  igemm_wgrad_kernel<DIM, NT, KP, PRE><<<grid, WG_THREADS, smem, st>>>(a);
+  igemm_wgrad_kernel<DIM, NT, KP, PRE, FOLD><<<grid, WG_THREADS, smem, st>>>(a);
   LSHM_CHECK_LAUNCH("igemm_wgrad");
   return LSHM_OK;
 }
@@ -343,7 +387,11 @@ int launch_wgrad(int dim, WgArgs a, cudaStream_t st, bool planes = false) {
   a.vec_ok = ((reinterpret_cast<uintptr_t>(a.big) & 15) == 0 && (a.big_ns & 3) == 0) ? 1 : 0;
   const int KP = (a.scols <= 2 && NT <= 32) ? 128 : 64;
   a.kblocks = ceil_div(a.Q, KP);
-  a.zslots = dim == 2 ? (KP + a.w + 2 + 7) / 8 * 8 : KP;
+  // taps folded into M (see the kernel): the 8 / 12-channel layers, whose un-folded form is bound by the tensor pipe
+  static const bool nofold = getenv("LSHM_WGRAD_NOFOLD") != nullptr;          // experiment switch
+  const bool fold = dim == 2 && a.A <= 16 && KP == 128 && !nofold;
+  if (fold) { a.acols = (a.A + 7) / 8; a.scols = 4 * a.acols; }
+  a.zslots = (dim == 2 && !fold) ? (KP + a.w + 2 + 7) / 8 * 8 : KP;
   if (planes) a.zslots = (a.zslots + PLANE_ROW - 1) / PLANE_ROW * PLANE_ROW;   // whole 512-byte rows of the tensor map
   a.d_zs = make_fastdiv((uint32_t)a.zslots);
   const size_t stage = (size_t)2 * a.scols * KP * 16 + (size_t)2 * (NT / 8) * a.zslots * 16;
@@ -356,9 +404,14 @@ int launch_wgrad(int dim, WgArgs a, cudaStream_t st, bool planes = false) {
   a.nstage = (int)std::min<int64_t>(a.nstage, std::max<int64_t>(1, a.kb_per_cta));
   if (planes) {
     LSHM_REQUIRE(NT <= 32 && KP == 128 && a.zslots <= 256, "lshm_wgrad*_planes: operand planes serve the first layers (A <= 16, Bc <= 8)");
+    if (dim == 2 && fold) { if (NT == 16) return launch_wgrad_t<2, 16, 128, true, true>(a, splits, mtiles, st); return launch_wgrad_t<2, 32, 128, true, true>(a, splits, mtiles, st); }
     if (dim == 2) { if (NT == 16) return launch_wgrad_t<2, 16, 128, true>(a, splits, mtiles, st); return launch_wgrad_t<2, 32, 128, true>(a, splits, mtiles, st); }
     if (NT == 16) return launch_wgrad_t<1, 16, 128, true>(a, splits, mtiles, st);
     return launch_wgrad_t<1, 32, 128, true>(a, splits, mtiles, st);
+  }
+  if (fold) {
+    if (NT == 16) return launch_wgrad_t<2, 16, 128, false, true>(a, splits, mtiles, st);
+    return launch_wgrad_t<2, 32, 128, false, true>(a, splits, mtiles, st);
   }
 #define LW(D, NTV, KPV) return launch_wgrad_t<D, NTV, KPV>(a, splits, mtiles, st)
   if (dim == 2) {

@@ -193,10 +193,16 @@ residual_split_planes_kernel(const float* __restrict__ x, const float* __restric
 
 // gx1 = g1p - 0.5 (gT + transpose(gF)) written as the 2-D planes of the 2-D net's last transposed conv
 // (block (by,bx) = pixel rows 2by-1, 2by x columns 2bx-1, 2bx), plus the per-channel sums (bias gradient).
-// Micro-tile scheme: the thread of the aligned block (t4, f4) evaluates gx1 on rows t4-1 .. t4+3 x columns
-// f4-1 .. f4+3 (row-major inputs: float4 + one scalar per row; the transposed input gF: float4 along t + one scalar
-// per column) and owns the 2 x 2 pixel blocks by = t4/2, t4/2+1, bx = f4/2, f4/2+1 - plus the last halo block row /
-// column (pixel row / column P-1 and the zero beyond it) when it sits on the bottom / right edge.
+// Micro-tile scheme with the tile SHIFTED by (-1,-1): the thread of (t4, f4) evaluates gx1 on rows t4-1 .. t4+2 x
+// columns f4-1 .. f4+2 (row-major inputs: one scalar + one float4 per row; the transposed input gF: one scalar + one
+// float4 along t per column) = the four 2 x 2 pixel blocks by = t4/2, t4/2+1, bx = f4/2, f4/2+1.  Threads on the
+// bottom / right edge also emit the last halo block row / column (pixel row / column P-1 and the zero beyond it).
+__device__ __forceinline__ float gx1_at(const float* __restrict__ ap, const float* __restrict__ bp,
+                                        const float* __restrict__ cp, int P, int t, int f) {
+  const int64_t off = (int64_t)t * P + f;
+  return __ldg(ap + off) - 0.5f * (__ldg(bp + off) + __ldg(cp + (int64_t)f * P + t));
+}
+
 __global__ void __launch_bounds__(256)
 combine_planes_kernel(const float* __restrict__ g1p, const float* __restrict__ gT, const float* __restrict__ gF,
                       uint8_t* __restrict__ planes, size_t half_bytes, int C, int P, int64_t Qs, int64_t items,
@@ -205,85 +211,121 @@ combine_planes_kernel(const float* __restrict__ g1p, const float* __restrict__ g
   const int strips = P / 32;
   const int ccn = C / 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int PW = P / 2 + 1;
   if (threadIdx.x < 64) cacc[threadIdx.x] = 0.f;
   __syncthreads();
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-  const int strip = (int)(item % strips);
-  const int64_t pair = item / strips;
-  const int n = (int)(pair / ccn), cc = (int)(pair % ccn);
-  const int t4 = strip * 32 + (lane >> 2) * 4;
-  const int f4 = warp * 16 + (lane & 3) * 4;
-  float v[2][5][5];
-  float part[2] = {0.f, 0.f};
-  const bool active = f4 < P;
-  if (active) {
+    const int strip = (int)(item % strips);
+    const int64_t pair = item / strips;
+    const int n = (int)(pair / ccn), cc = (int)(pair % ccn);
+    const int t4 = strip * 32 + (lane >> 2) * 4;
+    const int f4 = warp * 16 + (lane & 3) * 4;
+    if (f4 < P) {
+      float v[2][4][4];                      // [channel][row t4-1+r][column f4-1+c]
+      float part[2] = {0.f, 0.f};
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      const int64_t plane = ((int64_t)n * C + 2 * cc + ch) * P * (int64_t)P;
-      const float* ap = g1p + plane;
-      const float* bp = gT + plane;
-      const float* cp = gF + plane;
-      // transposed input first: w[c][r] = gF[f4-1+c][t4-1+r]
-      float w[5][5];
+      for (int ch = 0; ch < 2; ++ch) {
+        const int64_t plane = ((int64_t)n * C + 2 * cc + ch) * P * (int64_t)P;
+        const float* ap = g1p + plane;
+        const float* bp = gT + plane;
+        const float* cp = gF + plane;
+        float w[4][4];                       // w[c][r] = gF[f4-1+c][t4-1+r]
 #pragma unroll
-      for (int c = 0; c < 5; ++c) {
-        const int f = f4 - 1 + c;
-        if (f >= 0) {
-          const float* q = cp + (int64_t)f * P + t4;
-          const float4 d = __ldg(reinterpret_cast<const float4*>(q));
-          w[c][1] = d.x; w[c][2] = d.y; w[c][3] = d.z; w[c][4] = d.w;
-          w[c][0] = t4 > 0 ? __ldg(q - 1) : 0.f;
-        } else {
+        for (int c = 0; c < 4; ++c) {
+          const int f = f4 - 1 + c;
+          if (f >= 0) {
+            const float* q = cp + (int64_t)f * P + t4;
+            const float4 d = __ldg(reinterpret_cast<const float4*>(q));
+            w[c][1] = d.x; w[c][2] = d.y; w[c][3] = d.z;
+            w[c][0] = t4 > 0 ? __ldg(q - 1) : 0.f;
+          } else {
+            w[c][0] = w[c][1] = w[c][2] = w[c][3] = 0.f;
+          }
+        }
 #pragma unroll
-          for (int r = 0; r < 5; ++r) w[c][r] = 0.f;
+        for (int r = 0; r < 4; ++r) {
+          const int t = t4 - 1 + r;
+          if (t >= 0) {
+            const int64_t off = (int64_t)t * P + f4;
+            const float4 a = __ldg(reinterpret_cast<const float4*>(ap + off));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bp + off));
+            v[ch][r][1] = a.x - 0.5f * (b.x + w[1][r]); v[ch][r][2] = a.y - 0.5f * (b.y + w[2][r]);
+            v[ch][r][3] = a.z - 0.5f * (b.z + w[3][r]);
+            v[ch][r][0] = f4 > 0 ? __ldg(ap + off - 1) - 0.5f * (__ldg(bp + off - 1) + w[0][r]) : 0.f;
+            part[ch] += (v[ch][r][0] + v[ch][r][1]) + (v[ch][r][2] + v[ch][r][3]);
+          } else {
+            v[ch][r][0] = v[ch][r][1] = v[ch][r][2] = v[ch][r][3] = 0.f;
+          }
         }
       }
 #pragma unroll
-      for (int r = 0; r < 5; ++r) {
-        const int t = t4 - 1 + r;
-        if (t >= 0) {
-          const int64_t off = (int64_t)t * P + f4;
-          const float4 a = __ldg(reinterpret_cast<const float4*>(ap + off));
-          const float4 b = __ldg(reinterpret_cast<const float4*>(bp + off));
-          v[ch][r][1] = a.x - 0.5f * (b.x + w[1][r]); v[ch][r][2] = a.y - 0.5f * (b.y + w[2][r]);
-          v[ch][r][3] = a.z - 0.5f * (b.z + w[3][r]); v[ch][r][4] = a.w - 0.5f * (b.w + w[4][r]);
-          v[ch][r][0] = f4 > 0 ? __ldg(ap + off - 1) - 0.5f * (__ldg(bp + off - 1) + w[0][r]) : 0.f;
-          if (r > 0) part[ch] += (v[ch][r][1] + v[ch][r][2]) + (v[ch][r][3] + v[ch][r][4]);
-        } else {
+      for (int bi = 0; bi < 2; ++bi) {
 #pragma unroll
-          for (int c = 0; c < 5; ++c) v[ch][r][c] = 0.f;
+        for (int bj = 0; bj < 2; ++bj) {
+          float c[8];
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            c[ch * 4 + 0] = v[ch][2 * bi][2 * bj];     c[ch * 4 + 1] = v[ch][2 * bi][2 * bj + 1];
+            c[ch * 4 + 2] = v[ch][2 * bi + 1][2 * bj]; c[ch * 4 + 3] = v[ch][2 * bi + 1][2 * bj + 1];
+          }
+          store_chunk(planes, half_bytes, Qs, cc, ((int64_t)n * PW + (t4 / 2 + bi)) * PW + (f4 / 2 + bj), c);
         }
       }
-    }
-    const int PW = P / 2 + 1;
-    const int nbi = (t4 == P - 4) ? 3 : 2, nbj = (f4 == P - 4) ? 3 : 2;
+      // ---- bottom / right edge: pixel row P-1 / column P-1 pair with the zero beyond the map
+      const bool bot = t4 == P - 4, rgt = f4 == P - 4;
+      if (bot || rgt) {
+        const int64_t pl0 = ((int64_t)n * C + 2 * cc) * P * (int64_t)P, pl1 = pl0 + (int64_t)P * P;
+        if (bot) {
+          // blocks (by = P/2, bx = f4/2 + bj): pixel row P-1, columns f4-1+2bj, f4+2bj
 #pragma unroll
-    for (int bi = 0; bi < 3; ++bi) {
-      if (bi >= nbi) break;
+          for (int bj = 0; bj < 2; ++bj) {
+            float c[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int bj = 0; bj < 3; ++bj) {
-        if (bj >= nbj) break;
-        float c[8];
+            for (int e = 0; e < 2; ++e) {
+              const int f = f4 - 1 + 2 * bj + e;
+              if (f >= 0) {
+                c[e] = gx1_at(g1p + pl0, gT + pl0, gF + pl0, P, P - 1, f);
+                c[4 + e] = gx1_at(g1p + pl1, gT + pl1, gF + pl1, P, P - 1, f);
+                part[0] += c[e]; part[1] += c[4 + e];
+              }
+            }
+            store_chunk(planes, half_bytes, Qs, cc, ((int64_t)n * PW + P / 2) * PW + (f4 / 2 + bj), c);
+          }
+        }
+        if (rgt) {
+          // blocks (by = t4/2 + bi, bx = P/2): pixel column P-1, rows t4-1+2bi, t4+2bi
+#pragma unroll
+          for (int bi = 0; bi < 2; ++bi) {
+            float c[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int t = t4 - 1 + 2 * bi + e;
+              if (t >= 0) {
+                c[2 * e] = gx1_at(g1p + pl0, gT + pl0, gF + pl0, P, t, P - 1);
+                c[4 + 2 * e] = gx1_at(g1p + pl1, gT + pl1, gF + pl1, P, t, P - 1);
+                part[0] += c[2 * e]; part[1] += c[4 + 2 * e];
+              }
+            }
+            store_chunk(planes, half_bytes, Qs, cc, ((int64_t)n * PW + (t4 / 2 + bi)) * PW + P / 2, c);
+          }
+        }
+        if (bot && rgt) {
+          float c[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          c[0] = gx1_at(g1p + pl0, gT + pl0, gF + pl0, P, P - 1, P - 1);
+          c[4] = gx1_at(g1p + pl1, gT + pl1, gF + pl1, P, P - 1, P - 1);
+          part[0] += c[0]; part[1] += c[4];
+          store_chunk(planes, half_bytes, Qs, cc, ((int64_t)n * PW + P / 2) * PW + P / 2, c);
+        }
+      }
+      // per-channel sums: every lane of the warp reaches this point
+      if (db1 != nullptr) {
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
-          // rows 2bi, 2bi+1 / columns 2bj, 2bj+1 of the 5 x 5 grid; index 5 is beyond the map (zero)
-          c[ch * 4 + 0] = v[ch][2 * bi][2 * bj];
-          c[ch * 4 + 1] = (2 * bj + 1 < 5) ? v[ch][2 * bi][(2 * bj + 1) % 5] : 0.f;
-          c[ch * 4 + 2] = (2 * bi + 1 < 5) ? v[ch][(2 * bi + 1) % 5][2 * bj] : 0.f;
-          c[ch * 4 + 3] = (2 * bi + 1 < 5 && 2 * bj + 1 < 5) ? v[ch][(2 * bi + 1) % 5][(2 * bj + 1) % 5] : 0.f;
+          const float p = warp_sum(part[ch]);
+          if (lane == 0) atomicAdd(&cacc[2 * cc + ch], p);
         }
-        const int64_t q = ((int64_t)n * PW + (t4 / 2 + bi)) * PW + (f4 / 2 + bj);
-        store_chunk(planes, half_bytes, Qs, cc, q, c);
       }
     }
-  }
-  if (db1 != nullptr) {
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      const float p = warp_sum(part[ch]);
-      if (lane == 0) atomicAdd(&cacc[2 * cc + ch], p);
-    }
-  }
   }
   if (db1 != nullptr) {
     __syncthreads();
