@@ -389,7 +389,7 @@ int launch_wgrad(int dim, WgArgs a, cudaStream_t st, bool planes = false) {
   a.kblocks = ceil_div(a.Q, KP);
   // taps folded into M (see the kernel): the 8 / 12-channel layers, whose un-folded form is bound by the tensor pipe
   static const bool nofold = getenv("LSHM_WGRAD_NOFOLD") != nullptr;          // experiment switch
-  const bool fold = dim == 2 && a.A <= 16 && KP == 128 && !nofold;
+  const bool fold = dim == 2 && a.A <= 8 && KP == 128 && !nofold;   // (A = 12: staging the small map 4x costs more than it saves)
   if (fold) { a.acols = (a.A + 7) / 8; a.scols = 4 * a.acols; }
   a.zslots = (dim == 2 && !fold) ? (KP + a.w + 2 + 7) / 8 * 8 : KP;
   if (planes) a.zslots = (a.zslots + PLANE_ROW - 1) / PLANE_ROW * PLANE_ROW;   // whole 512-byte rows of the tensor map

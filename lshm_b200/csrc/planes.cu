@@ -208,6 +208,9 @@ combine_planes_kernel(const float* __restrict__ g1p, const float* __restrict__ g
                       uint8_t* __restrict__ planes, size_t half_bytes, int C, int P, int64_t Qs, int64_t items,
                       float* __restrict__ db1) {
   __shared__ float cacc[64];                 // per-channel sums of this (persistent) block
+  // the 4 chunks of a thread are 16 bytes at a 32-byte stride in the planes: they go through this per-warp staging
+  // area and leave as 128-byte runs (8 chunks of one block row)
+  __shared__ uint4 stg[8][2][16][8];         // [warp][half][block row 2 tg + bi][block column 2 fg + bj]
   const int strips = P / 32;
   const int ccn = C / 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -268,9 +271,21 @@ combine_planes_kernel(const float* __restrict__ g1p, const float* __restrict__ g
             c[ch * 4 + 0] = v[ch][2 * bi][2 * bj];     c[ch * 4 + 1] = v[ch][2 * bi][2 * bj + 1];
             c[ch * 4 + 2] = v[ch][2 * bi + 1][2 * bj]; c[ch * 4 + 3] = v[ch][2 * bi + 1][2 * bj + 1];
           }
-          store_chunk(planes, half_bytes, Qs, cc, ((int64_t)n * PW + (t4 / 2 + bi)) * PW + (f4 / 2 + bj), c);
+          uint4 hh, ll;
+          split8(c, hh, ll);
+          stg[warp][0][2 * (lane >> 2) + bi][2 * (lane & 3) + bj] = hh;
+          stg[warp][1][2 * (lane >> 2) + bi][2 * (lane & 3) + bj] = ll;
         }
       }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int idx = it * 32 + lane;
+        const int half = idx >> 7, r = (idx >> 3) & 15, cx = idx & 7;
+        const int64_t q = ((int64_t)n * PW + (strip * 16 + r)) * PW + (warp * 8 + cx);
+        *reinterpret_cast<uint4*>(planes + (size_t)half * half_bytes + ((size_t)cc * (size_t)Qs + (size_t)q) * 16) = stg[warp][half][r][cx];
+      }
+      __syncwarp();
       // ---- bottom / right edge: pixel row P-1 / column P-1 pair with the zero beyond the map
       const bool bot = t4 == P - 4, rgt = f4 == P - 4;
       if (bot || rgt) {
