@@ -204,7 +204,9 @@ LSHM_API int lshm_cascade_losses(const float* x, const float* x1, const float* x
 /* Same pass with the DEFERRED multiplier update of the previous ADMM iteration folded in
  * (src/kharmonic_lofar.py:187-202 followed by :150-158 on the same minibatch and parameters): when
  * update_y != 0 the kernel first does y_i += rho * r_i with the residuals it computes anyway, stores the
- * new multipliers, and evaluates the loss terms / gradients with them.  update_y == 0 is lshm_cascade_losses. */
+ * new multipliers, and evaluates the loss terms / gradients with them.  update_y == 0 is lshm_cascade_losses.
+ * Bit 1 of update_y (values 2, 3): the multipliers are identically ZERO (a new minibatch, :128-130) and are not read;
+ * with bit 0 as well the kernel writes y_i = rho * r_i.  (Saves the three memsets and three reads per minibatch.) */
 LSHM_API int lshm_cascade_losses_upd(const float* x, const float* x1, const float* x2, const float* x3f,
                             float* y1, float* y2, float* y3, float rho, int update_y,
                             int64_t N, int C, int P, float grad_scale, double* sums,
@@ -227,6 +229,10 @@ LSHM_API int lshm_cascade_combine_planes(const float* g1p, const float* gT, cons
 LSHM_API int lshm_multiplier_update(const float* x, const float* x1, const float* x2, const float* x3f,
                            float rho, float* y1, float* y2, float* y3,
                            int64_t N, int C, int P, lshm_stream_t stream);
+/* y_zero != 0: the multipliers start from zero (new minibatch): y_i = rho * r_i is written without reading y_i. */
+LSHM_API int lshm_multiplier_update_z(const float* x, const float* x1, const float* x2, const float* x3f,
+                             float rho, float* y1, float* y2, float* y3, int y_zero,
+                             int64_t N, int C, int P, lshm_stream_t stream);
 
 /* --------------------------------------------------------------- K-harmonic -----
  * Kmeans.forward (src/lofar_models.py:199-209): X [N,L] (row stride ldx), M [K,L].

@@ -45,7 +45,8 @@ constexpr int CASCADE_MAXC = 64;   // channels whose bias-gradient sums can be f
 // src/kharmonic_lofar.py:200-202) is applied on the fly - the residuals r_i are exactly the ones this
 // pass computes anyway (same parameters, same minibatch), so the stand-alone 10-pass update kernel and its
 // re-read of x, x1, x2, x3 disappear; the loss terms and gradients then use the UPDATED multipliers.
-template <bool GRADS, bool UPD>
+// YZ: the multipliers are identically zero (a new minibatch) and are not read; with UPD the kernel writes y_i = rho r_i.
+template <bool GRADS, bool UPD, bool YZ>
 __global__ void __launch_bounds__(TILE * TROWS, 6)
 cascade_losses_kernel(const float* __restrict__ x, const float* __restrict__ x1,
                       const float* __restrict__ x2, const float* __restrict__ x3f,
@@ -81,7 +82,8 @@ cascade_losses_kernel(const float* __restrict__ x, const float* __restrict__ x1,
     for (int i = 0; i < TILE; i += TROWS) {
       const int64_t off = plane + (int64_t)(t0 + ty + i) * P + f0 + tx;
       const float xv = x[off], a1 = x1[off], a2 = x2[off], a3 = tile[tx][ty + i];
-      float m1 = y1[off], m2 = y2[off], m3 = y3[off];
+      float m1 = 0.f, m2 = 0.f, m3 = 0.f;
+      if (!YZ) { m1 = y1[off]; m2 = y2[off]; m3 = y3[off]; }
       const float r0 = a1 + a2 + a3 - xv;
       const float r1 = xv - a1;
       const float x11 = 0.5f * r1;
@@ -176,6 +178,7 @@ cascade_combine_kernel(const float* __restrict__ g1p, const float* __restrict__ 
   }
 }
 
+template <bool YZ>
 __global__ void __launch_bounds__(TILE * TROWS)
 multiplier_update_kernel(const float* __restrict__ x, const float* __restrict__ x1,
                          const float* __restrict__ x2, const float* __restrict__ x3f, float rho,
@@ -193,9 +196,15 @@ multiplier_update_kernel(const float* __restrict__ x, const float* __restrict__ 
     const int64_t off = plane + (int64_t)(t0 + ty + i) * P + f0 + tx;
     const float r1 = x[off] - x1[off];
     const float x11 = 0.5f * r1;
-    y1[off] += rho * r1;
-    y2[off] += rho * (x11 - x2[off]);
-    y3[off] += rho * (x11 - tile[tx][ty + i]);
+    if (YZ) {       // multipliers start from zero (new minibatch): written, not read
+      y1[off] = rho * r1;
+      y2[off] = rho * (x11 - x2[off]);
+      y3[off] = rho * (x11 - tile[tx][ty + i]);
+    } else {
+      y1[off] += rho * r1;
+      y2[off] += rho * (x11 - x2[off]);
+      y3[off] += rho * (x11 - tile[tx][ty + i]);
+    }
   }
 }
 
@@ -441,10 +450,16 @@ int lshm_cascade_losses_upd(const float* x, const float* x1, const float* x2, co
     LSHM_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * C, as_stream(stream)), "lshm_cascade_losses");
     LSHM_CUDA(cudaMemsetAsync(db3, 0, sizeof(float) * C, as_stream(stream)), "lshm_cascade_losses");
   }
-#define LSHM_CL(G, U) cascade_losses_kernel<G, U><<<(unsigned)blocks, block, 0, as_stream(stream)>>>( \
+#define LSHM_CL(G, U, Z) cascade_losses_kernel<G, U, Z><<<(unsigned)blocks, block, 0, as_stream(stream)>>>( \
       x, x1, x2, x3f, y1, y2, y3, rho, inv_n, P, ntiles, sums, g1p, g2, g3f, C, db2, db3)
-  if (g1p) { if (update_y) LSHM_CL(true, true); else LSHM_CL(true, false); }
-  else { if (update_y) LSHM_CL(false, true); else LSHM_CL(false, false); }
+  const int mode = update_y & 3;     // bit 0: apply the deferred update; bit 1: the multipliers are zero (not read)
+  if (g1p) {
+    if (mode == 0) LSHM_CL(true, false, false); else if (mode == 1) LSHM_CL(true, true, false);
+    else if (mode == 2) LSHM_CL(true, false, true); else LSHM_CL(true, true, true);
+  } else {
+    if (mode == 0) LSHM_CL(false, false, false); else if (mode == 1) LSHM_CL(false, true, false);
+    else if (mode == 2) LSHM_CL(false, false, true); else LSHM_CL(false, true, true);
+  }
 #undef LSHM_CL
   LSHM_CHECK_LAUNCH("lshm_cascade_losses");
   return LSHM_OK;
@@ -468,6 +483,12 @@ int lshm_cascade_combine(const float* g1p, const float* gT, const float* gF, flo
 int lshm_multiplier_update(const float* x, const float* x1, const float* x2, const float* x3f,
                            float rho, float* y1, float* y2, float* y3,
                            int64_t N, int C, int P, lshm_stream_t stream) {
+  return lshm_multiplier_update_z(x, x1, x2, x3f, rho, y1, y2, y3, 0, N, C, P, stream);
+}
+
+int lshm_multiplier_update_z(const float* x, const float* x1, const float* x2, const float* x3f,
+                             float rho, float* y1, float* y2, float* y3, int y_zero,
+                             int64_t N, int C, int P, lshm_stream_t stream) {
   LSHM_REQUIRE(x && x1 && x2 && x3f && y1 && y2 && y3, "lshm_multiplier_update: null pointer");
   if (int rc = check_cascade("lshm_multiplier_update", N, C, P)) return rc;
   if (N == 0) return LSHM_OK;
@@ -476,7 +497,8 @@ int lshm_multiplier_update(const float* x, const float* x1, const float* x2, con
     const int64_t nz = planes - z0 < 65535 ? planes - z0 : 65535;
     const int64_t o = z0 * P * P;
     dim3 grid(P / TILE, P / TILE, (unsigned)nz), block(TILE, TROWS);
-    multiplier_update_kernel<<<grid, block, 0, as_stream(stream)>>>(x + o, x1 + o, x2 + o, x3f + o, rho, y1 + o, y2 + o, y3 + o, P);
+    if (y_zero) multiplier_update_kernel<true><<<grid, block, 0, as_stream(stream)>>>(x + o, x1 + o, x2 + o, x3f + o, rho, y1 + o, y2 + o, y3 + o, P);
+    else multiplier_update_kernel<false><<<grid, block, 0, as_stream(stream)>>>(x + o, x1 + o, x2 + o, x3f + o, rho, y1 + o, y2 + o, y3 + o, P);
   }
   LSHM_CHECK_LAUNCH("lshm_multiplier_update");
   return LSHM_OK;

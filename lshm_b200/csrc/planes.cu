@@ -353,7 +353,9 @@ combine_planes_kernel(const float* __restrict__ g1p, const float* __restrict__ g
 // [4j, 4j+3] of the flattened map: a row of the thread's 4 x 4 block for the time-axis net, a column for the
 // frequency-axis net).  Same micro-tile scheme; x3f is read along t (it is stored transposed), nothing goes through
 // shared memory.  Persistent blocks: the seven loss sums and the bias-gradient sums are flushed once per block.
-template <bool UPD>
+// UPD: apply the deferred multiplier update first; YZ: the multipliers are identically zero (a new minibatch,
+// src/kharmonic_lofar.py:128-130) and are not read - with UPD the kernel then writes y_i = rho r_i.
+template <bool UPD, bool YZ>
 __global__ void __launch_bounds__(256, 2)
 cascade_losses_planes_kernel(const float* __restrict__ x, const float* __restrict__ x1, const float* __restrict__ x2,
                              const float* __restrict__ x3f, float* __restrict__ y1, float* __restrict__ y2,
@@ -398,9 +400,12 @@ cascade_losses_planes_kernel(const float* __restrict__ x, const float* __restric
         const float4 X = __ldg(reinterpret_cast<const float4*>(x + off));
         const float4 A1 = __ldg(reinterpret_cast<const float4*>(x1 + off));
         const float4 A2 = __ldg(reinterpret_cast<const float4*>(x2 + off));
-        float4 M1 = *reinterpret_cast<const float4*>(y1 + off);
-        float4 M2 = *reinterpret_cast<const float4*>(y2 + off);
-        float4 M3 = *reinterpret_cast<const float4*>(y3 + off);
+        float4 M1 = make_float4(0.f, 0.f, 0.f, 0.f), M2 = M1, M3 = M1;
+        if (!YZ) {
+          M1 = *reinterpret_cast<const float4*>(y1 + off);
+          M2 = *reinterpret_cast<const float4*>(y2 + off);
+          M3 = *reinterpret_cast<const float4*>(y3 + off);
+        }
         const float xv[4] = {X.x, X.y, X.z, X.w}, a1[4] = {A1.x, A1.y, A1.z, A1.w}, a2[4] = {A2.x, A2.y, A2.z, A2.w};
         float m1[4] = {M1.x, M1.y, M1.z, M1.w}, m2[4] = {M2.x, M2.y, M2.z, M2.w}, m3[4] = {M3.x, M3.y, M3.z, M3.w};
         float g1[4];
@@ -556,9 +561,14 @@ int lshm_cascade_losses_planes(const float* x, const float* x1, const float* x2,
   const PlaneGeom g = plane_geom(1, N, C, 1, P * P / 4);
   const int64_t items = N * (C / 2) * (int64_t)(P / 32);
   const int64_t blocks = std::min<int64_t>(items, (int64_t)sm_count() * 2);
-#define LSHM_CLP(U) cascade_losses_planes_kernel<U><<<(unsigned)blocks, 256, 0, st>>>(x, x1, x2, x3f, y1, y2, y3, rho, grad_scale, \
+#define LSHM_CLP(U, Z) cascade_losses_planes_kernel<U, Z><<<(unsigned)blocks, 256, 0, st>>>(x, x1, x2, x3f, y1, y2, y3, rho, grad_scale, \
       C, P, items, sums, g1p, reinterpret_cast<uint8_t*>(planes2), reinterpret_cast<uint8_t*>(planes3), g.half_bytes, g.Qs, db2, db3)
-  if (update_y) LSHM_CLP(true); else LSHM_CLP(false);
+  switch (update_y & 3) {
+    case 0: LSHM_CLP(false, false); break;
+    case 1: LSHM_CLP(true, false); break;
+    case 2: LSHM_CLP(false, true); break;
+    default: LSHM_CLP(true, true); break;
+  }
 #undef LSHM_CLP
   LSHM_CHECK_LAUNCH("lshm_cascade_losses_planes");
   return LSHM_OK;

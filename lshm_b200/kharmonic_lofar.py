@@ -265,6 +265,7 @@ class DeepKHarmonicStep:
         self._loss_key = None            # same for the loss scalars in the tail (+ multiplier state)
         self._batch_id = 0
         self._pending = False            # multiplier update deferred into the next loss pass
+        self._y_zero = True              # y1..y3 are identically zero and not materialised (new minibatch)
         if distributed:
             self.broadcast_parameters()
 
@@ -328,8 +329,7 @@ class DeepKHarmonicStep:
     def reset_multipliers(self):
         """y1 = y2 = y3 = 0 (a new minibatch); a deferred update of the previous minibatch is dropped, as the
         reference drops the multipliers themselves (src/kharmonic_lofar.py:128-130)."""
-        for y in self._y:
-            y.zero_()
+        self._y_zero = True              # nothing is written: the next kernels treat the multipliers as zero
         self._pending = False
         self._loss_key = None
 
@@ -348,21 +348,26 @@ class DeepKHarmonicStep:
     # multipliers: reading them applies a deferred update first, so they always hold the reference's values
     @property
     def y1(self) -> torch.Tensor:
-        self.flush_multipliers()
-        self._loss_key = None        # the caller may write into the returned tensor
+        self._materialise_multipliers()
         return self._y[0]
 
     @property
     def y2(self) -> torch.Tensor:
-        self.flush_multipliers()
-        self._loss_key = None        # the caller may write into the returned tensor
+        self._materialise_multipliers()
         return self._y[1]
 
     @property
     def y3(self) -> torch.Tensor:
-        self.flush_multipliers()
-        self._loss_key = None        # the caller may write into the returned tensor
+        self._materialise_multipliers()
         return self._y[2]
+
+    def _materialise_multipliers(self):
+        self.flush_multipliers()
+        if self._y_zero:
+            for y in self._y:
+                y.zero_()
+            self._y_zero = False
+        self._loss_key = None            # the caller may write into the returned tensors
 
     # ------------------------------------------------------------------ launch sequences
     def _state_key(self):
@@ -426,7 +431,7 @@ class DeepKHarmonicStep:
         ev.record(side)
         torch.cuda.current_stream(self.device).wait_event(ev)
 
-    def _seq_closure(self, grads: bool, forward: bool, upd: bool):
+    def _seq_closure(self, grads: bool, forward: bool, upd: bool, yzero: bool = False):
         """The launch sequence of one closure evaluation (no host decisions inside: it can be captured)."""
         lb, st = lib(), _stream()
         N, C, L, Lt, Ltot, K = self.N, self.C, self.L, self.Lt, self.Ltot, self.mod.K
@@ -450,15 +455,16 @@ class DeepKHarmonicStep:
         # losses: forked here, joined before the backward passes
         lside = self._fork()
         y = self._y
+        ymode = (1 if upd else 0) | (2 if yzero else 0)    # include/lshm.h lshm_cascade_losses_upd
         if planes:
             # gradient closure: d/dx2 and d/dx3 leave the loss pass as the operand planes of the 1-D nets' last layers
             lb.cascade_losses_planes(self.x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(),
-                                     y[0].data_ptr(), y[1].data_ptr(), y[2].data_ptr(), self.rho, 1 if upd else 0,
+                                     y[0].data_ptr(), y[1].data_ptr(), y[2].data_ptr(), self.rho, ymode,
                                      N, C, 128, 1.0 / numel_g, tp, self.g1p.data_ptr(), self.p2.data_ptr(),
                                      self.p3.data_ptr(), db2, db3, st)
         else:
             lb.cascade_losses_upd(self.x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(),
-                                  y[0].data_ptr(), y[1].data_ptr(), y[2].data_ptr(), self.rho, 1 if upd else 0,
+                                  y[0].data_ptr(), y[1].data_ptr(), y[2].data_ptr(), self.rho, ymode,
                                   N, C, 128, 1.0 / numel_g, tp, g1p, g2, g3f, db2, db3, st)
         khm_scale = plan.khm_scale(self.alpha)
         p = float(self.mod.p)
@@ -518,11 +524,12 @@ class DeepKHarmonicStep:
     def _seq_forward(self):
         self._forward(_stream())
 
-    def _seq_flush(self):
+    def _seq_flush(self, yzero: bool = False):
         x1, x2, x3f = self._outputs()
         y = self._y
-        lib().multiplier_update(self.x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(), self.rho,
-                                y[0].data_ptr(), y[1].data_ptr(), y[2].data_ptr(), self.N, self.C, 128, _stream())
+        lib().multiplier_update_z(self.x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(), self.rho,
+                                  y[0].data_ptr(), y[1].data_ptr(), y[2].data_ptr(), 1 if yzero else 0,
+                                  self.N, self.C, 128, _stream())
 
     # ------------------------------------------------------------------ CUDA graphs
     def enable_graphs(self, on: bool = True):
@@ -576,11 +583,13 @@ class DeepKHarmonicStep:
         fresh = tracked and self._forward_is_current()
         if self._pending and not fresh:
             self.flush_multipliers()            # the deferred update belongs to the activations still held
-        upd = self._pending
+        upd, yz = self._pending, self._y_zero
         if grads:
             self.flat.attach_grads()
-        self._run(("closure", grads, not fresh, upd), lambda: self._seq_closure(grads, not fresh, upd))
+        self._run(("closure", grads, not fresh, upd, yz), lambda: self._seq_closure(grads, not fresh, upd, yz))
         self._pending = False
+        if upd:
+            self._y_zero = False            # the loss pass wrote the multipliers
         self._fwd_key = self._state_key() if tracked else None
         self._loss_key = self._state_key() if tracked else None
         if self.distributed:
@@ -617,8 +626,10 @@ class DeepKHarmonicStep:
         if self._pending:
             self._pending = False
             self._loss_key = None
+            yz = self._y_zero
             with torch.no_grad():
-                self._run(("flush",), self._seq_flush)
+                self._run(("flush", yz), lambda: self._seq_flush(yz))
+            self._y_zero = False
 
     # ------------------------------------------------------------------ public: centre update
     def centre_sums_view(self):
