@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
 }
 
 template <int DIM, int NT, int KP, bool PRE = false, bool FOLD = false>
-int launch_wgrad_t(WgArgs a, int64_t splits, int mtiles, cudaStream_t st) {
+int launch_wgrad_t(WgArgs a, int64_t /*splits_hint*/, int mtiles, cudaStream_t st) {
   if (PRE) {
     const PlaneGeom pg = plane_geom(DIM, a.N, a.Bc, a.h, a.w);
     const uint8_t* base = reinterpret_cast<const uint8_t*>(a.big);
@@ -368,6 +368,20 @@ int launch_wgrad_t(WgArgs a, int64_t splits, int mtiles, cudaStream_t st) {
   const size_t reach = (size_t)a.scols * KP * 16 + (size_t)16 * KP * 16;     // from the stage start
   const size_t smem = stage * a.nstage + (reach > stage ? reach - stage : 0) + 256;
   LSHM_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<DIM, NT, KP, PRE, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_wgrad");
+  // split-K so that the grid is ONE wave of resident CTAs (the first version assumed 3 CTAs per SM: where only 2 fit,
+  // e.g. the 12-channel 1-D layer, 1.46 waves left a third of the run to a half-empty machine - ncu, r2_ncu_layer2.md)
+  static int occ_cache = 0; static size_t occ_smem = 0;
+  if (occ_cache == 0 || occ_smem != smem) {
+    int occ = 0;
+    LSHM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, igemm_wgrad_kernel<DIM, NT, KP, PRE, FOLD>, WG_THREADS, smem), "igemm_wgrad");
+    occ_cache = std::max(1, occ); occ_smem = smem;
+  }
+  const int64_t tiles = (int64_t)mtiles * a.ntiles;
+  int64_t splits = std::max<int64_t>(1, ((int64_t)sm_count() * occ_cache) / tiles);
+  splits = std::min(splits, std::max<int64_t>(1, a.kblocks / 4));   // at least 4 K blocks per CTA
+  a.kb_per_cta = ceil_div(a.kblocks, splits);
+  splits = ceil_div(a.kblocks, a.kb_per_cta);
+  a.nstage = (int)std::min<int64_t>(a.nstage, std::max<int64_t>(1, a.kb_per_cta));
   dim3 grid((unsigned)splits, (unsigned)(mtiles * a.ntiles));
   igemm_wgrad_kernel<DIM, NT, KP, PRE, FOLD><<<grid, WG_THREADS, smem, st>>>(a);
   LSHM_CHECK_LAUNCH("igemm_wgrad");

@@ -133,7 +133,10 @@ constexpr int PT = 32;     // P must be a multiple of the 32-row strips
 // frequency-axis net (flattened s = f*P + t): window j of a flattened map covers samples [4j-1, 4j+2], i.e. the
 // element BEFORE the block's row / column and its first three elements (one halo row + one halo column per thread;
 // the flattened predecessor of (t, f=0) is (t-1, P-1), of (f, t=0) it is (f-1, P-1)).
-__global__ void __launch_bounds__(256)
+#ifndef LSHM_SPLIT_MINB
+#define LSHM_SPLIT_MINB 3
+#endif
+__global__ void __launch_bounds__(256, LSHM_SPLIT_MINB)
 residual_split_planes_kernel(const float* __restrict__ x, const float* __restrict__ x1, uint8_t* __restrict__ pT,
                              uint8_t* __restrict__ pF, size_t half_bytes, int C, int P, int64_t Qs) {
   const int strips = P / 32;
@@ -203,7 +206,10 @@ __device__ __forceinline__ float gx1_at(const float* __restrict__ ap, const floa
   return __ldg(ap + off) - 0.5f * (__ldg(bp + off) + __ldg(cp + (int64_t)f * P + t));
 }
 
-__global__ void __launch_bounds__(256)
+#ifndef LSHM_COMBINE_MINB
+#define LSHM_COMBINE_MINB 4
+#endif
+__global__ void __launch_bounds__(256, LSHM_COMBINE_MINB)
 combine_planes_kernel(const float* __restrict__ g1p, const float* __restrict__ gT, const float* __restrict__ gF,
                       uint8_t* __restrict__ planes, size_t half_bytes, int C, int P, int64_t Qs, int64_t items,
                       float* __restrict__ db1) {
