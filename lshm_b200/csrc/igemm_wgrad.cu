@@ -370,12 +370,9 @@ int launch_wgrad_t(WgArgs a, int64_t /*splits_hint*/, int mtiles, cudaStream_t s
   LSHM_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<DIM, NT, KP, PRE, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_wgrad");
   // split-K so that the grid is ONE wave of resident CTAs (the first version assumed 3 CTAs per SM: where only 2 fit,
   // e.g. the 12-channel 1-D layer, 1.46 waves left a third of the run to a half-empty machine - ncu, r2_ncu_layer2.md)
-  static int occ_cache = 0; static size_t occ_smem = 0;
-  if (occ_cache == 0 || occ_smem != smem) {
-    int occ = 0;
-    LSHM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, igemm_wgrad_kernel<DIM, NT, KP, PRE, FOLD>, WG_THREADS, smem), "igemm_wgrad");
-    occ_cache = std::max(1, occ); occ_smem = smem;
-  }
+  // resident CTAs per SM: the launch bound (registers) and the shared memory (227 KB per SM, 1 KB reserved per CTA).
+  // (cudaOccupancyMaxActiveBlocksPerMultiprocessor answered 1 for these kernels on the driver of the test box.)
+  const int occ_cache = (int)std::max<size_t>(1, std::min<size_t>(KP == 128 ? 3 : 2, (size_t)(227 * 1024) / (smem + 1024)));
   const int64_t tiles = (int64_t)mtiles * a.ntiles;
   int64_t splits = std::max<int64_t>(1, ((int64_t)sm_count() * occ_cache) / tiles);
   splits = std::min(splits, std::max<int64_t>(1, a.kblocks / 4));   // at least 4 K blocks per CTA
