@@ -359,3 +359,62 @@ class AEEngine:
             ev.record(wstream)
             main.wait_event(ev)
         return ws.dx if need_dx else None
+
+    # ------------------------------------------------------------------ encode() / decode() on their own
+    def backward_encode(self, x: torch.Tensor, uvh: torch.Tensor, p, g, ws: Workspace, st: int, g_out: torch.Tensor,
+                        need_dx: bool):
+        """Backward of `encode(x, uvh)` alone (src/lofar_models.py:71-84): g_out = gradient w.r.t. the returned
+        ELU(fc1(.)) [N,L].  Writes g[...] for conv0..5, fcuv1, fc1 and returns (dx or None, g_uvh [N,4H])."""
+        lb, N, L, H4, ch, sz = self.lib, ws.N, self.L, self.H4, self.ch, ws.sizes
+        ld1 = FLAT + H4
+        lb.delu(_p(g_out), g_out.stride(0), _p(ws.mu0), L, _p(ws.g_mu0), L, N, L, st)
+        lb.linear_bwd_weight(_p(ws.cat1), ld1, _p(ws.g_mu0), L, _p(g["fc1.weight"]), _p(g["fc1.bias"]), N, ld1, L, st)
+        lb.linear_bwd_data(_p(ws.g_mu0), L, _p(p["fc1.weight"]), None, 0, _p(ws.cat1), ld1, _p(ws.g_cat1), ld1, N, ld1, L, st)
+        lb.linear_bwd_weight(_p(uvh), uvh.stride(0), ws.g_cat1.data_ptr() + 4 * FLAT, ld1, _p(g["fcuv1.weight"]), _p(g["fcuv1.bias"]), N, H4, H4, st)
+        g_uvh = torch.empty(N, H4, dtype=torch.float32, device=x.device)
+        lb.linear_bwd_data(ws.g_cat1.data_ptr() + 4 * FLAT, ld1, _p(p["fcuv1.weight"]), None, 0, None, 0, _p(g_uvh), H4, N, H4, H4, st)
+        dz, dz_ns = ws.g_cat1, ld1
+        for i in range(5, -1, -1):
+            inp, inp_ns = (x, sz[0]) if i == 0 else (ws.enc[i], sz[i])
+            A, Bc, lvl = ch[i + 1], ch[i], i + 1
+            self._wgrad(_p(dz), dz_ns, _p(inp), inp_ns, _p(g[f"conv{i}.weight"]), N, A, Bc, lvl, 1, st)
+            lb.channel_sum(_p(dz), dz_ns, _p(g[f"conv{i}.bias"]), N, A, sz[lvl] // A, st)
+            if i > 0:
+                nxt = ws.g_enc[i]
+                self._up(_p(dz), dz_ns, _p(self.img[(f"conv{i}.weight", 1)]), None, _p(inp), inp_ns, _p(nxt), sz[i], N, A, Bc, lvl, 1, EPI_DELU, st)
+                dz, dz_ns = nxt, sz[i]
+            elif need_dx:
+                if ("conv0.weight", 1) not in self.img:
+                    self.img[("conv0.weight", 1)] = conv_image(p["conv0.weight"], self.ndim, 1, st)
+                elif not self.need_input_grad:
+                    conv_image(p["conv0.weight"], self.ndim, 1, st, self.img[("conv0.weight", 1)])
+                self._up(_p(dz), dz_ns, _p(self.img[("conv0.weight", 1)]), None, None, 0, _p(ws.dx), sz[0], N, A, Bc, lvl, 1, EPI_NONE, st)
+        return (ws.dx if need_dx else None), g_uvh
+
+    def backward_decode(self, uvh: torch.Tensor, p, g, ws: Workspace, st: int, g_xhat: torch.Tensor):
+        """Backward of `decode(z, uvh)` alone (src/lofar_models.py:86-99): writes g[...] for tconv0..5, fc3, fcuv3 and
+        returns (g_z [N,L], g_uvh [N,4H]).  z is an input here: no ELU' on its gradient."""
+        lb, N, L, H4, ch, sz = self.lib, ws.N, self.L, self.H4, self.ch, ws.sizes
+        zc_ld = L + H4
+        rch = ch[::-1]
+        dz = g_xhat
+        for i in range(5, -1, -1):
+            inp = ws.dec[i]
+            A, Bc, lvl = rch[i], rch[i + 1], 6 - i
+            self._wgrad(_p(inp), sz[lvl], _p(dz), sz[lvl - 1], _p(g[f"tconv{i}.weight"]), N, A, Bc, lvl, 0, st)
+            lb.channel_sum(_p(dz), sz[lvl - 1], _p(g[f"tconv{i}.bias"]), N, Bc, sz[lvl - 1] // Bc, st)
+            nxt = ws.g_dec[i]
+            self._down(_p(dz), sz[lvl - 1], _p(self.img[(f"tconv{i}.weight", 0)]), None,
+                       _p(inp) if i > 0 else None, sz[lvl], _p(nxt), sz[lvl], N, A, Bc, lvl, 0,
+                       EPI_DELU if i > 0 else EPI_NONE, st)
+            dz = nxt
+        lb.linear_bwd_weight(_p(ws.zcat), zc_ld, _p(dz), FLAT, _p(g["fc3.weight"]), _p(g["fc3.bias"]), N, zc_ld, FLAT, st)
+        lb.linear_bwd_data(_p(dz), FLAT, _p(p["fc3.weight"]), None, 0, None, 0, _p(ws.g_zcat), zc_ld, N, zc_ld, FLAT, st)
+        g_z = ws.g_zcat[:, :L].clone()
+        guv = torch.empty(N, H4, dtype=torch.float32, device=uvh.device)
+        lb.delu(ws.g_zcat.data_ptr() + 4 * L, zc_ld, ws.zcat.data_ptr() + 4 * L, zc_ld, _p(guv), H4, N, H4, st)   # through ELU(fcuv3(uvh))
+        lb.linear_bwd_weight(_p(uvh), uvh.stride(0), _p(guv), H4, _p(g["fcuv3.weight"]), _p(g["fcuv3.bias"]), N, H4, H4, st)
+        g_uvh = torch.empty(N, H4, dtype=torch.float32, device=uvh.device)
+        lb.linear_bwd_data(_p(guv), H4, _p(p["fcuv3.weight"]), None, 0, None, 0, _p(g_uvh), H4, N, H4, H4, st)
+        return g_z, g_uvh
+

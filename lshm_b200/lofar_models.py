@@ -61,6 +61,62 @@ class _AEFunction(torch.autograd.Function):
         return (None, None, None, None, dx, None) + tuple(g[nm] for nm in names)
 
 
+ENC_NAMES = tuple(f"conv{i}.{w}" for i in range(6) for w in ("weight", "bias")) + ("fcuv1.weight", "fcuv1.bias", "fc1.weight", "fc1.bias")
+DEC_NAMES = ("fcuv3.weight", "fcuv3.bias", "fc3.weight", "fc3.bias") + tuple(f"tconv{i}.{w}" for i in range(6) for w in ("weight", "bias"))
+
+
+class _EncodeFunction(torch.autograd.Function):
+    """encode(x, uvh) with its own backward (the reference's encode is an ordinary differentiable method)."""
+
+    @staticmethod
+    def forward(ctx, engine, names, track, x, uvh, *params):
+        N = x.shape[0]
+        xc, uc = x.contiguous(), uvh.contiguous()
+        need_dx = track and x.requires_grad
+        ws = engine.workspace(N, x.device, with_grad=track, need_dx=need_dx)
+        p = dict(zip(names, params))
+        engine.prepare_images(p, _stream(), track)
+        out = engine.encode(xc.view(N, -1), uc, p, ws, _stream())
+        if track:
+            ctx.engine, ctx.names, ctx.ws, ctx.need_dx, ctx.xc, ctx.uc, ctx.params = engine, names, ws, need_dx, xc, uc, params
+        return out.clone()
+
+    @staticmethod
+    def backward(ctx, g_out):
+        engine, ws, names = ctx.engine, ctx.ws, ctx.names
+        p = dict(zip(names, ctx.params))
+        g = {nm: torch.empty_like(p[nm]) for nm in ENC_NAMES}
+        dx, g_uvh = engine.backward_encode(ctx.xc.view(ws.N, -1), ctx.uc, p, g, ws, _stream(), g_out.contiguous(), ctx.need_dx)
+        if dx is not None:
+            dx = dx.view(ctx.xc.shape)
+        return (None, None, None, dx, g_uvh) + tuple(g.get(nm) for nm in names)
+
+
+class _DecodeFunction(torch.autograd.Function):
+    """decode(z, uvh) with its own backward."""
+
+    @staticmethod
+    def forward(ctx, engine, names, track, shape, z, uvh, *params):
+        N = z.shape[0]
+        uc = uvh.contiguous()
+        ws = engine.workspace(N, z.device, with_grad=track)
+        ws.zcat[:, :engine.L].copy_(z)
+        p = dict(zip(names, params))
+        engine.prepare_images(p, _stream(), track)
+        xhat = engine.decode(uc, p, ws, _stream())
+        if track:
+            ctx.engine, ctx.names, ctx.ws, ctx.uc, ctx.params = engine, names, ws, uc, params
+        return xhat.view(shape).clone()
+
+    @staticmethod
+    def backward(ctx, g_xhat):
+        engine, ws, names = ctx.engine, ctx.ws, ctx.names
+        p = dict(zip(names, ctx.params))
+        g = {nm: torch.empty_like(p[nm]) for nm in DEC_NAMES}
+        g_z, g_uvh = engine.backward_decode(ctx.uc, p, g, ws, _stream(), g_xhat.contiguous().view(ws.N, -1))
+        return (None, None, None, None, g_z, g_uvh) + tuple(g.get(nm) for nm in names)
+
+
 class _AutoEncoderBase(nn.Module):
     _ndim = 2
 
@@ -121,29 +177,22 @@ class _AutoEncoderBase(nn.Module):
                                  x, uv, *p.values())
 
     # encode / decode keep the reference signatures: `uv` here is the [N,4H] harmonic vector
-    # (src/lofar_models.py:71,86).  Inference helpers: they run without autograd.
-    @torch.no_grad()
+    # (src/lofar_models.py:71,86), and - like the reference's - they are differentiable.
     def encode(self, x, uv):
         _require_cuda(x, "x")
         _require_cuda(uv, "uv")
-        N = x.shape[0]
-        eng = self.engine()
-        ws = eng.workspace(N, x.device, with_grad=False)
-        eng.prepare_images(self.named_param_dict(), _stream(), False)
-        return eng.encode(x.contiguous().view(N, -1), uv.contiguous(), self.named_param_dict(), ws, _stream())
+        p = self.named_param_dict()
+        track = torch.is_grad_enabled() and (x.requires_grad or uv.requires_grad or any(t.requires_grad for t in p.values()))
+        return _EncodeFunction.apply(self.engine(), self._names, track, x, uv, *p.values())
 
-    @torch.no_grad()
     def decode(self, z, uv):
         _require_cuda(z, "z")
         _require_cuda(uv, "uv")
+        p = self.named_param_dict()
+        track = torch.is_grad_enabled() and (z.requires_grad or uv.requires_grad or any(t.requires_grad for t in p.values()))
         N = z.shape[0]
-        eng = self.engine()
-        ws = eng.workspace(N, z.device, with_grad=False)
-        ws.zcat[:, :self.latent_dim].copy_(z)
-        eng.prepare_images(self.named_param_dict(), _stream(), False)
-        xhat = eng.decode(uv.contiguous(), self.named_param_dict(), ws, _stream())
         shape = (N, self._channels, 128, 128) if self._ndim == 2 else (N, self._channels, 16384)
-        return xhat.view(shape)
+        return _DecodeFunction.apply(self.engine(), self._names, track, shape, z, uv, *p.values())
 
 
 class AutoEncoderCNN2(_AutoEncoderBase):

@@ -70,12 +70,41 @@ def test_autoencoder_module_forward_backward(cuda, ndim, C, L):
     with torch.no_grad():
         xh2, mu2 = net(xg, uv.to(cuda))
     assert max_abs(xh2, xh) == 0 and not xh2.requires_grad
-    # encode/decode helpers (reference signatures take the harmonic vector)
+    # encode/decode helpers (reference signatures take the harmonic vector); differentiable like the reference's
     uvh = O.uv_harmonics(uv, hs)
-    enc = net.encode(x.to(cuda), uvh.to(cuda))
-    assert rel_err(enc, O.ae_encode(p, x, uvh, ndim)) < ACT_TOL
+    pr2 = {k: v.clone().requires_grad_() for k, v in p.items()}
+    xr2, ur2 = x.clone().requires_grad_(), uvh.clone().requires_grad_()
+    enc_ref = O.ae_encode(pr2, xr2, ur2, ndim)
+    we = torch.randn_like(enc_ref)
+    (enc_ref * we).sum().backward()
+    net.zero_grad()
+    xg2, ug2 = x.to(cuda).requires_grad_(), uvh.to(cuda).requires_grad_()
+    enc = net.encode(xg2, ug2)
+    assert rel_err(enc, enc_ref) < ACT_TOL
+    (enc * we.to(cuda)).sum().backward()
+    got = {k: v.grad for k, v in net.named_parameters() if v.grad is not None}
+    want = {k: v.grad for k, v in pr2.items() if v.grad is not None}
+    assert set(got) == set(want) and len(want) == 16
+    check_grads(got, want)
+    assert rel_err(xg2.grad, xr2.grad) < GRAD_TOL and rel_err(ug2.grad, ur2.grad) < GRAD_TOL
     z = torch.randn(N, L)
-    assert rel_err(net.decode(z.to(cuda), uvh.to(cuda)), O.ae_decode(p, z, uvh, ndim)) < ACT_TOL
+    pr3 = {k: v.clone().requires_grad_() for k, v in p.items()}
+    zr, ur3 = z.clone().requires_grad_(), uvh.clone().requires_grad_()
+    dec_ref = O.ae_decode(pr3, zr, ur3, ndim)
+    wd = torch.randn_like(dec_ref)
+    (dec_ref * wd).sum().backward()
+    net.zero_grad()
+    zg, ug3 = z.to(cuda).requires_grad_(), uvh.to(cuda).requires_grad_()
+    dec = net.decode(zg, ug3)
+    assert rel_err(dec, dec_ref) < ACT_TOL
+    (dec * wd.to(cuda)).sum().backward()
+    got = {k: v.grad for k, v in net.named_parameters() if v.grad is not None}
+    want = {k: v.grad for k, v in pr3.items() if v.grad is not None}
+    assert set(got) == set(want) and len(want) == 16
+    check_grads(got, want)
+    assert rel_err(zg.grad, zr.grad) < GRAD_TOL and rel_err(ug3.grad, ur3.grad) < GRAD_TOL
+    with torch.no_grad():
+        assert not net.encode(x.to(cuda), uvh.to(cuda)).requires_grad
 
 
 def test_kmeans_module(cuda):
