@@ -81,8 +81,14 @@ LSHM_API int lshm_normalise_n(float* y, int64_t n, const double* stats, int64_t 
 
 /* ------------------------------------------------------------- FFT features -----
  * Replaces Demo.ipynb:169-174 + torch_fftshift (src/lofar_tools.py:24-30):
- * out[:, :C] = Re, out[:, C:] = Im of fftshift(fft2_ortho(x - xhat)), clamped to
- * +-clamp.  x, xhat [N,C,128,128] (xhat may be NULL), out [N,2C,128,128]. */
+ * F = fftshift(fft2_ortho(x - xhat)); mode LSHM_FFT_REIM: out[:, :C] = Re F, out[:, C:] = Im F, both clamped to
+ * +-clamp (the reference feature); mode LSHM_FFT_MAGPHASE: out[:, :C] = min(|F|, clamp), out[:, C:] = arg F
+ * in (-pi, pi] (torch.abs / torch.angle of the same F).  x, xhat [N,C,128,128] (xhat may be NULL),
+ * out [N,2C,128,128]; x and out 16-byte aligned. */
+enum lshm_fft_mode { LSHM_FFT_REIM = 0, LSHM_FFT_MAGPHASE = 1 };
+LSHM_API int lshm_fft2_features(const float* x, const float* xhat, float* out,
+                       int64_t N, int C, float clamp, int mode, lshm_stream_t stream);
+/* = lshm_fft2_features(..., LSHM_FFT_REIM, ...) */
 LSHM_API int lshm_fft2_reim_shift_clamp(const float* x, const float* xhat, float* out,
                                int64_t N, int C, float clamp, lshm_stream_t stream);
 

@@ -1,19 +1,22 @@
-// Fourier-space features: fftshift(fft2_ortho(x - xhat)) -> cat(Re, Im) -> clamp.
+// Fourier-space features: fftshift(fft2_ortho(x - xhat)) -> cat(Re, Im) (or cat(|F|, arg F)) -> clamp.
 //
 // Reference semantics: /root/reference/Demo.ipynb:169-174 with torch_fftshift,
 // /root/reference/src/lofar_tools.py:24-30 (roll by size//2 on dims 2,3).
 //
 // One CTA owns one 128x128 (patch, channel) plane: the plane is read once from HBM (64 KB, or
 // 128 KB with xhat) and the two output planes are written once (128 KB) - the algorithmic
-// minimum.  Each 128-point transform is 16 x 8 (Cooley-Tukey): a 16-point FFT in registers over
-// the stride-8 samples, the inter-stage twiddle, an exchange through shared memory, an 8-point
-// FFT in registers.  A warp owns 16 rows for the whole row pass and 8 columns for the whole
-// column pass, so the two register stages of a pass are separated by __syncwarp only; the block
-// synchronises once between the passes.  The input is real: rows go through the complex FFT in
-// pairs and only the half spectrum (columns 0..64) is computed, the rest is its conjugate mirror.  The first stage reads its samples straight from global
-// memory (8 lanes = one 32-byte sector), the last stage applies the ortho scale, the fftshift and
-// the clamp and stores rows coalesced (lanes = consecutive columns).
-#include "common.cuh"
+// minimum.  Round-2 structure (profiles/r2_ncu_fft.md: the round-1 kernel was bound by LSU wavefronts,
+// 4-8 different 128-byte lines per global load / store instruction):
+//  * the plane is staged by the copy engine: 128 bulk copies (cp.async.bulk, one 512-byte row each) into
+//    ONE shared-memory buffer of 128 rows at a 136-float pitch, completion on an mbarrier;
+//  * everything then happens IN PLACE in that buffer: the row pass reads real rows (paired r, r+64: the input
+//    is real, two rows go through one complex FFT), exchanges its two register stages through the same
+//    two rows, and leaves the half spectrum (columns 0..63 re | im, Nyquist column in the row's spare floats);
+//    the column pass (warp = 8 columns) transforms in place and leaves row u at position rho(u);
+//  * the output is then emitted row-contiguously: a half-warp writes 256 consecutive bytes per instruction
+//    (st.global.v4), the mirrored half F[-u,-v] = conj F[u,v] is read backwards from the same buffer.
+// Each 128-point transform is 16 x 8 (Cooley-Tukey) in registers.  69.6 KB of shared memory per CTA.
+#include "tc_common.cuh"
 
 namespace lshm {
 namespace {
@@ -64,64 +67,88 @@ __device__ __forceinline__ constexpr int brev4(int v) { return ((v & 1) << 3) | 
 
 __device__ __forceinline__ float clampn(float a, float c) { return a != a ? a : fminf(fmaxf(a, -c), c); }
 
-constexpr int YS = 136;   // row stride (floats) of the per-warp stage-1 -> stage-2 exchange buffer
-constexpr int XS = 64;    // row stride (floats) of the half-spectrum X[128 rows][columns 0..63]; column 64 apart
+constexpr int RS = 136;   // row pitch (floats) of the plane buffer: 128 samples / 64 re + 64 im, Nyquist re, im, 6 spare
 
-// X is addressed by lanes that differ in the column (8 consecutive) and in the row, where the row
-// step is 1 (first column stage: n2), 8 (second column stage: k1) or 2 (row-pass stores).  With any
-// padded row stride one of the three collides (a 72-float stride made every second-stage column load
-// a 4-way bank conflict: 37% extra shared-memory wavefronts in the ncu capture), so the 8-column
-// group is XOR-swizzled with two row bits taken from both the row's low and its /8 digits.
-__device__ __forceinline__ int xidx(int row, int col) { return row * XS + (col ^ (((row ^ (row >> 3)) & 3) << 3)); }
+// Half spectrum of row r: re at [r][pcol(r,k)], im at [r][64 + pcol(r,k)], k = 0..63.  The buffer is addressed by
+// lanes that differ in the column (8 consecutive) and in the row, where the row step is 1 (first column stage),
+// 8 (second column stage) or 2 (row-pass stores).  bank = 8*(row + group) + col%8 at a 136-float pitch, so the
+// 8-column group is XOR-ed with the row's /8 digit: every one of those access patterns is conflict-free.
+__device__ __forceinline__ int pcol(int row, int k) { return k ^ (((row >> 3) & 3) << 3); }
+// the column pass leaves row frequency u = k1 + 16*k2 where its second stage computed it: row 8*k1 + brev3(k2)
+__device__ __forceinline__ int rho(int u) { return ((u & 15) << 3) | brev3(u >> 4); }
 
-// Real input: rows are transformed in PAIRS (z = a + i*b, one complex 128-point FFT, then
-// A[k] = (Z[k] + conj Z[-k])/2, B[k] = (Z[k] - conj Z[-k])/(2i)), and only columns k = 0..64 are kept:
-// the other half of the 2-D spectrum is the conjugate mirror F[-u,-v] = conj F[u,v], written from
-// the same registers.  Half the butterflies, half the shared memory (two CTAs per SM).
+template <int MODE>
+__device__ __forceinline__ void emit4(float* __restrict__ o0, float* __restrict__ o1, float4 re, float4 im, float clamp) {
+  constexpr float sc = 1.f / 128.f;                  // ortho scale of the 2-D transform
+  float4 a, b;
+  if (MODE == LSHM_FFT_REIM) {
+    a = make_float4(clampn(re.x * sc, clamp), clampn(re.y * sc, clamp), clampn(re.z * sc, clamp), clampn(re.w * sc, clamp));
+    b = make_float4(clampn(im.x * sc, clamp), clampn(im.y * sc, clamp), clampn(im.z * sc, clamp), clampn(im.w * sc, clamp));
+  } else {
+    a = make_float4(clampn(sqrtf(re.x * re.x + im.x * im.x) * sc, clamp), clampn(sqrtf(re.y * re.y + im.y * im.y) * sc, clamp),
+                    clampn(sqrtf(re.z * re.z + im.z * im.z) * sc, clamp), clampn(sqrtf(re.w * re.w + im.w * im.w) * sc, clamp));
+    b = make_float4(atan2f(im.x, re.x), atan2f(im.y, re.y), atan2f(im.z, re.z), atan2f(im.w, re.w));
+  }
+  *reinterpret_cast<float4*>(o0) = a;
+  *reinterpret_cast<float4*>(o1) = b;
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(FFT_THREADS, 2)
 fft2_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* __restrict__ out,
             int C, float clamp) {
-  extern __shared__ __align__(16) float sm[];
-  float* xre = sm;                          // [128][XS] swizzled (xidx)
-  float* xim = xre + FN * XS;               // [128][XS]
-  float* ybase = xim + FN * XS;             // per warp: re[4][YS], im[4][YS]
+  extern __shared__ __align__(16) float B[];   // [128][RS]
   __shared__ float twr[FN], twi[FN];
-  __shared__ float nre[FN], nim[FN];        // the Nyquist column (k = 64) of the row transforms
-  const int64_t plane = blockIdx.x;         // n*C + c
+  __shared__ __align__(8) uint64_t bar;
+  const int64_t plane = blockIdx.x;            // n*C + c
   const int64_t n = plane / C;
   const int c = (int)(plane - n * C);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float* yre = ybase + warp * (8 * YS);
-  float* yim = yre + 4 * YS;
   const float* src = x + plane * FN * FN;
   const float* src2 = xhat ? xhat + plane * FN * FN : nullptr;
 
-  // ------------------------------------------------------------------ rows: warp w owns row pairs 8w..8w+7
-  // The samples of the second half are requested right after the first half's register stage, so their
-  // latency is covered by the first half's second stage (the load phase was 23 % of the stall samples).
+  // ------------------------------------------------------------------ stage the plane (copy engine), twiddles meanwhile
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_init_fence();
+    tc::mbar_arrive_expect_tx(&bar, FN * FN * 4);
+  }
+  __syncthreads();
+  if (tid < FN) {
+    tc::bulk_g2s(B + tid * RS, src + tid * FN, FN * 4, &bar);
+  } else {
+    float sn, cs;
+    sincospif(-(float)(tid - FN) / 64.f, &sn, &cs);    // exp(-2*pi*i*t/128)
+    twr[tid - FN] = cs; twi[tid - FN] = sn;
+  }
+  __syncthreads();
+  tc::mbar_wait(&bar, 0);
+
+  // ------------------------------------------------------------------ rows: warp w owns the pairs (r, r + 64), r = 8w..8w+7
+  // Real input: rows are transformed in PAIRS (z = a + i*b, one complex 128-point FFT, then
+  // A[k] = (Z[k] + conj Z[-k])/2, B[k] = (Z[k] - conj Z[-k])/(2i)), and only columns k = 0..64 are kept.
   cpx vin[16];
   auto load_half = [&](int half) {
     const int pl = lane >> 3, n2 = lane & 7;
-    const int ra = 2 * (warp * 8 + half * 4 + pl);
+    const int ra = warp * 8 + half * 4 + pl;
+    const float* pa = B + ra * RS + n2;
+    const float* pb = pa + 64 * RS;
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) {
-      float a = __ldg(src + ra * FN + n1 * 8 + n2), b = __ldg(src + (ra + 1) * FN + n1 * 8 + n2);
-      if (src2) { a -= __ldg(src2 + ra * FN + n1 * 8 + n2); b -= __ldg(src2 + (ra + 1) * FN + n1 * 8 + n2); }
+      float a = pa[n1 * 8], b = pb[n1 * 8];
+      if (src2) { a -= __ldg(src2 + ra * FN + n1 * 8 + n2); b -= __ldg(src2 + (ra + 64) * FN + n1 * 8 + n2); }
       vin[n1] = {a, b};
     }
   };
-  load_half(0);                                 // in flight while the twiddle table is built
-  if (tid < FN) {
-    float sn, cs;
-    sincospif(-(float)tid / 64.f, &sn, &cs);    // exp(-2*pi*i*tid/128)
-    twr[tid] = cs; twi[tid] = sn;
-  }
-  __syncthreads();
+  load_half(0);
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     {
-      // stage 1: lane -> (pair = 8w + 4*half + lane/8, n2 = lane%8): 16-point FFT over n = 8*n1 + n2
+      // stage 1: lane -> (pair = 8w + 4*half + lane/8, n2 = lane%8): 16-point FFT over n = 8*n1 + n2; the
+      // twiddled result replaces the lane's own samples (re in row r, im in row r + 64)
       const int pl = lane >> 3, n2 = lane & 7;
+      float* yre = B + (warp * 8 + half * 4 + pl) * RS;
+      float* yim = yre + 64 * RS;
       cpx v[16];
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) v[n1] = vin[n1];
@@ -131,23 +158,26 @@ fft2_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* 
         const int k1 = brev4(j);
         const int t = k1 * n2;                     // twiddle exp(-2*pi*i*k1*n2/128)
         const cpx y = cmul(v[j], cpx{twr[t], twi[t]});
-        yre[pl * YS + k1 * 8 + n2] = y.r;
-        yim[pl * YS + k1 * 8 + n2] = y.i;
+        yre[k1 * 8 + n2] = y.r;
+        yim[k1 * 8 + n2] = y.i;
       }
     }
     __syncwarp();
-    if (half == 0) load_half(1);
+    if (half == 0) load_half(1);                   // (xhat comes straight from global: in flight during stage 2)
+#pragma unroll
     for (int sub = 0; sub < 2; ++sub) {
-      // stage 2: lane -> (pair-in-half = 2*sub + lane/16, k1 = lane%16): 8-point FFT over n2, then unpack
-      const int pl = 2 * sub + (lane >> 4), k1 = lane & 15;
-      const int ra = 2 * (warp * 8 + half * 4 + pl);
+      // stage 2: lane -> (pair-in-half = sub + 2*(lane/16), k1 = lane%16): 8-point FFT over n2, then unpack
+      const int pl = sub + 2 * (lane >> 4), k1 = lane & 15;
+      const int ra = warp * 8 + half * 4 + pl;
+      float* rowa = B + ra * RS;
+      float* rowb = rowa + 64 * RS;
       cpx v[8];
       {
         // 16-byte loads at a 32-byte lane stride: lanes 4..7 of each quarter-warp fetch their upper
         // half first so the eight lanes of a wavefront cover all 32 banks
         const int sw = (k1 >> 2) & 1;
-        const float* yr_ = yre + pl * YS + k1 * 8;
-        const float* yi_ = yim + pl * YS + k1 * 8;
+        const float* yr_ = rowa + k1 * 8;
+        const float* yi_ = rowb + k1 * 8;
         const float4 ra0 = *reinterpret_cast<const float4*>(yr_ + 4 * sw);
         const float4 ra1 = *reinterpret_cast<const float4*>(yr_ + 4 * (sw ^ 1));
         const float4 rb0 = *reinterpret_cast<const float4*>(yi_ + 4 * sw);
@@ -156,6 +186,7 @@ fft2_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* 
         v[0] = {a0.x, b0.x}; v[1] = {a0.y, b0.y}; v[2] = {a0.z, b0.z}; v[3] = {a0.w, b0.w};
         v[4] = {a1.x, b1.x}; v[5] = {a1.y, b1.y}; v[6] = {a1.z, b1.z}; v[7] = {a1.w, b1.w};
       }
+      __syncwarp();                                // the half spectrum overwrites the exchange rows
       fft_dif<8>(v);                               // register j holds Z[k1 + 16*brev3(j)]
       const int srcl = (lane & 16) | ((16 - k1) & 15);   // lane holding k1' = 16 - k1 of the same pair
 #pragma unroll
@@ -174,10 +205,11 @@ fft2_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* 
           const float ar = 0.5f * (zr + pr), ai = 0.5f * (zi - pi);     // A[k] = (Z[k] + conj Zp)/2
           const float br = 0.5f * (zi + pi), bi = -0.5f * (zr - pr);    // B[k] = -i/2 (Z[k] - conj Zp)
           if (k2 < 4) {
-            xre[xidx(ra, k)] = ar; xim[xidx(ra, k)] = ai;
-            xre[xidx(ra + 1, k)] = br; xim[xidx(ra + 1, k)] = bi;
+            const int pc = pcol(ra, k);            // rows r and r + 64 share the swizzle
+            rowa[pc] = ar; rowa[64 + pc] = ai;
+            rowb[pc] = br; rowb[64 + pc] = bi;
           } else {
-            nre[ra] = ar; nim[ra] = ai; nre[ra + 1] = br; nim[ra + 1] = bi;
+            rowa[128] = ar; rowa[129] = ai; rowb[128] = br; rowb[129] = bi;
           }
         }
       }
@@ -187,17 +219,12 @@ fft2_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* 
   __syncthreads();
 
   // ------------------------------------------------------------------ columns 0..64: warp w owns 8w..8w+7, warp 0 also column 64
-  float* ore = out + ((n * 2 * C + c) * (int64_t)FN) * FN;
-  float* oim = out + ((n * 2 * C + C + c) * (int64_t)FN) * FN;
-  const float sc = 1.f / 128.f;
   for (int grp = 0; grp < 2; ++grp) {
     if (grp == 1 && warp != 0) break;              // the Nyquist column
-    const int ncol = grp == 0 ? 8 : 1;
     const int cl = grp == 0 ? (lane & 7) : 0;
     const int sub = grp == 0 ? (lane >> 3) : lane; // row-offset index within an iteration
     const int per_it = grp == 0 ? 4 : 32;
     const int col = grp == 0 ? warp * 8 + cl : 64;
-    (void)ncol;
     // stage 1: (col, n2): 16-point FFT over rows 8*n1 + n2, in place
     for (int it = 0; it * per_it < 8; ++it) {
       const int n2 = it * per_it + sub;
@@ -206,7 +233,8 @@ fft2_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* 
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) {
           const int r = n1 * 8 + n2;
-          v[n1] = grp == 0 ? cpx{xre[xidx(r, col)], xim[xidx(r, col)]} : cpx{nre[r], nim[r]};
+          const float* p = B + r * RS + (grp == 0 ? pcol(r, col) : 128);
+          v[n1] = cpx{p[0], p[grp == 0 ? 64 : 1]};
         }
         fft_dif<16>(v);
 #pragma unroll
@@ -215,13 +243,13 @@ fft2_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* 
           const int t = k1 * n2;
           const cpx y = cmul(v[j], cpx{twr[t], twi[t]});
           const int r = k1 * 8 + n2;
-          if (grp == 0) { xre[xidx(r, col)] = y.r; xim[xidx(r, col)] = y.i; }
-          else { nre[r] = y.r; nim[r] = y.i; }
+          float* p = B + r * RS + (grp == 0 ? pcol(r, col) : 128);
+          p[0] = y.r; p[grp == 0 ? 64 : 1] = y.i;
         }
       }
     }
     __syncwarp();
-    // stage 2: (col, k1): 8-point FFT over n2, then the two mirrored stores
+    // stage 2: (col, k1): 8-point FFT over n2, in place: register j = frequency k1 + 16*brev3(j) stays in row 8*k1 + j
     for (int it = 0; it * per_it < 16; ++it) {
       const int k1 = it * per_it + sub;
       if (k1 < 16) {
@@ -229,29 +257,55 @@ fft2_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* 
 #pragma unroll
         for (int n2 = 0; n2 < 8; ++n2) {
           const int r = k1 * 8 + n2;
-          v[n2] = grp == 0 ? cpx{xre[xidx(r, col)], xim[xidx(r, col)]} : cpx{nre[r], nim[r]};
+          const float* p = B + r * RS + (grp == 0 ? pcol(r, col) : 128);
+          v[n2] = cpx{p[0], p[grp == 0 ? 64 : 1]};
         }
         fft_dif<8>(v);
-        const int vc = (col + 64) & 127;             // fftshift of column v = col
-        const int vm = (128 - col + 64) & 127;       // ... and of the mirrored column -v
-        const bool mirror = col >= 1 && col <= 63;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int u = k1 + 16 * brev3(j);          // row frequency index
-          const float fr = clampn(v[j].r * sc, clamp), fi = clampn(v[j].i * sc, clamp);
-          const int ur = (u + 64) & 127;
-          ore[ur * FN + vc] = fr;
-          oim[ur * FN + vc] = fi;
-          if (mirror) {
-            const int um = ((128 - u) + 64) & 127;   // row of -u after the shift
-            ore[um * FN + vm] = fr;
-            oim[um * FN + vm] = clampn(-v[j].i * sc, clamp);
-          }
+          const int r = k1 * 8 + j;
+          float* p = B + r * RS + (grp == 0 ? pcol(r, col) : 128);
+          p[0] = v[j].r; p[grp == 0 ? 64 : 1] = v[j].i;
         }
       }
     }
     __syncwarp();
   }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ emit: scale, fftshift, clamp; whole rows, 16 bytes per lane
+  // Output row ur holds u = ur - 64: columns 64..127 are F[u, 0..63], column 0 is F[u, 64] and columns 1..63 are
+  // F[u, -(64 - vc)] = conj F[-u, 64 - vc], read backwards from row -u.  A half-warp writes one half row.
+  float* ore = out + ((n * 2 * C + c) * (int64_t)FN) * FN;
+  float* oim = out + ((n * 2 * C + C + c) * (int64_t)FN) * FN;
+#pragma unroll 2
+  for (int i = 0; i < 8; ++i) {
+    const int ur = (warp * 8 + i) * 2 + (lane >> 4), l = lane & 15;
+    const int u = (ur + 64) & 127;
+    const int rr = rho(u), rm = rho((128 - u) & 127);
+    {
+      const float* p = B + rr * RS + pcol(rr, 4 * l);
+      const float4 re = *reinterpret_cast<const float4*>(p), im = *reinterpret_cast<const float4*>(p + 64);
+      emit4<MODE>(ore + ur * FN + 64 + 4 * l, oim + ur * FN + 64 + 4 * l, re, im, clamp);
+    }
+    {
+      const float* p = B + rm * RS + pcol(rm, 60 - 4 * l);          // F[-u, 60-4l .. 63-4l]
+      const float4 re = *reinterpret_cast<const float4*>(p), im = *reinterpret_cast<const float4*>(p + 64);
+      float r0 = __shfl_up_sync(0xffffffffu, re.x, 1), i0 = -__shfl_up_sync(0xffffffffu, im.x, 1);   // F[-u, 64-4l]
+      if (l == 0) { r0 = B[rr * RS + 128]; i0 = B[rr * RS + 129]; }                                   // F[u, 64]
+      emit4<MODE>(ore + ur * FN + 4 * l, oim + ur * FN + 4 * l, make_float4(r0, re.w, re.z, re.y),
+                  make_float4(i0, -im.w, -im.z, -im.y), clamp);
+    }
+  }
+}
+
+template <int MODE>
+int launch_fft(const float* x, const float* xhat, float* out, int64_t N, int C, float clamp, cudaStream_t st) {
+  const size_t smem = (size_t)FN * RS * sizeof(float);
+  LSHM_CUDA(cudaFuncSetAttribute(fft2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "lshm_fft2");
+  fft2_kernel<MODE><<<(unsigned)(N * C), FFT_THREADS, smem, st>>>(x, xhat, out, C, clamp);
+  LSHM_CHECK_LAUNCH("lshm_fft2");
+  return LSHM_OK;
 }
 
 }  // namespace
@@ -261,17 +315,21 @@ using namespace lshm;
 
 extern "C" {
 
+int lshm_fft2_features(const float* x, const float* xhat, float* out,
+                       int64_t N, int C, float clamp, int mode, lshm_stream_t stream) {
+  LSHM_REQUIRE(x && out && N >= 0 && C > 0, "lshm_fft2_features: bad arguments");
+  LSHM_REQUIRE(mode == LSHM_FFT_REIM || mode == LSHM_FFT_MAGPHASE, "lshm_fft2_features: bad mode %d", mode);
+  LSHM_REQUIRE(N * C < (1LL << 31), "lshm_fft2_features: too many planes for one launch");
+  LSHM_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+               "lshm_fft2_features: x and out must be 16-byte aligned");
+  if (N == 0) return LSHM_OK;
+  if (mode == LSHM_FFT_MAGPHASE) return launch_fft<LSHM_FFT_MAGPHASE>(x, xhat, out, N, C, clamp, as_stream(stream));
+  return launch_fft<LSHM_FFT_REIM>(x, xhat, out, N, C, clamp, as_stream(stream));
+}
+
 int lshm_fft2_reim_shift_clamp(const float* x, const float* xhat, float* out,
                                int64_t N, int C, float clamp, lshm_stream_t stream) {
-  LSHM_REQUIRE(x && out && N >= 0 && C > 0, "lshm_fft2_reim_shift_clamp: bad arguments");
-  LSHM_REQUIRE(N * C < (1LL << 31), "lshm_fft2_reim_shift_clamp: too many planes for one launch");
-  if (N == 0) return LSHM_OK;
-  const size_t smem = (2 * FN * XS + 8 * 8 * YS) * sizeof(float);
-  LSHM_CUDA(cudaFuncSetAttribute(fft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-            "lshm_fft2_reim_shift_clamp");
-  fft2_kernel<<<(unsigned)(N * C), FFT_THREADS, smem, as_stream(stream)>>>(x, xhat, out, C, clamp);
-  LSHM_CHECK_LAUNCH("lshm_fft2_reim_shift_clamp");
-  return LSHM_OK;
+  return lshm_fft2_features(x, xhat, out, N, C, clamp, LSHM_FFT_REIM, stream);
 }
 
 }  // extern "C"

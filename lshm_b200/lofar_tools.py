@@ -55,18 +55,20 @@ def torch_fftshift(real, imag):
     return real, imag
 
 
-def fft_features(x: torch.Tensor, xhat: torch.Tensor = None, clamp: float = 10.0) -> torch.Tensor:
+def fft_features(x: torch.Tensor, xhat: torch.Tensor = None, clamp: float = 10.0, mode: str = "reim") -> torch.Tensor:
     """Demo.ipynb:169-174 as one kernel: cat(Re,Im)(fftshift(fft2_ortho(x - xhat))).clamp(+-10).
-    x [N,C,128,128] -> [N,2C,128,128]."""
+    x [N,C,128,128] -> [N,2C,128,128].  mode="magphase": cat(|F|.clamp(max=clamp), angle(F)) of the same F."""
     if not x.is_cuda or x.dtype != torch.float32 or tuple(x.shape[2:]) != (128, 128):
         raise RuntimeError("lshm_b200: fft_features expects a CUDA float32 [N,C,128,128] tensor")
+    if mode not in ("reim", "magphase"):
+        raise ValueError("fft_features: mode must be 'reim' or 'magphase'")
     x = x.contiguous()
     if xhat is not None:
         xhat = xhat.contiguous()
     N, C = x.shape[:2]
     out = torch.empty(N, 2 * C, 128, 128, dtype=torch.float32, device=x.device)
-    lib().fft2_reim_shift_clamp(x.data_ptr(), None if xhat is None else xhat.data_ptr(), out.data_ptr(),
-                                N, C, float(clamp), _stream())
+    lib().fft2_features(x.data_ptr(), None if xhat is None else xhat.data_ptr(), out.data_ptr(),
+                        N, C, float(clamp), 0 if mode == "reim" else 1, _stream())
     return out
 
 

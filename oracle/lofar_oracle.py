@@ -389,14 +389,18 @@ def load_minibatch(vis, scale, baselines, *, patch_size=128, num_channels=8, nor
 # --------------------------------------------------------------------------------------
 # Fourier features (notebook path)
 # --------------------------------------------------------------------------------------
-def fft_features(x, xhat: Optional[torch.Tensor] = None, clamp: float = 10.0):
+def fft_features(x, xhat: Optional[torch.Tensor] = None, clamp: float = 10.0, mode: str = "reim"):
     """Demo.ipynb:169-174 with src/lofar_tools.py:24-30: ortho 2-D FFT of (x - xhat),
-    roll by size//2 on dims 2,3, cat(Re, Im) on the channel axis, clamp to +-10."""
+    roll by size//2 on dims 2,3, cat(Re, Im) on the channel axis, clamp to +-10.
+    mode="magphase" (north_star's wording; the reference feature is Re / Im): cat(|F|, angle F) of the same
+    shifted spectrum, the magnitude clamped."""
     r = x if xhat is None else x - xhat
     f = torch.fft.fftn(r, dim=(2, 3), norm="ortho")
     re, im = f.real, f.imag
     for dim in (2, 3):
         re = torch.roll(re, dims=dim, shifts=re.size(dim) // 2)
         im = torch.roll(im, dims=dim, shifts=im.size(dim) // 2)
+    if mode == "magphase":
+        return torch.cat((torch.sqrt(re * re + im * im).clamp_(max=clamp), torch.atan2(im, re)), 1)
     y = torch.cat((re, im), 1)
     return y.clamp_(min=-clamp, max=clamp)
