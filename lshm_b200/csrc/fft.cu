@@ -65,7 +65,13 @@ __device__ __forceinline__ void fft_dif(cpx (&v)[N]) {
 __device__ __forceinline__ constexpr int brev3(int v) { return ((v & 1) << 2) | (v & 2) | ((v >> 2) & 1); }
 __device__ __forceinline__ constexpr int brev4(int v) { return ((v & 1) << 3) | ((v & 2) << 1) | ((v >> 1) & 2) | ((v >> 3) & 1); }
 
-__device__ __forceinline__ float clampn(float a, float c) { return a != a ? a : fminf(fmaxf(a, -c), c); }
+// torch.clamp semantics (NaN stays NaN) in two instructions
+__device__ __forceinline__ float clampn(float a, float c) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(c));
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(r), "f"(-c));
+  return r;
+}
 
 constexpr int RS = 136;   // row pitch (floats) of the plane buffer: 128 samples / 64 re + 64 im, Nyquist re, im, 6 spare
 
@@ -77,20 +83,72 @@ __device__ __forceinline__ int pcol(int row, int k) { return k ^ (((row >> 3) & 
 // the column pass leaves row frequency u = k1 + 16*k2 where its second stage computed it: row 8*k1 + brev3(k2)
 __device__ __forceinline__ int rho(int u) { return ((u & 15) << 3) | brev3(u >> 4); }
 
+// (the ortho scale 1/128 is already in the values: it rides in the column pass's inter-stage twiddles)
 template <int MODE>
 __device__ __forceinline__ void emit4(float* __restrict__ o0, float* __restrict__ o1, float4 re, float4 im, float clamp) {
-  constexpr float sc = 1.f / 128.f;                  // ortho scale of the 2-D transform
   float4 a, b;
   if (MODE == LSHM_FFT_REIM) {
-    a = make_float4(clampn(re.x * sc, clamp), clampn(re.y * sc, clamp), clampn(re.z * sc, clamp), clampn(re.w * sc, clamp));
-    b = make_float4(clampn(im.x * sc, clamp), clampn(im.y * sc, clamp), clampn(im.z * sc, clamp), clampn(im.w * sc, clamp));
+    a = make_float4(clampn(re.x, clamp), clampn(re.y, clamp), clampn(re.z, clamp), clampn(re.w, clamp));
+    b = make_float4(clampn(im.x, clamp), clampn(im.y, clamp), clampn(im.z, clamp), clampn(im.w, clamp));
   } else {
-    a = make_float4(clampn(sqrtf(re.x * re.x + im.x * im.x) * sc, clamp), clampn(sqrtf(re.y * re.y + im.y * im.y) * sc, clamp),
-                    clampn(sqrtf(re.z * re.z + im.z * im.z) * sc, clamp), clampn(sqrtf(re.w * re.w + im.w * im.w) * sc, clamp));
+    a = make_float4(clampn(sqrtf(re.x * re.x + im.x * im.x), clamp), clampn(sqrtf(re.y * re.y + im.y * im.y), clamp),
+                    clampn(sqrtf(re.z * re.z + im.z * im.z), clamp), clampn(sqrtf(re.w * re.w + im.w * im.w), clamp));
     b = make_float4(atan2f(im.x, re.x), atan2f(im.y, re.y), atan2f(im.z, re.z), atan2f(im.w, re.w));
   }
   *reinterpret_cast<float4*>(o0) = a;
   *reinterpret_cast<float4*>(o1) = b;
+}
+
+// Column pass over the half spectrum in the plane buffer, in place.  NYQ = false: lane -> (column 8*warp + lane%8,
+// row offset lane/8), four row offsets per iteration; NYQ = true: the Nyquist column (one warp), lane = row offset.
+// `tws` is the twiddle table times 1/128 (the ortho scale of the 2-D transform, exact: a power of two).
+template <bool NYQ>
+__device__ __forceinline__ void column_pass(float* __restrict__ B, const float2* __restrict__ tws, int warp, int lane) {
+  constexpr int IM = NYQ ? 1 : 64;                 // offset of the imaginary part
+  const int col = NYQ ? 128 : warp * 8 + (lane & 7);
+  const int sub = NYQ ? lane : (lane >> 3);
+  constexpr int PER_IT = NYQ ? 32 : 4;
+  const int cx[4] = {col, NYQ ? col : col ^ 8, NYQ ? col : col ^ 16, NYQ ? col : col ^ 24};   // pcol(r, col) by (r/8)%4
+  // stage 1: (col, n2): 16-point FFT over rows 8*n1 + n2
+#pragma unroll 1
+  for (int it = 0; it * PER_IT < 8; ++it) {
+    const int n2 = it * PER_IT + sub;
+    if (n2 < 8) {
+      float* base = B + n2 * RS;
+      cpx v[16];
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) {
+        const float* p = base + n1 * 8 * RS + cx[n1 & 3];
+        v[n1] = cpx{p[0], p[IM]};
+      }
+      fft_dif<16>(v);
+      const float2* twp = tws + n2;                // twiddle exp(-2*pi*i*k1*n2/128)/128 at tws[k1*n2]
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int k1 = brev4(j);
+        const float2 w = tws[k1 * n2];
+        const cpx y = cmul(v[j], cpx{w.x, w.y});
+        float* p = base + k1 * 8 * RS + cx[k1 & 3];
+        p[0] = y.r; p[IM] = y.i;
+      }
+      (void)twp;
+    }
+  }
+  __syncwarp();
+  // stage 2: (col, k1): 8-point FFT over n2; register j = frequency k1 + 16*brev3(j) stays in row 8*k1 + j
+#pragma unroll 1
+  for (int it = 0; it * PER_IT < 16; ++it) {
+    const int k1 = it * PER_IT + sub;
+    if (k1 < 16) {
+      float* base = B + k1 * 8 * RS + (NYQ ? col : (col ^ ((k1 & 3) << 3)));
+      cpx v[8];
+#pragma unroll
+      for (int n2 = 0; n2 < 8; ++n2) v[n2] = cpx{base[n2 * RS], base[n2 * RS + IM]};
+      fft_dif<8>(v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { base[j * RS] = v[j].r; base[j * RS + IM] = v[j].i; }
+    }
+  }
 }
 
 template <int MODE>
@@ -98,7 +156,7 @@ __global__ void __launch_bounds__(FFT_THREADS, 2)
 fft2_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* __restrict__ out,
             int C, float clamp) {
   extern __shared__ __align__(16) float B[];   // [128][RS]
-  __shared__ float twr[FN], twi[FN];
+  __shared__ float2 tw[FN], tws[FN];          // exp(-2*pi*i*t/128), and the same / 128
   __shared__ __align__(8) uint64_t bar;
   const int64_t plane = blockIdx.x;            // n*C + c
   const int64_t n = plane / C;
@@ -119,7 +177,8 @@ fft2_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* 
   } else {
     float sn, cs;
     sincospif(-(float)(tid - FN) / 64.f, &sn, &cs);    // exp(-2*pi*i*t/128)
-    twr[tid - FN] = cs; twi[tid - FN] = sn;
+    tw[tid - FN] = make_float2(cs, sn);
+    tws[tid - FN] = make_float2(cs * (1.f / 128.f), sn * (1.f / 128.f));
   }
   __syncthreads();
   tc::mbar_wait(&bar, 0);
@@ -157,7 +216,8 @@ fft2_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* 
       for (int j = 0; j < 16; ++j) {               // register j holds k1 = brev4(j)
         const int k1 = brev4(j);
         const int t = k1 * n2;                     // twiddle exp(-2*pi*i*k1*n2/128)
-        const cpx y = cmul(v[j], cpx{twr[t], twi[t]});
+        const float2 w = tw[t];
+        const cpx y = cmul(v[j], cpx{w.x, w.y});
         yre[k1 * 8 + n2] = y.r;
         yim[k1 * 8 + n2] = y.i;
       }
@@ -219,58 +279,8 @@ fft2_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* 
   __syncthreads();
 
   // ------------------------------------------------------------------ columns 0..64: warp w owns 8w..8w+7, warp 0 also column 64
-  for (int grp = 0; grp < 2; ++grp) {
-    if (grp == 1 && warp != 0) break;              // the Nyquist column
-    const int cl = grp == 0 ? (lane & 7) : 0;
-    const int sub = grp == 0 ? (lane >> 3) : lane; // row-offset index within an iteration
-    const int per_it = grp == 0 ? 4 : 32;
-    const int col = grp == 0 ? warp * 8 + cl : 64;
-    // stage 1: (col, n2): 16-point FFT over rows 8*n1 + n2, in place
-    for (int it = 0; it * per_it < 8; ++it) {
-      const int n2 = it * per_it + sub;
-      if (n2 < 8) {
-        cpx v[16];
-#pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) {
-          const int r = n1 * 8 + n2;
-          const float* p = B + r * RS + (grp == 0 ? pcol(r, col) : 128);
-          v[n1] = cpx{p[0], p[grp == 0 ? 64 : 1]};
-        }
-        fft_dif<16>(v);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int k1 = brev4(j);
-          const int t = k1 * n2;
-          const cpx y = cmul(v[j], cpx{twr[t], twi[t]});
-          const int r = k1 * 8 + n2;
-          float* p = B + r * RS + (grp == 0 ? pcol(r, col) : 128);
-          p[0] = y.r; p[grp == 0 ? 64 : 1] = y.i;
-        }
-      }
-    }
-    __syncwarp();
-    // stage 2: (col, k1): 8-point FFT over n2, in place: register j = frequency k1 + 16*brev3(j) stays in row 8*k1 + j
-    for (int it = 0; it * per_it < 16; ++it) {
-      const int k1 = it * per_it + sub;
-      if (k1 < 16) {
-        cpx v[8];
-#pragma unroll
-        for (int n2 = 0; n2 < 8; ++n2) {
-          const int r = k1 * 8 + n2;
-          const float* p = B + r * RS + (grp == 0 ? pcol(r, col) : 128);
-          v[n2] = cpx{p[0], p[grp == 0 ? 64 : 1]};
-        }
-        fft_dif<8>(v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = k1 * 8 + j;
-          float* p = B + r * RS + (grp == 0 ? pcol(r, col) : 128);
-          p[0] = v[j].r; p[grp == 0 ? 64 : 1] = v[j].i;
-        }
-      }
-    }
-    __syncwarp();
-  }
+  column_pass<false>(B, tws, warp, lane);
+  if (warp == 0) column_pass<true>(B, tws, warp, lane);
   __syncthreads();
 
   // ------------------------------------------------------------------ emit: scale, fftshift, clamp; whole rows, 16 bytes per lane
