@@ -11,6 +11,7 @@
 // warp shuffles.  The centre-gradient / centre-update sums are a [K x pts] x [pts x L] product,
 // done per tile from shared memory with one owner thread per output (no atomics inside the tile
 // loop); blocks are persistent (grid = multiple of the SM count) and flush once.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace lshm {
@@ -48,6 +49,7 @@ typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 // 1/x to 1 ulp in one MUFU op (the IEEE-rounded division is ~12 instructions per (point, centre) pair,
@@ -337,6 +339,203 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass2_kernel(KhmArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// pass 2, K <= 16 and L = 32*TPP (the HBM-side cases): two points per thread group, register-tiled tile product
+// ------------------------------------------------------------------------------------------
+// Same results as khm_pass2_kernel (same distances, harmonic sums and weights), about a third of its instructions:
+//  * two points per thread: every broadcast LDS.128 of a centre chunk feeds both points (as in pass 1);
+//  * the point gradient sum_k w_k (x - m_k) is accumulated as (sum_k w_k) x - sum_k w_k m_k: one packed FMA per two
+//    dimensions instead of a packed subtract + FMA (the distances keep the direct-difference form; here the terms that
+//    cancel carry weights ~ d^2, so the L2 error of the gradient stays at fp32 rounding);
+//  * the [K x pts] x [pts x L] product (centre gradient / centre sums) is register-tiled: a thread owns KT centres of one
+//    float4 column for every PS-th point of the tile, its 4*KT accumulators live in registers for the whole kernel and the
+//    weights are stored as duplicated pairs (w, w), so a 64-bit shared load IS the packed operand: per point and thread
+//    one LDS.128 of x, ~KT/2 loads of weights and 2*KT FFMA2 (the scalar loop: 7 instructions per 4 FMA, 62 % of the
+//    threads busy at K = 10, L = 64);
+//  * sum_i w_ik: per-thread partial sums in shared memory (counted TPP times, divided at the end: exact).
+template <int TPP, int KT, bool SUMS>
+__global__ void __launch_bounds__(KHM_THREADS, SUMS ? 3 : 2) khm_pass2_fast_kernel(KhmArgs a, int KG) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int PTS = KHM_THREADS / TPP;           // thread groups; a tile is 2*PTS points
+  constexpr int L = 32 * TPP, L4 = L / 4;
+  constexpr int GS = (2 * KT + 3) & ~3;            // floats per centre group in a weight row (16-byte aligned groups)
+  const int K = a.K;
+  const int WS = KG * GS;                          // weight row: KG groups of KT duplicated pairs
+  float* ms = smem;                                // [K][L] centres
+  float* xs = ms + K * L;                          // [2*PTS][L] x tile; [K][L] block sums at the end
+  float* ws = xs + 2 * PTS * L;                    // [2*PTS][WS]
+  float* d2s = ws + 2 * PTS * WS;                  // [K][2*PTS] squared distances of the harmonic-sum loop
+  float* wpart = d2s + K * 2 * PTS;                // [K][KHM_THREADS] per-thread partial sums of the weights
+  __shared__ double red[32];
+  const int tid = threadIdx.x, pt = tid / TPP, s = tid % TPP;
+  const int64_t ntiles = (a.N + 2 * PTS - 1) / (2 * PTS);
+  const float Kf = (float)K;
+  double lsum = 0.0;
+  stage_centres(ms, a.M, 0, K, L);
+  for (int i = tid; i < 2 * PTS * WS; i += KHM_THREADS) ws[i] = 0.f;      // pairs of unused centre slots stay zero
+  for (int i = tid; i < K * KHM_THREADS; i += KHM_THREADS) wpart[i] = 0.f;
+  // product role: column c4, centre group kg, point split ps
+  const int c4 = tid % L4, kg = (tid / L4) % KG, ps = tid / (L4 * KG), PS = KHM_THREADS / (L4 * KG);
+  f32x2 acc[KT][2];
+#pragma unroll
+  for (int j = 0; j < KT; ++j) acc[j][0] = acc[j][1] = 0ull;
+  __syncthreads();
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t ia = t * 2 * PTS + pt, ib = ia + PTS;
+    const bool va = ia < a.N, vb = ib < a.N;
+    float4 xa[KHM_MAXCH], xb[KHM_MAXCH];
+    load_point<TPP, KHM_MAXCH>(xa, a.X, a.ldx, ia, va, s, KHM_MAXCH);
+    load_point<TPP, KHM_MAXCH>(xb, a.X, a.ldx, ib, vb, s, KHM_MAXCH);
+    // ---- harmonic sums (identical arithmetic to pass 1)
+    float ea = 0.f, eb = 0.f;
+#pragma unroll 2
+    for (int kk = 0; kk < K; ++kk) {
+      float da, db;
+      dist2x2<TPP, KHM_MAXCH>(xa, xb, ms + kk * L, s, KHM_MAXCH, da, db);
+      d2s[kk * 2 * PTS + pt] = da;                  // every lane of the point writes (and later reads) the same value
+      d2s[kk * 2 * PTS + PTS + pt] = db;
+      ea += rcp_fast(pow_p(da, a.p, a.pmode) + KHM_EPS);
+      eb += rcp_fast(pow_p(db, a.p, a.pmode) + KHM_EPS);
+    }
+    if (s == 0) {
+      if (va) lsum += (double)(Kf / (ea + KHM_EPS));
+      if (vb) lsum += (double)(Kf / (eb + KHM_EPS));
+    }
+    // per-point coefficient: gradient K/(e+eps)^2 ; centre update alpha = 1/(e^2+eps)
+    const float ca = SUMS ? 1.0f / (ea * ea + KHM_EPS) : Kf / ((ea + KHM_EPS) * (ea + KHM_EPS));
+    const float cb = SUMS ? 1.0f / (eb * eb + KHM_EPS) : Kf / ((eb + KHM_EPS) * (eb + KHM_EPS));
+    __syncthreads();                                // the previous tile's product has read xs / ws
+#pragma unroll
+    for (int c = 0; c < KHM_MAXCH; ++c) {
+      *reinterpret_cast<float4*>(xs + pt * L + ((c * TPP + s) << 2)) = xa[c];
+      *reinterpret_cast<float4*>(xs + (PTS + pt) * L + ((c * TPP + s) << 2)) = xb[c];
+    }
+    // ---- weights, sum_k w_k m_k
+    f32x2 ga[KHM_MAXCH][2], gb[KHM_MAXCH][2];
+#pragma unroll
+    for (int c = 0; c < KHM_MAXCH; ++c) ga[c][0] = ga[c][1] = gb[c][0] = gb[c][1] = 0ull;
+    float swa = 0.f, swb = 0.f;
+    for (int g = 0; g < KG; ++g) {
+#pragma unroll
+      for (int j = 0; j < KT; ++j) {
+        const int kk = g * KT + j;
+        if (kk < K) {
+          const float da = d2s[kk * 2 * PTS + pt], db = d2s[kk * 2 * PTS + PTS + pt];
+          const float pa = pow_p(da, a.p, a.pmode), pb = pow_p(db, a.p, a.pmode);
+          float wa, wb;
+          if (SUMS) {
+            wa = ca * rcp_fast(pa * da + KHM_EPS);                  // alpha_i / (d^(p+2) + eps)
+            wb = cb * rcp_fast(pb * db + KHM_EPS);
+          } else {
+            const float ta = pa + KHM_EPS, tb = pb + KHM_EPS;
+            wa = da > 0.f ? ca * a.p * pow_pm2(da, a.p, a.pmode) * rcp_fast(ta * ta) : 0.f;
+            wb = db > 0.f ? cb * a.p * pow_pm2(db, a.p, a.pmode) * rcp_fast(tb * tb) : 0.f;
+          }
+          if (!va) wa = 0.f;
+          if (!vb) wb = 0.f;
+          if (!SUMS) {
+            const float* mrow = ms + kk * L;
+            const f32x2 wa2 = pk2(wa, wa), wb2 = pk2(wb, wb);
+#pragma unroll
+            for (int c = 0; c < KHM_MAXCH; ++c) {
+              const float4 m = *reinterpret_cast<const float4*>(mrow + ((c * TPP + s) << 2));
+              const f32x2 m0 = pk2(m.x, m.y), m1 = pk2(m.z, m.w);
+              ga[c][0] = fma2(wa2, m0, ga[c][0]); ga[c][1] = fma2(wa2, m1, ga[c][1]);
+              gb[c][0] = fma2(wb2, m0, gb[c][0]); gb[c][1] = fma2(wb2, m1, gb[c][1]);
+            }
+            swa += wa; swb += wb;
+          }
+          wpart[kk * KHM_THREADS + tid] += wa + wb;
+          if (s == 0) {
+            *reinterpret_cast<float2*>(ws + pt * WS + g * GS + 2 * j) = make_float2(wa, wa);
+            *reinterpret_cast<float2*>(ws + (PTS + pt) * WS + g * GS + 2 * j) = make_float2(wb, wb);
+          }
+        }
+      }
+    }
+    if (!SUMS && a.gX != nullptr) {
+      const f32x2 sa2 = pk2(swa * a.gscale, swa * a.gscale), sb2 = pk2(swb * a.gscale, swb * a.gscale);
+      const f32x2 ng = pk2(-a.gscale, -a.gscale);
+#pragma unroll
+      for (int c = 0; c < KHM_MAXCH; ++c) {
+        // gscale * (sw * x - sum_k w_k m_k)
+        float4 v, u;
+        upk2(fma2(sa2, pk2(xa[c].x, xa[c].y), mul2(ng, ga[c][0])), v.x, v.y);
+        upk2(fma2(sa2, pk2(xa[c].z, xa[c].w), mul2(ng, ga[c][1])), v.z, v.w);
+        upk2(fma2(sb2, pk2(xb[c].x, xb[c].y), mul2(ng, gb[c][0])), u.x, u.y);
+        upk2(fma2(sb2, pk2(xb[c].z, xb[c].w), mul2(ng, gb[c][1])), u.z, u.w);
+        if (va) {
+          float4* dst = reinterpret_cast<float4*>(a.gX + ia * a.ldg + ((c * TPP + s) << 2));
+          if (a.accumulate_x) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+          *dst = v;
+        }
+        if (vb) {
+          float4* dst = reinterpret_cast<float4*>(a.gX + ib * a.ldg + ((c * TPP + s) << 2));
+          if (a.accumulate_x) { const float4 o = *dst; u.x += o.x; u.y += o.y; u.z += o.z; u.w += o.w; }
+          *dst = u;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- tile product: acc[j] += w[q][kg*KT + j] * x[q][4*c4 .. 4*c4+3] over the thread's points
+    {
+      const float* xcol = xs + (c4 << 2);
+      const float* wrow = ws + kg * GS;
+#pragma unroll 2
+      for (int q = ps; q < 2 * PTS; q += PS) {
+        const float4 xv = *reinterpret_cast<const float4*>(xcol + q * L);
+        const f32x2 x0 = pk2(xv.x, xv.y), x1 = pk2(xv.z, xv.w);
+        const float* wq = wrow + q * WS;
+        f32x2 w2[KT];
+#pragma unroll
+        for (int j = 0; j + 1 < KT; j += 2) {
+          const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(wq + 2 * j);
+          w2[j] = v.x; w2[j + 1] = v.y;
+        }
+        if (KT & 1) w2[KT - 1] = *reinterpret_cast<const f32x2*>(wq + 2 * (KT - 1));
+#pragma unroll
+        for (int j = 0; j < KT; ++j) {
+          acc[j][0] = fma2(w2[j], x0, acc[j][0]);
+          acc[j][1] = fma2(w2[j], x1, acc[j][1]);
+        }
+      }
+    }
+  }
+  // ---- block sums -> global
+  __syncthreads();
+  float* acc_s = xs;
+  for (int i = tid; i < K * L; i += KHM_THREADS) acc_s[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < KT; ++j) {
+    const int k = kg * KT + j;
+    if (k < K) {
+      float p0, p1, p2, p3;
+      upk2(acc[j][0], p0, p1); upk2(acc[j][1], p2, p3);
+      float* dst = acc_s + k * L + (c4 << 2);
+      atomicAdd(dst + 0, p0); atomicAdd(dst + 1, p1); atomicAdd(dst + 2, p2); atomicAdd(dst + 3, p3);
+    }
+  }
+  // sum_i w_ik of the block: every lane of a point added the weight, so the total is TPP times too large
+  for (int k = tid >> 5; k < K; k += KHM_THREADS / 32) {
+    float v = 0.f;
+    for (int i = tid & 31; i < KHM_THREADS; i += 32) v += wpart[k * KHM_THREADS + i];
+    v = warp_sum(v);
+    if ((tid & 31) == 0) d2s[k] = v * (1.f / (float)TPP);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < K * L; idx += KHM_THREADS) {
+    const int k = idx / L;
+    if (SUMS) atomicAdd(a.num + idx, acc_s[idx]);
+    else atomicAdd(a.gM + idx, -a.gscale * (acc_s[idx] - ms[idx] * d2s[k]));
+  }
+  if (SUMS) for (int k = tid; k < K; k += KHM_THREADS) atomicAdd(a.den + k, d2s[k]);
+  if (a.loss_sum != nullptr) {
+    const double tot = block_sum<double>(lsum, red);
+    if (tid == 0) atomicAdd(a.loss_sum, tot);
+  }
+}
+
 __global__ void group_argmin_kernel(const float* dist, int64_t G, int K, int32_t* gid) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
@@ -443,9 +642,53 @@ int launch_pass1(const KhmArgs& a, cudaStream_t st) {
 #undef P1
 }
 
+// (KT, KG) of the register-tiled product: KG groups of KT centres cover K; 128 threads = L/4 columns x KG x point splits
+bool pick_fast(int K, int L, int tpp, int* kt, int* kg) {
+  if (K > 16 || tpp > 8 || L != 32 * tpp) return false;
+  for (int t : {4, 5, 8}) {
+    const int g = (K + t - 1) / t;
+    if ((g == 1 || g == 2 || g == 4) && (L / 4) * g <= KHM_THREADS) { *kt = t; *kg = g; return true; }
+  }
+  return false;
+}
+
+template <int TPP, int KT, bool SUMS>
+int launch_pass2_fast_k(const KhmArgs& a, int kg, cudaStream_t st) {
+  const int pts = KHM_THREADS / TPP, gs = (2 * KT + 3) & ~3;
+  const size_t smem = ((size_t)a.K * a.L + (size_t)2 * pts * a.L + (size_t)2 * pts * kg * gs + (size_t)a.K * 2 * pts +
+                       (size_t)a.K * KHM_THREADS) * sizeof(float);
+  if (smem > 48 * 1024)
+    LSHM_CUDA(cudaFuncSetAttribute(khm_pass2_fast_kernel<TPP, KT, SUMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "khm_pass2");
+  const int64_t ntiles = ceil_div(a.N, 2 * pts);
+  const int64_t cap = (int64_t)sm_count() * (SUMS ? 3 : 2);
+  const int grid = (int)std::max<int64_t>(1, std::min(ntiles, cap));
+  khm_pass2_fast_kernel<TPP, KT, SUMS><<<grid, KHM_THREADS, smem, st>>>(a, kg);
+  LSHM_CHECK_LAUNCH("khm_pass2");
+  return LSHM_OK;
+}
+
+template <int TPP, bool SUMS>
+int launch_pass2_fast(const KhmArgs& a, int kt, int kg, cudaStream_t st) {
+  switch (kt) {
+    case 4: return launch_pass2_fast_k<TPP, 4, SUMS>(a, kg, st);
+    case 5: return launch_pass2_fast_k<TPP, 5, SUMS>(a, kg, st);
+    default: return launch_pass2_fast_k<TPP, 8, SUMS>(a, kg, st);
+  }
+}
+
 template <bool SUMS>
 int launch_pass2(const KhmArgs& a, cudaStream_t st) {
   const int tpp = pick_tpp(a.L);
+  int kt = 0, kg = 0;
+  static const bool no_fast = getenv("LSHM_KHM_NOFAST") != nullptr;       // experiment switch
+  if (!no_fast && pick_fast(a.K, a.L, tpp, &kt, &kg)) {
+    switch (tpp) {
+      case 1: return launch_pass2_fast<1, SUMS>(a, kt, kg, st);
+      case 2: return launch_pass2_fast<2, SUMS>(a, kt, kg, st);
+      case 4: return launch_pass2_fast<4, SUMS>(a, kt, kg, st);
+      default: return launch_pass2_fast<8, SUMS>(a, kt, kg, st);
+    }
+  }
   const int pts = KHM_THREADS / tpp;
   const size_t tile = ((size_t)pts * a.L + (size_t)pts * KHM_KC + (a.K <= KHM_KC ? (size_t)pts * KHM_KC : 0)) * sizeof(float);
   const size_t res_bytes = ((size_t)2 * a.K * a.L + ((a.K + 3) & ~3)) * sizeof(float) + tile;

@@ -149,7 +149,7 @@ def test_conv1d_family_many_items_per_cta(cuda, lvl):
 
 
 # ---------------------------------------------------------------------------- K-harmonic at N = 200 000
-@pytest.mark.parametrize("K,L", [(10, 64), (64, 64), (10, 32), (64, 128)])
+@pytest.mark.parametrize("K,L", [(10, 64), (64, 64), (10, 32), (64, 128), (10, 256), (16, 128), (4, 32), (8, 64), (12, 64)])
 def test_khm_family_200k_points(cuda, K, L):
     N, p = 200_000, 4.0
     rng = np.random.default_rng(K * 1000 + L)
