@@ -162,6 +162,10 @@ LSHM_API int lshm_wgrad2d_planes(const float* small_, int64_t small_ns, const vo
                         float* dw, int64_t N, int A, int Bc, int h, int w_, lshm_stream_t stream);
 LSHM_API int lshm_wgrad1d_planes(const float* small_, int64_t small_ns, const void* planes,
                         float* dw, int64_t N, int A, int Bc, int l, lshm_stream_t stream);
+/* dst[i] += src[i], i < n (both 16-byte aligned): the parameter gradients of a second micro-batch join the flat
+ * gradient buffer before the data-parallel exchange. */
+LSHM_API int lshm_vec_add(float* dst, const float* src, int64_t n, lshm_stream_t stream);
+
 /* db[c] = sum over n and positions of g[n,c,:]  (bias gradients). g [N,Cn,len]. */
 LSHM_API int lshm_channel_sum(const float* g, int64_t g_ns, float* db, int64_t N, int Cn, int64_t len,
                      lshm_stream_t stream);

@@ -392,10 +392,24 @@ int launch_down(int dim, DownArgs a, cudaStream_t st, bool planes = false) {
   static const bool one_group = getenv("LSHM_DOWN_G1") != nullptr;       // experiment switch
   const bool two = g.KB >= 2 && !one_group;                              // two producer groups (see the kernel)
   if (planes) {
-    // operand planes exist for the input-sized tensors only: the 8- and 12-channel first layers (NT = 16)
-    LSHM_REQUIRE(g.NT == 16 && a.Bc <= 16, "lshm_down*_planes: operand planes serve layers with <= 16 output and <= 16 input channels");
-    if (dim == 2) return launch_down_t<2, 16, 32, 1, true>(a, g, st);
-    return launch_down_t<1, 16, 32, 1, true>(a, g, st);
+    // the copy engine is the producer: any layer whose input exists as operand planes
+#define LP(D, NTV, KCV) return launch_down_t<D, NTV, KCV, 1, true>(a, g, st)
+    if (dim == 2) {
+      switch (g.NT) {
+        case 16: LP(2, 16, 32);
+        case 32: LP(2, 32, 32);
+        case 48: LP(2, 48, 32);
+        default: LP(2, 96, 16);
+      }
+    } else {
+      switch (g.NT) {
+        case 16: LP(1, 16, 32);
+        case 32: LP(1, 32, 32);
+        case 48: LP(1, 48, 32);
+        default: LP(1, 96, 32);
+      }
+    }
+#undef LP
   }
 #define LD(D, NTV, KCV) do { if (two) return launch_down_t<D, NTV, KCV, 2>(a, g, st); return launch_down_t<D, NTV, KCV, 1>(a, g, st); } while (0)
   if (dim == 2) {

@@ -103,6 +103,18 @@ channel_sum_short_kernel(const float* __restrict__ g, int64_t g_ns, float* __res
   if (lane == 0) atomicAdd(db + c, s);
 }
 
+// dst += src (the gradients of a second micro-batch join the flat gradient buffer)
+__global__ void vec_add_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n4, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    float4 a = reinterpret_cast<float4*>(dst)[i];
+    const float4 b = reinterpret_cast<const float4*>(src)[i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    reinterpret_cast<float4*>(dst)[i] = a;
+  }
+  if (i == 0) for (int64_t j = n4 * 4; j < n; ++j) dst[j] += src[j];
+}
+
 }  // namespace
 }  // namespace lshm
 
@@ -133,6 +145,16 @@ int lshm_channel_sum(const float* g, int64_t g_ns, float* db, int64_t N, int Cn,
     channel_sum_short_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(g, g_ns, db, rows, Cn, (int)len);
   }
   LSHM_CHECK_LAUNCH("lshm_channel_sum");
+  return LSHM_OK;
+}
+
+int lshm_vec_add(float* dst, const float* src, int64_t n, lshm_stream_t stream) {
+  LSHM_REQUIRE(dst && src && n >= 0, "lshm_vec_add: bad arguments");
+  LSHM_REQUIRE(((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0, "lshm_vec_add: buffers must be 16-byte aligned");
+  if (n == 0) return LSHM_OK;
+  const int64_t n4 = n >> 2;
+  vec_add_kernel<<<(unsigned)std::max<int64_t>(1, ceil_div(n4, 256)), 256, 0, as_stream(stream)>>>(dst, src, n4, n);
+  LSHM_CHECK_LAUNCH("lshm_vec_add");
   return LSHM_OK;
 }
 

@@ -67,6 +67,23 @@ class Workspace:
             self.g_dec = [torch.empty(N, sz[6 - i], **f) for i in range(6)]
             self.dx = torch.empty(N, sz[0], **f) if need_dx else None
 
+    def rows(self, n0: int, n1: int) -> "Workspace":
+        """The same buffers restricted to samples [n0, n1): every buffer is [N, per-sample] row-major, so a micro-batch
+        is a contiguous slice of each.  The step runs its micro-batches on such views (one stream each) while the
+        whole-batch kernels (latent-space terms, multiplier update) keep using the full buffers."""
+        v = Workspace.__new__(Workspace)
+        v.N, v.sizes = n1 - n0, self.sizes
+        for k, t in self.__dict__.items():
+            if k in ("N", "sizes"):
+                continue
+            if isinstance(t, torch.Tensor):
+                setattr(v, k, t[n0:n1])
+            elif isinstance(t, list):
+                setattr(v, k, [None if u is None else u[n0:n1] for u in t])
+            else:
+                setattr(v, k, t)
+        return v
+
 
 def planes_buffer(dim: int, N: int, Bc: int, h: int, w: int, device) -> torch.Tensor:
     """Zero-filled operand-plane buffer (include/lshm.h "operand planes") for a big map [N,Bc,2h,2w] (dim 2) or
@@ -223,7 +240,8 @@ class AEEngine:
 
     def forward(self, x: torch.Tensor, uv: torch.Tensor, scales: torch.Tensor,
                 p: Dict[str, torch.Tensor], ws: Workspace, st: int,
-                mu_out: Optional[torch.Tensor] = None, decode: bool = True, x_planes: Optional[torch.Tensor] = None):
+                mu_out: Optional[torch.Tensor] = None, decode: bool = True, x_planes: Optional[torch.Tensor] = None,
+                prepare: bool = True):
         """Runs the network; returns (xhat [N,C*16384] in ws, mu view); decode=False stops at the
         latent (the 1-D nets of the clustering path, src/evaluate_clustering.py:86-89) and returns (None, mu).
 
@@ -231,7 +249,8 @@ class AEEngine:
         (lets the three nets write straight into the concatenated Mu buffer).
         """
         lb, N, L, H4 = self.lib, ws.N, self.L, self.H4
-        self.prepare_images(p, st, hasattr(ws, "g_enc"))
+        if prepare:     # (False: the caller made the weight images once for several micro-batches)
+            self.prepare_images(p, st, hasattr(ws, "g_enc"))
         lb.uv_harmonics(_p(uv), _p(scales), N, scales.numel(), _p(ws.uvh), st)
         mu_final = mu_out if mu_out is not None else ws.mu
         mu_ld, zc_ld = mu_final.stride(0), L + H4

@@ -202,6 +202,18 @@ class GraphedStep:
         return loss
 
 
+class _MicroBatch:
+    """Rows [n0, n1) of the minibatch as one launch chain of DeepKHarmonicStep: views of the workspaces, its own operand
+    planes, gradient views (chain 0 writes the flat gradient buffer, the others a buffer of their own) and streams."""
+
+    def __init__(self, index: int, n0: int, n1: int):
+        self.index, self.n0, self.n1, self.N = index, n0, n1, n1 - n0
+        self.ws = self.gd = self.gbuf = None
+        self.xp = self.gx1p = self.pT = self.pF = self.p2 = self.p3 = None
+        self.stream = self.side = None
+        self.wst = [None, None, None]
+
+
 class DeepKHarmonicStep:
     """Fused closure + multiplier update for one minibatch (see module docstring).
 
@@ -226,7 +238,7 @@ class DeepKHarmonicStep:
     def __init__(self, net: AutoEncoderCNN2, netT: AutoEncoder1DCNN, netF: AutoEncoder1DCNN, mod: Kmeans, *,
                  alpha=0.01, beta=0.01, gamma=0.01, rho=1.0, use_rica=True, rica_lambda=0.01,
                  group: Optional[dist.ProcessGroup] = None, distributed: bool = False, centre_sums: bool = False,
-                 use_planes: bool = True):
+                 use_planes: bool = True, micro_batches: Optional[int] = None):
         self.net, self.netT, self.netF, self.mod = net, netT, netF, mod
         self.alpha, self.beta, self.gamma, self.rho = alpha, beta, gamma, rho
         self.use_rica, self.rica_lambda = use_rica, rica_lambda
@@ -252,8 +264,14 @@ class DeepKHarmonicStep:
         for mi, m in enumerate((net, netT, netF)):
             self._gd.append({nm: views[f"{mi}.{nm}"] for nm in m._names})
         self._gM = views["3.M"]
+        # Micro-batches: the minibatch is cut into H row ranges that run the cascade (forward, loss pass, backward) as
+        # independent launch chains on their own streams; the latency-bound deep layers of one chain then overlap the
+        # HBM-bound first layers of another.  Each chain writes its parameter gradients into its own flat buffer, the
+        # buffers are summed (lshm_vec_add) before the loss scalars are totalled.  Default 1: on B200 at cfg2 the chains do not
+        # overlap enough (persistent kernels that own every SM), 8.76 / 9.19 / 10.07 ms per step for H = 1 / 2 / 4.
+        self.micro = micro_batches
         self.N = 0
-        self._side = None                # second stream for the frequency-axis net
+        self._side = None                # stream of the latent-space terms
         self.overlap_streams = True      # False: everything on the current stream (per-kernel profiling)
         self._wst = [None, None, None]   # per-net streams for the weight / bias gradients
         self.launches = 0
@@ -305,14 +323,32 @@ class DeepKHarmonicStep:
             self.ws = [e[0].workspace(N, dev, True, False), e[1].workspace(N, dev, True, True),
                        e[2].workspace(N, dev, True, True)]
             n = N * C * 16384
+            H = self.micro if self.micro is not None else 1
+            if H < 1 or N % H:
+                raise RuntimeError(f"lshm_b200: {N} patches do not split into {H} micro-batches")
+            old = getattr(self, "mb", [])
+            self.mb = []
+            for h in range(H):
+                m = _MicroBatch(h, h * (N // H), (h + 1) * (N // H))
+                m.ws = self.ws if H == 1 else [w.rows(m.n0, m.n1) for w in self.ws]
+                if h == 0:
+                    m.gd = self._gd
+                else:
+                    m.gbuf = torch.zeros(self.flat.numel, **f)
+                    views = {nm: m.gbuf[o:o + p_.numel()].view(p_.shape)
+                             for nm, o, p_ in zip(self.flat.names, self.flat.offsets, self.flat.params)}
+                    m.gd = [{nm: views[f"{mi}.{nm}"] for nm in mod_._names} for mi, mod_ in enumerate((self.net, self.netT, self.netF))]
+                if h < len(old):                     # keep the streams (captured graphs were dropped above)
+                    m.stream, m.side, m.wst = old[h].stream, old[h].side, old[h].wst
+                if self.use_planes:
+                    from .engine import planes_buffer
+                    m.xp, m.gx1p = planes_buffer(2, m.N, C, 64, 64, dev), planes_buffer(2, m.N, C, 64, 64, dev)
+                    m.pT, m.pF = planes_buffer(1, m.N, C, 1, 4096, dev), planes_buffer(1, m.N, C, 1, 4096, dev)
+                    m.p2, m.p3 = planes_buffer(1, m.N, C, 1, 4096, dev), planes_buffer(1, m.N, C, 1, 4096, dev)
+                self.mb.append(m)
             if self.use_planes:
-                from .engine import planes_buffer
-                self.xp, self.gx1p = planes_buffer(2, N, C, 64, 64, dev), planes_buffer(2, N, C, 64, 64, dev)
-                self.pT, self.pF = planes_buffer(1, N, C, 1, 4096, dev), planes_buffer(1, N, C, 1, 4096, dev)
-                self.p2, self.p3 = planes_buffer(1, N, C, 1, 4096, dev), planes_buffer(1, N, C, 1, 4096, dev)
                 self.iyT = self.iyF = self.gx1 = self.g2 = self.g3f = None
             else:
-                self.xp = self.gx1p = self.pT = self.pF = self.p2 = self.p3 = None
                 self.iyT, self.iyF, self.gx1 = torch.empty(n, **f), torch.empty(n, **f), torch.empty(n, **f)
                 self.g2, self.g3f = torch.empty(n, **f), torch.empty(n, **f)
             self.g1p = torch.empty(n, **f)
@@ -343,7 +379,8 @@ class DeepKHarmonicStep:
     def stage_input(self):
         """x -> operand planes for the 2-D net's first conv (forward and weight gradient); once per minibatch."""
         if self.use_planes and self.N:
-            lib().stage_planes2d(self.x.data_ptr(), self.C * 16384, self.xp.data_ptr(), self.N, self.C, 64, 64, _stream())
+            for m in self.mb:
+                lib().stage_planes2d(self.x[m.n0:m.n1].data_ptr(), self.C * 16384, m.xp.data_ptr(), m.N, self.C, 64, 64, _stream())
 
     # multipliers: reading them applies a deferred update first, so they always hold the reference's values
     @property
@@ -384,45 +421,67 @@ class DeepKHarmonicStep:
         return self.ws[0].xhat, self.ws[1].xhat, self.ws[2].xhat
 
     def _forward(self, st):
-        L, Lt, N, C = self.L, self.Lt, self.N, self.C
+        """The cascade forward of every micro-batch (each on its own stream when there are several)."""
         e = self.net.engine(), self.netT.engine(), self.netF.engine()
-        xf = self.x.view(N, -1)
-        x1, _ = e[0].forward(xf, self.uv, self.scales, self._pd[0], self.ws[0], st, mu_out=self.Mu[:, :L], x_planes=self.xp)
+        many = len(self.mb) > 1
+        if many:
+            for i in range(3):                      # the weight images are shared: made once, before the chains fork
+                e[i].prepare_images(self._pd[i], st, True)
+        for m in self.mb:
+            s = self._fork_to(m, "stream") if many else torch.cuda.current_stream(self.device)
+            with torch.cuda.stream(s):
+                self._forward_mb(m, s.cuda_stream, not many)
+        if many:
+            for m in self.mb:
+                self._join(m.stream)
+
+    def _forward_mb(self, m: "_MicroBatch", st: int, prepare: bool):
+        L, Lt, C = self.L, self.Lt, self.C
+        e = self.net.engine(), self.netT.engine(), self.netF.engine()
+        x = self.x[m.n0:m.n1]
+        xf, uv, Mu = x.view(m.N, -1), self.uv[m.n0:m.n1], self.Mu[m.n0:m.n1]
+        x1, _ = e[0].forward(xf, uv, self.scales, self._pd[0], m.ws[0], st, mu_out=Mu[:, :L], x_planes=m.xp, prepare=prepare)
         if self.use_planes:
-            lib().residual_split_planes(self.x.data_ptr(), x1.data_ptr(), self.pT.data_ptr(), self.pF.data_ptr(), N, C, 128, st)
+            lib().residual_split_planes(x.data_ptr(), x1.data_ptr(), m.pT.data_ptr(), m.pF.data_ptr(), m.N, C, 128, st)
             inT = inF = xf          # not read: the first conv of the 1-D nets takes the planes
         else:
-            lib().residual_split(self.x.data_ptr(), x1.data_ptr(), self.iyT.data_ptr(), self.iyF.data_ptr(), N, C, 128, st)
-            inT, inF = self.iyT.view(N, -1), self.iyF.view(N, -1)
+            iyT, iyF = self.iyT.view(self.N, -1)[m.n0:m.n1], self.iyF.view(self.N, -1)[m.n0:m.n1]
+            lib().residual_split(x.data_ptr(), x1.data_ptr(), iyT.data_ptr(), iyF.data_ptr(), m.N, C, 128, st)
+            inT, inF = iyT, iyF
         # The time-axis and frequency-axis nets are independent: they run on two streams (fork / join by
         # events, also inside a graph capture), so the latency-bound deep layers of one overlap the other's.
-        side = self._fork()
+        side = self._fork_to(m, "side")
         with torch.cuda.stream(side):
-            x3f, _ = e[2].forward(inF, self.uv, self.scales, self._pd[2], self.ws[2],
-                                  side.cuda_stream, mu_out=self.Mu[:, L + Lt:], x_planes=self.pF)
-        x2, _ = e[1].forward(inT, self.uv, self.scales, self._pd[1], self.ws[1], st,
-                             mu_out=self.Mu[:, L:L + Lt], x_planes=self.pT)
+            e[2].forward(inF, uv, self.scales, self._pd[2], m.ws[2], side.cuda_stream, mu_out=Mu[:, L + Lt:],
+                         x_planes=m.pF, prepare=prepare)
+        e[1].forward(inT, uv, self.scales, self._pd[1], m.ws[1], st, mu_out=Mu[:, L:L + Lt], x_planes=m.pT, prepare=prepare)
         self._join(side)
-        return x1, x2, x3f
 
-    def _wstream(self, i: int) -> Optional[torch.cuda.Stream]:
-        """Stream for the weight / bias gradients of net i (leaf work beside the data-gradient chain)."""
+    def _wstream(self, m: "_MicroBatch", i: int) -> Optional[torch.cuda.Stream]:
+        """Stream for the weight / bias gradients of net i of a micro-batch (leaf work beside the data-gradient chain)."""
         if not self.overlap_streams:
             return None
-        if self._wst[i] is None:
-            self._wst[i] = torch.cuda.Stream(self.device)
-        return self._wst[i]
+        if m.wst[i] is None:
+            m.wst[i] = torch.cuda.Stream(self.device)
+        return m.wst[i]
 
-    def _fork(self) -> torch.cuda.Stream:
-        """Side stream that starts after everything queued so far on the current stream."""
+    def _fork_to(self, owner, name: str) -> torch.cuda.Stream:
+        """The stream `owner.<name>` (created on first use), made to start after everything queued so far on the
+        current stream."""
         if not self.overlap_streams:
             return torch.cuda.current_stream(self.device)
-        if self._side is None:
-            self._side = torch.cuda.Stream(self.device)
+        st = getattr(owner, name)
+        if st is None:
+            st = torch.cuda.Stream(self.device)
+            setattr(owner, name, st)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
-        self._side.wait_event(ev)
-        return self._side
+        st.wait_event(ev)
+        return st
+
+    def _fork(self) -> torch.cuda.Stream:
+        """Side stream (latent-space terms) that starts after everything queued so far on the current stream."""
+        return self._fork_to(self, "_side")
 
     def _join(self, side: torch.cuda.Stream):
         if not self.overlap_streams:
@@ -442,30 +501,17 @@ class DeepKHarmonicStep:
         tp = self.terms.data_ptr()
         if forward:
             self._forward(st)
-        x1, x2, x3f = self._outputs()
-        # the bias gradients of the three last transposed convs (= channel sums of the reconstruction
-        # gradients) come out of the kernels that write those gradients
-        fuse_db = grads and C <= 64
-        planes = self.use_planes and fuse_db
-        g1p, g2, g3f = ((self.g1p.data_ptr(), self.g2.data_ptr(), self.g3f.data_ptr()) if (grads and not planes)
-                        else (None, None, None))
-        db2, db3 = ((self._gd[1]["tconv5.bias"].data_ptr(), self._gd[2]["tconv5.bias"].data_ptr()) if fuse_db
-                    else (None, None))
-        # the latent-space terms (a dozen small, latency-bound launches) run beside the HBM-bound cascade
-        # losses: forked here, joined before the backward passes
+        # the latent-space terms (a dozen small, latency-bound launches, whole minibatch) run beside the HBM-bound
+        # cascade losses: forked here (before the loss passes are queued, which go first so that they own the SMs),
+        # joined by every micro-batch chain before its backward passes
         lside = self._fork()
-        y = self._y
-        ymode = (1 if upd else 0) | (2 if yzero else 0)    # include/lshm.h lshm_cascade_losses_upd
-        if planes:
-            # gradient closure: d/dx2 and d/dx3 leave the loss pass as the operand planes of the 1-D nets' last layers
-            lb.cascade_losses_planes(self.x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(),
-                                     y[0].data_ptr(), y[1].data_ptr(), y[2].data_ptr(), self.rho, ymode,
-                                     N, C, 128, 1.0 / numel_g, tp, self.g1p.data_ptr(), self.p2.data_ptr(),
-                                     self.p3.data_ptr(), db2, db3, st)
-        else:
-            lb.cascade_losses_upd(self.x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(),
-                                  y[0].data_ptr(), y[1].data_ptr(), y[2].data_ptr(), self.rho, ymode,
-                                  N, C, 128, 1.0 / numel_g, tp, g1p, g2, g3f, db2, db3, st)
+        many = len(self.mb) > 1
+        chains = []
+        for m in self.mb:
+            s = self._fork_to(m, "stream") if many else torch.cuda.current_stream(self.device)
+            chains.append(s)
+            with torch.cuda.stream(s):
+                self._loss_mb(m, s.cuda_stream, grads, upd, yzero, numel_g)
         khm_scale = plan.khm_scale(self.alpha)
         p = float(self.mod.p)
         aug_scale = plan.aug_scale(self.gamma)
@@ -493,33 +539,81 @@ class DeepKHarmonicStep:
                 for off, width in ((0, L), (L, Lt), (L + Lt, Lt)):
                     lb.logcosh(Mu.data_ptr() + 4 * off, Ltot, N, width, rica_scale, tp + 11 * 8,
                                gMu.data_ptr() + 4 * off if grads else None, Ltot, sl)
-        self._join(lside)
-        if grads:
-            e = self.net.engine(), self.netT.engine(), self.netF.engine()
-            xf = self.x.view(N, -1)
-            inT, inF = (xf, xf) if self.use_planes else (self.iyT.view(N, -1), self.iyF.view(N, -1))
-            side = self._fork()
-            g2v, g3v = (None, None) if planes else (self.g2.view(N, -1), self.g3f.view(N, -1))
-            with torch.cuda.stream(side):
-                dF = e[2].backward(inF, self._pd[2], self._gd[2], self.ws[2], side.cuda_stream,
-                                   g3v, gMu[:, L + Lt:], Mu[:, L + Lt:], True, self._wstream(2), fuse_db,
-                                   x_planes=self.pF, g_xhat_planes=self.p3 if planes else None)
-            dT = e[1].backward(inT, self._pd[1], self._gd[1], self.ws[1], st, g2v,
-                               gMu[:, L:L + Lt], Mu[:, L:L + Lt], True, self._wstream(1), fuse_db, x_planes=self.pT,
-                               g_xhat_planes=self.p2 if planes else None)
-            self._join(side)
-            db1 = self._gd[0]["tconv5.bias"].data_ptr() if fuse_db else None
-            if planes:
-                lb.cascade_combine_planes(self.g1p.data_ptr(), dT.data_ptr(), dF.data_ptr(), self.gx1p.data_ptr(), N, C, 128, db1, st)
-                e[0].backward(xf, self._pd[0], self._gd[0], self.ws[0], st, None, gMu[:, :L], Mu[:, :L], False,
-                              self._wstream(0), True, x_planes=self.xp, g_xhat_planes=self.gx1p)
-            else:
-                if self.gx1 is None:
-                    self.gx1 = torch.empty(N * C * 16384, dtype=torch.float32, device=self.device)
-                lb.cascade_combine(self.g1p.data_ptr(), dT.data_ptr(), dF.data_ptr(), self.gx1.data_ptr(), N, C, 128, db1, st)
-                e[0].backward(xf, self._pd[0], self._gd[0], self.ws[0], st, self.gx1.view(N, -1),
-                              gMu[:, :L], Mu[:, :L], False, self._wstream(0), fuse_db, x_planes=self.xp)
+            latent_done = torch.cuda.Event()
+            latent_done.record(lside)
+        for m, s in zip(self.mb, chains):
+            if self.overlap_streams:
+                s.wait_event(latent_done)
+            if grads:
+                with torch.cuda.stream(s):
+                    self._backward_mb(m, s.cuda_stream)
+        if many:
+            for m in self.mb:
+                self._join(m.stream)
+            if grads:
+                for m in self.mb[1:]:
+                    lb.vec_add(self.flat.grad.data_ptr(), m.gbuf.data_ptr(), self.flat.numel, st)
         lb.closure_total(tp, self.rho, numel_g, khm_scale, self.flat.loss_tail.data_ptr(), st)
+
+    def _loss_mb(self, m: "_MicroBatch", st: int, grads: bool, upd: bool, yzero: bool, numel_g: float):
+        """Loss pass of one micro-batch (applies a deferred multiplier update, writes the reconstruction gradients)."""
+        lb, N, C = lib(), self.N, self.C
+        tp = self.terms.data_ptr()
+        x = self.x[m.n0:m.n1]
+        x1, x2, x3f = m.ws[0].xhat, m.ws[1].xhat, m.ws[2].xhat
+        rows = lambda t: t.view(N, -1)[m.n0:m.n1]
+        # the bias gradients of the three last transposed convs (= channel sums of the reconstruction
+        # gradients) come out of the kernels that write those gradients
+        fuse_db = grads and C <= 64
+        planes = self.use_planes and fuse_db
+        db2, db3 = ((m.gd[1]["tconv5.bias"].data_ptr(), m.gd[2]["tconv5.bias"].data_ptr()) if fuse_db else (None, None))
+        y = [rows(t) for t in self._y]
+        ymode = (1 if upd else 0) | (2 if yzero else 0)    # include/lshm.h lshm_cascade_losses_upd
+        if planes:
+            # gradient closure: d/dx2 and d/dx3 leave the loss pass as the operand planes of the 1-D nets' last layers
+            lb.cascade_losses_planes(x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(),
+                                     y[0].data_ptr(), y[1].data_ptr(), y[2].data_ptr(), self.rho, ymode,
+                                     m.N, C, 128, 1.0 / numel_g, tp, rows(self.g1p).data_ptr(), m.p2.data_ptr(),
+                                     m.p3.data_ptr(), db2, db3, st)
+        else:
+            g = [rows(t).data_ptr() for t in (self.g1p, self.g2, self.g3f)] if grads else [None, None, None]
+            lb.cascade_losses_upd(x.data_ptr(), x1.data_ptr(), x2.data_ptr(), x3f.data_ptr(),
+                                  y[0].data_ptr(), y[1].data_ptr(), y[2].data_ptr(), self.rho, ymode,
+                                  m.N, C, 128, 1.0 / numel_g, tp, g[0], g[1], g[2], db2, db3, st)
+
+    def _backward_mb(self, m: "_MicroBatch", st: int):
+        """The three backward passes of one micro-batch, on the current stream (+ its side / leaf streams)."""
+        lb, N, C, L, Lt = lib(), self.N, self.C, self.L, self.Lt
+        rows = lambda t: t.view(N, -1)[m.n0:m.n1]
+        fuse_db = C <= 64
+        planes = self.use_planes and fuse_db
+        e = self.net.engine(), self.netT.engine(), self.netF.engine()
+        Mu, gMu = self.Mu[m.n0:m.n1], self.gMu[m.n0:m.n1]
+        xf = self.x[m.n0:m.n1].view(m.N, -1)
+        inT, inF = (xf, xf) if self.use_planes else (rows(self.iyT), rows(self.iyF))
+        g1p = rows(self.g1p)
+        g2, g3f = (None, None) if planes else (rows(self.g2), rows(self.g3f))
+        side = self._fork_to(m, "side")
+        with torch.cuda.stream(side):
+            dF = e[2].backward(inF, self._pd[2], m.gd[2], m.ws[2], side.cuda_stream,
+                               g3f, gMu[:, L + Lt:], Mu[:, L + Lt:], True, self._wstream(m, 2), fuse_db,
+                               x_planes=m.pF, g_xhat_planes=m.p3 if planes else None)
+        dT = e[1].backward(inT, self._pd[1], m.gd[1], m.ws[1], st, g2,
+                           gMu[:, L:L + Lt], Mu[:, L:L + Lt], True, self._wstream(m, 1), fuse_db, x_planes=m.pT,
+                           g_xhat_planes=m.p2 if planes else None)
+        self._join(side)
+        db1 = m.gd[0]["tconv5.bias"].data_ptr() if fuse_db else None
+        if planes:
+            lb.cascade_combine_planes(g1p.data_ptr(), dT.data_ptr(), dF.data_ptr(), m.gx1p.data_ptr(), m.N, C, 128, db1, st)
+            e[0].backward(xf, self._pd[0], m.gd[0], m.ws[0], st, None, gMu[:, :L], Mu[:, :L], False,
+                          self._wstream(m, 0), True, x_planes=m.xp, g_xhat_planes=m.gx1p)
+        else:
+            if self.gx1 is None:
+                self.gx1 = torch.empty(N * C * 16384, dtype=torch.float32, device=self.device)
+            gx1 = rows(self.gx1)
+            lb.cascade_combine(g1p.data_ptr(), dT.data_ptr(), dF.data_ptr(), gx1.data_ptr(), m.N, C, 128, db1, st)
+            e[0].backward(xf, self._pd[0], m.gd[0], m.ws[0], st, gx1,
+                          gMu[:, :L], Mu[:, :L], False, self._wstream(m, 0), fuse_db, x_planes=m.xp)
 
     def _seq_forward(self):
         self._forward(_stream())

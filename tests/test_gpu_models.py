@@ -381,3 +381,43 @@ def test_graphed_step_matches_eager_steps(cuda):
     gt = GraphedStep(step_t, topt)
     torch_losses = [float(gt.replay()) for _ in range(4)]
     assert np.allclose(torch_losses, eager, rtol=2e-4), (torch_losses, eager)
+
+
+@pytest.mark.parametrize("H", [2, 4])
+def test_micro_batched_step_matches_single_chain(cuda, H):
+    """The minibatch cut into H launch chains (own streams, own operand planes, own gradient buffers summed at the end):
+    same losses, latents, gradients, multipliers and Adam trajectory as the single chain, eager and graphed; both
+    against the CPU oracle."""
+    from lshm_b200.kharmonic_lofar import DeepKHarmonicStep, FlatAdam
+    case = closure_case(N=8, bpb=2, seed=7)
+    ref = oracle_closure(case)
+    x, uv = case["x"].to(cuda), case["uv"].to(cuda)
+
+    def fresh(h):
+        step = DeepKHarmonicStep(*build_modules(case, cuda), micro_batches=h)
+        step.set_batch(x.clone(), uv.clone(), 2)
+        assert len(step.mb) == h
+        for dst, src in zip((step.y1, step.y2, step.y3), case["ys"]):
+            dst.copy_(src.to(cuda))
+        return step
+
+    one, many = fresh(1), fresh(H)
+    l1, lh = float(one.closure()), float(many.closure())
+    assert abs(lh - ref["total"]) <= LOSS_TOL * abs(ref["total"]) and abs(lh - l1) <= 1e-6 * abs(l1)
+    t1, th = one.loss_terms(), many.loss_terms()
+    for k in t1:
+        assert abs(th[k] - t1[k]) <= 1e-6 * abs(t1[k]) + 1e-12, k
+    assert rel_err(many.latents(), one.latents()) < 1e-6
+    check_grads({nm: p.grad for nm, p in zip(many.flat.names, many.flat.params)}, ref["grads"])
+    assert rel_err(many.flat.grad[:many.flat.numel], one.flat.grad[:one.flat.numel]) < 2e-5
+    # ADMM iterations with reuse, eager against graphed micro-batches
+    opt1, opth = FlatAdam(one.flat, lr=1e-3), FlatAdam(many.flat, lr=1e-3)
+    many.enable_graphs()
+    for _ in range(4):
+        a, b = float(opt1.step(one.closure)), float(opth.step(many.closure))
+        one.update_multipliers(); many.update_multipliers()
+        assert abs(a - b) <= 2e-4 * abs(a)
+    assert rel_err(many.flat.flat, one.flat.flat) < 2e-4
+    assert rel_err(many.y2, one.y2) < 2e-3
+    with pytest.raises(RuntimeError):
+        DeepKHarmonicStep(*build_modules(case, cuda), micro_batches=3).set_batch(x.clone(), uv.clone(), 2)

@@ -203,7 +203,7 @@ def test_training_closure_with_and_without_operand_planes(cuda, C, N):
         return step
 
     a, b = run(True), run(False)
-    assert a.xp is not None and b.xp is None
+    assert a.mb[0].xp is not None and b.mb[0].xp is None
     ta, tb = a.loss_terms(), b.loss_terms()
     for k in ta:
         assert abs(ta[k] - tb[k]) <= 1e-6 * abs(tb[k]) + 1e-12, (k, ta[k], tb[k])
