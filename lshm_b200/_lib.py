@@ -13,7 +13,7 @@ from typing import Dict, List, Tuple
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "lshm.h")
-LIBRARY = os.path.join(_HERE, "liblshm_sm100.so")
+LIBRARY = os.environ.get("LSHM_LIBRARY") or os.path.join(_HERE, "liblshm_sm100.so")   # (override: A/B runs of two builds)
 
 _CTYPES = {
     "int": ctypes.c_int,

@@ -38,7 +38,7 @@ __host__ __device__ inline UpGeom up_geom(int dim, int A, int Bc) {
   const int n16 = (g.ncols + 15) / 16 * 16;
   if (dim == 2) g.NT = n16 <= 16 ? 16 : (n16 <= 32 ? 32 : 48);
   else g.NT = n16 <= 16 ? 16 : (n16 <= 32 ? 32 : (n16 <= 48 ? 48 : 96));
-  g.KC = dim == 2 ? 16 : 32;
+  g.KC = (dim == 2 || A <= 16) ? 16 : 32;
   g.ntiles = (g.ncols + g.NT - 1) / g.NT;
   g.KB = ((A + 15) / 16 * 16 + g.KC - 1) / g.KC;
   g.combos = dim == 2 ? 16 : 1;

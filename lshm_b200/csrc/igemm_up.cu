@@ -171,6 +171,78 @@ __global__ void __launch_bounds__(up_threads(DIM, G), (DIM == 1 && G == 1 ? 3 : 
     uint32_t unit = 0;                                  // (item, K block) counter: group g fills units u % G == g
     const int64_t hw = DIM == 2 ? (int64_t)a.h * a.w : (int64_t)a.w;
     Ring ring{0, 0};
+    if constexpr (DIM == 1 && G == 1 && KC == 16) {
+      // Software-pipelined producer (1-D, one group): the loads of the NEXT (item, K block) unit are issued before the
+      // current one is converted, so two units' worth of global loads are in flight per CTA.  With one unit in flight
+      // the first / second layers were bound by the load -> convert -> hand-off latency chain (~1600 cycles per tile
+      // and CTA, "long scoreboard" the top stall in profiles/r2_ncu_layer2.md), not by bandwidth.
+      auto describe = [&](int64_t item, const float*& sp, bool& sv) {
+        const int64_t q = (int64_t)fdiv((uint32_t)item, a.d_ntn) * 128 + ptid;
+        sv = ptid < SLOTS && q < a.Q;
+        sp = a.small_;
+        if (sv) {
+          const uint32_t uq = (uint32_t)q;
+          const uint32_t n = fdiv(uq, a.d_w);
+          sp = a.small_ + (int64_t)n * a.small_ns + (uq - n * (uint32_t)a.w);
+        }
+      };
+      auto fetch = [&](const float* sp, bool sv, int kb, float (&v)[CC][8]) {
+        const int ccb = (min(KC, Apad - kb * KC)) >> 3;
+#pragma unroll
+        for (int cc = 0; cc < CC; ++cc) {
+          const int a0 = kb * KC + cc * 8;
+          const float* p = sp + (int64_t)a0 * hw;
+          const bool on = cc < ccb && sv;
+          if (on && a0 + 8 <= a.A) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { v[cc][e] = __ldg(p); p += hw; }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { v[cc][e] = (on && a0 + e < a.A) ? __ldg(p) : 0.f; p += hw; }
+          }
+        }
+      };
+      int64_t item = blockIdx.x;
+      int kb = 0;
+      const float* sp = a.small_; bool sv = false;
+      float v[CC][8];
+      if (item < total) { describe(item, sp, sv); fetch(sp, sv, 0, v); }
+      while (item < total) {
+        int64_t nitem = item; int nkb = kb + 1;
+        if (nkb == KB) { nkb = 0; nitem = item + gridDim.x; }
+        const float* nsp = sp; bool nsv = sv;
+        float vn[CC][8];
+        if (nitem < total) {
+          if (nitem != item) describe(nitem, nsp, nsv);
+          fetch(nsp, nsv, nkb, vn);
+        }
+        const int s = ring.s;
+        mbar_wait(&empty_bar[s], ring.ph ^ 1);
+        uint8_t* zhi = smem + (size_t)s * stage_bytes;
+        uint8_t* zlo = zhi + zbytes;
+        const int ccb = (min(KC, Apad - kb * KC)) >> 3;
+        if (ptid < SLOTS) {
+#pragma unroll
+          for (int cc = 0; cc < CC; ++cc) {
+            if (cc < ccb) {
+              uint4 hi, lo;
+              split8(v[cc], hi, lo);
+              *reinterpret_cast<uint4*>(zhi + ((size_t)cc * SLOTS + ptid) * 16) = hi;
+              *reinterpret_cast<uint4*>(zlo + ((size_t)cc * SLOTS + ptid) * 16) = lo;
+            }
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+        ring.next(NS);
+#pragma unroll
+        for (int cc = 0; cc < CC; ++cc)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[cc][e] = vn[cc][e];
+        item = nitem; kb = nkb; sp = nsp; sv = nsv;
+      }
+    } else
     for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
       const int64_t q0 = (int64_t)fdiv((uint32_t)item, a.d_ntn) * 128;
       const float* sp[NSLOT]; bool sv[NSLOT];
@@ -370,6 +442,10 @@ int launch_up(int dim, UpArgs a, cudaStream_t st) {
   if (dim == 2) {
     switch (g.NT) { case 16: LU(2, 16, 16); case 32: LU(2, 32, 16); default: LU(2, 48, 16); }
   } else {
+    if (g.KC == 16) {       // <= 16 small-map channels (the first two layers): one K block of 16
+      switch (g.NT) { case 16: return launch_up_t<1, 16, 16, 1>(a, g, st); case 32: return launch_up_t<1, 32, 16, 1>(a, g, st);
+                      case 48: return launch_up_t<1, 48, 16, 1>(a, g, st); default: return launch_up_t<1, 96, 16, 1>(a, g, st); }
+    }
     switch (g.NT) { case 16: LU(1, 16, 32); case 32: LU(1, 32, 32); case 48: LU(1, 48, 32); default: LU(1, 96, 32); }
   }
 #undef LU

@@ -340,10 +340,13 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass2_kernel(KhmArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// pass 2, K <= 16 and L = 32*TPP (the HBM-side cases): two points per thread group, register-tiled tile product
+// pass 2, K <= 16 and L = 16*TPP (the HBM-side cases): two points per thread group, register-tiled tile product
 // ------------------------------------------------------------------------------------------
 // Same results as khm_pass2_kernel (same distances, harmonic sums and weights), about a third of its instructions:
 //  * two points per thread: every broadcast LDS.128 of a centre chunk feeds both points (as in pass 1);
+//  * four float4 chunks per lane (TPP = L/16 lanes per point): 64 registers of point data and gradient sums instead of
+//    128, so four blocks fit per SM (the eight-chunk version ran 8 warps per SM at 240 registers and 32 % issue
+//    utilisation: latency-bound);
 //  * the point gradient sum_k w_k (x - m_k) is accumulated as (sum_k w_k) x - sum_k w_k m_k: one packed FMA per two
 //    dimensions instead of a packed subtract + FMA (the distances keep the direct-difference form; here the terms that
 //    cancel carry weights ~ d^2, so the L2 error of the gradient stays at fp32 rounding);
@@ -352,18 +355,51 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass2_kernel(KhmArgs a) {
 //    weights are stored as duplicated pairs (w, w), so a 64-bit shared load IS the packed operand: per point and thread
 //    one LDS.128 of x, ~KT/2 loads of weights and 2*KT FFMA2 (the scalar loop: 7 instructions per 4 FMA, 62 % of the
 //    threads busy at K = 10, L = 64);
-//  * sum_i w_ik: per-thread partial sums in shared memory (counted TPP times, divided at the end: exact).
-template <int TPP, int KT, bool SUMS>
-__global__ void __launch_bounds__(KHM_THREADS, SUMS ? 3 : 2) khm_pass2_fast_kernel(KhmArgs a, int KG) {
+//  * sum_i w_ik: per-thread partial sums in shared memory (counted TPP times, divided at the end: exact);
+//  * P4: p == 4 (the reference's Khp) known at compile time: no powf path in the code.
+constexpr int FCH = 4;            // float4 chunks per lane in the fast kernel
+
+template <int TPP>
+__device__ __forceinline__ void load_point4(float4 (&x4)[FCH], const float* X, int64_t ldx, int64_t i, bool valid, int s) {
+#pragma unroll
+  for (int c = 0; c < FCH; ++c)
+    x4[c] = valid ? *reinterpret_cast<const float4*>(X + i * ldx + ((c * TPP + s) << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// (same arithmetic, chunk order and reduction tree as dist2x2 for the same TPP: bit-identical harmonic sums)
+template <int TPP>
+__device__ __forceinline__ void dist2x2_4(const float4 (&xa)[FCH], const float4 (&xb)[FCH], const float* mrow, int s,
+                                          float& da, float& db) {
+  f32x2 a0 = 0ull, a1 = 0ull, b0 = 0ull, b1 = 0ull;
+#pragma unroll
+  for (int c = 0; c < FCH; ++c) {
+    const float4 m = *reinterpret_cast<const float4*>(mrow + ((c * TPP + s) << 2));
+    const f32x2 m0 = pk2(m.x, m.y), m1 = pk2(m.z, m.w);
+    const f32x2 p0 = sub2(pk2(xa[c].x, xa[c].y), m0), p1 = sub2(pk2(xa[c].z, xa[c].w), m1);
+    const f32x2 q0 = sub2(pk2(xb[c].x, xb[c].y), m0), q1 = sub2(pk2(xb[c].z, xb[c].w), m1);
+    a0 = fma2(p0, p0, a0); a1 = fma2(p1, p1, a1);
+    b0 = fma2(q0, q0, b0); b1 = fma2(q1, q1, b1);
+  }
+  float p, q, r, t;
+  upk2(a0, p, q); upk2(a1, r, t);
+  da = lanes_sum<TPP>((p + q) + (r + t));
+  upk2(b0, p, q); upk2(b1, r, t);
+  db = lanes_sum<TPP>((p + q) + (r + t));
+}
+
+template <int TPP, int KT, bool SUMS, bool P4>
+__global__ void __launch_bounds__(KHM_THREADS, 4) khm_pass2_fast_kernel(KhmArgs a, int KG) {
   extern __shared__ __align__(16) float smem[];
+  const int pmode = P4 ? 4 : a.pmode;
   constexpr int PTS = KHM_THREADS / TPP;           // thread groups; a tile is 2*PTS points
-  constexpr int L = 32 * TPP, L4 = L / 4;
+  constexpr int L = 4 * FCH * TPP, L4 = L / 4;
+  constexpr int XS = L + 4;                        // row pitch of the x tile: rows 16 bytes apart in the banks
   constexpr int GS = (2 * KT + 3) & ~3;            // floats per centre group in a weight row (16-byte aligned groups)
   const int K = a.K;
   const int WS = KG * GS;                          // weight row: KG groups of KT duplicated pairs
   float* ms = smem;                                // [K][L] centres
-  float* xs = ms + K * L;                          // [2*PTS][L] x tile; [K][L] block sums at the end
-  float* ws = xs + 2 * PTS * L;                    // [2*PTS][WS]
+  float* xs = ms + K * L;                          // [2*PTS][XS] x tile; [K][L] block sums at the end
+  float* ws = xs + 2 * PTS * XS;                   // [2*PTS][WS]
   float* d2s = ws + 2 * PTS * WS;                  // [K][2*PTS] squared distances of the harmonic-sum loop
   float* wpart = d2s + K * 2 * PTS;                // [K][KHM_THREADS] per-thread partial sums of the weights
   __shared__ double red[32];
@@ -383,19 +419,19 @@ __global__ void __launch_bounds__(KHM_THREADS, SUMS ? 3 : 2) khm_pass2_fast_kern
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t ia = t * 2 * PTS + pt, ib = ia + PTS;
     const bool va = ia < a.N, vb = ib < a.N;
-    float4 xa[KHM_MAXCH], xb[KHM_MAXCH];
-    load_point<TPP, KHM_MAXCH>(xa, a.X, a.ldx, ia, va, s, KHM_MAXCH);
-    load_point<TPP, KHM_MAXCH>(xb, a.X, a.ldx, ib, vb, s, KHM_MAXCH);
-    // ---- harmonic sums (identical arithmetic to pass 1)
+    float4 xa[FCH], xb[FCH];
+    load_point4<TPP>(xa, a.X, a.ldx, ia, va, s);
+    load_point4<TPP>(xb, a.X, a.ldx, ib, vb, s);
+    // ---- harmonic sums
     float ea = 0.f, eb = 0.f;
 #pragma unroll 2
     for (int kk = 0; kk < K; ++kk) {
       float da, db;
-      dist2x2<TPP, KHM_MAXCH>(xa, xb, ms + kk * L, s, KHM_MAXCH, da, db);
+      dist2x2_4<TPP>(xa, xb, ms + kk * L, s, da, db);
       d2s[kk * 2 * PTS + pt] = da;                  // every lane of the point writes (and later reads) the same value
       d2s[kk * 2 * PTS + PTS + pt] = db;
-      ea += rcp_fast(pow_p(da, a.p, a.pmode) + KHM_EPS);
-      eb += rcp_fast(pow_p(db, a.p, a.pmode) + KHM_EPS);
+      ea += rcp_fast(pow_p(da, a.p, pmode) + KHM_EPS);
+      eb += rcp_fast(pow_p(db, a.p, pmode) + KHM_EPS);
     }
     if (s == 0) {
       if (va) lsum += (double)(Kf / (ea + KHM_EPS));
@@ -406,14 +442,14 @@ __global__ void __launch_bounds__(KHM_THREADS, SUMS ? 3 : 2) khm_pass2_fast_kern
     const float cb = SUMS ? 1.0f / (eb * eb + KHM_EPS) : Kf / ((eb + KHM_EPS) * (eb + KHM_EPS));
     __syncthreads();                                // the previous tile's product has read xs / ws
 #pragma unroll
-    for (int c = 0; c < KHM_MAXCH; ++c) {
-      *reinterpret_cast<float4*>(xs + pt * L + ((c * TPP + s) << 2)) = xa[c];
-      *reinterpret_cast<float4*>(xs + (PTS + pt) * L + ((c * TPP + s) << 2)) = xb[c];
+    for (int c = 0; c < FCH; ++c) {
+      *reinterpret_cast<float4*>(xs + pt * XS + ((c * TPP + s) << 2)) = xa[c];
+      *reinterpret_cast<float4*>(xs + (PTS + pt) * XS + ((c * TPP + s) << 2)) = xb[c];
     }
     // ---- weights, sum_k w_k m_k
-    f32x2 ga[KHM_MAXCH][2], gb[KHM_MAXCH][2];
+    f32x2 ga[FCH][2], gb[FCH][2];
 #pragma unroll
-    for (int c = 0; c < KHM_MAXCH; ++c) ga[c][0] = ga[c][1] = gb[c][0] = gb[c][1] = 0ull;
+    for (int c = 0; c < FCH; ++c) ga[c][0] = ga[c][1] = gb[c][0] = gb[c][1] = 0ull;
     float swa = 0.f, swb = 0.f;
     for (int g = 0; g < KG; ++g) {
 #pragma unroll
@@ -421,15 +457,15 @@ __global__ void __launch_bounds__(KHM_THREADS, SUMS ? 3 : 2) khm_pass2_fast_kern
         const int kk = g * KT + j;
         if (kk < K) {
           const float da = d2s[kk * 2 * PTS + pt], db = d2s[kk * 2 * PTS + PTS + pt];
-          const float pa = pow_p(da, a.p, a.pmode), pb = pow_p(db, a.p, a.pmode);
+          const float pa = pow_p(da, a.p, pmode), pb = pow_p(db, a.p, pmode);
           float wa, wb;
           if (SUMS) {
             wa = ca * rcp_fast(pa * da + KHM_EPS);                  // alpha_i / (d^(p+2) + eps)
             wb = cb * rcp_fast(pb * db + KHM_EPS);
           } else {
             const float ta = pa + KHM_EPS, tb = pb + KHM_EPS;
-            wa = da > 0.f ? ca * a.p * pow_pm2(da, a.p, a.pmode) * rcp_fast(ta * ta) : 0.f;
-            wb = db > 0.f ? cb * a.p * pow_pm2(db, a.p, a.pmode) * rcp_fast(tb * tb) : 0.f;
+            wa = da > 0.f ? ca * a.p * pow_pm2(da, a.p, pmode) * rcp_fast(ta * ta) : 0.f;
+            wb = db > 0.f ? cb * a.p * pow_pm2(db, a.p, pmode) * rcp_fast(tb * tb) : 0.f;
           }
           if (!va) wa = 0.f;
           if (!vb) wb = 0.f;
@@ -437,7 +473,7 @@ __global__ void __launch_bounds__(KHM_THREADS, SUMS ? 3 : 2) khm_pass2_fast_kern
             const float* mrow = ms + kk * L;
             const f32x2 wa2 = pk2(wa, wa), wb2 = pk2(wb, wb);
 #pragma unroll
-            for (int c = 0; c < KHM_MAXCH; ++c) {
+            for (int c = 0; c < FCH; ++c) {
               const float4 m = *reinterpret_cast<const float4*>(mrow + ((c * TPP + s) << 2));
               const f32x2 m0 = pk2(m.x, m.y), m1 = pk2(m.z, m.w);
               ga[c][0] = fma2(wa2, m0, ga[c][0]); ga[c][1] = fma2(wa2, m1, ga[c][1]);
@@ -457,7 +493,7 @@ __global__ void __launch_bounds__(KHM_THREADS, SUMS ? 3 : 2) khm_pass2_fast_kern
       const f32x2 sa2 = pk2(swa * a.gscale, swa * a.gscale), sb2 = pk2(swb * a.gscale, swb * a.gscale);
       const f32x2 ng = pk2(-a.gscale, -a.gscale);
 #pragma unroll
-      for (int c = 0; c < KHM_MAXCH; ++c) {
+      for (int c = 0; c < FCH; ++c) {
         // gscale * (sw * x - sum_k w_k m_k)
         float4 v, u;
         upk2(fma2(sa2, pk2(xa[c].x, xa[c].y), mul2(ng, ga[c][0])), v.x, v.y);
@@ -479,13 +515,13 @@ __global__ void __launch_bounds__(KHM_THREADS, SUMS ? 3 : 2) khm_pass2_fast_kern
     __syncthreads();
     // ---- tile product: acc[j] += w[q][kg*KT + j] * x[q][4*c4 .. 4*c4+3] over the thread's points
     {
-      const float* xcol = xs + (c4 << 2);
-      const float* wrow = ws + kg * GS;
-#pragma unroll 2
-      for (int q = ps; q < 2 * PTS; q += PS) {
-        const float4 xv = *reinterpret_cast<const float4*>(xcol + q * L);
+      const float* xq = xs + (c4 << 2) + ps * XS;
+      const float* wq = ws + kg * GS + ps * WS;
+      const int xstep = PS * XS, wstep = PS * WS;
+#pragma unroll 4
+      for (int q = ps; q < 2 * PTS; q += PS, xq += xstep, wq += wstep) {
+        const float4 xv = *reinterpret_cast<const float4*>(xq);
         const f32x2 x0 = pk2(xv.x, xv.y), x1 = pk2(xv.z, xv.w);
-        const float* wq = wrow + q * WS;
         f32x2 w2[KT];
 #pragma unroll
         for (int j = 0; j + 1 < KT; j += 2) {
@@ -642,9 +678,11 @@ int launch_pass1(const KhmArgs& a, cudaStream_t st) {
 #undef P1
 }
 
-// (KT, KG) of the register-tiled product: KG groups of KT centres cover K; 128 threads = L/4 columns x KG x point splits
-bool pick_fast(int K, int L, int tpp, int* kt, int* kg) {
-  if (K > 16 || tpp > 8 || L != 32 * tpp) return false;
+// (KT, KG) of the register-tiled product: KG groups of KT centres cover K; 128 threads = L/4 columns x KG x point splits.
+// The fast kernel holds FCH = 4 chunks per lane: tpp = L/16 lanes per point.
+bool pick_fast(int K, int L, int* tpp, int* kt, int* kg) {
+  if (K > 16 || L < 32 || L > 256 || (L & (L - 1))) return false;
+  *tpp = L / 16;
   for (int t : {4, 5, 8}) {
     const int g = (K + t - 1) / t;
     if ((g == 1 || g == 2 || g == 4) && (L / 4) * g <= KHM_THREADS) { *kt = t; *kg = g; return true; }
@@ -652,19 +690,26 @@ bool pick_fast(int K, int L, int tpp, int* kt, int* kg) {
   return false;
 }
 
-template <int TPP, int KT, bool SUMS>
-int launch_pass2_fast_k(const KhmArgs& a, int kg, cudaStream_t st) {
+template <int TPP, int KT, bool SUMS, bool P4>
+int launch_pass2_fast_p(const KhmArgs& a, int kg, cudaStream_t st) {
   const int pts = KHM_THREADS / TPP, gs = (2 * KT + 3) & ~3;
-  const size_t smem = ((size_t)a.K * a.L + (size_t)2 * pts * a.L + (size_t)2 * pts * kg * gs + (size_t)a.K * 2 * pts +
+  const size_t smem = ((size_t)a.K * a.L + (size_t)2 * pts * (a.L + 4) + (size_t)2 * pts * kg * gs + (size_t)a.K * 2 * pts +
                        (size_t)a.K * KHM_THREADS) * sizeof(float);
   if (smem > 48 * 1024)
-    LSHM_CUDA(cudaFuncSetAttribute(khm_pass2_fast_kernel<TPP, KT, SUMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "khm_pass2");
+    LSHM_CUDA(cudaFuncSetAttribute(khm_pass2_fast_kernel<TPP, KT, SUMS, P4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "khm_pass2");
+  int per_sm = 4;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, khm_pass2_fast_kernel<TPP, KT, SUMS, P4>, KHM_THREADS, smem);
   const int64_t ntiles = ceil_div(a.N, 2 * pts);
-  const int64_t cap = (int64_t)sm_count() * (SUMS ? 3 : 2);
+  const int64_t cap = (int64_t)sm_count() * std::max(1, per_sm);
   const int grid = (int)std::max<int64_t>(1, std::min(ntiles, cap));
-  khm_pass2_fast_kernel<TPP, KT, SUMS><<<grid, KHM_THREADS, smem, st>>>(a, kg);
+  khm_pass2_fast_kernel<TPP, KT, SUMS, P4><<<grid, KHM_THREADS, smem, st>>>(a, kg);
   LSHM_CHECK_LAUNCH("khm_pass2");
   return LSHM_OK;
+}
+
+template <int TPP, int KT, bool SUMS>
+int launch_pass2_fast_k(const KhmArgs& a, int kg, cudaStream_t st) {
+  return a.pmode == 4 ? launch_pass2_fast_p<TPP, KT, SUMS, true>(a, kg, st) : launch_pass2_fast_p<TPP, KT, SUMS, false>(a, kg, st);
 }
 
 template <int TPP, bool SUMS>
@@ -679,14 +724,14 @@ int launch_pass2_fast(const KhmArgs& a, int kt, int kg, cudaStream_t st) {
 template <bool SUMS>
 int launch_pass2(const KhmArgs& a, cudaStream_t st) {
   const int tpp = pick_tpp(a.L);
-  int kt = 0, kg = 0;
+  int kt = 0, kg = 0, ftpp = 0;
   static const bool no_fast = getenv("LSHM_KHM_NOFAST") != nullptr;       // experiment switch
-  if (!no_fast && pick_fast(a.K, a.L, tpp, &kt, &kg)) {
-    switch (tpp) {
-      case 1: return launch_pass2_fast<1, SUMS>(a, kt, kg, st);
+  if (!no_fast && pick_fast(a.K, a.L, &ftpp, &kt, &kg)) {
+    switch (ftpp) {
       case 2: return launch_pass2_fast<2, SUMS>(a, kt, kg, st);
       case 4: return launch_pass2_fast<4, SUMS>(a, kt, kg, st);
-      default: return launch_pass2_fast<8, SUMS>(a, kt, kg, st);
+      case 8: return launch_pass2_fast<8, SUMS>(a, kt, kg, st);
+      default: return launch_pass2_fast<16, SUMS>(a, kt, kg, st);
     }
   }
   const int pts = KHM_THREADS / tpp;
