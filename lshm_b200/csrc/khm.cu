@@ -355,7 +355,11 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass2_kernel(KhmArgs a) {
 //    weights are stored as duplicated pairs (w, w), so a 64-bit shared load IS the packed operand: per point and thread
 //    one LDS.128 of x, ~KT/2 loads of weights and 2*KT FFMA2 (the scalar loop: 7 instructions per 4 FMA, 62 % of the
 //    threads busy at K = 10, L = 64);
-//  * sum_i w_ik: per-thread partial sums in shared memory (counted TPP times, divided at the end: exact);
+//  * ONE pass over the centres per tile: w_k = coef * u_k with coef = K / (e + eps)^2 known only after the harmonic sum,
+//    so the loop accumulates sum_k u_k m_k from the centre chunk that is still in registers for the distance, the x tile
+//    is stored pre-multiplied by coef and the point gradient is scaled at the end (no second sweep over the centres:
+//    the shared-memory pipe was the busiest unit, 82 % of its wavefront rate);
+//  * sum_i w_ik: per-point-slot partial sums in shared memory, added by the point's first lane;
 //  * P4: p == 4 (the reference's Khp) known at compile time: no powf path in the code.
 constexpr int FCH = 4;            // float4 chunks per lane in the fast kernel
 
@@ -366,42 +370,22 @@ __device__ __forceinline__ void load_point4(float4 (&x4)[FCH], const float* X, i
     x4[c] = valid ? *reinterpret_cast<const float4*>(X + i * ldx + ((c * TPP + s) << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// (same arithmetic, chunk order and reduction tree as dist2x2 for the same TPP: bit-identical harmonic sums)
-template <int TPP>
-__device__ __forceinline__ void dist2x2_4(const float4 (&xa)[FCH], const float4 (&xb)[FCH], const float* mrow, int s,
-                                          float& da, float& db) {
-  f32x2 a0 = 0ull, a1 = 0ull, b0 = 0ull, b1 = 0ull;
-#pragma unroll
-  for (int c = 0; c < FCH; ++c) {
-    const float4 m = *reinterpret_cast<const float4*>(mrow + ((c * TPP + s) << 2));
-    const f32x2 m0 = pk2(m.x, m.y), m1 = pk2(m.z, m.w);
-    const f32x2 p0 = sub2(pk2(xa[c].x, xa[c].y), m0), p1 = sub2(pk2(xa[c].z, xa[c].w), m1);
-    const f32x2 q0 = sub2(pk2(xb[c].x, xb[c].y), m0), q1 = sub2(pk2(xb[c].z, xb[c].w), m1);
-    a0 = fma2(p0, p0, a0); a1 = fma2(p1, p1, a1);
-    b0 = fma2(q0, q0, b0); b1 = fma2(q1, q1, b1);
-  }
-  float p, q, r, t;
-  upk2(a0, p, q); upk2(a1, r, t);
-  da = lanes_sum<TPP>((p + q) + (r + t));
-  upk2(b0, p, q); upk2(b1, r, t);
-  db = lanes_sum<TPP>((p + q) + (r + t));
-}
-
 template <int TPP, int KT, bool SUMS, bool P4>
 __global__ void __launch_bounds__(KHM_THREADS, 4) khm_pass2_fast_kernel(KhmArgs a, int KG) {
   extern __shared__ __align__(16) float smem[];
   const int pmode = P4 ? 4 : a.pmode;
   constexpr int PTS = KHM_THREADS / TPP;           // thread groups; a tile is 2*PTS points
   constexpr int L = 4 * FCH * TPP, L4 = L / 4;
-  constexpr int XS = L + 4;                        // row pitch of the x tile: rows 16 bytes apart in the banks
+  // row pitch of the x tile: a quarter-warp stores 8/TPP points x TPP float4 - the points' blocks must not share banks
+  constexpr int XS = L + (TPP < 8 ? 4 * TPP : 4);
   constexpr int GS = (2 * KT + 3) & ~3;            // floats per centre group in a weight row (16-byte aligned groups)
   const int K = a.K;
   const int WS = KG * GS;                          // weight row: KG groups of KT duplicated pairs
   float* ms = smem;                                // [K][L] centres
   float* xs = ms + K * L;                          // [2*PTS][XS] x tile; [K][L] block sums at the end
   float* ws = xs + 2 * PTS * XS;                   // [2*PTS][WS]
-  float* d2s = ws + 2 * PTS * WS;                  // [K][2*PTS] squared distances of the harmonic-sum loop
-  float* wpart = d2s + K * 2 * PTS;                // [K][KHM_THREADS] per-thread partial sums of the weights
+  float* wsum = ws + 2 * PTS * WS;                 // [K] block sums of the weights (filled at the end)
+  float* wpart = wsum + ((K + 3) & ~3);            // [K][PTS] per-point-slot partial sums of the weights
   __shared__ double red[32];
   const int tid = threadIdx.x, pt = tid / TPP, s = tid % TPP;
   const int64_t ntiles = (a.N + 2 * PTS - 1) / (2 * PTS);
@@ -409,7 +393,7 @@ __global__ void __launch_bounds__(KHM_THREADS, 4) khm_pass2_fast_kernel(KhmArgs 
   double lsum = 0.0;
   stage_centres(ms, a.M, 0, K, L);
   for (int i = tid; i < 2 * PTS * WS; i += KHM_THREADS) ws[i] = 0.f;      // pairs of unused centre slots stay zero
-  for (int i = tid; i < K * KHM_THREADS; i += KHM_THREADS) wpart[i] = 0.f;
+  for (int i = tid; i < K * PTS; i += KHM_THREADS) wpart[i] = 0.f;
   // product role: column c4, centre group kg, point split ps
   const int c4 = tid % L4, kg = (tid / L4) % KG, ps = tid / (L4 * KG), PS = KHM_THREADS / (L4 * KG);
   f32x2 acc[KT][2];
@@ -422,84 +406,109 @@ __global__ void __launch_bounds__(KHM_THREADS, 4) khm_pass2_fast_kernel(KhmArgs 
     float4 xa[FCH], xb[FCH];
     load_point4<TPP>(xa, a.X, a.ldx, ia, va, s);
     load_point4<TPP>(xb, a.X, a.ldx, ib, vb, s);
-    // ---- harmonic sums
-    float ea = 0.f, eb = 0.f;
-#pragma unroll 2
-    for (int kk = 0; kk < K; ++kk) {
-      float da, db;
-      dist2x2_4<TPP>(xa, xb, ms + kk * L, s, da, db);
-      d2s[kk * 2 * PTS + pt] = da;                  // every lane of the point writes (and later reads) the same value
-      d2s[kk * 2 * PTS + PTS + pt] = db;
-      ea += rcp_fast(pow_p(da, a.p, pmode) + KHM_EPS);
-      eb += rcp_fast(pow_p(db, a.p, pmode) + KHM_EPS);
-    }
-    if (s == 0) {
-      if (va) lsum += (double)(Kf / (ea + KHM_EPS));
-      if (vb) lsum += (double)(Kf / (eb + KHM_EPS));
-    }
-    // per-point coefficient: gradient K/(e+eps)^2 ; centre update alpha = 1/(e^2+eps)
-    const float ca = SUMS ? 1.0f / (ea * ea + KHM_EPS) : Kf / ((ea + KHM_EPS) * (ea + KHM_EPS));
-    const float cb = SUMS ? 1.0f / (eb * eb + KHM_EPS) : Kf / ((eb + KHM_EPS) * (eb + KHM_EPS));
+    // ---- ONE pass over the centres: distance, harmonic sum and the un-normalised weight u_k (w_k = coef * u_k, coef
+    // known only after the loop), whose products with the centre chunk accumulate while the chunk is still in registers
     __syncthreads();                                // the previous tile's product has read xs / ws
-#pragma unroll
-    for (int c = 0; c < FCH; ++c) {
-      *reinterpret_cast<float4*>(xs + pt * XS + ((c * TPP + s) << 2)) = xa[c];
-      *reinterpret_cast<float4*>(xs + (PTS + pt) * XS + ((c * TPP + s) << 2)) = xb[c];
-    }
-    // ---- weights, sum_k w_k m_k
+    float ea = 0.f, eb = 0.f, swa = 0.f, swb = 0.f;
     f32x2 ga[FCH][2], gb[FCH][2];
 #pragma unroll
     for (int c = 0; c < FCH; ++c) ga[c][0] = ga[c][1] = gb[c][0] = gb[c][1] = 0ull;
-    float swa = 0.f, swb = 0.f;
     for (int g = 0; g < KG; ++g) {
 #pragma unroll
       for (int j = 0; j < KT; ++j) {
         const int kk = g * KT + j;
         if (kk < K) {
-          const float da = d2s[kk * 2 * PTS + pt], db = d2s[kk * 2 * PTS + PTS + pt];
-          const float pa = pow_p(da, a.p, pmode), pb = pow_p(db, a.p, pmode);
-          float wa, wb;
-          if (SUMS) {
-            wa = ca * rcp_fast(pa * da + KHM_EPS);                  // alpha_i / (d^(p+2) + eps)
-            wb = cb * rcp_fast(pb * db + KHM_EPS);
-          } else {
-            const float ta = pa + KHM_EPS, tb = pb + KHM_EPS;
-            wa = da > 0.f ? ca * a.p * pow_pm2(da, a.p, pmode) * rcp_fast(ta * ta) : 0.f;
-            wb = db > 0.f ? cb * a.p * pow_pm2(db, a.p, pmode) * rcp_fast(tb * tb) : 0.f;
+          const float* mrow = ms + kk * L;
+          f32x2 m0[FCH], m1[FCH];
+          f32x2 a0 = 0ull, a1 = 0ull, b0 = 0ull, b1 = 0ull;
+#pragma unroll
+          for (int c = 0; c < FCH; ++c) {
+            const float4 m = *reinterpret_cast<const float4*>(mrow + ((c * TPP + s) << 2));
+            m0[c] = pk2(m.x, m.y); m1[c] = pk2(m.z, m.w);
+            const f32x2 p0 = sub2(pk2(xa[c].x, xa[c].y), m0[c]), p1 = sub2(pk2(xa[c].z, xa[c].w), m1[c]);
+            const f32x2 q0 = sub2(pk2(xb[c].x, xb[c].y), m0[c]), q1 = sub2(pk2(xb[c].z, xb[c].w), m1[c]);
+            a0 = fma2(p0, p0, a0); a1 = fma2(p1, p1, a1);
+            b0 = fma2(q0, q0, b0); b1 = fma2(q1, q1, b1);
           }
-          if (!va) wa = 0.f;
-          if (!vb) wb = 0.f;
+          float da, db;
+          {
+            float p, q, r, t;
+            upk2(a0, p, q); upk2(a1, r, t);
+            da = lanes_sum<TPP>((p + q) + (r + t));
+            upk2(b0, p, q); upk2(b1, r, t);
+            db = lanes_sum<TPP>((p + q) + (r + t));
+          }
+          const float pa = pow_p(da, a.p, pmode), pb = pow_p(db, a.p, pmode);
+          const float ra = rcp_fast(pa + KHM_EPS), rb = rcp_fast(pb + KHM_EPS);
+          ea += ra; eb += rb;
+          float ua, ub;
+          if (SUMS) {
+            ua = rcp_fast(pa * da + KHM_EPS);                       // 1 / (d^(p+2) + eps)
+            ub = rcp_fast(pb * db + KHM_EPS);
+          } else {
+            ua = da > 0.f ? a.p * pow_pm2(da, a.p, pmode) * (ra * ra) : 0.f;   // p d^(p-2) / (d^p + eps)^2
+            ub = db > 0.f ? a.p * pow_pm2(db, a.p, pmode) * (rb * rb) : 0.f;
+          }
           if (!SUMS) {
-            const float* mrow = ms + kk * L;
-            const f32x2 wa2 = pk2(wa, wa), wb2 = pk2(wb, wb);
+            const f32x2 ua2 = pk2(ua, ua), ub2 = pk2(ub, ub);
 #pragma unroll
             for (int c = 0; c < FCH; ++c) {
-              const float4 m = *reinterpret_cast<const float4*>(mrow + ((c * TPP + s) << 2));
-              const f32x2 m0 = pk2(m.x, m.y), m1 = pk2(m.z, m.w);
-              ga[c][0] = fma2(wa2, m0, ga[c][0]); ga[c][1] = fma2(wa2, m1, ga[c][1]);
-              gb[c][0] = fma2(wb2, m0, gb[c][0]); gb[c][1] = fma2(wb2, m1, gb[c][1]);
+              ga[c][0] = fma2(ua2, m0[c], ga[c][0]); ga[c][1] = fma2(ua2, m1[c], ga[c][1]);
+              gb[c][0] = fma2(ub2, m0[c], gb[c][0]); gb[c][1] = fma2(ub2, m1[c], gb[c][1]);
             }
-            swa += wa; swb += wb;
+            swa += ua; swb += ub;
           }
-          wpart[kk * KHM_THREADS + tid] += wa + wb;
           if (s == 0) {
-            *reinterpret_cast<float2*>(ws + pt * WS + g * GS + 2 * j) = make_float2(wa, wa);
-            *reinterpret_cast<float2*>(ws + (PTS + pt) * WS + g * GS + 2 * j) = make_float2(wb, wb);
+            *reinterpret_cast<float2*>(ws + pt * WS + g * GS + 2 * j) = make_float2(ua, ua);
+            *reinterpret_cast<float2*>(ws + (PTS + pt) * WS + g * GS + 2 * j) = make_float2(ub, ub);
           }
         }
       }
     }
-    if (!SUMS && a.gX != nullptr) {
-      const f32x2 sa2 = pk2(swa * a.gscale, swa * a.gscale), sb2 = pk2(swb * a.gscale, swb * a.gscale);
-      const f32x2 ng = pk2(-a.gscale, -a.gscale);
+    if (s == 0) {
+      if (va) lsum += (double)(Kf / (ea + KHM_EPS));
+      if (vb) lsum += (double)(Kf / (eb + KHM_EPS));
+    }
+    // per-point coefficient: gradient K/(e+eps)^2 ; centre update alpha = 1/(e^2+eps); zero for the padding points
+    float ca = SUMS ? 1.0f / (ea * ea + KHM_EPS) : Kf / ((ea + KHM_EPS) * (ea + KHM_EPS));
+    float cb = SUMS ? 1.0f / (eb * eb + KHM_EPS) : Kf / ((eb + KHM_EPS) * (eb + KHM_EPS));
+    if (!va) ca = 0.f;
+    if (!vb) cb = 0.f;
+    // the x tile carries the coefficient: sum_i w_ik x_i = sum_i u_ik (coef_i x_i)
+    {
+      const f32x2 ca2 = pk2(ca, ca), cb2 = pk2(cb, cb);
 #pragma unroll
       for (int c = 0; c < FCH; ++c) {
-        // gscale * (sw * x - sum_k w_k m_k)
         float4 v, u;
-        upk2(fma2(sa2, pk2(xa[c].x, xa[c].y), mul2(ng, ga[c][0])), v.x, v.y);
-        upk2(fma2(sa2, pk2(xa[c].z, xa[c].w), mul2(ng, ga[c][1])), v.z, v.w);
-        upk2(fma2(sb2, pk2(xb[c].x, xb[c].y), mul2(ng, gb[c][0])), u.x, u.y);
-        upk2(fma2(sb2, pk2(xb[c].z, xb[c].w), mul2(ng, gb[c][1])), u.z, u.w);
+        upk2(mul2(ca2, pk2(xa[c].x, xa[c].y)), v.x, v.y); upk2(mul2(ca2, pk2(xa[c].z, xa[c].w)), v.z, v.w);
+        upk2(mul2(cb2, pk2(xb[c].x, xb[c].y)), u.x, u.y); upk2(mul2(cb2, pk2(xb[c].z, xb[c].w)), u.z, u.w);
+        *reinterpret_cast<float4*>(xs + pt * XS + ((c * TPP + s) << 2)) = v;
+        *reinterpret_cast<float4*>(xs + (PTS + pt) * XS + ((c * TPP + s) << 2)) = u;
+      }
+    }
+    // sum_i w_ik: the point's first lane adds coef * u_k for its two points (it wrote the u_k pairs itself)
+    if (s == 0) {
+      for (int g = 0; g < KG; ++g) {
+#pragma unroll
+        for (int j = 0; j < KT; ++j) {
+          const int kk = g * KT + j;
+          if (kk < K)
+            wpart[kk * PTS + pt] += ca * ws[pt * WS + g * GS + 2 * j] + cb * ws[(PTS + pt) * WS + g * GS + 2 * j];
+        }
+      }
+    }
+    if (!SUMS && a.gX != nullptr) {
+      const float fa = ca * a.gscale, fb = cb * a.gscale;
+      const f32x2 sa2 = pk2(swa * fa, swa * fa), sb2 = pk2(swb * fb, swb * fb);
+      const f32x2 na = pk2(-fa, -fa), nb = pk2(-fb, -fb);
+#pragma unroll
+      for (int c = 0; c < FCH; ++c) {
+        // gscale * coef * (sum_k u_k * x - sum_k u_k m_k)
+        float4 v, u;
+        upk2(fma2(sa2, pk2(xa[c].x, xa[c].y), mul2(na, ga[c][0])), v.x, v.y);
+        upk2(fma2(sa2, pk2(xa[c].z, xa[c].w), mul2(na, ga[c][1])), v.z, v.w);
+        upk2(fma2(sb2, pk2(xb[c].x, xb[c].y), mul2(nb, gb[c][0])), u.x, u.y);
+        upk2(fma2(sb2, pk2(xb[c].z, xb[c].w), mul2(nb, gb[c][1])), u.z, u.w);
         if (va) {
           float4* dst = reinterpret_cast<float4*>(a.gX + ia * a.ldg + ((c * TPP + s) << 2));
           if (a.accumulate_x) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
@@ -552,20 +561,20 @@ __global__ void __launch_bounds__(KHM_THREADS, 4) khm_pass2_fast_kernel(KhmArgs 
       atomicAdd(dst + 0, p0); atomicAdd(dst + 1, p1); atomicAdd(dst + 2, p2); atomicAdd(dst + 3, p3);
     }
   }
-  // sum_i w_ik of the block: every lane of a point added the weight, so the total is TPP times too large
+  // sum_i w_ik of the block
   for (int k = tid >> 5; k < K; k += KHM_THREADS / 32) {
     float v = 0.f;
-    for (int i = tid & 31; i < KHM_THREADS; i += 32) v += wpart[k * KHM_THREADS + i];
+    for (int i = tid & 31; i < PTS; i += 32) v += wpart[k * PTS + i];
     v = warp_sum(v);
-    if ((tid & 31) == 0) d2s[k] = v * (1.f / (float)TPP);
+    if ((tid & 31) == 0) wsum[k] = v;
   }
   __syncthreads();
   for (int idx = tid; idx < K * L; idx += KHM_THREADS) {
     const int k = idx / L;
     if (SUMS) atomicAdd(a.num + idx, acc_s[idx]);
-    else atomicAdd(a.gM + idx, -a.gscale * (acc_s[idx] - ms[idx] * d2s[k]));
+    else atomicAdd(a.gM + idx, -a.gscale * (acc_s[idx] - ms[idx] * wsum[k]));
   }
-  if (SUMS) for (int k = tid; k < K; k += KHM_THREADS) atomicAdd(a.den + k, d2s[k]);
+  if (SUMS) for (int k = tid; k < K; k += KHM_THREADS) atomicAdd(a.den + k, wsum[k]);
   if (a.loss_sum != nullptr) {
     const double tot = block_sum<double>(lsum, red);
     if (tid == 0) atomicAdd(a.loss_sum, tot);
@@ -693,8 +702,9 @@ bool pick_fast(int K, int L, int* tpp, int* kt, int* kg) {
 template <int TPP, int KT, bool SUMS, bool P4>
 int launch_pass2_fast_p(const KhmArgs& a, int kg, cudaStream_t st) {
   const int pts = KHM_THREADS / TPP, gs = (2 * KT + 3) & ~3;
-  const size_t smem = ((size_t)a.K * a.L + (size_t)2 * pts * (a.L + 4) + (size_t)2 * pts * kg * gs + (size_t)a.K * 2 * pts +
-                       (size_t)a.K * KHM_THREADS) * sizeof(float);
+  const int xs = a.L + (TPP < 8 ? 4 * TPP : 4);
+  const size_t smem = ((size_t)a.K * a.L + (size_t)2 * pts * xs + (size_t)2 * pts * kg * gs + (size_t)((a.K + 3) & ~3) +
+                       (size_t)a.K * pts) * sizeof(float);
   if (smem > 48 * 1024)
     LSHM_CUDA(cudaFuncSetAttribute(khm_pass2_fast_kernel<TPP, KT, SUMS, P4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "khm_pass2");
   int per_sm = 4;
