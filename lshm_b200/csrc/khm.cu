@@ -69,7 +69,7 @@ __device__ __forceinline__ float dist2(const float4 (&x4)[KHM_MAXCH], const floa
   f32x2 a0 = 0ull, a1 = 0ull;   // two packed accumulators = four independent chains
 #pragma unroll
   for (int c = 0; c < KHM_MAXCH; ++c) {
-    if (NCH == KHM_MAXCH || c < nch) {
+    if (NCH > 0 ? c < NCH : c < nch) {
       const float4 m = *reinterpret_cast<const float4*>(mrow + ((c * TPP + s) << 2));
       const f32x2 d0 = sub2(pk2(x4[c].x, x4[c].y), pk2(m.x, m.y));
       const f32x2 d1 = sub2(pk2(x4[c].z, x4[c].w), pk2(m.z, m.w));
@@ -91,7 +91,7 @@ __device__ __forceinline__ void dist2x2(const float4 (&xa)[KHM_MAXCH], const flo
   f32x2 a0 = 0ull, a1 = 0ull, b0 = 0ull, b1 = 0ull;
 #pragma unroll
   for (int c = 0; c < KHM_MAXCH; ++c) {
-    if (NCH == KHM_MAXCH || c < nch) {
+    if (NCH > 0 ? c < NCH : c < nch) {
       const float4 m = *reinterpret_cast<const float4*>(mrow + ((c * TPP + s) << 2));
       const f32x2 m0 = pk2(m.x, m.y), m1 = pk2(m.z, m.w);
       const f32x2 p0 = sub2(pk2(xa[c].x, xa[c].y), m0), p1 = sub2(pk2(xa[c].z, xa[c].w), m1);
@@ -113,7 +113,7 @@ __device__ __forceinline__ void load_point(float4 (&x4)[KHM_MAXCH], const float*
 #pragma unroll
   for (int c = 0; c < KHM_MAXCH; ++c) {
     x4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if ((NCH == KHM_MAXCH || c < nch) && valid) x4[c] = *reinterpret_cast<const float4*>(X + i * ldx + ((c * TPP + s) << 2));
+    if ((NCH > 0 ? c < NCH : c < nch) && valid) x4[c] = *reinterpret_cast<const float4*>(X + i * ldx + ((c * TPP + s) << 2));
   }
 }
 
@@ -150,8 +150,43 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass1_kernel(KhmArgs a) {
     const int64_t ia = t * 2 * PTS + pt, ib = ia + PTS;
     const bool va = ia < a.N, vb = ib < a.N;
     float4 xa[KHM_MAXCH], xb[KHM_MAXCH];
-    load_point<TPP, NCH>(xa, a.X, a.ldx, ia, va, s, nch);
-    load_point<TPP, NCH>(xb, a.X, a.ldx, ib, vb, s, nch);
+    if constexpr (TPP == 1 && NCH == KHM_MAXCH) {
+      // L = 32, a whole point per lane: lane i reading row i directly makes every LDG.128 touch 32 different 128-byte
+      // lines (8 load wavefronts per point, the bound of this case).  The warp's 32 rows are 4 KB contiguous when the
+      // rows are dense: fetch them as consecutive 16-byte words (4 lines per instruction) and transpose through a
+      // padded per-warp buffer (144-byte row pitch: both sides conflict-free).
+      if (a.ldx == 32) {
+        float* stg = smem + (RESIDENT ? K * L : KHM_KC * L) + (threadIdx.x >> 5) * (32 * 36);
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int64_t row0 = t * 2 * PTS + h * PTS + (threadIdx.x & ~31);   // first row of the warp's 32
+          float4 (&x4)[KHM_MAXCH] = h == 0 ? xa : xb;
+          float4 w[KHM_MAXCH];
+#pragma unroll
+          for (int c = 0; c < KHM_MAXCH; ++c) {
+            const int word = c * 32 + lane;                                  // 16-byte word of the 4 KB block
+            w[c] = row0 + (word >> 3) < a.N ? *reinterpret_cast<const float4*>(a.X + row0 * 32 + word * 4)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < KHM_MAXCH; ++c) {
+            const int word = c * 32 + lane;
+            *reinterpret_cast<float4*>(stg + (word >> 3) * 36 + (word & 7) * 4) = w[c];
+          }
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < KHM_MAXCH; ++c) x4[c] = *reinterpret_cast<const float4*>(stg + lane * 36 + c * 4);
+        }
+      } else {
+        load_point<TPP, NCH>(xa, a.X, a.ldx, ia, va, s, nch);
+        load_point<TPP, NCH>(xb, a.X, a.ldx, ib, vb, s, nch);
+      }
+    } else {
+      load_point<TPP, NCH>(xa, a.X, a.ldx, ia, va, s, nch);
+      load_point<TPP, NCH>(xb, a.X, a.ldx, ib, vb, s, nch);
+    }
     float ea = 0.f, eb = 0.f, besta = 3.4e38f, bestb = 3.4e38f;
     int bia = 0, bib = 0;
     for (int k0 = 0; k0 < K; k0 += (RESIDENT ? K : KHM_KC)) {
@@ -240,7 +275,7 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass2_kernel(KhmArgs a) {
     // ---- x tile to shared memory for the [K x pts] x [pts x L] product
 #pragma unroll
     for (int c = 0; c < KHM_MAXCH; ++c)
-      if (NCH == KHM_MAXCH || c < nch) *reinterpret_cast<float4*>(xs + pt * L + ((c * TPP + s) << 2)) = x4[c];
+      if (NCH > 0 ? c < NCH : c < nch) *reinterpret_cast<float4*>(xs + pt * L + ((c * TPP + s) << 2)) = x4[c];
     float4 g4[KHM_MAXCH];
 #pragma unroll
     for (int c = 0; c < KHM_MAXCH; ++c) g4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -263,7 +298,7 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass2_kernel(KhmArgs a) {
         if (!SUMS) {
 #pragma unroll
           for (int c = 0; c < KHM_MAXCH; ++c) {
-            if (NCH == KHM_MAXCH || c < nch) {
+            if (NCH > 0 ? c < NCH : c < nch) {
               const float4 m = *reinterpret_cast<const float4*>(mrow + ((c * TPP + s) << 2));
               const f32x2 w2 = pk2(w, w);
               const f32x2 r0 = fma2(w2, sub2(pk2(x4[c].x, x4[c].y), pk2(m.x, m.y)), pk2(g4[c].x, g4[c].y));
@@ -315,7 +350,7 @@ __global__ void __launch_bounds__(KHM_THREADS) khm_pass2_kernel(KhmArgs a) {
     if (!SUMS && valid && a.gX != nullptr) {
 #pragma unroll
       for (int c = 0; c < KHM_MAXCH; ++c) {
-        if (NCH == KHM_MAXCH || c < nch) {
+        if (NCH > 0 ? c < NCH : c < nch) {
           float4* dst = reinterpret_cast<float4*>(a.gX + i * a.ldg + ((c * TPP + s) << 2));
           float4 v = make_float4(a.gscale * g4[c].x, a.gscale * g4[c].y, a.gscale * g4[c].z, a.gscale * g4[c].w);
           if (a.accumulate_x) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
@@ -643,8 +678,9 @@ int launch_pass1_n(const KhmArgs& a, size_t smem, int grid, cudaStream_t st) {
 
 template <int TPP, bool RES>
 int launch_pass1_t(const KhmArgs& a, size_t smem, int grid, cudaStream_t st) {
-  return a.L == 4 * TPP * KHM_MAXCH ? launch_pass1_n<TPP, RES, KHM_MAXCH>(a, smem, grid, st)
-                                    : launch_pass1_n<TPP, RES, 0>(a, smem, grid, st);
+  if (a.L == 4 * TPP * KHM_MAXCH) return launch_pass1_n<TPP, RES, KHM_MAXCH>(a, smem, grid, st);
+  if (a.L == 4 * TPP * 4) return launch_pass1_n<TPP, RES, 4>(a, smem, grid, st);
+  return launch_pass1_n<TPP, RES, 0>(a, smem, grid, st);
 }
 
 template <int TPP, bool RES, bool SUMS, int NCH>
@@ -673,7 +709,8 @@ int launch_pass1(const KhmArgs& a, cudaStream_t st) {
   const int tpp = pick_tpp(a.L);
   const size_t res_bytes = (size_t)a.K * a.L * sizeof(float);
   const bool res = res_bytes <= RESIDENT_SMEM_LIMIT;
-  const size_t smem = res ? res_bytes : (size_t)KHM_KC * a.L * sizeof(float);
+  size_t smem = res ? res_bytes : (size_t)KHM_KC * a.L * sizeof(float);
+  if (tpp == 1 && a.L == 32) smem += (size_t)(KHM_THREADS / 32) * 32 * 36 * sizeof(float);   // per-warp transpose buffers
   const int grid = grid_for(a.N, tpp, 8, 2);
 #define P1(T) (res ? launch_pass1_t<T, true>(a, smem, grid, st) : launch_pass1_t<T, false>(a, smem, grid, st))
   switch (tpp) {
