@@ -158,6 +158,91 @@ __global__ void __launch_bounds__(256) sgemm_skinny_kernel(GemmArgs g) {
   }
 }
 
+// Small products (the dense head at minibatch sizes: M x N x K ~ 1024 x 16..816 x 16..816, and the weight-gradient
+// products J x K over N samples): 32 x 32 output tiles, 256 threads (2 x 2 outputs each), the whole reduction inside the
+// block - no split-K, so no atomics and no memset of the output; `colsum` (weight gradients) also writes the row sums of
+// A (= the bias gradient sum_n dz[n, j]) from the tiles that pass through shared memory anyway.  The 64 x 64 kernel
+// left these problems on 16 blocks (47-66 us) or needed two memsets + split-K atomics + a column-sum kernel per call.
+constexpr int SB = 32;
+__global__ void __launch_bounds__(256) sgemm32_kernel(GemmArgs g, float* __restrict__ colsum) {
+  __shared__ __align__(16) float As[2][SB][SB + 2];
+  __shared__ __align__(16) float Bs[2][SB][SB + 2];
+  const int64_t m0 = (int64_t)blockIdx.x * SB;
+  const int n0 = blockIdx.y * SB;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  float rsum = 0.f;                                   // colsum: thread t < 32 owns row m0 + t
+  const bool a_kfast = g.sak == 1, b_kfast = g.sbk == 1;
+  constexpr int PER = (SB * SB) / 256;
+  // element (row, k) of each operand tile this thread moves: along whichever stride is 1
+  int amm[PER], akk[PER], bnn[PER], bkk[PER];
+#pragma unroll
+  for (int it = 0; it < PER; ++it) {
+    const int idx = threadIdx.x + it * 256;
+    if (a_kfast) { akk[it] = idx % SB; amm[it] = idx / SB; } else { amm[it] = idx % SB; akk[it] = idx / SB; }
+    if (b_kfast) { bkk[it] = idx % SB; bnn[it] = idx / SB; } else { bnn[it] = idx % SB; bkk[it] = idx / SB; }
+  }
+  float ra[PER], rb[PER];
+  auto fetch = [&](int64_t k0) {
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+      const int64_t m = m0 + amm[it], ka = k0 + akk[it], n = n0 + bnn[it], kb = k0 + bkk[it];
+      ra[it] = (m < g.M && ka < g.K) ? __ldg(g.A + m * g.sam + ka * g.sak) : 0.f;
+      rb[it] = (n < g.N && kb < g.K) ? __ldg(g.B + n * g.sbn + kb * g.sbk) : 0.f;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int it = 0; it < PER; ++it) { As[buf][akk[it]][amm[it]] = ra[it]; Bs[buf][bkk[it]][bnn[it]] = rb[it]; }
+  };
+  // the next tile's loads are in flight while the current one is multiplied (the loop is a chain of global-load
+  // latencies otherwise: 32 steps x ~1 us for the 1024-sample weight-gradient reductions)
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (int64_t k0 = 0; k0 < g.K; k0 += SB, buf ^= 1) {
+    const bool more = k0 + SB < g.K;
+    if (more) fetch(k0 + SB);
+#pragma unroll
+    for (int kk = 0; kk < SB; ++kk) {
+      const float2 a = *reinterpret_cast<const float2*>(&As[buf][kk][ty * 2]);
+      const float2 b = *reinterpret_cast<const float2*>(&Bs[buf][kk][tx * 2]);
+      acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
+      acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
+    }
+    if (colsum != nullptr && blockIdx.y == 0 && threadIdx.x < SB) {
+#pragma unroll
+      for (int kk = 0; kk < SB; ++kk) rsum += As[buf][kk][threadIdx.x];
+    }
+    if (more) stash(buf ^ 1);
+    __syncthreads();
+  }
+  if (colsum != nullptr && blockIdx.y == 0 && threadIdx.x < SB && m0 + threadIdx.x < g.M) colsum[m0 + threadIdx.x] = rsum;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int64_t m = m0 + ty * 2 + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int n = n0 + tx * 2 + j;
+      if (n >= g.N) continue;
+      float v = acc[i][j];
+      if (g.bias) v += g.bias[n];
+      if (g.add) v += g.add[m * g.ldadd + n];
+      if (g.epi == LSHM_EPI_ELU) v = elu_f(v);
+      else if (g.epi == LSHM_EPI_DELU) v *= delu_from_out(g.aux[m * g.ldaux + n]);
+      g.C[m * g.ldc + n] = v;
+    }
+  }
+}
+
+// the small-problem kernel serves a call when its grid stays small and the reduction short enough for one block
+bool small_problem(const GemmArgs& g) {
+  static const bool off = getenv("LSHM_NO_SGEMM32") != nullptr;        // experiment switch
+  return !off && g.K <= 8192 && ceil_div(g.M, SB) * ceil_div(g.N, SB) <= 4096;
+}
+
 template <int NN, bool VECN>
 void launch_skinny(const GemmArgs& g, cudaStream_t st) {
   if (g.K >= 128) {
@@ -170,6 +255,13 @@ void launch_skinny(const GemmArgs& g, cudaStream_t st) {
 }
 
 int launch_gemm(GemmArgs g, int ksplit, cudaStream_t st, const char* name) {
+  // (a narrow output with a long reduction stays on the row-per-block kernel below: 23 us against 29 us for 784 -> 16)
+  if (!g.atomic && ksplit == 1 && small_problem(g) && !(g.N <= 16 && g.K >= 128)) {
+    dim3 grid((unsigned)ceil_div(g.M, SB), (unsigned)ceil_div(g.N, SB));
+    sgemm32_kernel<<<grid, 256, 0, st>>>(g, nullptr);
+    LSHM_CHECK_LAUNCH(name);
+    return LSHM_OK;
+  }
   static const bool no_skinny = getenv("LSHM_NO_SKINNY") != nullptr;   // experiment switch
   if (!no_skinny && !g.atomic && ksplit == 1 && g.N <= 32 && g.K >= 16) {
     const bool vecn = g.sbn == 1 && (g.sbk & 3) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0 && (g.N & 3) == 0;
@@ -274,13 +366,23 @@ int lshm_linear_bwd_weight(const float* x, int64_t ldx, const float* dz, int64_t
                            float* dw, float* db, int64_t N, int K, int J, lshm_stream_t stream) {
   LSHM_REQUIRE(x && dz && dw && N >= 0 && K > 0 && J > 0, "lshm_linear_bwd_weight: bad arguments");
   cudaStream_t st = as_stream(stream);
-  LSHM_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)J * K, st), "lshm_linear_bwd_weight");
-  if (db) LSHM_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * J, st), "lshm_linear_bwd_weight");
-  if (N == 0) return LSHM_OK;
   GemmArgs g{};
   g.A = dz; g.sam = 1; g.sak = lddz;          // A(j, n) = dz[n*lddz + j]
   g.B = x; g.sbn = 1; g.sbk = ldx;            // B(k, n) = x[n*ldx + k]
-  g.C = dw; g.ldc = K; g.M = J; g.N = K; g.K = N; g.atomic = 1;
+  g.C = dw; g.ldc = K; g.M = J; g.N = K; g.K = N;
+  static const bool one_launch = getenv("LSHM_WGRAD_SGEMM32") != nullptr;   // experiment switch
+  if (one_launch && N > 0 && small_problem(g)) {
+    // one launch, every output (and the bias gradient) written exactly once - but the whole 1024-sample reduction
+    // then runs inside one or a few blocks: measured 39 us per call against 19 us for memsets + split-K atomics + column sums
+    dim3 grid((unsigned)ceil_div(g.M, SB), (unsigned)ceil_div(g.N, SB));
+    sgemm32_kernel<<<grid, 256, 0, st>>>(g, db);
+    LSHM_CHECK_LAUNCH("lshm_linear_bwd_weight");
+    return LSHM_OK;
+  }
+  LSHM_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)J * K, st), "lshm_linear_bwd_weight");
+  if (db) LSHM_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * J, st), "lshm_linear_bwd_weight");
+  if (N == 0) return LSHM_OK;
+  g.atomic = 1;
   const int64_t tiles = ceil_div(J, BM) * ceil_div(K, BN);
   int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(N, 4 * BK), (int64_t)sm_count() * 4 / tiles));
   if (int rc = launch_gemm(g, ksplit, st, "lshm_linear_bwd_weight")) return rc;
