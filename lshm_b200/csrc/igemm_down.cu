@@ -88,7 +88,7 @@ __device__ __forceinline__ void down_epilogue_tile(const DownArgs& a, uint32_t t
 // PRE: the input arrives as operand planes (already space-to-depth, already split into bf16 hi / lo): the producer
 // warps are replaced by ONE thread that issues two tensor-TMA box loads per stage (cp.async.bulk.tensor.3d).
 template <int DIM, int NT, int KC, int G, bool PRE>
-__global__ void __launch_bounds__(down_threads(G), (G == 1 ? 3 : 2)) igemm_down_kernel(const __grid_constant__ DownArgs a) {
+__global__ void __launch_bounds__(down_threads(G), (G == 1 ? 3 : (G == 2 ? 2 : 1))) igemm_down_kernel(const __grid_constant__ DownArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[MAXST], empty_bar[MAXST], acc_full[2], acc_empty[2], w_bar;
   __shared__ uint32_t tmem_base;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(down_threads(G), (G == 1 ? 3 : 2)) igemm_down_
     }
   } else if ((warp >= 4 && warp < 8) || warp >= 10) {
     // ------------------------------------------------ producers: stage the Z tile (hi/lo bf16)
-    const int grp = warp >= 10 ? 1 : 0;                 // producer group
+    const int grp = warp >= 10 ? 1 + ((warp - 10) >> 2) : 0;   // producer group
     const int ptid = (tid & 127);                       // 0..127 within the group (warps 4-7 / 10-13... tid-128, tid-320)
     const int H = 2 * a.h, W = 2 * a.w;
     const int64_t HW = (int64_t)H * W;
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(down_threads(G), (G == 1 ? 3 : 2)) igemm_down_
         }
       }
       for (int kb = 0; kb < KB; ++kb, ring.next(NS), ++unit) {
-        if (G == 2 && (int)(unit & 1) != grp) continue;   // the other group's stage
+        if (G > 1 && (int)(unit & (G - 1)) != grp) continue;   // another group's stage
         const int s = ring.s;
         uint8_t* zhi = smem + (size_t)s * stage_bytes;
         uint8_t* zlo = zhi + zbytes;
@@ -359,6 +359,12 @@ int launch_down_t(DownArgs a, const DownGeom& g, cudaStream_t st) {
   int ns = (int)((third_sm - g.img) / stage);
   if (ns < 2) ns = (int)((half_sm - g.img) / stage);
   if (ns < 2) ns = (int)((full_sm - g.img) / stage);
+  // Few work items, many K blocks (the deep layers: one or two items per SM, 12-24 K blocks each): several CTAs per SM
+  // buy nothing, but with two stages every K block waits for its weight image (a 12-25 KB bulk copy from L2, ~1 us of
+  // latency): one CTA per SM with the deepest ring instead.
+  static const bool no_deep_ring = getenv("LSHM_DOWN_NODEEP") != nullptr;   // experiment switch
+  if (!no_deep_ring && g.KB >= 4 && a.mtiles * g.ntiles <= 2 * (int64_t)sm_count())
+    ns = std::max(ns, (int)((full_sm - g.img) / stage));
   ns = std::min(ns, MAXST);
   LSHM_REQUIRE(ns >= 1, "igemm_down: tile does not fit in shared memory");
   a.nstage = (int)std::min<int64_t>(ns, std::max<int64_t>(1, units));
@@ -370,7 +376,7 @@ int launch_down_t(DownArgs a, const DownGeom& g, cudaStream_t st) {
     if (int rc = make_plane_tmap(&a.tm_lo, base + pg.half_bytes, pg.Qs, pg.chunks, a.slots, KC / 8)) return rc;
   }
   LSHM_CUDA(cudaFuncSetAttribute(igemm_down_kernel<DIM, NT, KC, G, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_down");
-  const int per_sm = std::min(G == 1 ? 3 : 2, smem <= 74 * 1024 ? 3 : (smem <= 112 * 1024 ? 2 : 1));
+  const int per_sm = std::min(G == 1 ? 3 : (G == 2 ? 2 : 1), smem <= 74 * 1024 ? 3 : (smem <= 112 * 1024 ? 2 : 1));
   const int64_t grid = std::min<int64_t>(a.mtiles * g.ntiles, (int64_t)sm_count() * per_sm);
   igemm_down_kernel<DIM, NT, KC, G, PRE><<<(unsigned)grid, down_threads(G), smem, st>>>(a);
   LSHM_CHECK_LAUNCH("igemm_down");
@@ -411,7 +417,15 @@ int launch_down(int dim, DownArgs a, cudaStream_t st, bool planes = false) {
     }
 #undef LP
   }
+  // four producer groups for the deepest layers (one or two items per SM, >= 8 K blocks each: the kernel is a chain of
+  // gather -> convert -> hand-off latencies, four of them in flight instead of two)
+  static const bool no_g4 = getenv("LSHM_DOWN_NOG4") != nullptr;          // experiment switch
+  const bool four = two && !no_g4 && g.NT == 96 && g.KB >= 8 && a.mtiles * g.ntiles <= 2 * (int64_t)sm_count();
 #define LD(D, NTV, KCV) do { if (two) return launch_down_t<D, NTV, KCV, 2>(a, g, st); return launch_down_t<D, NTV, KCV, 1>(a, g, st); } while (0)
+  if (four) {
+    if (dim == 2) return launch_down_t<2, 96, 16, 4>(a, g, st);
+    return launch_down_t<1, 96, 32, 4>(a, g, st);
+  }
   if (dim == 2) {
     switch (g.NT) {
       case 16: LD(2, 16, 32);
