@@ -94,3 +94,28 @@ def test_fastdiv_constants_match_integer_division():
         bad = ctypes.c_int64(-1)
         assert check(d, n.ctypes.data, len(n), ctypes.addressof(bad)) == 0
         assert bad.value == 0, (d, bad.value)
+
+
+def test_workspace_rows_are_contiguous_views():
+    """A micro-batch workspace is the same memory restricted to rows [n0, n1) of every buffer (engine.Workspace.rows)."""
+    from lshm_b200.engine import Workspace
+    w = Workspace(8, 8, 32, 16, "cpu", True, True)
+    v = w.rows(2, 6)
+    assert v.N == 4 and v.sizes == w.sizes and hasattr(v, "g_enc") and v.enc[0] is None
+    for name in ("xhat", "cat1", "mu", "zcat", "g_cat1", "dx", "uvh"):
+        a, b = getattr(v, name), getattr(w, name)
+        assert a.shape[0] == 4 and a.is_contiguous() and a.data_ptr() == b[2:].data_ptr(), name
+    for lst in ("enc", "dec", "g_enc", "g_dec"):
+        for a, b in zip(getattr(v, lst), getattr(w, lst)):
+            assert (a is None and b is None) or a.data_ptr() == b[2:].data_ptr()
+    w.xhat.zero_()
+    v.xhat.fill_(3.0)
+    assert float(w.xhat[2:6].min()) == 3.0 and float(w.xhat[:2].abs().max()) == 0.0 and float(w.xhat[6:].abs().max()) == 0.0
+    no_grad = Workspace(4, 4, 16, 16, "cpu", False, False).rows(0, 2)
+    assert not hasattr(no_grad, "g_enc")
+
+
+def test_fft_features_argument_checks():
+    from lshm_b200 import lofar_tools as T
+    with pytest.raises(RuntimeError, match="CUDA"):
+        T.fft_features(torch.zeros(1, 2, 128, 128))
