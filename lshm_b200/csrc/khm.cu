@@ -52,6 +52,10 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.f32x
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
+// acc += a * b in place (the "+l" form keeps the accumulator in its register pair: with the three-operand form the
+// compiler wrote half of the gradient sums into the operand's registers and moved them back - 16 MOVs per centre)
+__device__ __forceinline__ void fma2_acc(f32x2& acc, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+
 // 1/x to 1 ulp in one MUFU op (the IEEE-rounded division is ~12 instructions per (point, centre) pair,
 // a sixth of the K = 10 inner loop)
 __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -448,7 +452,11 @@ __global__ void __launch_bounds__(KHM_THREADS, 4) khm_pass2_fast_kernel(KhmArgs 
     f32x2 ga[FCH][2], gb[FCH][2];
 #pragma unroll
     for (int c = 0; c < FCH; ++c) ga[c][0] = ga[c][1] = gb[c][0] = gb[c][1] = 0ull;
+    float* const wsa = ws + pt * WS;                // this point pair's weight rows
+    float* const wsb = ws + (PTS + pt) * WS;
     for (int g = 0; g < KG; ++g) {
+      float* const wga = wsa + g * GS;
+      float* const wgb = wsb + g * GS;
 #pragma unroll
       for (int j = 0; j < KT; ++j) {
         const int kk = g * KT + j;
@@ -488,14 +496,14 @@ __global__ void __launch_bounds__(KHM_THREADS, 4) khm_pass2_fast_kernel(KhmArgs 
             const f32x2 ua2 = pk2(ua, ua), ub2 = pk2(ub, ub);
 #pragma unroll
             for (int c = 0; c < FCH; ++c) {
-              ga[c][0] = fma2(ua2, m0[c], ga[c][0]); ga[c][1] = fma2(ua2, m1[c], ga[c][1]);
-              gb[c][0] = fma2(ub2, m0[c], gb[c][0]); gb[c][1] = fma2(ub2, m1[c], gb[c][1]);
+              fma2_acc(ga[c][0], ua2, m0[c]); fma2_acc(ga[c][1], ua2, m1[c]);
+              fma2_acc(gb[c][0], ub2, m0[c]); fma2_acc(gb[c][1], ub2, m1[c]);
             }
             swa += ua; swb += ub;
           }
           if (s == 0) {
-            *reinterpret_cast<float2*>(ws + pt * WS + g * GS + 2 * j) = make_float2(ua, ua);
-            *reinterpret_cast<float2*>(ws + (PTS + pt) * WS + g * GS + 2 * j) = make_float2(ub, ub);
+            *reinterpret_cast<float2*>(wga + 2 * j) = make_float2(ua, ua);
+            *reinterpret_cast<float2*>(wgb + 2 * j) = make_float2(ub, ub);
           }
         }
       }
@@ -521,16 +529,12 @@ __global__ void __launch_bounds__(KHM_THREADS, 4) khm_pass2_fast_kernel(KhmArgs 
         *reinterpret_cast<float4*>(xs + (PTS + pt) * XS + ((c * TPP + s) << 2)) = u;
       }
     }
-    // sum_i w_ik: the point's first lane adds coef * u_k for its two points (it wrote the u_k pairs itself)
-    if (s == 0) {
-      for (int g = 0; g < KG; ++g) {
-#pragma unroll
-        for (int j = 0; j < KT; ++j) {
-          const int kk = g * KT + j;
-          if (kk < K)
-            wpart[kk * PTS + pt] += ca * ws[pt * WS + g * GS + 2 * j] + cb * ws[(PTS + pt) * WS + g * GS + 2 * j];
-        }
-      }
+    // sum_i w_ik: the TPP lanes of a point share its K centres (lane s takes k = s, s + TPP, ...) and add coef * u_k of
+    // the two points to the slot's partial sums (the u_k pairs were written by the point's first lane)
+    __syncwarp();
+    for (int kk = s; kk < K; kk += TPP) {
+      const int o = (kk / KT) * GS + 2 * (kk % KT);
+      wpart[kk * PTS + pt] += ca * wsa[o] + cb * wsb[o];
     }
     if (!SUMS && a.gX != nullptr) {
       const float fa = ca * a.gscale, fb = cb * a.gscale;
