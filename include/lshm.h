@@ -162,6 +162,11 @@ LSHM_API int lshm_wgrad2d_planes(const float* small_, int64_t small_ns, const vo
                         float* dw, int64_t N, int A, int Bc, int h, int w_, lshm_stream_t stream);
 LSHM_API int lshm_wgrad1d_planes(const float* small_, int64_t small_ns, const void* planes,
                         float* dw, int64_t N, int A, int Bc, int l, lshm_stream_t stream);
+/* Both gradients of the LAST transposed conv of a 1-D net in one launch, the reconstruction gradient read once:
+ * = lshm_wgrad1d_planes(small_, planes -> dw) + lshm_down1d_planes(planes, wimg_down, NULL, aux = small_, ... ->
+ * dz, LSHM_EPI_DELU).  A <= 16 small-map channels, Bc in {4, 8}. */
+LSHM_API int lshm_tconv_bwd1d_planes(const float* small_, int64_t small_ns, const void* planes, const void* wimg_down,
+                            float* dz, int64_t dz_ns, float* dw, int64_t N, int A, int Bc, int l, lshm_stream_t stream);
 /* dst[i] += src[i], i < n (both 16-byte aligned): the parameter gradients of a second micro-batch join the flat
  * gradient buffer before the data-parallel exchange. */
 LSHM_API int lshm_vec_add(float* dst, const float* src, int64_t n, lshm_stream_t stream);

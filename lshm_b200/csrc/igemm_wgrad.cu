@@ -27,6 +27,8 @@ struct WgArgs {
   const float* small_; int64_t small_ns;
   const float* big; int64_t big_ns;
   float* dw;
+  // FUSED (1-D, operand planes): the data gradient of the same transposed conv from the same staged tiles
+  const uint8_t* dimg; float* dz; int64_t dz_ns; uint32_t dimg_off;
   int64_t N; int A; int Bc; int h; int w; int pad;
   int zslots; int nstage; int64_t Q; int64_t kblocks; int64_t kb_per_cta; int ntiles; int scols; int vec_ok;
   int acols;                        // FOLD: chunk columns (8 channels each) per tap, scols = 4 * acols
@@ -47,14 +49,25 @@ constexpr int WG_THREADS = WG_PT + 32;             // + the MMA warp
 // groups of chunk columns, and one accumulator [(tap,a), c] replaces the four per-tap ones - 24 instead of 96 MMAs
 // per 128 positions (the un-folded first layer ran the tensor pipe at 98 %: every MMA costs max(M,128)*N/256 cycles
 // whatever the number of real rows, profiles/r2_ncu_planes.md), and the big-map tile needs no halo.
-template <int DIM, int NT, int KP, bool PRE, bool FOLD>
+// FUSED (1-D, PRE): the kernel also computes the DATA gradient of the same layer - dz[q, a] = ELU'(S[q, a]) *
+// sum_c Z[q, c] Wt[a, c] - from the Z tile it has staged for the weight gradient (the same bytes read as a K-major
+// operand, igemm_down.cu) and the small-map values it loads anyway: the gradient planes (the largest tensor of the
+// layer) are read from HBM once instead of twice.  Warps 0-3 stage S, warps 4-7 drain the data-gradient accumulator of
+// every K block (two TMEM buffers), the MMA warp issues both products.
+template <int DIM, int NT, int KP, bool PRE, bool FOLD, bool FUSED>
 __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_kernel(const __grid_constant__ WgArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], acc_bar;
+  __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], acc_bar, dacc_full[2], dacc_empty[2], dimg_bar;
   __shared__ uint32_t tmem_base;
+  static_assert(!FUSED || (DIM == 1 && PRE && !FOLD && KP == 128), "fused data gradient: 1-D plane instances only");
   constexpr int T = (DIM == 2 && !FOLD) ? 4 : 1;      // accumulators / descriptor shifts per K block
   constexpr int CZ = NT / 8;
-  constexpr uint32_t TCOLS = T * NT;
+  constexpr int NTD = 16;                              // FUSED: channel tile of the data gradient (A <= 16)
+  constexpr uint32_t DCOL = T * NT;                    // FUSED: first TMEM column of its two accumulators
+  constexpr uint32_t DIMG = 2u * 4 * NTD * 16;         // FUSED: its weight image (lshm_conv_prep "down": hi | lo, 4 chunk columns)
+  constexpr int NPW = FUSED ? 4 : WG_NPW;              // producer warps
+  constexpr int NPT = NPW * 32;
+  constexpr uint32_t TCOLS = T * NT + (FUSED ? 2 * NTD : 0);
   constexpr uint32_t TMEM_COLS = TCOLS <= 32 ? 32 : (TCOLS <= 64 ? 64 : (TCOLS <= 128 ? 128 : (TCOLS <= 256 ? 256 : 512)));
   const int ZS = a.zslots, NS = a.nstage;
   // S tile: only the chunk columns that hold data are staged.  The M=128 MMA still walks 16 column
@@ -74,9 +87,15 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
 
   if (warp == WG_NPW) tmem_alloc(&tmem_base, TMEM_COLS);
   if (tid == 0) {
-    for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], WG_NPW + (PRE ? 1 : 0)); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], NPW + (PRE ? 1 : 0)); mbar_init(&empty_bar[s], 1); }
     mbar_init(&acc_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&dacc_full[b], 1); mbar_init(&dacc_empty[b], 4); }
+    mbar_init(&dimg_bar, 1);
     mbar_init_fence();
+    if (FUSED) {      // the data gradient's weight image stays resident behind the stage ring
+      mbar_arrive_expect_tx(&dimg_bar, DIMG);
+      bulk_g2s(smem + a.dimg_off, a.dimg, DIMG, &dimg_bar);
+    }
   }
   fence_async_smem();
   fence_before();
@@ -84,7 +103,7 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
   fence_after();
   const uint32_t tmem = tmem_base;
 
-  if (warp < WG_NPW) {
+  if (warp < NPW) {
     const int W = 2 * a.w;
     const int64_t HW2 = 4 * (int64_t)a.h * a.w;     // big-map plane size
     const int64_t hw = DIM == 2 ? (int64_t)a.h * a.w : (int64_t)a.w;
@@ -106,11 +125,11 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
       const uint32_t uQ = (uint32_t)a.Q, uPW = (uint32_t)PW, upp = (uint32_t)(PH * PW), uw = (uint32_t)a.w;
       // ---- S tile: item = (position, chunk of 8 channels); U items are fetched before any is converted
       constexpr int U = 2;
-      for (int item0 = tid; item0 < KP * a.scols; item0 += WG_PT * U) {
+      for (int item0 = tid; item0 < KP * a.scols; item0 += NPT * U) {
         float v[U][8];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int item = item0 + u * WG_PT;
+          const int item = item0 + u * NPT;
           const int p = item % KP, ca = item / KP;
           // FOLD: chunk column ca = tap * acols + channel chunk; this copy is shifted by the tap offset
           const int tap = FOLD ? ca / a.acols : 0;
@@ -140,7 +159,7 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int item = item0 + u * WG_PT;
+          const int item = item0 + u * NPT;
           if (item < KP * a.scols) {
             const int p = item % KP, ca = item / KP;
             uint4 hi, lo;
@@ -152,11 +171,11 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
       }
       // ---- Z tile: item = (slot, chunk of 8 s2d channels)
       constexpr int UZ = 4;
-      for (int item0 = tid; !PRE && item0 < ZS * CZ; item0 += WG_PT * UZ) {
+      for (int item0 = tid; !PRE && item0 < ZS * CZ; item0 += NPT * UZ) {
         float v[UZ][8];
 #pragma unroll
         for (int u = 0; u < UZ; ++u) {
-          const int item = item0 + u * WG_PT;
+          const int item = item0 + u * NPT;
           const int cz = (int)fdiv((uint32_t)item, a.d_zs), slot = item - cz * ZS;
           const uint32_t q = up0 + slot;
           const int b0 = (c0 + cz * 8) >> 2;
@@ -208,7 +227,7 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
         }
 #pragma unroll
         for (int u = 0; u < UZ; ++u) {
-          const int item = item0 + u * WG_PT;
+          const int item = item0 + u * NPT;
           if (item < ZS * CZ) {
             const int cz = (int)fdiv((uint32_t)item, a.d_zs), slot = item - cz * ZS;
             uint4 hi, lo;
@@ -314,6 +333,35 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
     }
     }
     }
+  } else if (FUSED && warp < WG_NPW) {
+    // ------------------------------------------------ data-gradient epilogue (warps 4-7 = TMEM lane quarters 0-3)
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + DCOL;
+    for (int it = 0; it < nkb; ++it) {
+      const uint32_t buf = (uint32_t)it & 1u;
+      const uint32_t q = (uint32_t)((kb0 + it) * KP) + (uint32_t)row;
+      const bool ok = q < (uint32_t)a.Q;
+      const uint32_t n = fdiv(ok ? q : 0u, a.d_w);
+      const int64_t off = (int64_t)n * a.small_ns + ((ok ? q : 0u) - n * (uint32_t)a.w);
+      const float* sp = a.small_ + off;
+      float* op = a.dz + (int64_t)n * a.dz_ns + ((ok ? q : 0u) - n * (uint32_t)a.w);
+      mbar_wait(&dacc_full[buf], ((uint32_t)it >> 1) & 1u);
+      fence_after();
+#pragma unroll 1
+      for (int h8 = 0; h8 < NTD / 8; ++h8) {
+        if (h8 * 8 >= a.A) break;                    // warp-uniform
+        float ax[8], v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ax[e] = (ok && h8 * 8 + e < a.A) ? __ldg(sp + (int64_t)(h8 * 8 + e) * a.w) : 0.f;
+        tmem_ld8(trow + buf * NTD + h8 * 8, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (ok && h8 * 8 + e < a.A) op[(int64_t)(h8 * 8 + e) * a.w] = v[e] * delu_from_out(ax[e]);
+      }
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dacc_empty[buf]);
+    }
   } else {
     // ------------------------------------------------ MMA issuer: warp-uniform loop, one elected lane issues
     // M = 64 when the layer has at most 16 output channels (rows 0-15 of the accumulator sit in TMEM lanes
@@ -321,11 +369,30 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
     // 8 rows are real in the first layer) is what bounds the wide first layers.
     const uint32_t idesc = make_idesc(NT, 1, 1, FOLD ? (32 * a.acols <= 64 ? 64 : 128) : (a.A <= 16 ? 64 : 128));
     const uint32_t leader = elect_one();
+    const uint32_t idesc_d = make_idesc(NTD, 0, 0);
+    if (FUSED) mbar_wait(&dimg_bar, 0);
     Ring ring{0, 0};
     for (int it = 0; it < nkb; ++it, ring.next(NS)) {
       const int s = ring.s;
       mbar_wait(&full_bar[s], ring.ph);
       fence_after();
+      if (FUSED) {
+        // data gradient first (its epilogue warps start while the weight-gradient MMAs of the block are issued): the Z
+        // tile as a K-major operand, chunk columns ZS * 16 bytes apart (igemm_down.cu), against the resident image
+        const uint32_t buf = (uint32_t)it & 1u;
+        mbar_wait(&dacc_empty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        fence_after();
+        const uint32_t zh = smem_u32(smem + (size_t)s * stage_bytes) + 2 * SBYTES;
+        const uint32_t bh = smem_u32(smem + a.dimg_off);
+        const uint64_t dah = make_desc(zh, ZS * 16, 128), dal = make_desc(zh + zbytes, ZS * 16, 128);
+        const uint64_t dbh = make_desc(bh, NTD * 16, 128), dbl = make_desc(bh + DIMG / 2, NTD * 16, 128);
+#pragma unroll
+        for (int ks = 0; ks < NT / 16; ++ks)
+          mma_split3_warp(tmem + DCOL + buf * NTD, desc_off(dah, (uint32_t)(2 * ks) * ZS), desc_off(dal, (uint32_t)(2 * ks) * ZS),
+                          desc_off(dbh, (uint32_t)(2 * ks) * NTD), desc_off(dbl, (uint32_t)(2 * ks) * NTD), idesc_d,
+                          ks > 0 ? 1u : 0u, leader);
+        commit_warp(&dacc_full[buf], leader);
+      }
       const uint32_t shi = smem_u32(smem + (size_t)s * stage_bytes);
       const uint32_t slo = shi + SBYTES;
       const uint32_t zhi = slo + SBYTES;
@@ -355,7 +422,7 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
   if (warp == WG_NPW) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-template <int DIM, int NT, int KP, bool PRE = false, bool FOLD = false>
+template <int DIM, int NT, int KP, bool PRE = false, bool FOLD = false, bool FUSED = false>
 int launch_wgrad_t(WgArgs a, int64_t /*splits_hint*/, int mtiles, cudaStream_t st) {
   if (PRE) {
     const PlaneGeom pg = plane_geom(DIM, a.N, a.Bc, a.h, a.w);
@@ -366,8 +433,9 @@ int launch_wgrad_t(WgArgs a, int64_t /*splits_hint*/, int mtiles, cudaStream_t s
   const size_t stage = (size_t)2 * a.scols * KP * 16 + (size_t)2 * (NT / 8) * a.zslots * 16;
   // slack: the padding row groups of the last stage's S tiles are read (and ignored) up to 16 groups
   const size_t reach = (size_t)a.scols * KP * 16 + (size_t)16 * KP * 16;     // from the stage start
-  const size_t smem = stage * a.nstage + (reach > stage ? reach - stage : 0) + 256;
-  LSHM_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<DIM, NT, KP, PRE, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_wgrad");
+  size_t smem = stage * a.nstage + (reach > stage ? reach - stage : 0) + 256;
+  if (FUSED) { a.dimg_off = (uint32_t)((smem + 127) / 128 * 128); smem = a.dimg_off + (size_t)2 * 4 * 16 * 16; }
+  LSHM_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<DIM, NT, KP, PRE, FOLD, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_wgrad");
   // split-K so that the grid is ONE wave of resident CTAs (the first version assumed 3 CTAs per SM: where only 2 fit,
   // e.g. the 12-channel 1-D layer, 1.46 waves left a third of the run to a half-empty machine - ncu, r2_ncu_layer2.md)
   // resident CTAs per SM: the launch bound (registers) and the shared memory (227 KB per SM, 1 KB reserved per CTA).
@@ -380,12 +448,12 @@ int launch_wgrad_t(WgArgs a, int64_t /*splits_hint*/, int mtiles, cudaStream_t s
   splits = ceil_div(a.kblocks, a.kb_per_cta);
   a.nstage = (int)std::min<int64_t>(a.nstage, std::max<int64_t>(1, a.kb_per_cta));
   dim3 grid((unsigned)splits, (unsigned)(mtiles * a.ntiles));
-  igemm_wgrad_kernel<DIM, NT, KP, PRE, FOLD><<<grid, WG_THREADS, smem, st>>>(a);
+  igemm_wgrad_kernel<DIM, NT, KP, PRE, FOLD, FUSED><<<grid, WG_THREADS, smem, st>>>(a);
   LSHM_CHECK_LAUNCH("igemm_wgrad");
   return LSHM_OK;
 }
 
-int launch_wgrad(int dim, WgArgs a, cudaStream_t st, bool planes = false) {
+int launch_wgrad(int dim, WgArgs a, cudaStream_t st, bool planes = false, bool fused = false) {
   const int Kc = 4 * a.Bc;
   const int k16 = (Kc + 15) / 16 * 16;
   const int NT = k16 <= 16 ? 16 : (k16 <= 32 ? 32 : (k16 <= 48 ? 48 : 96));
@@ -417,6 +485,11 @@ int launch_wgrad(int dim, WgArgs a, cudaStream_t st, bool planes = false) {
     LSHM_REQUIRE(NT <= 32 && KP == 128 && a.zslots <= 256, "lshm_wgrad*_planes: operand planes serve the first layers (A <= 16, Bc <= 8)");
     if (dim == 2 && fold) { if (NT == 16) return launch_wgrad_t<2, 16, 128, true, true>(a, splits, mtiles, st); return launch_wgrad_t<2, 32, 128, true, true>(a, splits, mtiles, st); }
     if (dim == 2) { if (NT == 16) return launch_wgrad_t<2, 16, 128, true>(a, splits, mtiles, st); return launch_wgrad_t<2, 32, 128, true>(a, splits, mtiles, st); }
+    if (fused) {
+      LSHM_REQUIRE(dim == 1 && a.A <= 16, "lshm_tconv_bwd1d_planes: at most 16 small-map channels");
+      if (NT == 16) return launch_wgrad_t<1, 16, 128, true, false, true>(a, splits, mtiles, st);
+      return launch_wgrad_t<1, 32, 128, true, false, true>(a, splits, mtiles, st);
+    }
     if (NT == 16) return launch_wgrad_t<1, 16, 128, true>(a, splits, mtiles, st);
     return launch_wgrad_t<1, 32, 128, true>(a, splits, mtiles, st);
   }
@@ -501,6 +574,24 @@ int lshm_wgrad1d_planes(const float* small_, int64_t small_ns, const void* plane
   a.small_ = small_; a.small_ns = small_ns; a.big = reinterpret_cast<const float*>(planes); a.big_ns = 0; a.dw = dw;
   a.N = N; a.A = A; a.Bc = Bc; a.h = 1; a.w = l; a.pad = 0;
   return launch_wgrad(1, a, st, true);
+}
+
+// Weight gradient AND data gradient of a k4/s4 transposed conv whose output gradient is given as operand planes:
+// = lshm_wgrad1d_planes(small_, planes -> dw) + lshm_down1d_planes(planes, wimg_down, aux = small_, LSHM_EPI_DELU -> dz)
+// with the planes read once.
+int lshm_tconv_bwd1d_planes(const float* small_, int64_t small_ns, const void* planes, const void* wimg_down,
+                            float* dz, int64_t dz_ns, float* dw, int64_t N, int A, int Bc, int l, lshm_stream_t stream) {
+  LSHM_REQUIRE(small_ && planes && wimg_down && dz && dw, "lshm_tconv_bwd1d_planes: null pointer");
+  LSHM_REQUIRE(N >= 0 && A > 0 && A <= 16 && Bc > 0 && (Bc & 3) == 0 && Bc <= 8 && l > 0, "lshm_tconv_bwd1d_planes: bad sizes (A <= 16, Bc in {4, 8})");
+  LSHM_REQUIRE((reinterpret_cast<uintptr_t>(wimg_down) & 15) == 0, "lshm_tconv_bwd1d_planes: weight image must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  LSHM_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)A * Bc * 4, st), "lshm_tconv_bwd1d_planes");
+  if (N == 0) return LSHM_OK;
+  WgArgs a{};
+  a.small_ = small_; a.small_ns = small_ns; a.big = reinterpret_cast<const float*>(planes); a.big_ns = 0; a.dw = dw;
+  a.dimg = reinterpret_cast<const uint8_t*>(wimg_down); a.dz = dz; a.dz_ns = dz_ns;
+  a.N = N; a.A = A; a.Bc = Bc; a.h = 1; a.w = l; a.pad = 0;
+  return launch_wgrad(1, a, st, true, true);
 }
 
 }  // extern "C"

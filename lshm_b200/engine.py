@@ -19,7 +19,9 @@ import torch
 
 from ._lib import lib
 
+import os
 EPI_NONE, EPI_ELU, EPI_DELU = 0, 1, 2
+FUSE_LAST_1D = os.environ.get("LSHM_NO_FUSED_LAST1D") is None   # (switch for A/B measurements)
 CONV_CHANNELS = (8, 12, 24, 48, 96, 192)   # src/lofar_models.py:31-41
 FLAT = 768                                  # 192*2*2 (2-D) = 192*4 (1-D)
 INPUT_ELEMS = 16384                         # 128*128 pixels or 16384 samples per channel
@@ -317,9 +319,14 @@ class AEEngine:
                 fork()
                 nxt = ws.g_dec[i]
                 if i == 5 and g_xhat_planes is not None:
-                    self._wgrad_planes(_p(inp), sz[lvl], _p(g_xhat_planes), _p(g["tconv5.weight"]), N, A, Bc, lvl, wst)
-                    self._down_planes(_p(g_xhat_planes), _p(self.img[("tconv5.weight", 0)]), None, _p(inp), sz[lvl],
-                                      _p(nxt), sz[lvl], N, A, Bc, lvl, EPI_DELU, st)
+                    if self.ndim == 1 and A <= 16 and Bc <= 8 and FUSE_LAST_1D:
+                        # both gradients of the last transposed conv from ONE read of the reconstruction gradient
+                        lb.tconv_bwd1d_planes(_p(inp), sz[lvl], _p(g_xhat_planes), _p(self.img[("tconv5.weight", 0)]),
+                                              _p(nxt), sz[lvl], _p(g["tconv5.weight"]), N, A, Bc, INPUT_ELEMS >> (2 * lvl), st)
+                    else:
+                        self._wgrad_planes(_p(inp), sz[lvl], _p(g_xhat_planes), _p(g["tconv5.weight"]), N, A, Bc, lvl, wst)
+                        self._down_planes(_p(g_xhat_planes), _p(self.img[("tconv5.weight", 0)]), None, _p(inp), sz[lvl],
+                                          _p(nxt), sz[lvl], N, A, Bc, lvl, EPI_DELU, st)
                     dz = nxt
                     continue
                 self._wgrad(_p(inp), sz[lvl], _p(dz), sz[lvl - 1], _p(g[f"tconv{i}.weight"]), N, A, Bc, lvl, 0, wst)

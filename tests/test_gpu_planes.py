@@ -150,6 +150,33 @@ def test_down1d_and_wgrad1d_from_planes(cuda, N, A, pad):
     assert rel_err(dw, wr.grad) < 2e-5
 
 
+@pytest.mark.parametrize("N,A,Bc,l", [(2, 8, 8, 4096), (64, 8, 8, 4096), (5, 8, 4, 4096), (3, 12, 8, 256), (1024, 8, 8, 256)])
+def test_fused_last_layer_backward_1d(cuda, N, A, Bc, l):
+    """lshm_tconv_bwd1d_planes = lshm_wgrad1d_planes + lshm_down1d_planes(ELU') with the gradient planes read once:
+    the data gradient is bit-identical to the separate kernel's (same MMA sequence per tile), the weight gradient
+    agrees to split-K summation order; both against torch."""
+    torch.manual_seed(N + A + l)
+    big = torch.randn(N, Bc, 4 * l)                       # gradient w.r.t. the layer's output
+    w = torch.randn(A, Bc, 4) * 0.1                       # ConvTranspose1d weight [in = A, out = Bc, 4]
+    act = F.elu(torch.randn(N, A, l))                     # the layer's input (post-ELU activation of the layer before)
+    bg, wg, ag = big.to(cuda), w.to(cuda), act.to(cuda)
+    wdn = image(wg, 1)
+    pl = planes_buffer(1, N, Bc, 1, l, cuda)
+    lib().stage_planes1d(dp(bg), Bc * 4 * l, dp(pl), N, Bc, l, 0, st())
+    dz_s, dw_s = torch.empty(N, A, l, device=cuda), torch.empty(A, Bc, 4, device=cuda)
+    lib().down1d_planes(dp(pl), dp(wdn), None, dp(ag), A * l, dp(dz_s), A * l, N, A, Bc, l, 2, st())
+    lib().wgrad1d_planes(dp(ag), A * l, dp(pl), dp(dw_s), N, A, Bc, l, st())
+    dz_f, dw_f = torch.full((N, A, l), 7.0, device=cuda), torch.full((A, Bc, 4), 7.0, device=cuda)
+    lib().tconv_bwd1d_planes(dp(ag), A * l, dp(pl), dp(wdn), dp(dz_f), A * l, dp(dw_f), N, A, Bc, l, st())
+    assert torch.equal(dz_f, dz_s)
+    assert rel_err(dw_f, dw_s) < 1e-5
+    ar = act.clone().requires_grad_()
+    wr = w.clone().requires_grad_()
+    F.conv_transpose1d(ar, wr, None, stride=4, padding=0).backward(big)
+    assert rel_err(dz_f, ar.grad * torch.where(act > 0, torch.ones_like(act), act + 1)) < TC_TOL
+    assert rel_err(dw_f, wr.grad) < 2e-5
+
+
 @pytest.mark.parametrize("N,C", [(3, 8), (2, 4)])
 def test_fused_plane_writers(cuda, N, C):
     torch.manual_seed(N * C)
