@@ -167,6 +167,10 @@ LSHM_API int lshm_wgrad1d_planes(const float* small_, int64_t small_ns, const vo
  * dz, LSHM_EPI_DELU).  A <= 16 small-map channels, Bc in {4, 8}. */
 LSHM_API int lshm_tconv_bwd1d_planes(const float* small_, int64_t small_ns, const void* planes, const void* wimg_down,
                             float* dz, int64_t dz_ns, float* dw, int64_t N, int A, int Bc, int l, lshm_stream_t stream);
+/* The same for the 2-D net (k4/s2/p1): = lshm_wgrad2d_planes + lshm_down2d_planes(..., aux = small_, LSHM_EPI_DELU).
+ * A <= 8 small-map channels, Bc in {4, 8}, w <= 118. */
+LSHM_API int lshm_tconv_bwd2d_planes(const float* small_, int64_t small_ns, const void* planes, const void* wimg_down,
+                            float* dz, int64_t dz_ns, float* dw, int64_t N, int A, int Bc, int h, int w_, lshm_stream_t stream);
 /* dst[i] += src[i], i < n (both 16-byte aligned): the parameter gradients of a second micro-batch join the flat
  * gradient buffer before the data-parallel exchange. */
 LSHM_API int lshm_vec_add(float* dst, const float* src, int64_t n, lshm_stream_t stream);

@@ -59,12 +59,13 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], acc_bar, dacc_full[2], dacc_empty[2], dimg_bar;
   __shared__ uint32_t tmem_base;
-  static_assert(!FUSED || (DIM == 1 && PRE && !FOLD && KP == 128), "fused data gradient: 1-D plane instances only");
+  static_assert(!FUSED || (PRE && KP == 128 && (DIM == 1 ? !FOLD : FOLD)), "fused data gradient: plane instances (2-D: folded) only");
   constexpr int T = (DIM == 2 && !FOLD) ? 4 : 1;      // accumulators / descriptor shifts per K block
   constexpr int CZ = NT / 8;
   constexpr int NTD = 16;                              // FUSED: channel tile of the data gradient (A <= 16)
   constexpr uint32_t DCOL = T * NT;                    // FUSED: first TMEM column of its two accumulators
-  constexpr uint32_t DIMG = 2u * 4 * NTD * 16;         // FUSED: its weight image (lshm_conv_prep "down": hi | lo, 4 chunk columns)
+  constexpr int TD = DIM == 2 ? 4 : 1;                 // FUSED: taps of the data gradient
+  constexpr uint32_t DIMG = 2u * TD * 4 * NTD * 16;    // FUSED: its weight image (lshm_conv_prep "down": hi | lo, [tap][4 chunk columns][16])
   constexpr int NPW = FUSED ? 4 : WG_NPW;              // producer warps
   constexpr int NPT = NPW * 32;
   constexpr uint32_t TCOLS = T * NT + (FUSED ? 2 * NTD : 0);
@@ -340,11 +341,23 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
     for (int it = 0; it < nkb; ++it) {
       const uint32_t buf = (uint32_t)it & 1u;
       const uint32_t q = (uint32_t)((kb0 + it) * KP) + (uint32_t)row;
-      const bool ok = q < (uint32_t)a.Q;
-      const uint32_t n = fdiv(ok ? q : 0u, a.d_w);
-      const int64_t off = (int64_t)n * a.small_ns + ((ok ? q : 0u) - n * (uint32_t)a.w);
-      const float* sp = a.small_ + off;
-      float* op = a.dz + (int64_t)n * a.dz_ns + ((ok ? q : 0u) - n * (uint32_t)a.w);
+      bool ok = q < (uint32_t)a.Q;
+      uint32_t n = 0, pos = 0;
+      if (ok) {
+        if (DIM == 2) {
+          n = fdiv(q, a.d_pp);
+          const uint32_t r = q - n * (uint32_t)(PH * PW);
+          const uint32_t by = fdiv(r, a.d_pw), bx = r - by * (uint32_t)PW;
+          ok = by < (uint32_t)a.h && bx < (uint32_t)a.w;
+          pos = by * (uint32_t)a.w + bx;
+        } else {
+          n = fdiv(q, a.d_w);
+          pos = q - n * (uint32_t)a.w;
+        }
+      }
+      const int64_t chs = DIM == 2 ? (int64_t)a.h * a.w : (int64_t)a.w;   // channel stride of the small map
+      const float* sp = a.small_ + (int64_t)n * a.small_ns + pos;
+      float* op = a.dz + (int64_t)n * a.dz_ns + pos;
       mbar_wait(&dacc_full[buf], ((uint32_t)it >> 1) & 1u);
       fence_after();
 #pragma unroll 1
@@ -352,11 +365,11 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
         if (h8 * 8 >= a.A) break;                    // warp-uniform
         float ax[8], v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) ax[e] = (ok && h8 * 8 + e < a.A) ? __ldg(sp + (int64_t)(h8 * 8 + e) * a.w) : 0.f;
+        for (int e = 0; e < 8; ++e) ax[e] = (ok && h8 * 8 + e < a.A) ? __ldg(sp + (int64_t)(h8 * 8 + e) * chs) : 0.f;
         tmem_ld8(trow + buf * NTD + h8 * 8, v);
 #pragma unroll
         for (int e = 0; e < 8; ++e)
-          if (ok && h8 * 8 + e < a.A) op[(int64_t)(h8 * 8 + e) * a.w] = v[e] * delu_from_out(ax[e]);
+          if (ok && h8 * 8 + e < a.A) op[(int64_t)(h8 * 8 + e) * chs] = v[e] * delu_from_out(ax[e]);
       }
       fence_before();
       __syncwarp();
@@ -386,11 +399,16 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
         const uint32_t bh = smem_u32(smem + a.dimg_off);
         const uint64_t dah = make_desc(zh, ZS * 16, 128), dal = make_desc(zh + zbytes, ZS * 16, 128);
         const uint64_t dbh = make_desc(bh, NTD * 16, 128), dbl = make_desc(bh + DIMG / 2, NTD * 16, 128);
+#pragma unroll 1
+        for (int tap = 0; tap < TD; ++tap) {
+          const uint32_t shift = DIM == 2 ? (uint32_t)((tap >> 1) * PW + (tap & 1)) : 0u;   // the tile carries a halo
 #pragma unroll
-        for (int ks = 0; ks < NT / 16; ++ks)
-          mma_split3_warp(tmem + DCOL + buf * NTD, desc_off(dah, (uint32_t)(2 * ks) * ZS), desc_off(dal, (uint32_t)(2 * ks) * ZS),
-                          desc_off(dbh, (uint32_t)(2 * ks) * NTD), desc_off(dbl, (uint32_t)(2 * ks) * NTD), idesc_d,
-                          ks > 0 ? 1u : 0u, leader);
+          for (int ks = 0; ks < NT / 16; ++ks) {
+            const uint32_t ao = (uint32_t)(2 * ks) * ZS + shift, bo = (uint32_t)(tap * 4 + 2 * ks) * NTD;
+            mma_split3_warp(tmem + DCOL + buf * NTD, desc_off(dah, ao), desc_off(dal, ao), desc_off(dbh, bo), desc_off(dbl, bo),
+                            idesc_d, (tap > 0 || ks > 0) ? 1u : 0u, leader);
+          }
+        }
         commit_warp(&dacc_full[buf], leader);
       }
       const uint32_t shi = smem_u32(smem + (size_t)s * stage_bytes);
@@ -434,7 +452,7 @@ int launch_wgrad_t(WgArgs a, int64_t /*splits_hint*/, int mtiles, cudaStream_t s
   // slack: the padding row groups of the last stage's S tiles are read (and ignored) up to 16 groups
   const size_t reach = (size_t)a.scols * KP * 16 + (size_t)16 * KP * 16;     // from the stage start
   size_t smem = stage * a.nstage + (reach > stage ? reach - stage : 0) + 256;
-  if (FUSED) { a.dimg_off = (uint32_t)((smem + 127) / 128 * 128); smem = a.dimg_off + (size_t)2 * 4 * 16 * 16; }
+  if (FUSED) { a.dimg_off = (uint32_t)((smem + 127) / 128 * 128); smem = a.dimg_off + (size_t)2 * (DIM == 2 ? 4 : 1) * 4 * 16 * 16; }
   LSHM_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<DIM, NT, KP, PRE, FOLD, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_wgrad");
   // split-K so that the grid is ONE wave of resident CTAs (the first version assumed 3 CTAs per SM: where only 2 fit,
   // e.g. the 12-channel 1-D layer, 1.46 waves left a third of the run to a half-empty machine - ncu, r2_ncu_layer2.md)
@@ -470,7 +488,7 @@ int launch_wgrad(int dim, WgArgs a, cudaStream_t st, bool planes = false, bool f
   static const bool nofold = getenv("LSHM_WGRAD_NOFOLD") != nullptr;          // experiment switch
   const bool fold = dim == 2 && a.A <= 8 && KP == 128 && !nofold;   // (A = 12: staging the small map 4x costs more than it saves)
   if (fold) { a.acols = (a.A + 7) / 8; a.scols = 4 * a.acols; }
-  a.zslots = (dim == 2 && !fold) ? (KP + a.w + 2 + 7) / 8 * 8 : KP;
+  a.zslots = (dim == 2 && (!fold || fused)) ? (KP + a.w + 2 + 7) / 8 * 8 : KP;   // (fused: the data gradient reads a halo)
   if (planes) a.zslots = (a.zslots + PLANE_ROW - 1) / PLANE_ROW * PLANE_ROW;   // whole 512-byte rows of the tensor map
   a.d_zs = make_fastdiv((uint32_t)a.zslots);
   const size_t stage = (size_t)2 * a.scols * KP * 16 + (size_t)2 * (NT / 8) * a.zslots * 16;
@@ -483,10 +501,15 @@ int launch_wgrad(int dim, WgArgs a, cudaStream_t st, bool planes = false, bool f
   a.nstage = (int)std::min<int64_t>(a.nstage, std::max<int64_t>(1, a.kb_per_cta));
   if (planes) {
     LSHM_REQUIRE(NT <= 32 && KP == 128 && a.zslots <= 256, "lshm_wgrad*_planes: operand planes serve the first layers (A <= 16, Bc <= 8)");
+    if (fused && dim == 2) {
+      LSHM_REQUIRE(fold, "lshm_tconv_bwd2d_planes: at most 8 small-map channels");
+      if (NT == 16) return launch_wgrad_t<2, 16, 128, true, true, true>(a, splits, mtiles, st);
+      return launch_wgrad_t<2, 32, 128, true, true, true>(a, splits, mtiles, st);
+    }
     if (dim == 2 && fold) { if (NT == 16) return launch_wgrad_t<2, 16, 128, true, true>(a, splits, mtiles, st); return launch_wgrad_t<2, 32, 128, true, true>(a, splits, mtiles, st); }
     if (dim == 2) { if (NT == 16) return launch_wgrad_t<2, 16, 128, true>(a, splits, mtiles, st); return launch_wgrad_t<2, 32, 128, true>(a, splits, mtiles, st); }
     if (fused) {
-      LSHM_REQUIRE(dim == 1 && a.A <= 16, "lshm_tconv_bwd1d_planes: at most 16 small-map channels");
+      LSHM_REQUIRE(a.A <= 16, "lshm_tconv_bwd1d_planes: at most 16 small-map channels");
       if (NT == 16) return launch_wgrad_t<1, 16, 128, true, false, true>(a, splits, mtiles, st);
       return launch_wgrad_t<1, 32, 128, true, false, true>(a, splits, mtiles, st);
     }
@@ -592,6 +615,22 @@ int lshm_tconv_bwd1d_planes(const float* small_, int64_t small_ns, const void* p
   a.dimg = reinterpret_cast<const uint8_t*>(wimg_down); a.dz = dz; a.dz_ns = dz_ns;
   a.N = N; a.A = A; a.Bc = Bc; a.h = 1; a.w = l; a.pad = 0;
   return launch_wgrad(1, a, st, true, true);
+}
+
+int lshm_tconv_bwd2d_planes(const float* small_, int64_t small_ns, const void* planes, const void* wimg_down,
+                            float* dz, int64_t dz_ns, float* dw, int64_t N, int A, int Bc, int h, int w_, lshm_stream_t stream) {
+  LSHM_REQUIRE(small_ && planes && wimg_down && dz && dw, "lshm_tconv_bwd2d_planes: null pointer");
+  LSHM_REQUIRE(N >= 0 && A > 0 && A <= 8 && Bc > 0 && (Bc & 3) == 0 && Bc <= 8 && h > 0 && w_ > 0 && w_ <= 118,
+               "lshm_tconv_bwd2d_planes: bad sizes (A <= 8, Bc in {4, 8}, w <= 118)");
+  LSHM_REQUIRE((reinterpret_cast<uintptr_t>(wimg_down) & 15) == 0, "lshm_tconv_bwd2d_planes: weight image must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  LSHM_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)A * Bc * 16, st), "lshm_tconv_bwd2d_planes");
+  if (N == 0) return LSHM_OK;
+  WgArgs a{};
+  a.small_ = small_; a.small_ns = small_ns; a.big = reinterpret_cast<const float*>(planes); a.big_ns = 0; a.dw = dw;
+  a.dimg = reinterpret_cast<const uint8_t*>(wimg_down); a.dz = dz; a.dz_ns = dz_ns;
+  a.N = N; a.A = A; a.Bc = Bc; a.h = h; a.w = w_; a.pad = 0;
+  return launch_wgrad(2, a, st, true, true);
 }
 
 }  // extern "C"

@@ -21,7 +21,7 @@ from ._lib import lib
 
 import os
 EPI_NONE, EPI_ELU, EPI_DELU = 0, 1, 2
-FUSE_LAST_1D = os.environ.get("LSHM_NO_FUSED_LAST1D") is None   # (switch for A/B measurements)
+FUSE_LAST = os.environ.get("LSHM_NO_FUSED_LAST") is None   # (switch for A/B measurements)
 CONV_CHANNELS = (8, 12, 24, 48, 96, 192)   # src/lofar_models.py:31-41
 FLAT = 768                                  # 192*2*2 (2-D) = 192*4 (1-D)
 INPUT_ELEMS = 16384                         # 128*128 pixels or 16384 samples per channel
@@ -319,10 +319,14 @@ class AEEngine:
                 fork()
                 nxt = ws.g_dec[i]
                 if i == 5 and g_xhat_planes is not None:
-                    if self.ndim == 1 and A <= 16 and Bc <= 8 and FUSE_LAST_1D:
+                    if self.ndim == 1 and A <= 16 and Bc <= 8 and FUSE_LAST:
                         # both gradients of the last transposed conv from ONE read of the reconstruction gradient
                         lb.tconv_bwd1d_planes(_p(inp), sz[lvl], _p(g_xhat_planes), _p(self.img[("tconv5.weight", 0)]),
                                               _p(nxt), sz[lvl], _p(g["tconv5.weight"]), N, A, Bc, INPUT_ELEMS >> (2 * lvl), st)
+                    elif self.ndim == 2 and A <= 8 and Bc <= 8 and FUSE_LAST:
+                        s2 = 128 >> lvl
+                        lb.tconv_bwd2d_planes(_p(inp), sz[lvl], _p(g_xhat_planes), _p(self.img[("tconv5.weight", 0)]),
+                                              _p(nxt), sz[lvl], _p(g["tconv5.weight"]), N, A, Bc, s2, s2, st)
                     else:
                         self._wgrad_planes(_p(inp), sz[lvl], _p(g_xhat_planes), _p(g["tconv5.weight"]), N, A, Bc, lvl, wst)
                         self._down_planes(_p(g_xhat_planes), _p(self.img[("tconv5.weight", 0)]), None, _p(inp), sz[lvl],

@@ -177,6 +177,31 @@ def test_fused_last_layer_backward_1d(cuda, N, A, Bc, l):
     assert rel_err(dw_f, wr.grad) < 2e-5
 
 
+@pytest.mark.parametrize("N,A,Bc,s", [(2, 8, 8, 64), (40, 8, 8, 64), (3, 8, 4, 64), (5, 4, 8, 16), (300, 8, 8, 16)])
+def test_fused_last_layer_backward_2d(cuda, N, A, Bc, s):
+    """lshm_tconv_bwd2d_planes = lshm_wgrad2d_planes + lshm_down2d_planes(ELU') from one read of the gradient planes."""
+    torch.manual_seed(N + A + s)
+    big = torch.randn(N, Bc, 2 * s, 2 * s)
+    w = torch.randn(A, Bc, 4, 4) * 0.1                    # ConvTranspose2d weight [in = A, out = Bc, 4, 4]
+    act = F.elu(torch.randn(N, A, s, s))
+    bg, wg, ag = big.to(cuda), w.to(cuda), act.to(cuda)
+    wdn = image(wg, 2)
+    pl = planes_buffer(2, N, Bc, s, s, cuda)
+    lib().stage_planes2d(dp(bg), Bc * 4 * s * s, dp(pl), N, Bc, s, s, st())
+    dz_s, dw_s = torch.empty(N, A, s, s, device=cuda), torch.empty(A, Bc, 4, 4, device=cuda)
+    lib().down2d_planes(dp(pl), dp(wdn), None, dp(ag), A * s * s, dp(dz_s), A * s * s, N, A, Bc, s, s, 2, st())
+    lib().wgrad2d_planes(dp(ag), A * s * s, dp(pl), dp(dw_s), N, A, Bc, s, s, st())
+    dz_f, dw_f = torch.full((N, A, s, s), 7.0, device=cuda), torch.full((A, Bc, 4, 4), 7.0, device=cuda)
+    lib().tconv_bwd2d_planes(dp(ag), A * s * s, dp(pl), dp(wdn), dp(dz_f), A * s * s, dp(dw_f), N, A, Bc, s, s, st())
+    assert torch.equal(dz_f, dz_s)
+    assert rel_err(dw_f, dw_s) < 1e-5
+    ar = act.clone().requires_grad_()
+    wr = w.clone().requires_grad_()
+    F.conv_transpose2d(ar, wr, None, stride=2, padding=1).backward(big)
+    assert rel_err(dz_f, ar.grad * torch.where(act > 0, torch.ones_like(act), act + 1)) < TC_TOL
+    assert rel_err(dw_f, wr.grad) < 2e-5
+
+
 @pytest.mark.parametrize("N,C", [(3, 8), (2, 4)])
 def test_fused_plane_writers(cuda, N, C):
     torch.manual_seed(N * C)
