@@ -42,6 +42,12 @@ struct WgArgs {
 constexpr int WG_NPW = 8;
 constexpr int WG_PT = WG_NPW * 32;                 // producer threads
 constexpr int WG_THREADS = WG_PT + 32;             // + the MMA warp
+// warp roles: producers [0, NPW), (FUSED) data-gradient epilogue [NPW, NPW + 4), then the MMA warp.  The fused 1-D
+// instance stages one small tile per K block: four producer warps (the other four become the epilogue); the fused 2-D
+// instance stages the small map four times (taps folded into M): all eight, plus four epilogue warps.
+__host__ __device__ constexpr int wg_npw(int dim, bool fused) { return (fused && dim == 1) ? 4 : WG_NPW; }
+__host__ __device__ constexpr int wg_mma_warp(int dim, bool fused) { return wg_npw(dim, fused) + (fused ? 4 : 0); }
+__host__ __device__ constexpr int wg_threads(int dim, bool fused) { return (wg_mma_warp(dim, fused) + 1) * 32; }
 // PRE: the big map arrives as operand planes; its tile is one tensor-TMA box per half (issued by thread 0),
 // the producer warps stage the (8x smaller) small-map tile only.
 // FOLD (2-D, A <= 32): the four taps are folded into the M dimension.  D_tap[a,c] = sum_q S[q,a] Z[q+shift_tap,c]
@@ -55,7 +61,7 @@ constexpr int WG_THREADS = WG_PT + 32;             // + the MMA warp
 // layer) are read from HBM once instead of twice.  Warps 0-3 stage S, warps 4-7 drain the data-gradient accumulator of
 // every K block (two TMEM buffers), the MMA warp issues both products.
 template <int DIM, int NT, int KP, bool PRE, bool FOLD, bool FUSED>
-__global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_kernel(const __grid_constant__ WgArgs a) {
+__global__ void __launch_bounds__(wg_threads(DIM, FUSED), (KP == 128 && !(FUSED && DIM == 2) ? 3 : 2)) igemm_wgrad_kernel(const __grid_constant__ WgArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], acc_bar, dacc_full[2], dacc_empty[2], dimg_bar;
   __shared__ uint32_t tmem_base;
@@ -66,7 +72,8 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
   constexpr uint32_t DCOL = T * NT;                    // FUSED: first TMEM column of its two accumulators
   constexpr int TD = DIM == 2 ? 4 : 1;                 // FUSED: taps of the data gradient
   constexpr uint32_t DIMG = 2u * TD * 4 * NTD * 16;    // FUSED: its weight image (lshm_conv_prep "down": hi | lo, [tap][4 chunk columns][16])
-  constexpr int NPW = FUSED ? 4 : WG_NPW;              // producer warps
+  constexpr int NPW = wg_npw(DIM, FUSED);              // producer warps
+  constexpr int MMAW = wg_mma_warp(DIM, FUSED);        // the MMA-issuing warp
   constexpr int NPT = NPW * 32;
   constexpr uint32_t TCOLS = T * NT + (FUSED ? 2 * NTD : 0);
   constexpr uint32_t TMEM_COLS = TCOLS <= 32 ? 32 : (TCOLS <= 64 ? 64 : (TCOLS <= 128 ? 128 : (TCOLS <= 256 ? 256 : 512)));
@@ -86,7 +93,7 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
   const int a0 = mt * 128, c0 = nt * NT;
   const int sch = FOLD ? a.scols : min(a.scols, (a.A - a0 + 7) / 8);     // S chunk columns that hold data in this M tile
 
-  if (warp == WG_NPW) tmem_alloc(&tmem_base, TMEM_COLS);
+  if (warp == MMAW) tmem_alloc(&tmem_base, TMEM_COLS);
   if (tid == 0) {
     for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], NPW + (PRE ? 1 : 0)); mbar_init(&empty_bar[s], 1); }
     mbar_init(&acc_bar, 1);
@@ -334,7 +341,7 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
     }
     }
     }
-  } else if (FUSED && warp < WG_NPW) {
+  } else if (FUSED && warp < MMAW) {
     // ------------------------------------------------ data-gradient epilogue (warps 4-7 = TMEM lane quarters 0-3)
     const int row = (warp & 3) * 32 + lane;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + DCOL;
@@ -437,7 +444,7 @@ __global__ void __launch_bounds__(WG_THREADS, (KP == 128 ? 3 : 2)) igemm_wgrad_k
   }
   fence_before();
   __syncthreads();
-  if (warp == WG_NPW) tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == MMAW) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 template <int DIM, int NT, int KP, bool PRE = false, bool FOLD = false, bool FUSED = false>
@@ -466,7 +473,7 @@ int launch_wgrad_t(WgArgs a, int64_t /*splits_hint*/, int mtiles, cudaStream_t s
   splits = ceil_div(a.kblocks, a.kb_per_cta);
   a.nstage = (int)std::min<int64_t>(a.nstage, std::max<int64_t>(1, a.kb_per_cta));
   dim3 grid((unsigned)splits, (unsigned)(mtiles * a.ntiles));
-  igemm_wgrad_kernel<DIM, NT, KP, PRE, FOLD, FUSED><<<grid, WG_THREADS, smem, st>>>(a);
+  igemm_wgrad_kernel<DIM, NT, KP, PRE, FOLD, FUSED><<<grid, wg_threads(DIM, FUSED), smem, st>>>(a);
   LSHM_CHECK_LAUNCH("igemm_wgrad");
   return LSHM_OK;
 }
