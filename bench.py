@@ -147,6 +147,13 @@ def call_cost(name, a):
         N, A, B = a[4], a[5], a[6]
         small_px = a[7] * a[8] if two_d else a[7]
         return f"{name}[A={A},B={B},px={small_px}]", 4.0 * (N * A * small_px + N * B * small_px * 4), 2.0 * N * small_px * A * B * (16 if two_d else 4)
+    if name in ("tconv_bwd1d_planes", "tconv_bwd2d_planes"):
+        # fused weight + data gradient of the last transposed conv: planes once, small map read (operand + ELU') and written
+        two_d = name.endswith("2d_planes")
+        N, A, B = a[7], a[8], a[9]
+        small_px = a[10] * a[11] if two_d else a[10]
+        small, big = N * A * small_px, N * B * small_px * 4
+        return f"{name}[A={A},B={B},px={small_px}]", 4.0 * (2 * small + big), 4.0 * N * small_px * A * B * (16 if two_d else 4)
     if name == "stage_planes2d":
         n = a[3] * a[4] * a[5] * a[6] * 4
         return name, 8.0 * n, 3.0 * n

@@ -457,7 +457,9 @@ int launch_wgrad_t(WgArgs a, int64_t /*splits_hint*/, int mtiles, cudaStream_t s
   }
   const size_t stage = (size_t)2 * a.scols * KP * 16 + (size_t)2 * (NT / 8) * a.zslots * 16;
   // slack: the padding row groups of the last stage's S tiles are read (and ignored) up to 16 groups
-  const size_t reach = (size_t)a.scols * KP * 16 + (size_t)16 * KP * 16;     // from the stage start
+  // (M = 64 instances - at most 16 small-map channels, or the folded 8-channel layer - walk 8 groups only)
+  const bool m64 = FOLD ? 32 * a.acols <= 64 : a.A <= 16;
+  const size_t reach = (size_t)a.scols * KP * 16 + (size_t)(m64 ? 8 : 16) * KP * 16;     // from the stage start
   size_t smem = stage * a.nstage + (reach > stage ? reach - stage : 0) + 256;
   if (FUSED) { a.dimg_off = (uint32_t)((smem + 127) / 128 * 128); smem = a.dimg_off + (size_t)2 * (DIM == 2 ? 4 : 1) * 4 * 16 * 16; }
   LSHM_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<DIM, NT, KP, PRE, FOLD, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "igemm_wgrad");

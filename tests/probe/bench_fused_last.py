@@ -28,4 +28,4 @@ t_d = timeit(lambda: L.down1d_planes(d(pl), d(img), None, d(act), A * l, d(dz), 
 t_w = timeit(lambda: L.wgrad1d_planes(d(act), A * l, d(pl), d(dw), N, A, Bc, l, st))
 t_f = timeit(lambda: L.tconv_bwd1d_planes(d(act), A * l, d(pl), d(img), d(dz), A * l, d(dw), N, A, Bc, l, st))
 mb = (pl.numel() + 2 * act.numel() * 4) / 1e6
-print(f"down1d_planes {t_d:.1f} us, wgrad1d_planes {t_w:.1f} us, fused {t_f:.1f} us ({mb:.0f} MB algorithmic -> {mb / t_f * 1e-3:.2f} TB/s)")
+print(f"down1d_planes {t_d:.1f} us, wgrad1d_planes {t_w:.1f} us, fused {t_f:.1f} us ({mb:.0f} MB algorithmic -> {mb / t_f:.2f} TB/s)")
