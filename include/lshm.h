@@ -171,6 +171,12 @@ LSHM_API int lshm_tconv_bwd1d_planes(const float* small_, int64_t small_ns, cons
  * A <= 8 small-map channels, Bc in {4, 8}, w <= 118. */
 LSHM_API int lshm_tconv_bwd2d_planes(const float* small_, int64_t small_ns, const void* planes, const void* wimg_down,
                             float* dz, int64_t dz_ns, float* dw, int64_t N, int A, int Bc, int h, int w_, lshm_stream_t stream);
+/* The same with the output gradient as an fp32 map `big` (the second-to-last transposed convs, 9..16 -> 8 channels):
+ * = lshm_wgrad*d + lshm_down*d(..., aux = small_, LSHM_EPI_DELU), the big map gathered and converted once. */
+LSHM_API int lshm_tconv_bwd1d(const float* small_, int64_t small_ns, const float* big, int64_t big_ns, const void* wimg_down,
+                     float* dz, int64_t dz_ns, float* dw, int64_t N, int A, int Bc, int l, lshm_stream_t stream);
+LSHM_API int lshm_tconv_bwd2d(const float* small_, int64_t small_ns, const float* big, int64_t big_ns, const void* wimg_down,
+                     float* dz, int64_t dz_ns, float* dw, int64_t N, int A, int Bc, int h, int w_, lshm_stream_t stream);
 /* dst[i] += src[i], i < n (both 16-byte aligned): the parameter gradients of a second micro-batch join the flat
  * gradient buffer before the data-parallel exchange. */
 LSHM_API int lshm_vec_add(float* dst, const float* src, int64_t n, lshm_stream_t stream);

@@ -44,10 +44,11 @@ constexpr int WG_PT = WG_NPW * 32;                 // producer threads
 constexpr int WG_THREADS = WG_PT + 32;             // + the MMA warp
 // warp roles: producers [0, NPW), (FUSED) data-gradient epilogue [NPW, NPW + 4), then the MMA warp.  The fused 1-D
 // instance stages one small tile per K block: four producer warps (the other four become the epilogue); the fused 2-D
-// instance stages the small map four times (taps folded into M): all eight, plus four epilogue warps.
-__host__ __device__ constexpr int wg_npw(int dim, bool fused) { return (fused && dim == 1) ? 4 : WG_NPW; }
-__host__ __device__ constexpr int wg_mma_warp(int dim, bool fused) { return wg_npw(dim, fused) + (fused ? 4 : 0); }
-__host__ __device__ constexpr int wg_threads(int dim, bool fused) { return (wg_mma_warp(dim, fused) + 1) * 32; }
+// instance stages the small map four times (taps folded into M) and the fp32-input instances gather the big-map tile as
+// well: all eight, plus four epilogue warps.
+__host__ __device__ constexpr int wg_npw(int dim, bool fused, bool pre) { return (fused && dim == 1 && pre) ? 4 : WG_NPW; }
+__host__ __device__ constexpr int wg_mma_warp(int dim, bool fused, bool pre) { return wg_npw(dim, fused, pre) + (fused ? 4 : 0); }
+__host__ __device__ constexpr int wg_threads(int dim, bool fused, bool pre) { return (wg_mma_warp(dim, fused, pre) + 1) * 32; }
 // PRE: the big map arrives as operand planes; its tile is one tensor-TMA box per half (issued by thread 0),
 // the producer warps stage the (8x smaller) small-map tile only.
 // FOLD (2-D, A <= 32): the four taps are folded into the M dimension.  D_tap[a,c] = sum_q S[q,a] Z[q+shift_tap,c]
@@ -61,19 +62,19 @@ __host__ __device__ constexpr int wg_threads(int dim, bool fused) { return (wg_m
 // layer) are read from HBM once instead of twice.  Warps 0-3 stage S, warps 4-7 drain the data-gradient accumulator of
 // every K block (two TMEM buffers), the MMA warp issues both products.
 template <int DIM, int NT, int KP, bool PRE, bool FOLD, bool FUSED>
-__global__ void __launch_bounds__(wg_threads(DIM, FUSED), (KP == 128 && !(FUSED && DIM == 2) ? 3 : 2)) igemm_wgrad_kernel(const __grid_constant__ WgArgs a) {
+__global__ void __launch_bounds__(wg_threads(DIM, FUSED, PRE), (KP == 128 && !(FUSED && (DIM == 2 || !PRE)) ? 3 : 2)) igemm_wgrad_kernel(const __grid_constant__ WgArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], acc_bar, dacc_full[2], dacc_empty[2], dimg_bar;
   __shared__ uint32_t tmem_base;
-  static_assert(!FUSED || (PRE && KP == 128 && (DIM == 1 ? !FOLD : FOLD)), "fused data gradient: plane instances (2-D: folded) only");
+  static_assert(!FUSED || (KP == 128 && (DIM == 1 ? !FOLD : (FOLD == PRE))), "fused data gradient: KP = 128; 2-D: folded plane instance or un-folded fp32 instance");
   constexpr int T = (DIM == 2 && !FOLD) ? 4 : 1;      // accumulators / descriptor shifts per K block
   constexpr int CZ = NT / 8;
   constexpr int NTD = 16;                              // FUSED: channel tile of the data gradient (A <= 16)
   constexpr uint32_t DCOL = T * NT;                    // FUSED: first TMEM column of its two accumulators
   constexpr int TD = DIM == 2 ? 4 : 1;                 // FUSED: taps of the data gradient
   constexpr uint32_t DIMG = 2u * TD * 4 * NTD * 16;    // FUSED: its weight image (lshm_conv_prep "down": hi | lo, [tap][4 chunk columns][16])
-  constexpr int NPW = wg_npw(DIM, FUSED);              // producer warps
-  constexpr int MMAW = wg_mma_warp(DIM, FUSED);        // the MMA-issuing warp
+  constexpr int NPW = wg_npw(DIM, FUSED, PRE);         // producer warps
+  constexpr int MMAW = wg_mma_warp(DIM, FUSED, PRE);   // the MMA-issuing warp
   constexpr int NPT = NPW * 32;
   constexpr uint32_t TCOLS = T * NT + (FUSED ? 2 * NTD : 0);
   constexpr uint32_t TMEM_COLS = TCOLS <= 32 ? 32 : (TCOLS <= 64 ? 64 : (TCOLS <= 128 ? 128 : (TCOLS <= 256 ? 256 : 512)));
@@ -467,7 +468,7 @@ int launch_wgrad_t(WgArgs a, int64_t /*splits_hint*/, int mtiles, cudaStream_t s
   // e.g. the 12-channel 1-D layer, 1.46 waves left a third of the run to a half-empty machine - ncu, r2_ncu_layer2.md)
   // resident CTAs per SM: the launch bound (registers) and the shared memory (227 KB per SM, 1 KB reserved per CTA).
   // (cudaOccupancyMaxActiveBlocksPerMultiprocessor answered 1 for these kernels on the driver of the test box.)
-  const int occ_cache = (int)std::max<size_t>(1, std::min<size_t>(KP == 128 ? 3 : 2, (size_t)(227 * 1024) / (smem + 1024)));
+  const int occ_cache = (int)std::max<size_t>(1, std::min<size_t>((KP == 128 && !(FUSED && (DIM == 2 || !PRE))) ? 3 : 2, (size_t)(227 * 1024) / (smem + 1024)));
   const int64_t tiles = (int64_t)mtiles * a.ntiles;
   int64_t splits = std::max<int64_t>(1, ((int64_t)sm_count() * occ_cache) / tiles);
   splits = std::min(splits, std::max<int64_t>(1, a.kblocks / 4));   // at least 4 K blocks per CTA
@@ -475,7 +476,7 @@ int launch_wgrad_t(WgArgs a, int64_t /*splits_hint*/, int mtiles, cudaStream_t s
   splits = ceil_div(a.kblocks, a.kb_per_cta);
   a.nstage = (int)std::min<int64_t>(a.nstage, std::max<int64_t>(1, a.kb_per_cta));
   dim3 grid((unsigned)splits, (unsigned)(mtiles * a.ntiles));
-  igemm_wgrad_kernel<DIM, NT, KP, PRE, FOLD, FUSED><<<grid, wg_threads(DIM, FUSED), smem, st>>>(a);
+  igemm_wgrad_kernel<DIM, NT, KP, PRE, FOLD, FUSED><<<grid, wg_threads(DIM, FUSED, PRE), smem, st>>>(a);
   LSHM_CHECK_LAUNCH("igemm_wgrad");
   return LSHM_OK;
 }
@@ -524,6 +525,12 @@ int launch_wgrad(int dim, WgArgs a, cudaStream_t st, bool planes = false, bool f
     }
     if (NT == 16) return launch_wgrad_t<1, 16, 128, true>(a, splits, mtiles, st);
     return launch_wgrad_t<1, 32, 128, true>(a, splits, mtiles, st);
+  }
+  if (fused) {
+    // fp32 big map: the second layers (12 -> 8 channels); the kernel then gathers the big-map tile once for both products
+    LSHM_REQUIRE(!fold && KP == 128 && NT == 32 && a.A <= 16, "lshm_tconv_bwd*: 9..16 small-map channels and 8 big-map channels");
+    if (dim == 2) return launch_wgrad_t<2, 32, 128, false, false, true>(a, splits, mtiles, st);
+    return launch_wgrad_t<1, 32, 128, false, false, true>(a, splits, mtiles, st);
   }
   if (fold) {
     if (NT == 16) return launch_wgrad_t<2, 16, 128, false, true>(a, splits, mtiles, st);
@@ -624,6 +631,39 @@ int lshm_tconv_bwd1d_planes(const float* small_, int64_t small_ns, const void* p
   a.dimg = reinterpret_cast<const uint8_t*>(wimg_down); a.dz = dz; a.dz_ns = dz_ns;
   a.N = N; a.A = A; a.Bc = Bc; a.h = 1; a.w = l; a.pad = 0;
   return launch_wgrad(1, a, st, true, true);
+}
+
+// The same with the gradient w.r.t. the layer's output given as an fp32 map (the second-to-last transposed convs):
+// = lshm_wgrad*d(small_, big -> dw) + lshm_down*d(big, wimg_down, aux = small_, LSHM_EPI_DELU -> dz), the big map
+// gathered and converted once.
+int lshm_tconv_bwd1d(const float* small_, int64_t small_ns, const float* big, int64_t big_ns, const void* wimg_down,
+                     float* dz, int64_t dz_ns, float* dw, int64_t N, int A, int Bc, int l, lshm_stream_t stream) {
+  LSHM_REQUIRE(small_ && big && wimg_down && dz && dw, "lshm_tconv_bwd1d: null pointer");
+  LSHM_REQUIRE(N >= 0 && A > 8 && A <= 16 && Bc == 8 && l > 0, "lshm_tconv_bwd1d: bad sizes (9 <= A <= 16, Bc = 8)");
+  LSHM_REQUIRE((reinterpret_cast<uintptr_t>(wimg_down) & 15) == 0, "lshm_tconv_bwd1d: weight image must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  LSHM_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)A * Bc * 4, st), "lshm_tconv_bwd1d");
+  if (N == 0) return LSHM_OK;
+  WgArgs a{};
+  a.small_ = small_; a.small_ns = small_ns; a.big = big; a.big_ns = big_ns; a.dw = dw;
+  a.dimg = reinterpret_cast<const uint8_t*>(wimg_down); a.dz = dz; a.dz_ns = dz_ns;
+  a.N = N; a.A = A; a.Bc = Bc; a.h = 1; a.w = l; a.pad = 0;
+  return launch_wgrad(1, a, st, false, true);
+}
+
+int lshm_tconv_bwd2d(const float* small_, int64_t small_ns, const float* big, int64_t big_ns, const void* wimg_down,
+                     float* dz, int64_t dz_ns, float* dw, int64_t N, int A, int Bc, int h, int w_, lshm_stream_t stream) {
+  LSHM_REQUIRE(small_ && big && wimg_down && dz && dw, "lshm_tconv_bwd2d: null pointer");
+  LSHM_REQUIRE(N >= 0 && A > 8 && A <= 16 && Bc == 8 && h > 0 && w_ > 0 && w_ <= 126, "lshm_tconv_bwd2d: bad sizes (9 <= A <= 16, Bc = 8, w <= 126)");
+  LSHM_REQUIRE((reinterpret_cast<uintptr_t>(wimg_down) & 15) == 0, "lshm_tconv_bwd2d: weight image must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  LSHM_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)A * Bc * 16, st), "lshm_tconv_bwd2d");
+  if (N == 0) return LSHM_OK;
+  WgArgs a{};
+  a.small_ = small_; a.small_ns = small_ns; a.big = big; a.big_ns = big_ns; a.dw = dw;
+  a.dimg = reinterpret_cast<const uint8_t*>(wimg_down); a.dz = dz; a.dz_ns = dz_ns;
+  a.N = N; a.A = A; a.Bc = Bc; a.h = h; a.w = w_; a.pad = 0;
+  return launch_wgrad(2, a, st, false, true);
 }
 
 int lshm_tconv_bwd2d_planes(const float* small_, int64_t small_ns, const void* planes, const void* wimg_down,

@@ -333,9 +333,22 @@ class AEEngine:
                                           _p(nxt), sz[lvl], N, A, Bc, lvl, EPI_DELU, st)
                     dz = nxt
                     continue
-                self._wgrad(_p(inp), sz[lvl], _p(dz), sz[lvl - 1], _p(g[f"tconv{i}.weight"]), N, A, Bc, lvl, 0, wst)
+                fused = FUSE_LAST and i > 0 and 8 < A <= 16 and Bc == 8     # the 12 -> 8 channel layer
+                if not fused:
+                    self._wgrad(_p(inp), sz[lvl], _p(dz), sz[lvl - 1], _p(g[f"tconv{i}.weight"]), N, A, Bc, lvl, 0, wst)
                 if not (i == 5 and out_bias_done):
                     lb.channel_sum(_p(dz), sz[lvl - 1], _p(g[f"tconv{i}.bias"]), N, Bc, sz[lvl - 1] // Bc, wst)
+                if fused:
+                    # weight and data gradient from one gather of the output gradient (lshm_tconv_bwd*)
+                    if self.ndim == 2:
+                        s2 = 128 >> lvl
+                        lb.tconv_bwd2d(_p(inp), sz[lvl], _p(dz), sz[lvl - 1], _p(self.img[(f"tconv{i}.weight", 0)]),
+                                       _p(nxt), sz[lvl], _p(g[f"tconv{i}.weight"]), N, A, Bc, s2, s2, st)
+                    else:
+                        lb.tconv_bwd1d(_p(inp), sz[lvl], _p(dz), sz[lvl - 1], _p(self.img[(f"tconv{i}.weight", 0)]),
+                                       _p(nxt), sz[lvl], _p(g[f"tconv{i}.weight"]), N, A, Bc, INPUT_ELEMS >> (2 * lvl), st)
+                    dz = nxt
+                    continue
                 # dgrad of the transposed conv = "down"; ELU' of the producing layer unless it is fc3
                 self._down(_p(dz), sz[lvl - 1], _p(self.img[(f"tconv{i}.weight", 0)]), None,
                            _p(inp) if i > 0 else None, sz[lvl], _p(nxt), sz[lvl], N, A, Bc, lvl, 0,

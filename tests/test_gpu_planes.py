@@ -202,6 +202,37 @@ def test_fused_last_layer_backward_2d(cuda, N, A, Bc, s):
     assert rel_err(dw_f, wr.grad) < 2e-5
 
 
+@pytest.mark.parametrize("dim,N,A,small", [(1, 3, 12, 1024), (1, 256, 12, 1024), (1, 5, 16, 256), (2, 3, 12, 32), (2, 130, 12, 32), (2, 7, 10, 16)])
+def test_fused_second_layer_backward(cuda, dim, N, A, small):
+    """lshm_tconv_bwd1d / 2d = lshm_wgrad*d + lshm_down*d(ELU') on an fp32 output gradient gathered once."""
+    torch.manual_seed(N + A + small)
+    Bc = 8
+    if dim == 2:
+        big = torch.randn(N, Bc, 2 * small, 2 * small); act = F.elu(torch.randn(N, A, small, small)); w = torch.randn(A, Bc, 4, 4) * 0.1
+    else:
+        big = torch.randn(N, Bc, 4 * small); act = F.elu(torch.randn(N, A, small)); w = torch.randn(A, Bc, 4) * 0.1
+    bg, wg, ag = big.to(cuda), w.to(cuda), act.to(cuda)
+    wdn = image(wg, dim)
+    bns, sns = big[0].numel(), act[0].numel()
+    dz_s, dw_s = torch.empty_like(ag), torch.empty_like(wg)
+    dz_f, dw_f = torch.full_like(ag, 7.0), torch.full_like(wg, 7.0)
+    if dim == 2:
+        lib().down2d(dp(bg), bns, dp(wdn), None, dp(ag), sns, dp(dz_s), sns, N, A, Bc, small, small, 2, st())
+        lib().wgrad2d(dp(ag), sns, dp(bg), bns, dp(dw_s), N, A, Bc, small, small, st())
+        lib().tconv_bwd2d(dp(ag), sns, dp(bg), bns, dp(wdn), dp(dz_f), sns, dp(dw_f), N, A, Bc, small, small, st())
+    else:
+        lib().down1d(dp(bg), bns, dp(wdn), None, dp(ag), sns, dp(dz_s), sns, N, A, Bc, small, 0, 2, st())
+        lib().wgrad1d(dp(ag), sns, dp(bg), bns, dp(dw_s), N, A, Bc, small, 0, st())
+        lib().tconv_bwd1d(dp(ag), sns, dp(bg), bns, dp(wdn), dp(dz_f), sns, dp(dw_f), N, A, Bc, small, st())
+    assert torch.equal(dz_f, dz_s)
+    assert rel_err(dw_f, dw_s) < 1e-5
+    ar = act.clone().requires_grad_()
+    wr = w.clone().requires_grad_()
+    (F.conv_transpose2d(ar, wr, None, stride=2, padding=1) if dim == 2 else F.conv_transpose1d(ar, wr, None, stride=4)).backward(big)
+    assert rel_err(dz_f, ar.grad * torch.where(act > 0, torch.ones_like(act), act + 1)) < TC_TOL
+    assert rel_err(dw_f, wr.grad) < 2e-5
+
+
 @pytest.mark.parametrize("N,C", [(3, 8), (2, 4)])
 def test_fused_plane_writers(cuda, N, C):
     torch.manual_seed(N * C)
