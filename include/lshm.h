@@ -22,7 +22,9 @@
  *                     big pos   = 4*j - pad + t      (pad=1 Conv1d, pad=0 ConvTranspose1d)
  *  Conv:          S = act(W * B + bias[A])        ("down")
  *  ConvTranspose: B = act(W^T * S + bias[Bc])     ("up")
- *  and the backward of one is the other, so three kernels serve six layer types.
+ *  and the backward of one is the other, so three kernels serve six layer types; the weight gradient
+ *  ("wgrad") and the data gradient of the last two transposed convs also exist as ONE launch
+ *  (lshm_tconv_bwd*: their output gradient, the layer's largest tensor, is read once).
  *  act / epilogue codes: LSHM_EPI_*.
  */
 #ifndef LSHM_H_

@@ -12,7 +12,8 @@ def test_header_declares_expected_entry_points():
                  "lshm_wgrad2d", "lshm_down1d", "lshm_up1d", "lshm_wgrad1d", "lshm_linear_fwd", "lshm_cascade_losses",
                  "lshm_khm_fwd", "lshm_khm_bwd", "lshm_khm_assign", "lshm_khm_center_sums", "lshm_similarity",
                  "lshm_augment", "lshm_multiplier_update", "lshm_adam_step", "lshm_last_error", "lshm_fft2_features",
-                 "lshm_vec_add", "lshm_down2d_planes", "lshm_wgrad1d_planes", "lshm_cascade_losses_planes"):
+                 "lshm_vec_add", "lshm_down2d_planes", "lshm_wgrad1d_planes", "lshm_cascade_losses_planes",
+                 "lshm_tconv_bwd1d_planes", "lshm_tconv_bwd2d_planes", "lshm_tconv_bwd1d", "lshm_tconv_bwd2d"):
         assert name in protos, name
     # every LSHM_API line was understood by the parser
     text = open(_lib.HEADER).read()
