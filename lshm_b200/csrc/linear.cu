@@ -25,6 +25,7 @@ struct GemmArgs {
   int64_t M; int N; int64_t K;
   int64_t kchunk;                      // K range per blockIdx.z
   int epi; int atomic;
+  float* rowsum;                       // atomic mode: rowsum[m] += sum_k A(m,k) (the bias gradient of a weight-gradient product)
 };
 
 __global__ void __launch_bounds__(GEMM_THREADS) sgemm_strided_kernel(GemmArgs g) {
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_strided_kernel(GemmArgs g)
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float rsum = 0.f;
   const bool a_kfast = g.sak == 1, b_kfast = g.sbk == 1;
   for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
 #pragma unroll
@@ -69,8 +71,14 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_strided_kernel(GemmArgs g)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
+    // the A tile is in shared memory anyway: its row sums are the bias gradient (was a separate column-sum launch)
+    if (g.rowsum != nullptr && blockIdx.y == 0 && threadIdx.x < BM) {
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) rsum += As[kk][threadIdx.x];
+    }
     __syncthreads();
   }
+  if (g.rowsum != nullptr && blockIdx.y == 0 && threadIdx.x < BM && m0 + threadIdx.x < g.M) atomicAdd(g.rowsum + m0 + threadIdx.x, rsum);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int64_t m = m0 + ty * 4 + i;
@@ -279,23 +287,6 @@ int launch_gemm(GemmArgs g, int ksplit, cudaStream_t st, const char* name) {
   return LSHM_OK;
 }
 
-__global__ void colsum_kernel(const float* __restrict__ dz, int64_t ld, float* __restrict__ db,
-                              int64_t N, int J, int64_t chunk) {
-  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int64_t start = (int64_t)blockIdx.y * chunk, stop = min(start + chunk, N);
-  float s = 0.f;
-  if (j < J)
-    for (int64_t n = start + (threadIdx.x >> 5); n < stop; n += blockDim.x >> 5) s += __ldg(dz + n * ld + j);
-  __shared__ float red[8][33];
-  red[threadIdx.x >> 5][threadIdx.x & 31] = s;
-  __syncthreads();
-  if (threadIdx.x < 32 && j < J) {
-    float t = 0.f;
-    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) t += red[q][threadIdx.x];
-    atomicAdd(db + j, t);
-  }
-}
-
 __global__ void uv_harmonics_kernel(const float* __restrict__ uv, const float* __restrict__ scales,
                                     int64_t N, int H, float* __restrict__ out) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -383,16 +374,10 @@ int lshm_linear_bwd_weight(const float* x, int64_t ldx, const float* dz, int64_t
   if (db) LSHM_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * J, st), "lshm_linear_bwd_weight");
   if (N == 0) return LSHM_OK;
   g.atomic = 1;
+  g.rowsum = db;                               // the split-K blocks of the first column tile add the bias gradient
   const int64_t tiles = ceil_div(J, BM) * ceil_div(K, BN);
   int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(N, 4 * BK), (int64_t)sm_count() * 4 / tiles));
-  if (int rc = launch_gemm(g, ksplit, st, "lshm_linear_bwd_weight")) return rc;
-  if (db) {
-    const int64_t chunk = std::max<int64_t>(64, ceil_div(N, (int64_t)sm_count()));
-    dim3 grid((unsigned)ceil_div(J, 32), (unsigned)ceil_div(N, chunk));
-    colsum_kernel<<<grid, 256, 0, st>>>(dz, lddz, db, N, J, chunk);
-    LSHM_CHECK_LAUNCH("lshm_linear_bwd_weight(colsum)");
-  }
-  return LSHM_OK;
+  return launch_gemm(g, ksplit, st, "lshm_linear_bwd_weight");
 }
 
 int lshm_delu(const float* g, int64_t ldg, const float* aux, int64_t ldaux, float* dz,
